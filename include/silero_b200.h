@@ -1,0 +1,151 @@
+/* include/silero_b200.h -- C ABI of the B200-native Silero VAD v3.1 (16 kHz) engine.
+ *
+ * Drop-in boundary for the C backend of IntendedConsequence/vadc (citations relative to the
+ * reference tree). Plain pointers and sizes only; implemented by libsilero_b200.so
+ * (vadc_b200/csrc/, hand-written sm_100a CUDA + C host code). There is no CPU fallback: every
+ * compute entry point returns SILERO_B200_ERR_CUDA when no usable device exists.
+ *
+ *   reference interface                                     replaced by
+ *   ------------------------------------------------------  -----------------------------------
+ *   backend_init            silero.h:48-51 (silero_init :21) silero_b200_create[_from_file]
+ *   backend_run             silero.h:53-74                   silero_b200_run_chunks
+ *   silero_run_one_batch_with_context   silero_v3.c:72-215   silero_b200_run_chunks
+ *   Silero_Context.state_lstm_h/c       tensor.h:89-95       per-stream device state + get/set/reset
+ *   run_inference s16->f32 + process_chunks vadc.c:56-103,873-909   silero_b200_run_streams
+ *   feed_probability / combine / emit   vadc.c:165-299,1005-1027    vadc_segments_* (vadc_segmenter.h)
+ *   load_testtensor(_from_bytes)        tensor.h:201-325     the .testtensor blob passed to create
+ *   my_stft, adaptive_audio_normalization_inplace, transformer_layer, lstm_tensor_minibatched,
+ *   decoder_tensor (stft.c:226, misc.c:1, transformer.c:237, lstm.c:228, silero_v3.c:305)
+ *                                                            silero_b200_stage_* (parity taps)
+ *
+ * include/vadc_dropin/silero.h implements the reference's three backend_* functions on top of this
+ * ABI so that the reference's vadc.c builds against it unchanged.
+ *
+ * Threading: calls on one handle must not overlap; one handle drives one GPU. Use one handle per GPU
+ * (one process per GPU, or several handles in one process).
+ */
+#ifndef SILERO_B200_H
+#define SILERO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SILERO_B200_CHUNK_SAMPLES 1536   /* silero.h:41-42: input_size_min == input_size_max == 1536 */
+#define SILERO_B200_SAMPLE_RATE 16000
+#define SILERO_B200_STATE_FLOATS 128     /* h or c: [2 layers][64] (tensor.h:93-94) */
+
+enum
+{
+   SILERO_B200_OK = 0,
+   SILERO_B200_ERR_ARG = -1,      /* bad argument (NULL, negative count, stream out of range) */
+   SILERO_B200_ERR_WEIGHTS = -2,  /* .testtensor blob malformed or not the 99-tensor v3.1 layout */
+   SILERO_B200_ERR_CUDA = -3,     /* CUDA runtime error or no device; see silero_b200_last_error */
+   SILERO_B200_ERR_NOMEM = -4
+};
+
+typedef struct silero_b200 silero_b200; /* opaque engine handle */
+
+typedef struct silero_b200_opts
+{
+   int device;          /* CUDA device ordinal (default 0) */
+   int max_streams;     /* number of independent streams whose LSTM state is kept on device (default 1) */
+   int window_chunks;   /* chunks per stream processed per internal pass; 0 = choose from memory budget */
+   int reserved[5];
+} silero_b200_opts;
+
+void silero_b200_default_opts( silero_b200_opts *opts );
+
+/* What backend_init reports through Silero_Config (silero.h:39-43) */
+typedef struct silero_b200_info
+{
+   int batch_size_restriction; /* -1: any batch */
+   int is_silero_v5;           /* 0 */
+   int input_size_min;         /* 1536 */
+   int input_size_max;         /* 1536 */
+   int output_dims;            /* 3  => probability index 1, stride 2 (vadc.c:704-708) */
+   int sm_count;
+   int max_streams;
+   int window_chunks;
+} silero_b200_info;
+
+/* Create an engine from a .testtensor weights blob (tensor.h:201-253; 99 tensors, silero.h:31-33). */
+int silero_b200_create( const void *testtensor_bytes, size_t nbytes, const silero_b200_opts *opts, silero_b200 **out );
+int silero_b200_create_from_file( const char *path, const silero_b200_opts *opts, silero_b200 **out );
+void silero_b200_destroy( silero_b200 *h );
+int silero_b200_get_info( const silero_b200 *h, silero_b200_info *info );
+/* thread-local description of the last failure in the calling thread */
+const char *silero_b200_last_error( void );
+
+/* ---- single stream, stateful: backend_run / silero_run_one_batch_with_context ----------------
+   samples: host f32 [nchunks][1536] in [-1,1) (consecutive chunks of stream `stream`);
+   out: host f32 [nchunks][2] (index 1 = speech probability). State of `stream` advances. */
+int silero_b200_run_chunks( silero_b200 *h, int stream, const float *samples, int nchunks, float *out );
+
+/* ---- many streams: the multi-stream chunk scheduler ------------------------------------------
+   pcm: HOST s16le, stream s starts at pcm + s*stream_stride (in samples), each holding at least
+   nchunks*1536 samples; streams first_stream..first_stream+nstreams-1 of the handle are advanced.
+   probs: host f32 [nstreams][nchunks] speech probabilities (may be NULL);
+   out2:  host f32 [nstreams][nchunks][2] both decoder heads (may be NULL).
+   s16 -> f32 is x/32768.0f exactly as vadc.c:884,898. Copies are pipelined with compute. */
+int silero_b200_run_streams( silero_b200 *h, const int16_t *pcm, long long stream_stride,
+                             int first_stream, int nstreams, int nchunks, float *probs, float *out2 );
+
+/* Same, with pcm/probs/out2 already resident in DEVICE memory (no copies inside the call).
+   Asynchronous on the engine's stream; silero_b200_sync waits for completion. */
+int silero_b200_run_streams_device( silero_b200 *h, const int16_t *d_pcm, long long stream_stride,
+                                    int first_stream, int nstreams, int nchunks, float *d_probs, float *d_out2 );
+int silero_b200_sync( silero_b200 *h );
+
+/* per-stream LSTM state (zero after create / reset); h_out,c_out: host f32 [128] = [2][64] */
+int silero_b200_reset( silero_b200 *h, int first_stream, int nstreams );
+int silero_b200_get_state( silero_b200 *h, int stream, float *h_out, float *c_out );
+int silero_b200_set_state( silero_b200 *h, int stream, const float *h_in, const float *c_in );
+
+/* ---- device helpers for callers that keep audio in HBM (bench, pipelines) --------------------- */
+int silero_b200_device_alloc( silero_b200 *h, size_t nbytes, void **d_ptr );
+int silero_b200_device_free( silero_b200 *h, void *d_ptr );
+int silero_b200_memcpy_h2d( silero_b200 *h, void *d_dst, const void *src, size_t nbytes );
+int silero_b200_memcpy_d2h( silero_b200 *h, void *dst, const void *d_src, size_t nbytes );
+int silero_b200_host_alloc_pinned( size_t nbytes, void **ptr );
+int silero_b200_host_free_pinned( void *ptr );
+/* device time (ms) of the most recent run_streams[_device] call, and of its kernels by stage:
+   ms[0]=total, [1]=stft, [2]=layer1, [3]=layer2, [4]=layer3, [5]=layer4, [6]=lstm0, [7]=lstm1+decoder;
+   kernel_launches = number of kernels launched by that call. Valid after silero_b200_sync. */
+int silero_b200_last_timing( silero_b200 *h, float ms[8], long long *kernel_launches );
+/* enable (1) / disable (0) per-stage CUDA-event timing (adds events between kernels) */
+int silero_b200_set_profiling( silero_b200 *h, int enabled );
+
+/* ---- parity taps (the reference's per-stage functions; host pointers; stateless unless noted) -
+   Layouts are the reference's: spectrogram [B,129,25]; layer outputs [B,16,13] [B,32,7] [B,32,7]
+   [B,64,7]; lstm sequence [B,7,64]. Any output pointer may be NULL. */
+/* my_stft + adaptive_audio_normalization_inplace: samples [B,1536] -> log1p spectrogram minus mean.
+   If logmag_out != NULL it receives log1p(mag*2^20) before the mean subtraction. */
+int silero_b200_stage_stft_norm( silero_b200 *h, const float *samples, int batch, float *norm_out, float *logmag_out );
+/* my_stft alone (stft.c:226): samples [B,1536] -> magnitude [B,129,25] */
+int silero_b200_stage_stft_magnitude( silero_b200 *h, const float *samples, int batch, float *mag_out );
+/* the production kernels end to end from samples (STFT -> first layer with in-kernel normalization
+   -> layers 2..4), every layer output tapped in the reference layout */
+int silero_b200_stage_pipeline( silero_b200 *h, const float *samples, int batch, float *l1, float *l2, float *l3, float *l4 );
+/* adaptive_audio_normalization_inplace on a caller-supplied magnitude spectrogram [B,129,25] */
+int silero_b200_stage_norm( silero_b200 *h, const float *magnitude, int batch, float *norm_out );
+/* encoder (silero_v3.c:4-64) from a normalized spectrogram, every layer's output tapped */
+int silero_b200_stage_encoder( silero_b200 *h, const float *norm, int batch,
+                               float *l1, float *l2, float *l3, float *l4 );
+/* one transformer_layer (transformer.c:237-295), layer = 0..3, input in the reference layout
+   [B,cin,T] with (cin,T) = (129,25) (16,13) (32,7) (32,7) */
+int silero_b200_stage_layer( silero_b200 *h, int layer, const float *in, int batch, float *out );
+/* lstm_tensor_minibatched (lstm.c:228) over batch*7 steps of ONE sequence from explicit state:
+   x [B,7,64]; h0,c0 [2,64]; out [B,7,64]; hn,cn [2,64] */
+int silero_b200_stage_lstm( silero_b200 *h, const float *x, int batch, const float *h0, const float *c0,
+                            float *out, float *hn, float *cn );
+/* decoder_tensor (silero_v3.c:305): in [B,64,7] -> out [B,2] */
+int silero_b200_stage_decoder( silero_b200 *h, const float *in, int batch, float *out );
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SILERO_B200_H */

@@ -1,0 +1,1093 @@
+// vadc_b200/csrc/engine.cu -- the C-ABI engine: weight packing, device memory, the multi-stream
+// chunk scheduler (windows of chunks x streams), and kernel launches. See include/silero_b200.h.
+//
+// Replaces the orchestration of silero_run_one_batch_with_context (silero_v3.c:72-215), backend_run
+// (silero.h:53-74), process_chunks (vadc.c:56-103) and the s16->f32 step of run_inference
+// (vadc.c:873-909). No CPU fallback exists: without a CUDA device every entry point fails.
+#include "silero_b200.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "layer_kernel.cuh"
+#include "lstm_kernel.cuh"
+#include "stft_kernel.cuh"
+#include "testtensor.h"
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int set_err( int code, const char *fmt, ... )
+{
+   va_list ap;
+   va_start( ap, fmt );
+   vsnprintf( g_err, sizeof( g_err ), fmt, ap );
+   va_end( ap );
+   return code;
+}
+
+extern "C" const char *silero_b200_last_error( void ) { return g_err; }
+
+#define CU( call )                                                                                          \
+   do                                                                                                       \
+   {                                                                                                        \
+      cudaError_t e_ = ( call );                                                                            \
+      if ( e_ != cudaSuccess )                                                                              \
+         return set_err( SILERO_B200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString( e_ ), __FILE__, __LINE__ ); \
+   } while ( 0 )
+
+// ---------------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------------
+#define N_STAGE_EVENTS 9
+
+struct silero_b200
+{
+   int device;
+   int sm_count;
+   int max_streams;
+   int window_chunks_opt;
+   cudaStream_t stream;      // compute
+   cudaStream_t copy_stream; // H2D of the next window
+   float *d_weights;         // one allocation holding every packed weight
+   DeviceWeights w;
+   float *state_h, *state_c; // [max_streams][2][64]
+   // window scratch (grow-only)
+   size_t cap_chunks;
+   float *spec, *a1, *a2, *a3, *a4, *h0;
+   // host-call staging
+   int16_t *pcm_stage[2];
+   size_t pcm_stage_cap; // samples per buffer
+   cudaEvent_t pcm_ready[2], pcm_free[2];
+   float *d_probs;
+   size_t d_probs_cap;
+   float *d_out2;
+   size_t d_out2_cap;
+   float *d_f32;
+   size_t d_f32_cap;
+   // timing
+   int profiling;
+   cudaEvent_t ev_begin, ev_end;
+   cudaEvent_t ev_stage[N_STAGE_EVENTS];
+   float stage_ms[8];
+   long long launches;
+   int timing_valid;
+};
+
+static int use_device( const silero_b200 *h )
+{
+   CU( cudaSetDevice( h->device ) );
+   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing (host)
+// ---------------------------------------------------------------------------------------------
+static void pack_basis( const float *basis /*[258][256]*/, float *out /*[2][64][128][4]*/ )
+{
+   for ( int half = 0; half < 2; ++half )
+      for ( int rho = 0; rho < 128; ++rho )
+      {
+         int row;
+         if ( half == 0 )
+            row = rho < 64 ? rho : ( rho == 64 ? 128 : 129 + ( rho - 64 ) );
+         else
+            row = rho < 64 ? 64 + rho : 129 + rho;
+         for ( int l = 0; l < 8; ++l )
+            for ( int g = 0; g < 4; ++g )
+               for ( int v = 0; v < 8; ++v )
+               {
+                  int k = 64 * g + 8 * v + l;
+                  int kq = l * 8 + g * 2 + ( v >> 2 );
+                  out[( ( (size_t)half * 64 + kq ) * 128 + rho ) * 4 + ( v & 3 )] = basis[(size_t)row * 256 + k];
+               }
+      }
+}
+
+template <int L>
+static void pack_layer( const vb_tensor *t, float *blob )
+{
+   using P = LayerPack<L>;
+   constexpr int CIN = P::CIN, C = P::C, D = P::D;
+   memset( blob, 0, sizeof( float ) * P::TOTAL );
+   int i = 0;
+   const float *dw_w = t[i++].data, *dw_b = t[i++].data, *pw_w = t[i++].data, *pw_b = t[i++].data;
+   const float *proj_w = 0, *proj_b = 0;
+   if ( P::PROJ )
+   {
+      proj_w = t[i++].data;
+      proj_b = t[i++].data;
+   }
+   const float *qkv_w = t[i++].data, *qkv_b = t[i++].data, *ao_w = t[i++].data, *ao_b = t[i++].data;
+   const float *n1w = t[i++].data, *n1b = t[i++].data, *f1w = t[i++].data, *f1b = t[i++].data;
+   const float *f2w = t[i++].data, *f2b = t[i++].data, *n2w = t[i++].data, *n2b = t[i++].data;
+   const float *cvw = t[i++].data, *cvb = t[i++].data;
+   const float *bnw = t[i++].data, *bnb = t[i++].data, *bnm = t[i++].data, *bnv = t[i++].data;
+
+   for ( int c = 0; c < CIN; ++c )
+   {
+      for ( int k = 0; k < 5; ++k ) blob[P::DW + c * 8 + k] = dw_w[c * 5 + k];
+      blob[P::DW + c * 8 + 5] = dw_b[c];
+   }
+   if ( L == 0 )
+   {
+      for ( int f = 0; f < CIN; ++f )
+         for ( int o = 0; o < C; ++o )
+         {
+            blob[P::PW + f * 2 * C + o] = pw_w[o * CIN + f];
+            blob[P::PW + f * 2 * C + C + o] = proj_w[o * CIN + f];
+         }
+   }
+   else
+   {
+      for ( int o = 0; o < C; ++o )
+         for ( int c = 0; c < CIN; ++c )
+         {
+            blob[P::PW + o * P::KP + c] = pw_w[o * CIN + c];
+            if ( P::PROJ ) blob[P::PW + o * P::KP + CIN + c] = proj_w[o * CIN + c];
+         }
+   }
+   for ( int o = 0; o < C; ++o ) blob[P::PWB + o] = P::PROJ ? pw_b[o] + proj_b[o] : pw_b[o];
+   for ( int h = 0; h < 2; ++h )
+   {
+      float *q = blob + P::QKV + h * P::QH;
+      for ( int part = 0; part < 3; ++part ) // q, k, v column blocks of the fused QKV (transformer.c:72-99)
+         for ( int j = 0; j < D; ++j )
+         {
+            int src_row = part * C + h * D + j;
+            for ( int c = 0; c < C; ++c ) q[( part * D + j ) * C + c] = qkv_w[src_row * C + c];
+            q[3 * D * C + part * D + j] = qkv_b[src_row];
+         }
+   }
+   memcpy( blob + P::AO, ao_w, sizeof( float ) * C * C );
+   memcpy( blob + P::AOB, ao_b, sizeof( float ) * C );
+   memcpy( blob + P::LN1W, n1w, sizeof( float ) * C );
+   memcpy( blob + P::LN1B, n1b, sizeof( float ) * C );
+   memcpy( blob + P::F1, f1w, sizeof( float ) * C * C );
+   memcpy( blob + P::F1B, f1b, sizeof( float ) * C );
+   memcpy( blob + P::F2, f2w, sizeof( float ) * C * C );
+   memcpy( blob + P::F2B, f2b, sizeof( float ) * C );
+   memcpy( blob + P::LN2W, n2w, sizeof( float ) * C );
+   memcpy( blob + P::LN2B, n2b, sizeof( float ) * C );
+   memcpy( blob + P::CV, cvw, sizeof( float ) * C * C );
+   memcpy( blob + P::CVB, cvb, sizeof( float ) * C );
+   for ( int o = 0; o < C; ++o )
+   {
+      blob[P::BNM + o] = bnm[o];
+      blob[P::BNS + o] = sqrtf( bnv[o] + 1e-5f ); // misc.c:245
+      blob[P::BNW + o] = bnw[o];
+      blob[P::BNB + o] = bnb[o];
+   }
+}
+
+static void pack_lstm( const float *w /*[2][256][128]*/, float *out /*[2][32][256][4]*/ )
+{
+   for ( int l = 0; l < 2; ++l )
+      for ( int r = 0; r < 256; ++r )
+         for ( int k = 0; k < 128; ++k ) out[( ( (size_t)l * 32 + ( k >> 2 ) ) * 256 + r ) * 4 + ( k & 3 )] = w[( (size_t)l * 256 + r ) * 128 + k];
+}
+
+// ---------------------------------------------------------------------------------------------
+// create / destroy
+// ---------------------------------------------------------------------------------------------
+extern "C" void silero_b200_default_opts( silero_b200_opts *o )
+{
+   memset( o, 0, sizeof( *o ) );
+   o->device = 0;
+   o->max_streams = 1;
+   o->window_chunks = 0;
+}
+
+template <typename K>
+static cudaError_t allow_smem( K kernel, int bytes )
+{
+   return cudaFuncSetAttribute( kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes );
+}
+
+static int configure_kernels()
+{
+   CU( allow_smem( stft_logmag_kernel<false>, STFT_SMEM_BYTES ) );
+   CU( allow_smem( stft_logmag_kernel<true>, STFT_SMEM_BYTES ) );
+   CU( allow_smem( layer_kernel<0, true>, LayerCfg<0>::SMEM_BYTES ) );
+   CU( allow_smem( layer_kernel<0, false>, LayerCfg<0>::SMEM_BYTES ) );
+   CU( allow_smem( layer_kernel<1, false>, LayerCfg<1>::SMEM_BYTES ) );
+   CU( allow_smem( layer_kernel<2, false>, LayerCfg<2>::SMEM_BYTES ) );
+   CU( allow_smem( layer_kernel<3, false>, LayerCfg<3>::SMEM_BYTES ) );
+   CU( allow_smem( lstm_layer_kernel<0, 4>, LstmSmem<4>::BYTES ) );
+   CU( allow_smem( lstm_layer_kernel<1, 4>, LstmSmem<4>::BYTES ) );
+   CU( allow_smem( lstm_layer_kernel<0, 1>, LstmSmem<1>::BYTES ) );
+   CU( allow_smem( lstm_layer_kernel<1, 1>, LstmSmem<1>::BYTES ) );
+   return 0;
+}
+
+extern "C" void silero_b200_destroy( silero_b200 *h )
+{
+   if ( !h ) return;
+   cudaSetDevice( h->device );
+   if ( h->stream ) cudaStreamSynchronize( h->stream );
+   cudaFree( h->d_weights );
+   cudaFree( h->state_h );
+   cudaFree( h->state_c );
+   cudaFree( h->spec );
+   cudaFree( h->a1 );
+   cudaFree( h->a2 );
+   cudaFree( h->a3 );
+   cudaFree( h->a4 );
+   cudaFree( h->h0 );
+   cudaFree( h->d_probs );
+   cudaFree( h->d_out2 );
+   cudaFree( h->d_f32 );
+   for ( int i = 0; i < 2; ++i )
+   {
+      cudaFree( h->pcm_stage[i] );
+      if ( h->pcm_ready[i] ) cudaEventDestroy( h->pcm_ready[i] );
+      if ( h->pcm_free[i] ) cudaEventDestroy( h->pcm_free[i] );
+   }
+   if ( h->ev_begin ) cudaEventDestroy( h->ev_begin );
+   if ( h->ev_end ) cudaEventDestroy( h->ev_end );
+   for ( int i = 0; i < N_STAGE_EVENTS; ++i )
+      if ( h->ev_stage[i] ) cudaEventDestroy( h->ev_stage[i] );
+   if ( h->stream ) cudaStreamDestroy( h->stream );
+   if ( h->copy_stream ) cudaStreamDestroy( h->copy_stream );
+   free( h );
+}
+
+static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts *opts_in, silero_b200 **out )
+{
+   silero_b200_opts opts;
+   if ( opts_in )
+      opts = *opts_in;
+   else
+      silero_b200_default_opts( &opts );
+   if ( opts.max_streams < 1 ) opts.max_streams = 1;
+
+   vb_tensor_file tf;
+   char perr[160];
+   if ( vb_testtensor_parse( bytes, nbytes, &tf, perr, sizeof( perr ) ) ) return set_err( SILERO_B200_ERR_WEIGHTS, "weights: %s", perr );
+   if ( vb_silero_v31_check( &tf, perr, sizeof( perr ) ) )
+   {
+      vb_testtensor_free( &tf );
+      return set_err( SILERO_B200_ERR_WEIGHTS, "weights: %s", perr );
+   }
+
+   int ndev = 0;
+   cudaError_t e = cudaGetDeviceCount( &ndev );
+   if ( e != cudaSuccess || ndev <= 0 || opts.device >= ndev )
+   {
+      vb_testtensor_free( &tf );
+      return set_err( SILERO_B200_ERR_CUDA, "no usable CUDA device (count=%d, requested=%d): %s; this engine has no CPU fallback", ndev,
+                      opts.device, cudaGetErrorString( e ) );
+   }
+
+   silero_b200 *h = (silero_b200 *)calloc( 1, sizeof( silero_b200 ) );
+   if ( !h )
+   {
+      vb_testtensor_free( &tf );
+      return set_err( SILERO_B200_ERR_NOMEM, "out of host memory" );
+   }
+   h->device = opts.device;
+   h->max_streams = opts.max_streams;
+   h->window_chunks_opt = opts.window_chunks;
+
+#define CU_H( call )                                                                                   \
+   do                                                                                                  \
+   {                                                                                                   \
+      cudaError_t e_ = ( call );                                                                       \
+      if ( e_ != cudaSuccess )                                                                         \
+      {                                                                                                \
+         set_err( SILERO_B200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString( e_ ), __FILE__, __LINE__ ); \
+         vb_testtensor_free( &tf );                                                                    \
+         silero_b200_destroy( h );                                                                     \
+         return SILERO_B200_ERR_CUDA;                                                                  \
+      }                                                                                                \
+   } while ( 0 )
+
+   CU_H( cudaSetDevice( h->device ) );
+   cudaDeviceProp prop;
+   CU_H( cudaGetDeviceProperties( &prop, h->device ) );
+   h->sm_count = prop.multiProcessorCount;
+   if ( prop.major < 10 )
+   {
+      set_err( SILERO_B200_ERR_CUDA, "device %d is sm_%d%d; this build targets sm_100a (B200)", h->device, prop.major, prop.minor );
+      vb_testtensor_free( &tf );
+      silero_b200_destroy( h );
+      return SILERO_B200_ERR_CUDA;
+   }
+   if ( configure_kernels() )
+   {
+      vb_testtensor_free( &tf );
+      silero_b200_destroy( h );
+      return SILERO_B200_ERR_CUDA;
+   }
+   CU_H( cudaStreamCreateWithFlags( &h->stream, cudaStreamNonBlocking ) );
+   CU_H( cudaStreamCreateWithFlags( &h->copy_stream, cudaStreamNonBlocking ) );
+   CU_H( cudaEventCreate( &h->ev_begin ) );
+   CU_H( cudaEventCreate( &h->ev_end ) );
+   for ( int i = 0; i < N_STAGE_EVENTS; ++i ) CU_H( cudaEventCreate( &h->ev_stage[i] ) );
+   for ( int i = 0; i < 2; ++i )
+   {
+      CU_H( cudaEventCreateWithFlags( &h->pcm_ready[i], cudaEventDisableTiming ) );
+      CU_H( cudaEventCreateWithFlags( &h->pcm_free[i], cudaEventDisableTiming ) );
+   }
+
+   // pack every weight into one host blob, upload once
+   const size_t n_basis = 2 * STFT_BS_FLOATS;
+   const size_t n_l0 = LayerPack<0>::TOTAL, n_l1 = LayerPack<1>::TOTAL, n_l2 = LayerPack<2>::TOTAL, n_l3 = LayerPack<3>::TOTAL;
+   const size_t n_lstm = 2 * LSTM_WS_FLOATS, n_lb = 512, n_dw = 128, n_db = 4;
+   const size_t total = n_basis + n_l0 + n_l1 + n_l2 + n_l3 + n_lstm + n_lb + n_dw + n_db;
+   float *host = (float *)calloc( total, sizeof( float ) );
+   if ( !host )
+   {
+      vb_testtensor_free( &tf );
+      silero_b200_destroy( h );
+      return set_err( SILERO_B200_ERR_NOMEM, "out of host memory" );
+   }
+   size_t off = 0;
+   size_t o_basis = off; off += n_basis;
+   size_t o_l0 = off; off += n_l0;
+   size_t o_l1 = off; off += n_l1;
+   size_t o_l2 = off; off += n_l2;
+   size_t o_l3 = off; off += n_l3;
+   size_t o_lstm = off; off += n_lstm;
+   size_t o_lb = off; off += n_lb;
+   size_t o_dw = off; off += n_dw;
+   size_t o_db = off; off += n_db;
+   pack_basis( tf.tensors[0].data, host + o_basis );
+   pack_layer<0>( tf.tensors + 1, host + o_l0 );
+   pack_layer<1>( tf.tensors + 25, host + o_l1 );
+   pack_layer<2>( tf.tensors + 49, host + o_l2 );
+   pack_layer<3>( tf.tensors + 71, host + o_l3 );
+   pack_lstm( tf.tensors[95].data, host + o_lstm );
+   memcpy( host + o_lb, tf.tensors[96].data, sizeof( float ) * 512 );
+   memcpy( host + o_dw, tf.tensors[97].data, sizeof( float ) * 128 );
+   memcpy( host + o_db, tf.tensors[98].data, sizeof( float ) * 2 );
+   vb_testtensor_free( &tf );
+   memset( &tf, 0, sizeof( tf ) );
+
+   cudaError_t ce = cudaMalloc( &h->d_weights, total * sizeof( float ) );
+   if ( ce == cudaSuccess ) ce = cudaMemcpy( h->d_weights, host, total * sizeof( float ), cudaMemcpyHostToDevice );
+   free( host );
+   CU_H( ce );
+   h->w.basis_pack = h->d_weights + o_basis;
+   h->w.layer[0] = h->d_weights + o_l0;
+   h->w.layer[1] = h->d_weights + o_l1;
+   h->w.layer[2] = h->d_weights + o_l2;
+   h->w.layer[3] = h->d_weights + o_l3;
+   h->w.lstm_w = h->d_weights + o_lstm;
+   h->w.lstm_b = h->d_weights + o_lb;
+   h->w.dec_w = h->d_weights + o_dw;
+   h->w.dec_b = h->d_weights + o_db;
+
+   size_t sbytes = (size_t)h->max_streams * SILERO_B200_STATE_FLOATS * sizeof( float );
+   CU_H( cudaMalloc( &h->state_h, sbytes ) );
+   CU_H( cudaMalloc( &h->state_c, sbytes ) );
+   CU_H( cudaMemset( h->state_h, 0, sbytes ) );
+   CU_H( cudaMemset( h->state_c, 0, sbytes ) );
+#undef CU_H
+   *out = h;
+   return SILERO_B200_OK;
+}
+
+extern "C" int silero_b200_create( const void *bytes, size_t nbytes, const silero_b200_opts *opts, silero_b200 **out )
+{
+   if ( !bytes || !out ) return set_err( SILERO_B200_ERR_ARG, "null argument" );
+   *out = 0;
+   return create_impl( bytes, nbytes, opts, out );
+}
+
+extern "C" int silero_b200_create_from_file( const char *path, const silero_b200_opts *opts, silero_b200 **out )
+{
+   if ( !path || !out ) return set_err( SILERO_B200_ERR_ARG, "null argument" );
+   *out = 0;
+   FILE *f = fopen( path, "rb" );
+   if ( !f ) return set_err( SILERO_B200_ERR_WEIGHTS, "cannot open %s", path );
+   fseek( f, 0, SEEK_END );
+   long n = ftell( f );
+   fseek( f, 0, SEEK_SET );
+   void *b = malloc( n > 0 ? (size_t)n : 1 );
+   size_t got = b ? fread( b, 1, (size_t)n, f ) : 0;
+   fclose( f );
+   int rc = ( b && got == (size_t)n ) ? create_impl( b, (size_t)n, opts, out ) : set_err( SILERO_B200_ERR_WEIGHTS, "cannot read %s", path );
+   free( b );
+   return rc;
+}
+
+extern "C" int silero_b200_get_info( const silero_b200 *h, silero_b200_info *info )
+{
+   if ( !h || !info ) return set_err( SILERO_B200_ERR_ARG, "null argument" );
+   info->batch_size_restriction = -1; // silero.h:39
+   info->is_silero_v5 = 0;            // silero.h:40
+   info->input_size_min = 1536;       // silero.h:41
+   info->input_size_max = 1536;       // silero.h:42
+   info->output_dims = 3;             // silero.h:43
+   info->sm_count = h->sm_count;
+   info->max_streams = h->max_streams;
+   info->window_chunks = h->window_chunks_opt;
+   return SILERO_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// scratch
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+static int grow( T **p, size_t *cap, size_t need )
+{
+   if ( need <= *cap ) return 0;
+   if ( *p ) CU( cudaFree( *p ) );
+   *p = 0;
+   *cap = 0;
+   CU( cudaMalloc( p, need * sizeof( T ) ) );
+   *cap = need;
+   return 0;
+}
+
+static int ensure_scratch( silero_b200 *h, size_t chunks )
+{
+   if ( chunks <= h->cap_chunks ) return 0;
+   CU( cudaStreamSynchronize( h->stream ) );
+   cudaFree( h->spec ); cudaFree( h->a1 ); cudaFree( h->a2 ); cudaFree( h->a3 ); cudaFree( h->a4 ); cudaFree( h->h0 );
+   h->spec = h->a1 = h->a2 = h->a3 = h->a4 = h->h0 = 0;
+   h->cap_chunks = 0;
+   CU( cudaMalloc( &h->spec, chunks * VB_BINS * VB_FRAMES * sizeof( float ) ) );
+   CU( cudaMalloc( &h->a1, chunks * 13 * 16 * sizeof( float ) ) );
+   CU( cudaMalloc( &h->a2, chunks * 7 * 32 * sizeof( float ) ) );
+   CU( cudaMalloc( &h->a3, chunks * 7 * 32 * sizeof( float ) ) );
+   CU( cudaMalloc( &h->a4, chunks * 7 * 64 * sizeof( float ) ) );
+   CU( cudaMalloc( &h->h0, chunks * 7 * 64 * sizeof( float ) ) );
+   h->cap_chunks = chunks;
+   return 0;
+}
+
+// bytes of window scratch per chunk: spec + a1..a4 + h0
+static const size_t kScratchPerChunk = ( VB_BINS * VB_FRAMES + 13 * 16 + 7 * 32 * 2 + 7 * 64 * 2 ) * sizeof( float );
+
+static int pick_window( const silero_b200 *h, int nstreams, int nchunks )
+{
+   if ( h->window_chunks_opt > 0 ) return h->window_chunks_opt < nchunks ? h->window_chunks_opt : nchunks;
+   // ~1.5 GB of scratch: enough chunks in flight to fill the GPU many times over
+   const size_t budget = (size_t)1536 << 20;
+   long long per_stream = (long long)( budget / kScratchPerChunk ) / ( nstreams > 0 ? nstreams : 1 );
+   if ( per_stream < 1 ) per_stream = 1;
+   if ( per_stream > nchunks ) per_stream = nchunks;
+   return (int)per_stream;
+}
+
+// ---------------------------------------------------------------------------------------------
+// launches
+// ---------------------------------------------------------------------------------------------
+static inline int imin( int a, int b ) { return a < b ? a : b; }
+
+static int launch_stft( silero_b200 *h, const void *d_in, int in_f32, long long stream_stride, int nw, int nchunks, float *spec, int out_mode )
+{
+   int npairs = imin( h->sm_count / 2, ( nchunks + 1 ) / 2 );
+   if ( npairs < 1 ) npairs = 1;
+   if ( in_f32 )
+      stft_logmag_kernel<true><<<npairs * 2, STFT_THREADS, STFT_SMEM_BYTES, h->stream>>>( d_in, stream_stride, nw, nchunks, h->w.basis_pack, spec, out_mode );
+   else
+      stft_logmag_kernel<false><<<npairs * 2, STFT_THREADS, STFT_SMEM_BYTES, h->stream>>>( d_in, stream_stride, nw, nchunks, h->w.basis_pack, spec, out_mode );
+   h->launches++;
+   CU( cudaGetLastError() );
+   return 0;
+}
+
+template <int L, bool NORM>
+static int launch_layer( silero_b200 *h, const float *in, float *out, int nchunks )
+{
+   using Cfg = LayerCfg<L>;
+   int ntiles = ( nchunks + Cfg::G - 1 ) / Cfg::G;
+   int per_sm = ( 227 * 1024 ) / ( Cfg::SMEM_BYTES + 1024 );
+   if ( per_sm < 1 ) per_sm = 1;
+   if ( per_sm > 8 ) per_sm = 8;
+   int grid = imin( ntiles, h->sm_count * per_sm );
+   layer_kernel<L, NORM><<<grid, LAYER_THREADS, Cfg::SMEM_BYTES, h->stream>>>( in, out, h->w.layer[L], nchunks );
+   h->launches++;
+   CU( cudaGetLastError() );
+   return 0;
+}
+
+template <int LAYER>
+static int launch_lstm( silero_b200 *h, const float *x, float *hseq, int first_stream, int nstreams, int nw, float *d_out2, float *d_probs,
+                        long long out_stride, long long out_off )
+{
+   float *sh = h->state_h + (size_t)first_stream * SILERO_B200_STATE_FLOATS;
+   float *sc = h->state_c + (size_t)first_stream * SILERO_B200_STATE_FLOATS;
+   const bool wide = nstreams >= 4 * h->sm_count / 2;
+   const int st = wide ? 4 : 1;
+   int tiles = ( nstreams + st - 1 ) / st;
+   int ng = ( tiles + h->sm_count - 1 ) / h->sm_count;
+   if ( ng > LSTM_MAX_GROUPS ) ng = LSTM_MAX_GROUPS;
+   if ( ng < 1 ) ng = 1;
+   int grid = imin( ( tiles + ng - 1 ) / ng, h->sm_count );
+   if ( wide )
+      lstm_layer_kernel<LAYER, 4><<<grid, 64 * ng, LstmSmem<4>::BYTES, h->stream>>>( x, hseq, sh, sc, h->w.lstm_w, h->w.lstm_b, h->w.dec_w, h->w.dec_b, nstreams,
+                                                                                     nw, d_out2, d_probs, out_stride, out_off );
+   else
+      lstm_layer_kernel<LAYER, 1><<<grid, 64 * ng, LstmSmem<1>::BYTES, h->stream>>>( x, hseq, sh, sc, h->w.lstm_w, h->w.lstm_b, h->w.dec_w, h->w.dec_b, nstreams,
+                                                                                     nw, d_out2, d_probs, out_stride, out_off );
+   h->launches++;
+   CU( cudaGetLastError() );
+   return 0;
+}
+
+static void stage_mark( silero_b200 *h, int i )
+{
+   if ( h->profiling ) cudaEventRecord( h->ev_stage[i], h->stream );
+}
+
+// one window: nstreams x nw chunks; input chunk (s, n) at d_in + s*stream_stride + n*1536
+static int run_window( silero_b200 *h, const void *d_in, int in_f32, long long stream_stride, int first_stream, int nstreams, int nw, float *d_out2,
+                       float *d_probs, long long out_stride, long long out_off, int accumulate_timing )
+{
+   const int nchunks = nstreams * nw;
+   if ( ensure_scratch( h, (size_t)nchunks ) ) return SILERO_B200_ERR_CUDA;
+   stage_mark( h, 0 );
+   if ( launch_stft( h, d_in, in_f32, stream_stride, nw, nchunks, h->spec, 0 ) ) return SILERO_B200_ERR_CUDA;
+   stage_mark( h, 1 );
+   if ( launch_layer<0, true>( h, h->spec, h->a1, nchunks ) ) return SILERO_B200_ERR_CUDA;
+   stage_mark( h, 2 );
+   if ( launch_layer<1, false>( h, h->a1, h->a2, nchunks ) ) return SILERO_B200_ERR_CUDA;
+   stage_mark( h, 3 );
+   if ( launch_layer<2, false>( h, h->a2, h->a3, nchunks ) ) return SILERO_B200_ERR_CUDA;
+   stage_mark( h, 4 );
+   if ( launch_layer<3, false>( h, h->a3, h->a4, nchunks ) ) return SILERO_B200_ERR_CUDA;
+   stage_mark( h, 5 );
+   if ( launch_lstm<0>( h, h->a4, h->h0, first_stream, nstreams, nw, 0, 0, 0, 0 ) ) return SILERO_B200_ERR_CUDA;
+   stage_mark( h, 6 );
+   if ( launch_lstm<1>( h, h->h0, 0, first_stream, nstreams, nw, d_out2, d_probs, out_stride, out_off ) ) return SILERO_B200_ERR_CUDA;
+   stage_mark( h, 7 );
+   if ( h->profiling && accumulate_timing )
+   {
+      // per-window stage times are accumulated on the host after a sync (profiling mode only)
+      CU( cudaEventSynchronize( h->ev_stage[7] ) );
+      for ( int i = 0; i < 7; ++i )
+      {
+         float ms = 0.0f;
+         cudaEventElapsedTime( &ms, h->ev_stage[i], h->ev_stage[i + 1] );
+         h->stage_ms[1 + i] += ms;
+      }
+   }
+   return 0;
+}
+
+static int check_streams( const silero_b200 *h, int first_stream, int nstreams, int nchunks )
+{
+   if ( !h ) return set_err( SILERO_B200_ERR_ARG, "null handle" );
+   if ( nstreams < 0 || nchunks < 0 || first_stream < 0 || first_stream + nstreams > h->max_streams )
+      return set_err( SILERO_B200_ERR_ARG, "streams [%d,%d) outside [0,%d) or negative count", first_stream, first_stream + nstreams, h->max_streams );
+   if ( (long long)nstreams * nchunks > 2000000000ll ) return set_err( SILERO_B200_ERR_ARG, "too many chunks in one call" );
+   return 0;
+}
+
+static void timing_begin( silero_b200 *h )
+{
+   memset( h->stage_ms, 0, sizeof( h->stage_ms ) );
+   h->launches = 0;
+   h->timing_valid = 0;
+   cudaEventRecord( h->ev_begin, h->stream );
+}
+
+static void timing_end( silero_b200 *h )
+{
+   cudaEventRecord( h->ev_end, h->stream );
+   h->timing_valid = 1;
+}
+
+extern "C" int silero_b200_run_streams_device( silero_b200 *h, const int16_t *d_pcm, long long stream_stride, int first_stream, int nstreams, int nchunks,
+                                               float *d_probs, float *d_out2 )
+{
+   int rc = check_streams( h, first_stream, nstreams, nchunks );
+   if ( rc ) return rc;
+   if ( nstreams == 0 || nchunks == 0 ) return SILERO_B200_OK;
+   if ( !d_pcm ) return set_err( SILERO_B200_ERR_ARG, "null pcm" );
+   if ( ( stream_stride % 8 ) != 0 || ( (uintptr_t)d_pcm % 16 ) != 0 ) return set_err( SILERO_B200_ERR_ARG, "device pcm must be 16-byte aligned with stream_stride %% 8 == 0" );
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+   timing_begin( h );
+   const int nw_max = pick_window( h, nstreams, nchunks );
+   for ( int n0 = 0; n0 < nchunks; n0 += nw_max )
+   {
+      int nw = imin( nw_max, nchunks - n0 );
+      rc = run_window( h, d_pcm + (long long)n0 * VB_CHUNK, 0, stream_stride, first_stream, nstreams, nw, d_out2, d_probs, nchunks, n0, 1 );
+      if ( rc ) return rc;
+   }
+   timing_end( h );
+   return SILERO_B200_OK;
+}
+
+extern "C" int silero_b200_sync( silero_b200 *h )
+{
+   if ( !h ) return set_err( SILERO_B200_ERR_ARG, "null handle" );
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+   CU( cudaStreamSynchronize( h->stream ) );
+   return SILERO_B200_OK;
+}
+
+extern "C" int silero_b200_run_streams( silero_b200 *h, const int16_t *pcm, long long stream_stride, int first_stream, int nstreams, int nchunks,
+                                        float *probs, float *out2 )
+{
+   int rc = check_streams( h, first_stream, nstreams, nchunks );
+   if ( rc ) return rc;
+   if ( nstreams == 0 || nchunks == 0 ) return SILERO_B200_OK;
+   if ( !pcm ) return set_err( SILERO_B200_ERR_ARG, "null pcm" );
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+
+   const int nw_max = pick_window( h, nstreams, nchunks );
+   const size_t win_samples = (size_t)nstreams * nw_max * VB_CHUNK;
+   if ( win_samples > h->pcm_stage_cap )
+   {
+      CU( cudaStreamSynchronize( h->stream ) );
+      CU( cudaStreamSynchronize( h->copy_stream ) );
+      for ( int i = 0; i < 2; ++i )
+      {
+         if ( h->pcm_stage[i] ) CU( cudaFree( h->pcm_stage[i] ) );
+         h->pcm_stage[i] = 0;
+      }
+      h->pcm_stage_cap = 0;
+      for ( int i = 0; i < 2; ++i ) CU( cudaMalloc( &h->pcm_stage[i], win_samples * sizeof( int16_t ) ) );
+      h->pcm_stage_cap = win_samples;
+   }
+   const size_t nout = (size_t)nstreams * nchunks;
+   if ( probs && grow( &h->d_probs, &h->d_probs_cap, nout ) ) return SILERO_B200_ERR_CUDA;
+   if ( out2 && grow( &h->d_out2, &h->d_out2_cap, nout * 2 ) ) return SILERO_B200_ERR_CUDA;
+
+   timing_begin( h );
+   const int nwin = ( nchunks + nw_max - 1 ) / nw_max;
+   // window w is copied on copy_stream into stage[w&1] while window w-1 computes
+   auto issue_copy = [&]( int w ) -> int {
+      int n0 = w * nw_max, nw = imin( nw_max, nchunks - n0 ), b = w & 1;
+      if ( w >= 2 ) CU( cudaStreamWaitEvent( h->copy_stream, h->pcm_free[b], 0 ) );
+      CU( cudaMemcpy2DAsync( h->pcm_stage[b], (size_t)nw * VB_CHUNK * sizeof( int16_t ), pcm + (long long)n0 * VB_CHUNK,
+                             (size_t)stream_stride * sizeof( int16_t ), (size_t)nw * VB_CHUNK * sizeof( int16_t ), (size_t)nstreams,
+                             cudaMemcpyHostToDevice, h->copy_stream ) );
+      CU( cudaEventRecord( h->pcm_ready[b], h->copy_stream ) );
+      return 0;
+   };
+   if ( issue_copy( 0 ) ) return SILERO_B200_ERR_CUDA;
+   for ( int w = 0; w < nwin; ++w )
+   {
+      int n0 = w * nw_max, nw = imin( nw_max, nchunks - n0 ), b = w & 1;
+      if ( w + 1 < nwin && issue_copy( w + 1 ) ) return SILERO_B200_ERR_CUDA;
+      CU( cudaStreamWaitEvent( h->stream, h->pcm_ready[b], 0 ) );
+      rc = run_window( h, h->pcm_stage[b], 0, (long long)nw * VB_CHUNK, first_stream, nstreams, nw, out2 ? h->d_out2 : 0, probs ? h->d_probs : 0, nchunks, n0, 1 );
+      if ( rc ) return rc;
+      CU( cudaEventRecord( h->pcm_free[b], h->stream ) );
+   }
+   if ( probs ) CU( cudaMemcpyAsync( probs, h->d_probs, nout * sizeof( float ), cudaMemcpyDeviceToHost, h->stream ) );
+   if ( out2 ) CU( cudaMemcpyAsync( out2, h->d_out2, nout * 2 * sizeof( float ), cudaMemcpyDeviceToHost, h->stream ) );
+   timing_end( h );
+   CU( cudaStreamSynchronize( h->stream ) );
+   return SILERO_B200_OK;
+}
+
+extern "C" int silero_b200_run_chunks( silero_b200 *h, int stream, const float *samples, int nchunks, float *out )
+{
+   int rc = check_streams( h, stream, 1, nchunks );
+   if ( rc ) return rc;
+   if ( nchunks == 0 ) return SILERO_B200_OK;
+   if ( !samples || !out ) return set_err( SILERO_B200_ERR_ARG, "null buffer" );
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+   const size_t n = (size_t)nchunks * VB_CHUNK;
+   if ( grow( &h->d_f32, &h->d_f32_cap, n ) ) return SILERO_B200_ERR_CUDA;
+   if ( grow( &h->d_out2, &h->d_out2_cap, (size_t)nchunks * 2 ) ) return SILERO_B200_ERR_CUDA;
+   timing_begin( h );
+   CU( cudaMemcpyAsync( h->d_f32, samples, n * sizeof( float ), cudaMemcpyHostToDevice, h->stream ) );
+   const int nw_max = pick_window( h, 1, nchunks );
+   for ( int n0 = 0; n0 < nchunks; n0 += nw_max )
+   {
+      int nw = imin( nw_max, nchunks - n0 );
+      rc = run_window( h, h->d_f32 + (size_t)n0 * VB_CHUNK, 1, 0, stream, 1, nw, h->d_out2, 0, nchunks, n0, 1 );
+      if ( rc ) return rc;
+   }
+   CU( cudaMemcpyAsync( out, h->d_out2, (size_t)nchunks * 2 * sizeof( float ), cudaMemcpyDeviceToHost, h->stream ) );
+   timing_end( h );
+   CU( cudaStreamSynchronize( h->stream ) );
+   return SILERO_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// state
+// ---------------------------------------------------------------------------------------------
+extern "C" int silero_b200_reset( silero_b200 *h, int first_stream, int nstreams )
+{
+   int rc = check_streams( h, first_stream, nstreams, 0 );
+   if ( rc ) return rc;
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+   size_t off = (size_t)first_stream * SILERO_B200_STATE_FLOATS, n = (size_t)nstreams * SILERO_B200_STATE_FLOATS * sizeof( float );
+   CU( cudaMemsetAsync( h->state_h + off, 0, n, h->stream ) );
+   CU( cudaMemsetAsync( h->state_c + off, 0, n, h->stream ) );
+   CU( cudaStreamSynchronize( h->stream ) );
+   return SILERO_B200_OK;
+}
+
+extern "C" int silero_b200_get_state( silero_b200 *h, int stream, float *h_out, float *c_out )
+{
+   int rc = check_streams( h, stream, 1, 0 );
+   if ( rc ) return rc;
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+   CU( cudaStreamSynchronize( h->stream ) );
+   size_t off = (size_t)stream * SILERO_B200_STATE_FLOATS;
+   if ( h_out ) CU( cudaMemcpy( h_out, h->state_h + off, SILERO_B200_STATE_FLOATS * sizeof( float ), cudaMemcpyDeviceToHost ) );
+   if ( c_out ) CU( cudaMemcpy( c_out, h->state_c + off, SILERO_B200_STATE_FLOATS * sizeof( float ), cudaMemcpyDeviceToHost ) );
+   return SILERO_B200_OK;
+}
+
+extern "C" int silero_b200_set_state( silero_b200 *h, int stream, const float *h_in, const float *c_in )
+{
+   int rc = check_streams( h, stream, 1, 0 );
+   if ( rc ) return rc;
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+   CU( cudaStreamSynchronize( h->stream ) );
+   size_t off = (size_t)stream * SILERO_B200_STATE_FLOATS;
+   if ( h_in ) CU( cudaMemcpy( h->state_h + off, h_in, SILERO_B200_STATE_FLOATS * sizeof( float ), cudaMemcpyHostToDevice ) );
+   if ( c_in ) CU( cudaMemcpy( h->state_c + off, c_in, SILERO_B200_STATE_FLOATS * sizeof( float ), cudaMemcpyHostToDevice ) );
+   return SILERO_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+extern "C" int silero_b200_device_alloc( silero_b200 *h, size_t nbytes, void **d_ptr )
+{
+   if ( !h || !d_ptr ) return set_err( SILERO_B200_ERR_ARG, "null argument" );
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+   CU( cudaMalloc( d_ptr, nbytes ) );
+   return SILERO_B200_OK;
+}
+extern "C" int silero_b200_device_free( silero_b200 *h, void *d_ptr )
+{
+   if ( !h ) return set_err( SILERO_B200_ERR_ARG, "null argument" );
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+   CU( cudaFree( d_ptr ) );
+   return SILERO_B200_OK;
+}
+extern "C" int silero_b200_memcpy_h2d( silero_b200 *h, void *d_dst, const void *src, size_t nbytes )
+{
+   if ( !h ) return set_err( SILERO_B200_ERR_ARG, "null argument" );
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+   CU( cudaMemcpyAsync( d_dst, src, nbytes, cudaMemcpyHostToDevice, h->stream ) );
+   CU( cudaStreamSynchronize( h->stream ) );
+   return SILERO_B200_OK;
+}
+extern "C" int silero_b200_memcpy_d2h( silero_b200 *h, void *dst, const void *d_src, size_t nbytes )
+{
+   if ( !h ) return set_err( SILERO_B200_ERR_ARG, "null argument" );
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+   CU( cudaMemcpyAsync( dst, d_src, nbytes, cudaMemcpyDeviceToHost, h->stream ) );
+   CU( cudaStreamSynchronize( h->stream ) );
+   return SILERO_B200_OK;
+}
+extern "C" int silero_b200_host_alloc_pinned( size_t nbytes, void **ptr )
+{
+   if ( !ptr ) return set_err( SILERO_B200_ERR_ARG, "null argument" );
+   CU( cudaHostAlloc( ptr, nbytes, cudaHostAllocDefault ) );
+   return SILERO_B200_OK;
+}
+extern "C" int silero_b200_host_free_pinned( void *ptr )
+{
+   CU( cudaFreeHost( ptr ) );
+   return SILERO_B200_OK;
+}
+
+extern "C" int silero_b200_set_profiling( silero_b200 *h, int enabled )
+{
+   if ( !h ) return set_err( SILERO_B200_ERR_ARG, "null handle" );
+   h->profiling = enabled ? 1 : 0;
+   return SILERO_B200_OK;
+}
+
+extern "C" int silero_b200_last_timing( silero_b200 *h, float ms[8], long long *kernel_launches )
+{
+   if ( !h || !ms ) return set_err( SILERO_B200_ERR_ARG, "null argument" );
+   if ( !h->timing_valid ) return set_err( SILERO_B200_ERR_ARG, "no completed run to report" );
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+   CU( cudaEventSynchronize( h->ev_end ) );
+   float total = 0.0f;
+   CU( cudaEventElapsedTime( &total, h->ev_begin, h->ev_end ) );
+   h->stage_ms[0] = total;
+   for ( int i = 0; i < 8; ++i ) ms[i] = h->stage_ms[i];
+   if ( kernel_launches ) *kernel_launches = h->launches;
+   return SILERO_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// parity taps (test-facing; layouts converted on the host, compute on the device)
+// ---------------------------------------------------------------------------------------------
+struct DevBuf
+{
+   float *p = 0;
+   ~DevBuf() { cudaFree( p ); }
+   int alloc( size_t n )
+   {
+      CU( cudaMalloc( &p, ( n ? n : 1 ) * sizeof( float ) ) );
+      return 0;
+   }
+};
+
+static int up( silero_b200 *h, float *d, const float *src, size_t n )
+{
+   CU( cudaMemcpyAsync( d, src, n * sizeof( float ), cudaMemcpyHostToDevice, h->stream ) );
+   return 0;
+}
+static int down( silero_b200 *h, float *dst, const float *d, size_t n )
+{
+   CU( cudaMemcpyAsync( dst, d, n * sizeof( float ), cudaMemcpyDeviceToHost, h->stream ) );
+   CU( cudaStreamSynchronize( h->stream ) );
+   return 0;
+}
+
+// [B][T][C] (token-major, engine) <-> [B][C][T] (reference)
+static void tok_to_ref( const float *tok, int B, int T, int C, float *ref )
+{
+   for ( int b = 0; b < B; ++b )
+      for ( int t = 0; t < T; ++t )
+         for ( int c = 0; c < C; ++c ) ref[( (size_t)b * C + c ) * T + t] = tok[( (size_t)b * T + t ) * C + c];
+}
+static void ref_to_tok( const float *ref, int B, int C, int T, float *tok )
+{
+   for ( int b = 0; b < B; ++b )
+      for ( int c = 0; c < C; ++c )
+         for ( int t = 0; t < T; ++t ) tok[( (size_t)b * T + t ) * C + c] = ref[( (size_t)b * C + c ) * T + t];
+}
+
+__global__ void subtract_chunk_mean_kernel( const float *__restrict__ logmag, float *__restrict__ out, int nchunks );
+
+extern "C" int silero_b200_stage_stft_norm( silero_b200 *h, const float *samples, int batch, float *norm_out, float *logmag_out )
+{
+   if ( !h || !samples || batch <= 0 ) return set_err( SILERO_B200_ERR_ARG, "bad argument" );
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+   const size_t nin = (size_t)batch * VB_CHUNK, nsp = (size_t)batch * VB_BINS * VB_FRAMES;
+   DevBuf in, sp, nm;
+   if ( in.alloc( nin ) || sp.alloc( nsp ) || nm.alloc( nsp ) ) return SILERO_B200_ERR_CUDA;
+   if ( up( h, in.p, samples, nin ) ) return SILERO_B200_ERR_CUDA;
+   if ( launch_stft( h, in.p, 1, 0, batch, batch, sp.p, 0 ) ) return SILERO_B200_ERR_CUDA;
+   if ( logmag_out && down( h, logmag_out, sp.p, nsp ) ) return SILERO_B200_ERR_CUDA;
+   if ( norm_out )
+   {
+      subtract_chunk_mean_kernel<<<batch, 32, 0, h->stream>>>( sp.p, nm.p, batch );
+      CU( cudaGetLastError() );
+      if ( down( h, norm_out, nm.p, nsp ) ) return SILERO_B200_ERR_CUDA;
+   }
+   return SILERO_B200_OK;
+}
+
+// tap for stft.c alone: raw magnitudes
+extern "C" int silero_b200_stage_stft_magnitude( silero_b200 *h, const float *samples, int batch, float *mag_out )
+{
+   if ( !h || !samples || !mag_out || batch <= 0 ) return set_err( SILERO_B200_ERR_ARG, "bad argument" );
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+   const size_t nin = (size_t)batch * VB_CHUNK, nsp = (size_t)batch * VB_BINS * VB_FRAMES;
+   DevBuf in, sp;
+   if ( in.alloc( nin ) || sp.alloc( nsp ) ) return SILERO_B200_ERR_CUDA;
+   if ( up( h, in.p, samples, nin ) ) return SILERO_B200_ERR_CUDA;
+   if ( launch_stft( h, in.p, 1, 0, batch, batch, sp.p, 1 ) ) return SILERO_B200_ERR_CUDA;
+   return down( h, mag_out, sp.p, nsp ) ? SILERO_B200_ERR_CUDA : SILERO_B200_OK;
+}
+
+__global__ void log1p_scale_kernel( const float *__restrict__ mag, float *__restrict__ out, size_t n )
+{
+   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if ( i < n ) out[i] = log1pf( __fmul_rn( mag[i], 1048576.0f ) );
+}
+
+// the mean part of adaptive_audio_normalization_inplace (misc.c:48-121), one warp per chunk; the
+// production path computes the same quantity inside layer_kernel<0,true>
+__global__ void subtract_chunk_mean_kernel( const float *__restrict__ logmag, float *__restrict__ out, int nchunks )
+{
+   __shared__ float m[VB_FRAMES], s[VB_FRAMES];
+   const int ci = blockIdx.x, t = threadIdx.x;
+   if ( ci >= nchunks ) return;
+   const float *sp = logmag + (size_t)ci * VB_BINS * VB_FRAMES;
+   if ( t < VB_FRAMES )
+   {
+      float a = 0.0f;
+      for ( int f = 0; f < VB_BINS; ++f ) a = __fadd_rn( a, sp[f * VB_FRAMES + t] );
+      m[t] = a / (float)VB_BINS;
+   }
+   __syncwarp();
+   if ( t < VB_FRAMES )
+   {
+      const float gk[7] = { 0.03663284704089164733887f, 0.11128076165914535522461f, 0.21674531698226928710938f, 0.27068215608596801757812f,
+                            0.21674531698226928710938f, 0.11128076165914535522461f, 0.03663284704089164733887f };
+      float v = 0.0f;
+      for ( int k = 0; k < 7; ++k )
+      {
+         int idx = t + k - 3;
+         if ( idx < 0 ) idx = -idx;
+         if ( idx >= VB_FRAMES ) idx = 2 * ( VB_FRAMES - 1 ) - idx;
+         v = __fadd_rn( v, __fmul_rn( m[idx], gk[k] ) );
+      }
+      s[t] = v;
+   }
+   __syncwarp();
+   float mu = 0.0f;
+   for ( int i = 0; i < VB_FRAMES; ++i ) mu = __fadd_rn( mu, s[i] );
+   mu = mu / (float)VB_FRAMES;
+   for ( int i = t; i < VB_BINS * VB_FRAMES; i += 32 ) out[(size_t)ci * VB_BINS * VB_FRAMES + i] = sp[i] - mu;
+}
+
+extern "C" int silero_b200_stage_norm( silero_b200 *h, const float *magnitude, int batch, float *norm_out )
+{
+   if ( !h || !magnitude || !norm_out || batch <= 0 ) return set_err( SILERO_B200_ERR_ARG, "bad argument" );
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+   const size_t nsp = (size_t)batch * VB_BINS * VB_FRAMES;
+   DevBuf mg, lg, nm;
+   if ( mg.alloc( nsp ) || lg.alloc( nsp ) || nm.alloc( nsp ) ) return SILERO_B200_ERR_CUDA;
+   if ( up( h, mg.p, magnitude, nsp ) ) return SILERO_B200_ERR_CUDA;
+   log1p_scale_kernel<<<(unsigned)( ( nsp + 255 ) / 256 ), 256, 0, h->stream>>>( mg.p, lg.p, nsp );
+   subtract_chunk_mean_kernel<<<batch, 32, 0, h->stream>>>( lg.p, nm.p, batch );
+   CU( cudaGetLastError() );
+   return down( h, norm_out, nm.p, nsp ) ? SILERO_B200_ERR_CUDA : SILERO_B200_OK;
+}
+
+// production kernels from raw samples to every encoder layer output (stft -> layer<0,NORM> -> ...)
+extern "C" int silero_b200_stage_pipeline( silero_b200 *h, const float *samples, int batch, float *l1, float *l2, float *l3, float *l4 )
+{
+   if ( !h || !samples || batch <= 0 ) return set_err( SILERO_B200_ERR_ARG, "bad argument" );
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+   const size_t B = (size_t)batch;
+   DevBuf in, sp, d1, d2, d3, d4;
+   if ( in.alloc( B * VB_CHUNK ) || sp.alloc( B * 3225 ) || d1.alloc( B * 208 ) || d2.alloc( B * 224 ) || d3.alloc( B * 224 ) || d4.alloc( B * 448 ) )
+      return SILERO_B200_ERR_CUDA;
+   if ( up( h, in.p, samples, B * VB_CHUNK ) ) return SILERO_B200_ERR_CUDA;
+   if ( launch_stft( h, in.p, 1, 0, batch, batch, sp.p, 0 ) ) return SILERO_B200_ERR_CUDA;
+   if ( launch_layer<0, true>( h, sp.p, d1.p, batch ) ) return SILERO_B200_ERR_CUDA;
+   if ( launch_layer<1, false>( h, d1.p, d2.p, batch ) ) return SILERO_B200_ERR_CUDA;
+   if ( launch_layer<2, false>( h, d2.p, d3.p, batch ) ) return SILERO_B200_ERR_CUDA;
+   if ( launch_layer<3, false>( h, d3.p, d4.p, batch ) ) return SILERO_B200_ERR_CUDA;
+   float *tmp = (float *)malloc( B * 448 * sizeof( float ) );
+   if ( !tmp ) return set_err( SILERO_B200_ERR_NOMEM, "out of host memory" );
+   int rc = 0;
+   if ( l1 && !( rc = down( h, tmp, d1.p, B * 208 ) ) ) tok_to_ref( tmp, batch, 13, 16, l1 );
+   if ( !rc && l2 && !( rc = down( h, tmp, d2.p, B * 224 ) ) ) tok_to_ref( tmp, batch, 7, 32, l2 );
+   if ( !rc && l3 && !( rc = down( h, tmp, d3.p, B * 224 ) ) ) tok_to_ref( tmp, batch, 7, 32, l3 );
+   if ( !rc && l4 && !( rc = down( h, tmp, d4.p, B * 448 ) ) ) tok_to_ref( tmp, batch, 7, 64, l4 );
+   free( tmp );
+   return rc ? SILERO_B200_ERR_CUDA : SILERO_B200_OK;
+}
+
+static int run_encoder_from( silero_b200 *h, int first_layer, const float *d_in, int batch, float *d1, float *d2, float *d3, float *d4 )
+{
+   if ( first_layer <= 0 && launch_layer<0, false>( h, d_in, d1, batch ) ) return SILERO_B200_ERR_CUDA;
+   if ( first_layer <= 1 && launch_layer<1, false>( h, first_layer == 1 ? d_in : d1, d2, batch ) ) return SILERO_B200_ERR_CUDA;
+   if ( first_layer <= 2 && launch_layer<2, false>( h, first_layer == 2 ? d_in : d2, d3, batch ) ) return SILERO_B200_ERR_CUDA;
+   if ( first_layer <= 3 && launch_layer<3, false>( h, first_layer == 3 ? d_in : d3, d4, batch ) ) return SILERO_B200_ERR_CUDA;
+   return 0;
+}
+
+extern "C" int silero_b200_stage_encoder( silero_b200 *h, const float *norm, int batch, float *l1, float *l2, float *l3, float *l4 )
+{
+   if ( !h || !norm || batch <= 0 ) return set_err( SILERO_B200_ERR_ARG, "bad argument" );
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+   const size_t B = (size_t)batch;
+   DevBuf in, d1, d2, d3, d4;
+   if ( in.alloc( B * 3225 ) || d1.alloc( B * 208 ) || d2.alloc( B * 224 ) || d3.alloc( B * 224 ) || d4.alloc( B * 448 ) ) return SILERO_B200_ERR_CUDA;
+   if ( up( h, in.p, norm, B * 3225 ) ) return SILERO_B200_ERR_CUDA;
+   if ( run_encoder_from( h, 0, in.p, batch, d1.p, d2.p, d3.p, d4.p ) ) return SILERO_B200_ERR_CUDA;
+   float *tmp = (float *)malloc( B * 448 * sizeof( float ) );
+   if ( !tmp ) return set_err( SILERO_B200_ERR_NOMEM, "out of host memory" );
+   int rc = 0;
+   if ( l1 && !( rc = down( h, tmp, d1.p, B * 208 ) ) ) tok_to_ref( tmp, batch, 13, 16, l1 );
+   if ( !rc && l2 && !( rc = down( h, tmp, d2.p, B * 224 ) ) ) tok_to_ref( tmp, batch, 7, 32, l2 );
+   if ( !rc && l3 && !( rc = down( h, tmp, d3.p, B * 224 ) ) ) tok_to_ref( tmp, batch, 7, 32, l3 );
+   if ( !rc && l4 && !( rc = down( h, tmp, d4.p, B * 448 ) ) ) tok_to_ref( tmp, batch, 7, 64, l4 );
+   free( tmp );
+   return rc ? SILERO_B200_ERR_CUDA : SILERO_B200_OK;
+}
+
+extern "C" int silero_b200_stage_layer( silero_b200 *h, int layer, const float *in, int batch, float *out )
+{
+   if ( !h || !in || !out || batch <= 0 || layer < 0 || layer > 3 ) return set_err( SILERO_B200_ERR_ARG, "bad argument" );
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+   const LayerDims d = layer_dims( layer );
+   const int tout = 1 + ( d.t - 1 ) / d.stride;
+   const size_t nin = (size_t)batch * d.cin * d.t, nout = (size_t)batch * d.c * tout;
+   DevBuf din, dout;
+   if ( din.alloc( nin ) || dout.alloc( nout ) ) return SILERO_B200_ERR_CUDA;
+   float *tmp = (float *)malloc( ( nin > nout ? nin : nout ) * sizeof( float ) );
+   if ( !tmp ) return set_err( SILERO_B200_ERR_NOMEM, "out of host memory" );
+   int rc = 0;
+   if ( layer == 0 )
+      rc = up( h, din.p, in, nin ); // the first layer consumes the reference's [B,129,25] layout directly
+   else
+   {
+      ref_to_tok( in, batch, d.cin, d.t, tmp );
+      rc = up( h, din.p, tmp, nin );
+      if ( !rc ) rc = cudaStreamSynchronize( h->stream ) != cudaSuccess;
+   }
+   if ( !rc )
+   {
+      switch ( layer )
+      {
+         case 0: rc = launch_layer<0, false>( h, din.p, dout.p, batch ); break;
+         case 1: rc = launch_layer<1, false>( h, din.p, dout.p, batch ); break;
+         case 2: rc = launch_layer<2, false>( h, din.p, dout.p, batch ); break;
+         default: rc = launch_layer<3, false>( h, din.p, dout.p, batch ); break;
+      }
+   }
+   if ( !rc ) rc = down( h, tmp, dout.p, nout );
+   if ( !rc ) tok_to_ref( tmp, batch, tout, d.c, out );
+   free( tmp );
+   return rc ? SILERO_B200_ERR_CUDA : SILERO_B200_OK;
+}
+
+extern "C" int silero_b200_stage_lstm( silero_b200 *h, const float *x, int batch, const float *h0, const float *c0, float *out, float *hn, float *cn )
+{
+   if ( !h || !x || batch <= 0 ) return set_err( SILERO_B200_ERR_ARG, "bad argument" );
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+   const size_t n = (size_t)batch * 7 * 64;
+   DevBuf dx, dh0, dtop, sh, sc;
+   if ( dx.alloc( n ) || dh0.alloc( n ) || dtop.alloc( n ) || sh.alloc( 128 ) || sc.alloc( 128 ) ) return SILERO_B200_ERR_CUDA;
+   if ( up( h, dx.p, x, n ) ) return SILERO_B200_ERR_CUDA;
+   if ( h0 ) { if ( up( h, sh.p, h0, 128 ) ) return SILERO_B200_ERR_CUDA; } else CU( cudaMemsetAsync( sh.p, 0, 512, h->stream ) );
+   if ( c0 ) { if ( up( h, sc.p, c0, 128 ) ) return SILERO_B200_ERR_CUDA; } else CU( cudaMemsetAsync( sc.p, 0, 512, h->stream ) );
+   // run on a private state buffer: temporarily swap it in
+   float *save_h = h->state_h, *save_c = h->state_c;
+   h->state_h = sh.p;
+   h->state_c = sc.p;
+   int rc = launch_lstm<0>( h, dx.p, dh0.p, 0, 1, batch, 0, 0, 0, 0 );
+   if ( !rc ) rc = launch_lstm<1>( h, dh0.p, dtop.p, 0, 1, batch, 0, 0, 0, 0 );
+   h->state_h = save_h;
+   h->state_c = save_c;
+   if ( rc ) return rc;
+   if ( out && down( h, out, dtop.p, n ) ) return SILERO_B200_ERR_CUDA;
+   if ( hn && down( h, hn, sh.p, 128 ) ) return SILERO_B200_ERR_CUDA;
+   if ( cn && down( h, cn, sc.p, 128 ) ) return SILERO_B200_ERR_CUDA;
+   CU( cudaStreamSynchronize( h->stream ) );
+   return SILERO_B200_OK;
+}
+
+// decoder alone (silero_v3.c:231-303): one thread per (chunk, head); the production path fuses the
+// same arithmetic into lstm_layer_kernel<1>
+__global__ void decoder_kernel( const float *__restrict__ in /*[B][64][7]*/, const float *__restrict__ w, const float *__restrict__ b, float *__restrict__ out, int batch )
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if ( i >= batch * 2 ) return;
+   int n = i >> 1, head = i & 1;
+   float sum = 0.0f;
+   for ( int t = 0; t < 7; ++t )
+   {
+      float q = 0.0f;
+      for ( int c = 0; c < 64; ++c ) q = fmaf( w[head * 64 + c], fmaxf( in[( (size_t)n * 64 + c ) * 7 + t], 0.0f ), q );
+      sum += q + b[head];
+   }
+   float mean = sum / 7.0f;
+   out[i] = 1.0f / ( 1.0f + expf( -mean ) );
+}
+
+extern "C" int silero_b200_stage_decoder( silero_b200 *h, const float *in, int batch, float *out )
+{
+   if ( !h || !in || !out || batch <= 0 ) return set_err( SILERO_B200_ERR_ARG, "bad argument" );
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+   DevBuf din, dout;
+   if ( din.alloc( (size_t)batch * 448 ) || dout.alloc( (size_t)batch * 2 ) ) return SILERO_B200_ERR_CUDA;
+   if ( up( h, din.p, in, (size_t)batch * 448 ) ) return SILERO_B200_ERR_CUDA;
+   decoder_kernel<<<( batch * 2 + 127 ) / 128, 128, 0, h->stream>>>( din.p, h->w.dec_w, h->w.dec_b, dout.p, batch );
+   CU( cudaGetLastError() );
+   return down( h, out, dout.p, (size_t)batch * 2 ) ? SILERO_B200_ERR_CUDA : SILERO_B200_OK;
+}

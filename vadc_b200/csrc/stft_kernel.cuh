@@ -1,0 +1,245 @@
+// vadc_b200/csrc/stft_kernel.cuh -- conv-basis STFT + magnitude + log1p, bit-faithful to the
+// reference's AVX2 reduction tree.
+//
+// Replaces my_stft (stft.c:15-229: reflect pad tensor.h:912-958, basis correlation stft.c:82-190,
+// magnitude stft.c:194-213) and the log1p of adaptive_audio_normalization_inplace (misc.c:40-46).
+//
+// Why bit-faithful: log1p(m * 2^20) amplifies an absolute STFT error d at a bin of magnitude m to
+// d/m, and the LSTM carries the damage for seconds. Measured on synthetic speech with a noise floor
+// (DESIGN.md "Numerics"): an *exact* (fp64) STFT lands 1e-3 away from the reference's probabilities,
+// i.e. 10x outside the 1e-4 bar, while every other stage tolerates FMA/reordering (7e-6). So each
+// output is evaluated with the reference's own rounding sequence: 256 rounded products, combined
+// as  lane l = k%8, vector v = (k/8)%8, group g = k/64:
+//     r[g][l] = ((p0+p1)+(p2+p3))+((p4+p5)+(p6+p7))   over v
+//     R[l]    = (r[0][l]+r[1][l])+(r[2][l]+r[3][l])
+//     y       = ((R0+R1)+(R2+R3))+((R4+R5)+(R6+R7))
+// with separate mul/add (no FMA contraction).  511 FP32 pipe ops per output, 3.30 M per chunk.
+//
+// Mapping: the 256 non-zero basis rows are split in two halves of 128 rows (64 bins, re+im; the
+// all-zero imaginary row of bin 0 is replaced by the real row of bin 128, the all-zero row 257 is
+// dropped). One persistent CTA per SM keeps its half (128 KB) resident in shared memory for the
+// whole launch in a [k-quad][row][4] layout so that lanes (= bins) read consecutive 16-byte words;
+// the padded audio of a chunk lives in shared memory as X[r][l][v] (r = 64-sample row, l = k%8,
+// v = (k/8)%8) so that the 8 taps of one tree leaf are two float4 broadcasts. A thread owns
+// 2 bins (re+im = 4 rows) x 5 frames; 160 threads cover a chunk-half, a CTA runs 2 chunks at once.
+#pragma once
+#include "common.cuh"
+
+#define STFT_THREADS 320
+#define STFT_GROUP 160
+#define STFT_BS_FLOATS ( 64 * 128 * 4 )
+#define STFT_XS_FLOATS ( 28 * 64 )
+#define STFT_SMEM_BYTES ( ( STFT_BS_FLOATS + 2 * 2 * STFT_XS_FLOATS ) * 4 )
+
+__device__ __forceinline__ float stft_tree8( const float x[8], const float4 b0, const float4 b1 )
+{
+   float p0 = __fmul_rn( x[0], b0.x ), p1 = __fmul_rn( x[1], b0.y );
+   float p2 = __fmul_rn( x[2], b0.z ), p3 = __fmul_rn( x[3], b0.w );
+   float p4 = __fmul_rn( x[4], b1.x ), p5 = __fmul_rn( x[5], b1.y );
+   float p6 = __fmul_rn( x[6], b1.z ), p7 = __fmul_rn( x[7], b1.w );
+   float s01 = __fadd_rn( p0, p1 ), s23 = __fadd_rn( p2, p3 );
+   float s45 = __fadd_rn( p4, p5 ), s67 = __fadd_rn( p6, p7 );
+   return __fadd_rn( __fadd_rn( s01, s23 ), __fadd_rn( s45, s67 ) );
+}
+
+// position of padded sample j (0..1791) inside the permuted chunk tile
+__device__ __forceinline__ int stft_xidx( int j ) { return ( j >> 6 ) * 64 + ( j & 7 ) * 8 + ( ( j >> 3 ) & 7 ); }
+
+template <bool F32>
+struct StftRaw
+{
+   int4 v[F32 ? 3 : 2];
+};
+
+// chunk ci of the window -> first sample. Window layout: ci = s * nw + n.
+template <bool F32>
+__device__ __forceinline__ const void *stft_chunk_ptr( const void *in, long long stream_stride, int nw, int ci )
+{
+   int s = ci / nw, n = ci - s * nw;
+   long long off = (long long)s * stream_stride + (long long)n * VB_CHUNK;
+   return F32 ? (const void *)( (const float *)in + off ) : (const void *)( (const int16_t *)in + off );
+}
+
+template <bool F32>
+__device__ __forceinline__ void stft_load_raw( StftRaw<F32> &raw, const void *chunk, int t )
+{
+   constexpr int NV = F32 ? 384 : 192; // 16-byte vectors per chunk
+   constexpr int PER = F32 ? 3 : 2;
+#pragma unroll
+   for ( int i = 0; i < PER; ++i )
+   {
+      int q = t + i * STFT_GROUP;
+      if ( q < NV ) raw.v[i] = __ldg( (const int4 *)chunk + q );
+   }
+}
+
+template <bool F32>
+__device__ __forceinline__ void stft_store_x( float *xs, const StftRaw<F32> &raw, int t )
+{
+   constexpr int NV = F32 ? 384 : 192;
+   constexpr int PER = F32 ? 3 : 2;
+#pragma unroll
+   for ( int i = 0; i < PER; ++i )
+   {
+      int q = t + i * STFT_GROUP;
+      if ( q < NV )
+      {
+         if ( F32 )
+         {
+            const float *f = reinterpret_cast<const float *>( &raw.v[i] );
+#pragma unroll
+            for ( int e = 0; e < 4; ++e ) xs[stft_xidx( 128 + 4 * q + e )] = f[e];
+         }
+         else
+         {
+            const short *h = reinterpret_cast<const short *>( &raw.v[i] );
+            // (float)s16 / 32768.0f (vadc.c:884,898); the division by a power of two is exact
+#pragma unroll
+            for ( int e = 0; e < 8; ++e ) xs[stft_xidx( 128 + 8 * q + e )] = (float)h[e] * ( 1.0f / 32768.0f );
+         }
+      }
+   }
+}
+
+// reflect padding without repeating the edge sample (tensor.h:942-953): xp[j] = xp[256-j] for j<128,
+// xp[1664+j] = xp[1662-j] for j<128
+__device__ __forceinline__ void stft_pad_x( float *xs, int t )
+{
+   if ( t < 128 )
+   {
+      xs[stft_xidx( t )] = xs[stft_xidx( 256 - t )];
+      xs[stft_xidx( 1664 + t )] = xs[stft_xidx( 1662 - t )];
+   }
+}
+
+// out_mode 0: log1p(mag * 2^20) (production); 1: raw magnitude (parity tap for stft.c alone)
+template <bool F32>
+__global__ void __launch_bounds__( STFT_THREADS, 1 )
+stft_logmag_kernel( const void *__restrict__ in, long long stream_stride, int nw, int nchunks,
+                    const float *__restrict__ basis_pack, float *__restrict__ spec, int out_mode )
+{
+   extern __shared__ __align__( 16 ) float smem[];
+   float *Bs = smem;
+   float *Xs_all = smem + STFT_BS_FLOATS; // [2 buffers][2 groups][1792]
+
+   const int tid = threadIdx.x;
+   const int half = blockIdx.x & 1;
+   const int pair = blockIdx.x >> 1;
+   const int npairs = gridDim.x >> 1;
+   const int cg = tid / STFT_GROUP;      // chunk group 0/1
+   const int t = tid - cg * STFT_GROUP;  // thread within group
+   const int tg = t >> 5;                // frame group: frames 5*tg .. 5*tg+4
+   const int fl = t & 31;                // bin lane
+
+   // resident half basis
+   {
+      const float4 *src = reinterpret_cast<const float4 *>( basis_pack ) + (size_t)half * ( STFT_BS_FLOATS / 4 );
+      float4 *dst = reinterpret_cast<float4 *>( Bs );
+      for ( int i = tid; i < STFT_BS_FLOATS / 4; i += STFT_THREADS ) dst[i] = __ldg( src + i );
+   }
+
+   StftRaw<F32> raw;
+   int ci = pair * 2 + cg;
+   if ( ci < nchunks ) stft_load_raw<F32>( raw, stft_chunk_ptr<F32>( in, stream_stride, nw, ci ), t );
+   __syncthreads();
+
+   int buf = 0;
+   for ( ; ci < nchunks; ci += npairs * 2, buf ^= 1 )
+   {
+      float *xs = Xs_all + ( buf * 2 + cg ) * STFT_XS_FLOATS;
+      stft_store_x<F32>( xs, raw, t );
+      bar_sync( 1 + cg, STFT_GROUP );
+      stft_pad_x( xs, t );
+      bar_sync( 1 + cg, STFT_GROUP );
+
+      // prefetch the next chunk of this group while computing this one
+      int cn = ci + npairs * 2;
+      if ( cn < nchunks ) stft_load_raw<F32>( raw, stft_chunk_ptr<F32>( in, stream_stride, nw, cn ), t );
+
+      float S0[4][5], S1[4][5], TL[4][5];
+#pragma unroll
+      for ( int a = 0; a < 4; ++a )
+#pragma unroll
+         for ( int i = 0; i < 5; ++i ) S0[a][i] = S1[a][i] = TL[a][i] = 0.0f;
+
+#pragma unroll 1
+      for ( int l = 0; l < 8; ++l )
+      {
+         float A[4][5], Bv[4][5];
+#pragma unroll
+         for ( int g = 0; g < 4; ++g )
+         {
+            float xr[5][8];
+#pragma unroll
+            for ( int i = 0; i < 5; ++i )
+            {
+               const float *xp = xs + ( 5 * tg + i + g ) * 64 + l * 8;
+               float4 a = ld4( xp ), b = ld4( xp + 4 );
+               xr[i][0] = a.x; xr[i][1] = a.y; xr[i][2] = a.z; xr[i][3] = a.w;
+               xr[i][4] = b.x; xr[i][5] = b.y; xr[i][6] = b.z; xr[i][7] = b.w;
+            }
+            const float *bq = Bs + ( ( l * 8 + g * 2 ) * 128 + fl ) * 4;
+#pragma unroll
+            for ( int fr = 0; fr < 4; ++fr )
+            {
+               float4 b0 = ld4( bq + fr * 32 * 4 );
+               float4 b1 = ld4( bq + fr * 32 * 4 + 128 * 4 );
+#pragma unroll
+               for ( int i = 0; i < 5; ++i )
+               {
+                  float r = stft_tree8( xr[i], b0, b1 );
+                  if ( g == 0 ) A[fr][i] = r;
+                  else if ( g == 1 ) A[fr][i] = __fadd_rn( A[fr][i], r );
+                  else if ( g == 2 ) Bv[fr][i] = r;
+                  else Bv[fr][i] = __fadd_rn( Bv[fr][i], r );
+               }
+            }
+         }
+#pragma unroll
+         for ( int fr = 0; fr < 4; ++fr )
+#pragma unroll
+            for ( int i = 0; i < 5; ++i )
+            {
+               float R = __fadd_rn( A[fr][i], Bv[fr][i] );
+               if ( ( l & 1 ) == 0 )
+                  TL[fr][i] = R;
+               else
+               {
+                  float pr = __fadd_rn( TL[fr][i], R );
+                  if ( l == 1 ) S0[fr][i] = pr;
+                  else if ( l == 3 ) S0[fr][i] = __fadd_rn( S0[fr][i], pr );
+                  else if ( l == 5 ) S1[fr][i] = pr;
+                  else S1[fr][i] = __fadd_rn( S1[fr][i], pr );
+               }
+            }
+      }
+
+      // magnitude (stft.c:194-213) and log1p(m * 2^20) (misc.c:40-46)
+      float *o = spec + (size_t)ci * ( VB_BINS * VB_FRAMES );
+      const bool special = ( half == 0 && fl == 0 ); // im slot of bin 0 carries re of bin 128
+#pragma unroll
+      for ( int a = 0; a < 2; ++a )
+      {
+         int f = half * 64 + fl + a * 32;
+#pragma unroll
+         for ( int i = 0; i < 5; ++i )
+         {
+            float re = __fadd_rn( S0[a][i], S1[a][i] );
+            float im = __fadd_rn( S0[a + 2][i], S1[a + 2][i] );
+            float extra = 0.0f;
+            if ( a == 0 && special )
+            {
+               extra = im;
+               im = 0.0f;
+            }
+            float m = sqrtf( __fadd_rn( __fmul_rn( re, re ), __fmul_rn( im, im ) ) );
+            o[f * VB_FRAMES + 5 * tg + i] = out_mode ? m : log1pf( __fmul_rn( m, 1048576.0f ) );
+            if ( a == 0 && special )
+            {
+               float m2 = sqrtf( __fadd_rn( __fmul_rn( extra, extra ), 0.0f ) );
+               o[128 * VB_FRAMES + 5 * tg + i] = out_mode ? m2 : log1pf( __fmul_rn( m2, 1048576.0f ) );
+            }
+         }
+      }
+   }
+}
