@@ -1,0 +1,207 @@
+"""GPU: end-to-end parity of the CUDA path (through the C ABI) with the oracle and with the golden
+vectors generated from the unmodified reference. Bars (BASELINE.json north_star): per-chunk
+probabilities within 1e-4 max abs error, segment text bit-exact; STFT magnitudes bit-exact."""
+import ctypes as C
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import vadc_b200
+from oracle_lib import ROOT, Oracle, have_ref, ref_cli
+
+pytestmark = pytest.mark.gpu
+PTOL = 1e-4
+CASES = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "e2e_*.npz")))
+
+
+def f32(pcm):
+    n = len(pcm) // 1536
+    return (pcm[: n * 1536].astype(np.float32) / np.float32(32768.0)).reshape(n, 1536)
+
+
+def margins(p):
+    return float(np.abs(p - 0.5).min()), float(np.abs(p - np.float32(0.5) + np.float32(0.15)).min())
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p) for p in CASES])
+def test_golden_reference_vectors(engine, path):
+    g = np.load(path)
+    pcm = g["pcm"]
+    engine.reset()
+    probs, out2 = engine.run_streams(pcm[None, :], want_out2=True)
+    assert out2.shape[1:] == g["out2"].shape            # trailing partial chunk dropped (vadc.c:964)
+    err = np.abs(out2[0] - g["out2"]).max()
+    assert err <= PTOL, err
+    assert np.array_equal(probs[0], out2[0, :, 1])
+    assert vadc_b200.segments_text(probs[0]) == str(g["stdout"])
+    assert vadc_b200.segments_text(probs[0], vadc_b200.seg_params(centiseconds=1)) == str(g["stdout_centi"])
+    # per-stage tensors of the first 8 chunks
+    x = f32(pcm[: 8 * 1536])
+    assert np.array_equal(engine.stage_stft_magnitude(x), g["stages_stft"])          # bit-exact
+    norm, logmag = engine.stage_stft_norm(x)
+    assert np.abs(norm - g["stages_norm"]).max() < 5e-6
+    for got, k in zip(engine.stage_pipeline(x), ("l1", "l2", "l3", "l4")):
+        ref = g["stages_" + k]
+        assert np.abs(got - ref).max() <= 2e-4 * max(1.0, float(np.abs(ref).max())), k
+
+
+def test_stft_bit_exact_on_edge_signals(engine, oracle):
+    rng = np.random.default_rng(0)
+    x = np.zeros((6, 1536), np.float32)
+    x[1] = 1.0 - 2.0 ** -15                      # full-scale DC
+    x[2] = rng.uniform(-1, 1, 1536)              # white
+    x[3, ::2] = 0.999; x[3, 1::2] = -1.0         # Nyquist
+    x[4, 700] = 1.0                              # impulse
+    x[5] = (rng.integers(-3, 4, 1536) / 32768.0) # near-silent LSB noise (worst case for log1p)
+    oracle.reset()
+    st = oracle.run_stages(x)
+    assert np.array_equal(engine.stage_stft_magnitude(x), st["stft"])
+    norm, _ = engine.stage_stft_norm(x)
+    assert np.abs(norm - st["norm"]).max() < 5e-6
+
+
+@pytest.mark.parametrize("S,N,window", [(1, 1, 0), (3, 7, 0), (37, 70, 16), (130, 33, 5), (64, 96, 0)])
+def test_multi_stream_vs_oracle(oracle, S, N, window):
+    e = vadc_b200.Engine(max_streams=S, window_chunks=window)
+    pcm = np.stack([vadc_b200.synth_pcm(1000 + s, N * 1536, kind=(0 if s % 11 else (1 if s % 2 else 2))) for s in range(S)])
+    probs, out2 = e.run_streams(pcm, want_out2=True)
+    worst = 0.0
+    for s in sorted(set([0, 1, S // 2, S - 1]) | set(range(0, S, 13))):
+        if s >= S:
+            continue
+        oracle.reset()
+        ref = oracle.run_pcm(pcm[s])
+        worst = max(worst, float(np.abs(out2[s] - ref).max()))
+        assert vadc_b200.segments_text(probs[s]) == oracle.segments_text(ref[:, 1]), s
+    assert worst <= PTOL, worst
+    e.close()
+
+
+def test_state_carries_across_calls_and_windows():
+    S, N = 9, 50
+    pcm = np.stack([vadc_b200.synth_pcm(50 + s, N * 1536) for s in range(S)])
+    e1 = vadc_b200.Engine(max_streams=S, window_chunks=64)
+    whole = e1.run_streams(pcm)
+    e2 = vadc_b200.Engine(max_streams=S, window_chunks=7)      # ragged windows: 7*7+1
+    assert np.array_equal(e2.run_streams(pcm), whole)
+    e2.reset()
+    a = e2.run_streams(np.ascontiguousarray(pcm[:, : 20 * 1536]))
+    b = e2.run_streams(np.ascontiguousarray(pcm[:, 20 * 1536:]))
+    assert np.array_equal(np.concatenate([a, b], 1), whole)    # split calls == one call, bit for bit
+    # reset really zeroes, set/get round-trips
+    h, c = e2.get_state(3)
+    assert np.abs(h).max() > 0
+    e2.reset()
+    h0, c0 = e2.get_state(3)
+    assert not h0.any() and not c0.any()
+    e2.set_state(h, c, stream=3)
+    h1, c1 = e2.get_state(3)
+    assert np.array_equal(h, h1) and np.array_equal(c, c1)
+    e1.close(); e2.close()
+
+
+def test_run_chunks_is_backend_run(engine, oracle):
+    """silero_b200_run_chunks == backend_run semantics: consecutive chunks of one stream, any batch,
+    state carried; identical bits for batch 1 / 7 / 96 (finding F6) and for the s16 entry point."""
+    pcm = vadc_b200.synth_pcm(77, 96 * 2 * 1536)
+    x = f32(pcm)
+    engine.reset()
+    ref_all = engine.run_chunks(x, stream=5)
+    for batch in (1, 7, 96):
+        engine.reset()
+        got = np.concatenate([engine.run_chunks(x[i:i + batch], stream=5) for i in range(0, len(x), batch)])
+        assert np.array_equal(got, ref_all), batch
+    engine.reset()
+    probs, out2 = engine.run_streams(pcm[None, :], first_stream=5, want_out2=True)
+    assert np.array_equal(out2[0], ref_all)
+    oracle.reset()
+    assert np.abs(ref_all - oracle.run_pcm(pcm)).max() <= PTOL
+    # other streams' state untouched
+    h, c = engine.get_state(4)
+    assert not h.any() and not c.any()
+
+
+def test_streams_are_independent_and_order_invariant():
+    S, N = 40, 24
+    base = [vadc_b200.synth_pcm(300 + i, N * 1536) for i in range(5)]
+    pcm = np.stack([base[s % 5] for s in range(S)])
+    e = vadc_b200.Engine(max_streams=S)
+    p = e.run_streams(pcm)
+    for s in range(S):
+        assert np.array_equal(p[s], p[s % 5])          # duplicates in different slots / tiles agree bit for bit
+    perm = np.random.default_rng(1).permutation(S)
+    e.reset()
+    assert np.array_equal(e.run_streams(np.ascontiguousarray(pcm[perm])), p[perm])
+    e.close()
+
+
+def test_device_resident_path_equals_host_path():
+    S, N = 33, 40
+    pcm = np.stack([vadc_b200.synth_pcm(900 + s, N * 1536) for s in range(S)])
+    e = vadc_b200.Engine(max_streams=S, window_chunks=16)
+    host = e.run_streams(pcm)
+    e.reset()
+    d_pcm, d_probs = e.device_alloc(pcm.nbytes), e.device_alloc(S * N * 4)
+    e.h2d(d_pcm, pcm)
+    e.run_streams_device(d_pcm, pcm.shape[1], S, N, d_probs)
+    e.sync()
+    dev = np.zeros((S, N), np.float32)
+    e.d2h(dev, d_probs)
+    assert np.array_equal(dev, host)
+    ms, launches = e.last_timing()
+    assert launches == 7 * 3 and ms["total"] > 0     # 7 kernels per window, windows of 16+16+8
+    e.device_free(d_pcm); e.device_free(d_probs); e.close()
+
+
+def test_argument_errors(engine):
+    L = vadc_b200.lib()
+    with pytest.raises(vadc_b200.EngineError):
+        engine.run_streams(np.zeros((65, 1536), np.int16))                 # more streams than max_streams=64
+    with pytest.raises(vadc_b200.EngineError):
+        engine.run_chunks(np.zeros((1, 1536), np.float32), stream=64)
+    assert engine.run_streams(np.zeros((2, 100), np.int16)).shape == (2, 0)  # shorter than one chunk: nothing to do
+    assert L.silero_b200_run_chunks(None, 0, None, 1, None) == -1
+    i = engine.info()
+    assert (i["batch_size_restriction"], i["is_silero_v5"], i["input_size_min"], i["input_size_max"], i["output_dims"]) == (-1, 0, 1536, 1536, 3)
+
+
+def test_full_width_properties_and_sampled_parity(oracle):
+    """BASELINE cfg3 width (4096 concurrent streams), shortened in time: size-independent properties
+    (duplicate streams agree bit for bit across tiles, split == whole) plus oracle parity on a sample."""
+    S, N, nb = 4096, 24, 16
+    base = [vadc_b200.synth_pcm(7000 + i, N * 1536) for i in range(nb)]
+    shift = lambda s: ((s // nb) * 5) % N
+    pcm = np.stack([np.roll(base[s % nb].reshape(N, 1536), shift(s), 0).reshape(-1) for s in range(S)])
+    e = vadc_b200.Engine(max_streams=S)
+    p = e.run_streams(pcm)
+    groups = {}
+    for s in range(S):
+        groups.setdefault((s % nb, shift(s)), []).append(s)
+    for members in groups.values():
+        for s in members[1:]:
+            assert np.array_equal(p[s], p[members[0]])
+    e.reset()
+    a = e.run_streams(np.ascontiguousarray(pcm[:, : 10 * 1536]))
+    b = e.run_streams(np.ascontiguousarray(pcm[:, 10 * 1536:]))
+    assert np.array_equal(np.concatenate([a, b], 1), p)
+    worst = 0.0
+    for s in (0, 17, 2049, 4095):
+        oracle.reset()
+        worst = max(worst, float(np.abs(p[s] - oracle.run_pcm(pcm[s])[:, 1]).max()))
+    assert worst <= PTOL, worst
+    e.close()
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not present")
+def test_timestamps_bit_exact_vs_reference_cli(engine):
+    """cfg1: one 60 s synthetic stream: stdout of the unmodified reference CLI == our segments."""
+    pcm = vadc_b200.synth_pcm(2024, 16000 * 60)
+    engine.reset()
+    p = engine.run_streams(pcm[None, :])[0]
+    assert vadc_b200.segments_text(p) == ref_cli(pcm)
+    raw = np.array([float(v) for v in ref_cli(pcm, "--raw_probabilities").split()])
+    assert np.abs(raw - p).max() <= PTOL + 1e-6
+    m = margins(p)
+    print("threshold margins: min|p-0.5|=%.2e min|p-0.35|=%.2e" % m)

@@ -17,7 +17,10 @@ __host__ __device__ constexpr LayerDims layer_dims( int l )
    return l == 0 ? LayerDims{129, 16, 25, 2, 1}
         : l == 1 ? LayerDims{16, 32, 13, 2, 1}
         : l == 2 ? LayerDims{32, 32, 7, 1, 0}
-                 : LayerDims{32, 64, 7, 1, 1};
+        : l == 3 ? LayerDims{32, 64, 7, 1, 1}
+                 : LayerDims{129, 16, 64, 2, 1}; // l == 4: first-layer shapes at T=64, the size of the
+                                                 // reference's dw_conv_129 / pw_conv_129_16 /
+                                                 // first_layer_conv_block fixtures (parity taps only)
 }
 
 // ---- packed per-layer weights (device global memory, floats) ---------------------------------
@@ -44,7 +47,7 @@ struct LayerPack
    static constexpr int al4( int x ) { return ( x + 3 ) & ~3; }
    static constexpr int DW = 0;
    static constexpr int PW = DW + CIN * 8;
-   static constexpr int PWB = PW + al4( L == 0 ? CIN * 2 * C : C * KP );
+   static constexpr int PWB = PW + al4( CIN == VB_BINS ? CIN * 2 * C : C * KP );
    static constexpr int QKV = PWB + al4( C );
    static constexpr int QH = 3 * D * C + 3 * D; // per-head stride inside QKV
    static constexpr int AO = QKV + 2 * QH;

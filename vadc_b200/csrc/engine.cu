@@ -136,7 +136,7 @@ static void pack_layer( const vb_tensor *t, float *blob )
       for ( int k = 0; k < 5; ++k ) blob[P::DW + c * 8 + k] = dw_w[c * 5 + k];
       blob[P::DW + c * 8 + 5] = dw_b[c];
    }
-   if ( L == 0 )
+   if ( CIN == VB_BINS )
    {
       for ( int f = 0; f < CIN; ++f )
          for ( int o = 0; o < C; ++o )
@@ -220,6 +220,7 @@ static int configure_kernels()
    CU( allow_smem( layer_kernel<1, false>, LayerCfg<1>::SMEM_BYTES ) );
    CU( allow_smem( layer_kernel<2, false>, LayerCfg<2>::SMEM_BYTES ) );
    CU( allow_smem( layer_kernel<3, false>, LayerCfg<3>::SMEM_BYTES ) );
+   CU( allow_smem( layer_kernel<4, false>, LayerCfg<4>::SMEM_BYTES ) );
    CU( allow_smem( lstm_layer_kernel<0, 4>, LstmSmem<4>::BYTES ) );
    CU( allow_smem( lstm_layer_kernel<1, 4>, LstmSmem<4>::BYTES ) );
    CU( allow_smem( lstm_layer_kernel<0, 1>, LstmSmem<1>::BYTES ) );
@@ -498,7 +499,7 @@ static int launch_stft( silero_b200 *h, const void *d_in, int in_f32, long long 
 }
 
 template <int L, bool NORM>
-static int launch_layer( silero_b200 *h, const float *in, float *out, int nchunks )
+static int launch_layer( silero_b200 *h, const float *in, float *out, int nchunks, int entry = ENTRY_LAYER, int tap = TAP_LAYER )
 {
    using Cfg = LayerCfg<L>;
    int ntiles = ( nchunks + Cfg::G - 1 ) / Cfg::G;
@@ -506,7 +507,7 @@ static int launch_layer( silero_b200 *h, const float *in, float *out, int nchunk
    if ( per_sm < 1 ) per_sm = 1;
    if ( per_sm > 8 ) per_sm = 8;
    int grid = imin( ntiles, h->sm_count * per_sm );
-   layer_kernel<L, NORM><<<grid, LAYER_THREADS, Cfg::SMEM_BYTES, h->stream>>>( in, out, h->w.layer[L], nchunks );
+   layer_kernel<L, NORM><<<grid, LAYER_THREADS, Cfg::SMEM_BYTES, h->stream>>>( in, out, h->w.layer[L == 4 ? 0 : L], nchunks, entry, tap );
    h->launches++;
    CU( cudaGetLastError() );
    return 0;
@@ -1032,6 +1033,52 @@ extern "C" int silero_b200_stage_layer( silero_b200 *h, int layer, const float *
    }
    if ( !rc ) rc = down( h, tmp, dout.p, nout );
    if ( !rc ) tok_to_ref( tmp, batch, tout, d.c, out );
+   free( tmp );
+   return rc ? SILERO_B200_ERR_CUDA : SILERO_B200_OK;
+}
+
+// Sub-stage taps of one layer for the reference's op/block-level fixtures (layer_kernel.cuh).
+// layer 0..3, or 4 = the first layer's weights at T=64. in: entry 0 -> reference layout [B,cin,T];
+// entry 1/2 -> token-major [B,T,C]. out: tap 0 -> reference layout [B,C,TOUT]; else token-major [B,T,C].
+extern "C" int silero_b200_stage_layer_tap( silero_b200 *h, int layer, int entry, int tap, const float *in, int batch, float *out )
+{
+   if ( !h || !in || !out || batch <= 0 || layer < 0 || layer > 4 || entry < 0 || entry > 2 || tap < 0 || tap > 4 ) return set_err( SILERO_B200_ERR_ARG, "bad argument" );
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+   const LayerDims d = layer_dims( layer );
+   const int tout = 1 + ( d.t - 1 ) / d.stride;
+   const size_t nin = (size_t)batch * ( entry == ENTRY_LAYER ? d.cin : d.c ) * d.t;
+   const size_t nout = (size_t)batch * d.c * ( tap == TAP_LAYER ? tout : d.t );
+   DevBuf din, dout;
+   if ( din.alloc( nin ) || dout.alloc( nout ) ) return SILERO_B200_ERR_CUDA;
+   float *tmp = (float *)malloc( ( nin > nout ? nin : nout ) * sizeof( float ) );
+   if ( !tmp ) return set_err( SILERO_B200_ERR_NOMEM, "out of host memory" );
+   int rc = 0;
+   if ( entry == ENTRY_LAYER && d.cin != VB_BINS )
+   {
+      ref_to_tok( in, batch, d.cin, d.t, tmp );
+      rc = up( h, din.p, tmp, nin );
+      if ( !rc ) rc = cudaStreamSynchronize( h->stream ) != cudaSuccess;
+   }
+   else
+      rc = up( h, din.p, in, nin );
+   if ( !rc )
+   {
+      switch ( layer )
+      {
+         case 0: rc = launch_layer<0, false>( h, din.p, dout.p, batch, entry, tap ); break;
+         case 1: rc = launch_layer<1, false>( h, din.p, dout.p, batch, entry, tap ); break;
+         case 2: rc = launch_layer<2, false>( h, din.p, dout.p, batch, entry, tap ); break;
+         case 3: rc = launch_layer<3, false>( h, din.p, dout.p, batch, entry, tap ); break;
+         default: rc = launch_layer<4, false>( h, din.p, dout.p, batch, entry, tap ); break;
+      }
+   }
+   if ( !rc && tap == TAP_LAYER )
+   {
+      rc = down( h, tmp, dout.p, nout );
+      if ( !rc ) tok_to_ref( tmp, batch, tout, d.c, out );
+   }
+   else if ( !rc )
+      rc = down( h, out, dout.p, nout );
    free( tmp );
    return rc ? SILERO_B200_ERR_CUDA : SILERO_B200_OK;
 }
