@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- audio-seconds/sec (x realtime) of Silero VAD v3.1 (16 kHz) on B200, beside the
+reference C backend on the host CPU.   python bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[2]): 4096 concurrent synthetic 16 kHz s16le streams per GPU with
+per-stream LSTM state kept on device. A "step" is one pass of the hot path over 4096 streams x 125
+chunks (12 s of audio each, 512 000 chunks, 1.57 GB of PCM); 50 steps are the full 10 minutes. Under
+torchrun every rank owns its own 4096 streams (weak scaling, no data-path collective).
+
+value : device-resident throughput (PCM already in HBM), CUDA events on the engine's stream, max over ranks.
+e2e   : the same steps through silero_b200_run_streams with pinned HOST buffers (H2D of the PCM and
+        D2H of the probabilities inside the timed region).
+--impl reference : the reference's own C backend (oracle/_ref, built from /root/reference; else the
+        oracle port) on the host cores, one process per core.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+CHUNK = 1536
+CHUNK_SECONDS = CHUNK / 16000.0
+FLOP_PER_CHUNK = 5404954          # 2 x 2 702 477 MAC, reference's dense formulation
+STFT_FLOP_PER_CHUNK = 2 * 1651200 # K1: 258 x 25 x 256 MAC
+STREAMS_PER_GPU = 4096
+STEP_CHUNKS = 125
+N_BASE = 32                       # distinct synthetic base streams
+BASE_CHUNKS = 1250                # 120 s each; streams are chunk-rotated views of the bases
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the reference C backend, one process per core (it is not thread-safe: conv.c:172)
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    kind, seeds, nsamples = args
+    import vadc_b200
+    from oracle_lib import Oracle, Reference
+    impl = Reference() if kind == "reference" else Oracle()
+    pcms = [vadc_b200.synth_pcm(s, nsamples) for s in seeds]
+    impl.run_pcm(pcms[0][: CHUNK * 20])  # warm caches / page in
+    impl.reset()
+    t0 = time.perf_counter()
+    n = 0
+    for p in pcms:
+        impl.reset()
+        out = impl.run_pcm(p)
+        n += out.shape[0]
+    return n, time.perf_counter() - t0
+
+
+def cpu_reference_run(streams_per_core=2, seconds=60.0):
+    """Times the reference backend on every host core. Returns (audio_s_per_s, cores, kind, sample, per_core)."""
+    from oracle_lib import have_ref
+    kind = "reference" if have_ref() else "port"
+    cores = len(os.sched_getaffinity(0))
+    nsamples = int(seconds * 16000)
+    jobs = [(kind, [90000 + c * streams_per_core + i for i in range(streams_per_core)], nsamples) for c in range(cores)]
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, [(kind, [1], CHUNK * 8)] * cores)   # spawn + import cost outside the timed region
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_worker, jobs)
+        wall = time.perf_counter() - t0
+    chunks = sum(r[0] for r in res)
+    per_core = float(np.mean([r[0] * CHUNK_SECONDS / r[1] for r in res]))
+    sample = "%d procs x %d streams x %.0f s synthetic bursts, batch 96, %s" % (
+        cores, streams_per_core, seconds, "oracle/_ref (unmodified reference, gcc -O2 -mavx2 -ffp-contract=off)" if kind == "reference"
+        else "oracle/libsilero_oracle.so (C port)")
+    return chunks * CHUNK_SECONDS / wall, cores, kind, sample, per_core
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def build_step_inputs(torch, dev, nbuf):
+    """PCM of `nbuf` steps for this rank's 4096 streams, resident in HBM: [nbuf][S][STEP_CHUNKS*1536] s16."""
+    import vadc_b200
+    rank = int(os.environ.get("RANK", "0"))
+    base = np.stack([vadc_b200.synth_pcm(5000 + 97 * rank + i, BASE_CHUNKS * CHUNK) for i in range(N_BASE)])
+    d_base = torch.from_numpy(base).to(dev).view(N_BASE, BASE_CHUNKS, CHUNK)
+    s = torch.arange(STREAMS_PER_GPU, device=dev)
+    sid, off = s % N_BASE, (s // N_BASE) * 37
+    n = torch.arange(STEP_CHUNKS, device=dev)
+    bufs = []
+    for k in range(nbuf):
+        idx = (off[:, None] + k * STEP_CHUNKS + n[None, :]) % BASE_CHUNKS
+        bufs.append(d_base[sid[:, None], idx].contiguous().view(STREAMS_PER_GPU, STEP_CHUNKS * CHUNK))
+    torch.cuda.synchronize()
+    return base, bufs
+
+
+def host_stream(base, s, k0, nchunks):
+    """The s16 stream that rank-0 stream `s` sees from step k0 on (for the oracle spot check)."""
+    sid, off = s % N_BASE, (s // N_BASE) * 37
+    idx = (off + k0 * STEP_CHUNKS + np.arange(nchunks)) % BASE_CHUNKS
+    return base[sid].reshape(BASE_CHUNKS, CHUNK)[idx].reshape(-1)
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return 0
+    vals = []
+    for _ in range(args.warmup):
+        cpu_reference_run(1, 10.0)
+    t_total, audio_total = 0.0, 0.0
+    last = None
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        last = cpu_reference_run(2, 60.0)
+        dt = time.perf_counter() - t0
+        vals.append(last[0])
+    value = float(np.mean(vals))
+    _, cores, kind, sample, per_core = last
+    line = {
+        "impl": "reference", "metric": "audio-seconds/sec (RTF) Silero v3.1 at 1/2/4/8 B200 vs host-CPU C backend",
+        "value": value, "unit": "audio-seconds/sec", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * cores * 2 * 60.0 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg3: 4096 concurrent 16 kHz s16le streams x 10 min per GPU (reference arm: bounded sample per step, see cpu_baseline.sample)",
+                   "cpu": cpu_model()},
+        "cpu_baseline": {"value": value, "unit": "audio-seconds/sec", "cores": cores, "kind": kind, "sample": sample, "per_core": per_core},
+        "e2e": {"value": value, "unit": "audio-seconds/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        return run_reference_arm(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+
+    import vadc_b200
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    S, C = STREAMS_PER_GPU, STEP_CHUNKS
+    eng = vadc_b200.Engine(device=local, max_streams=S)
+    nbuf = min(args.steps + args.warmup, 6)
+    base, bufs = build_step_inputs(torch, dev, nbuf)
+    d_probs = torch.empty((S, C), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+
+    def step(k):
+        eng.run_streams_device(bufs[k % nbuf].data_ptr(), C * CHUNK, S, C, d_probs.data_ptr())
+
+    # ---- parity spot check on this exact workload (rank 0, not timed) ---------------------------
+    parity = None
+    if rank == 0:
+        from oracle_lib import Oracle
+        step(0)
+        eng.sync()
+        got = d_probs.cpu().numpy()
+        o = Oracle()
+        worst = 0.0
+        for s in (0, 1337, S - 1):
+            o.reset()
+            worst = max(worst, float(np.abs(got[s] - o.run_pcm(host_stream(base, s, 0, C))[:, 1]).max()))
+        parity = worst
+        assert worst <= 1e-4, "parity lost on the bench workload: %g" % worst
+    eng.reset()
+
+    # ---- device-resident timed region ---------------------------------------------------------------
+    for k in range(args.warmup):
+        step(k)
+    eng.sync()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    eng.timer_start()
+    for k in range(args.steps):
+        step(args.warmup + k)
+    ms = eng.timer_stop()
+    barrier()
+    launches = args.steps * eng.last_timing()[1]   # kernels launched per run_streams_device call, counted by the engine
+    clocks = sampler.stop() if rank == 0 else None
+    ms = max_over_ranks(ms)
+    audio_s = world * S * C * CHUNK_SECONDS * args.steps
+    value = audio_s / (ms / 1e3)
+
+    # ---- per-kernel profile of the same step (CUDA events between kernels; separate pass) -----------
+    eng.set_profiling(True)
+    stage_ms = None
+    for k in range(2):
+        step(k)
+        eng.sync()
+        stage_ms, n_launch = eng.last_timing()
+    eng.set_profiling(False)
+    windows = n_launch // 7
+    stft_ms_per_launch = stage_ms["stft"] / windows
+    chunks_per_launch = S * C / windows
+    fp32_peak = eng.measure_fp32_peak()
+    stft_tflops = STFT_FLOP_PER_CHUNK * chunks_per_launch / (stft_ms_per_launch * 1e-3) / 1e12
+    kernel_sum = sum(v for k, v in stage_ms.items() if k != "total")
+    roofline = {
+        "kernel": "stft_logmag_kernel<s16>", "bound": "fp32",
+        "achieved": stft_tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": stft_tflops / fp32_peak,
+        "peak_source": "FP32 FMA pipe measured live by silero_b200_measure_fp32_peak (independent FFMA chains); MEASURED_PEAKS.json has no FP32 figure "
+                       "(its bf16 tensor peak does not bound this kernel: the reference's rounding sequence must be reproduced, see DESIGN.md)",
+        "algorithmic_flop_per_launch": STFT_FLOP_PER_CHUNK * chunks_per_launch, "ms_per_launch": stft_ms_per_launch,
+        "share_of_step": stage_ms["stft"] / kernel_sum,
+        "executed_fp32_ops_frac": (511.0 / 512.0) * 2 * stft_tflops / fp32_peak,  # mul+add issued separately: 511 pipe ops per 256-MAC output
+        "traffic": TRAFFIC_STFT_BYTES_PER_CHUNK * chunks_per_launch if TRAFFIC_STFT_BYTES_PER_CHUNK else None,
+        "stage_ms": stage_ms,
+        "pipeline_algorithmic_tflops": FLOP_PER_CHUNK * (value / world / CHUNK_SECONDS) / 1e12,
+        "pipeline_frac_of_fp32_peak": FLOP_PER_CHUNK * (value / world / CHUNK_SECONDS) / 1e12 / fp32_peak,
+    }
+
+    # ---- end to end through the C ABI with host buffers --------------------------------------------
+    h_pcm, h_pcm_ptr = vadc_b200.pinned_empty((S, C * CHUNK), np.int16)
+    h_probs, h_probs_ptr = vadc_b200.pinned_empty((S, C), np.float32)
+    h_pcm[:] = bufs[0].cpu().numpy()
+    eng.reset()
+    for k in range(2):
+        eng.run_streams_ptr(h_pcm_ptr, C * CHUNK, S, C, h_probs_ptr)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        eng.run_streams_ptr(h_pcm_ptr, C * CHUNK, S, C, h_probs_ptr)   # synchronous: returns with the probabilities on the host
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    e2e_ms = max_over_ranks(e2e_ms)
+    e2e_value = audio_s / (e2e_ms / 1e3)
+    # the "final gather of per-stream segments": segment a few streams per rank, gather counts on rank 0
+    seg_count = sum(vadc_b200.segments_text(h_probs[s]).count("\n") for s in range(0, S, 512))
+    if world > 1:
+        counts = [None] * world
+        dist.all_gather_object(counts, seg_count)
+        seg_count = sum(counts)
+
+    # ---- CPU baseline (rank 0, N=1 only) --------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, kind, sample, per_core = cpu_reference_run(2, 60.0)
+        cpu = {"value": v, "unit": "audio-seconds/sec", "cores": cores, "kind": kind, "sample": sample, "per_core": per_core, "cpu": cpu_model()}
+
+    if rank == 0:
+        line = {
+            "metric": "audio-seconds/sec (RTF) Silero v3.1 at 1/2/4/8 B200 vs host-CPU C backend",
+            "value": value, "unit": "audio-seconds/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg3: 4096 concurrent synthetic 16 kHz s16le streams x 10 min per GPU, per-stream LSTM state on device; "
+                                   "step = 4096 streams x 125 chunks (12 s); 50 steps = the 10 minutes",
+                       "streams_per_gpu": S, "chunks_per_step": C, "l2_policy": "inputs larger than L2 (1.57 GB PCM per step, rotating step buffers)",
+                       "parity_max_abs_err_vs_oracle": parity, "segments_gathered": seg_count, "sharding": "streams across ranks, no collective on the data path"},
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "audio-seconds/sec", "h2d_bytes_per_step": S * C * CHUNK * 2, "d2h_bytes_per_step": S * C * 4,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches,
+        }
+        print(json.dumps(line))
+    vadc_b200.pinned_free(h_pcm_ptr)
+    vadc_b200.pinned_free(h_probs_ptr)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+# dram bytes per chunk of the STFT kernel from the committed ncu capture (profiles/); None until measured
+TRAFFIC_STFT_BYTES_PER_CHUNK = None
+
+if __name__ == "__main__":
+    sys.exit(main())

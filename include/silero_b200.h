@@ -119,6 +119,13 @@ int silero_b200_last_timing( silero_b200 *h, float ms[8], long long *kernel_laun
 /* enable (1) / disable (0) per-stage CUDA-event timing (adds events between kernels) */
 int silero_b200_set_profiling( silero_b200 *h, int enabled );
 
+/* device-side stopwatch on the engine's stream (CUDA events): start, run any number of calls, stop */
+int silero_b200_timer_start( silero_b200 *h );
+int silero_b200_timer_stop( silero_b200 *h, float *ms );
+/* FP32 FMA-pipe throughput this device sustains (TFLOP/s, independent FFMA chains): the roofline
+   denominator for the CUDA-core kernels of this engine */
+int silero_b200_measure_fp32_peak( silero_b200 *h, float *tflops );
+
 /* ---- parity taps (the reference's per-stage functions; host pointers; stateless unless noted) -
    Layouts are the reference's: spectrogram [B,129,25]; layer outputs [B,16,13] [B,32,7] [B,32,7]
    [B,64,7]; lstm sequence [B,7,64]. Any output pointer may be NULL. */

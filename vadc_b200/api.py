@@ -183,6 +183,19 @@ class Engine:
         names = ("total", "stft", "layer1", "layer2", "layer3", "layer4", "lstm0", "lstm1_decoder")
         return dict(zip(names, [float(v) for v in ms])), int(n.value)
 
+    def timer_start(self):
+        self._check(lib().silero_b200_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._check(lib().silero_b200_timer_stop(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def measure_fp32_peak(self):
+        tf = C.c_float()
+        self._check(lib().silero_b200_measure_fp32_peak(self._h, C.byref(tf)))
+        return float(tf.value)
+
     # ---- parity taps ----------------------------------------------------------------------------
     def stage_stft_magnitude(self, samples):
         x = _f32(samples).reshape(-1, CHUNK)

@@ -816,9 +816,6 @@ extern "C" int silero_b200_last_timing( silero_b200 *h, float ms[8], long long *
    return SILERO_B200_OK;
 }
 
-// ---------------------------------------------------------------------------------------------
-// parity taps (test-facing; layouts converted on the host, compute on the device)
-// ---------------------------------------------------------------------------------------------
 struct DevBuf
 {
    float *p = 0;
@@ -829,6 +826,71 @@ struct DevBuf
       return 0;
    }
 };
+
+// ---------------------------------------------------------------------------------------------
+// measurement helpers (bench.py): device-side timer on the engine's stream, FP32 pipe peak
+// ---------------------------------------------------------------------------------------------
+extern "C" int silero_b200_timer_start( silero_b200 *h )
+{
+   if ( !h ) return set_err( SILERO_B200_ERR_ARG, "null handle" );
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+   CU( cudaEventRecord( h->ev_stage[N_STAGE_EVENTS - 1], h->stream ) );
+   return SILERO_B200_OK;
+}
+
+extern "C" int silero_b200_timer_stop( silero_b200 *h, float *ms )
+{
+   if ( !h || !ms ) return set_err( SILERO_B200_ERR_ARG, "null argument" );
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+   CU( cudaEventRecord( h->ev_stage[N_STAGE_EVENTS - 2], h->stream ) );
+   CU( cudaEventSynchronize( h->ev_stage[N_STAGE_EVENTS - 2] ) );
+   CU( cudaEventElapsedTime( ms, h->ev_stage[N_STAGE_EVENTS - 1], h->ev_stage[N_STAGE_EVENTS - 2] ) );
+   return SILERO_B200_OK;
+}
+
+// 16 independent FFMA chains per thread: the FP32 FMA-pipe roofline this part actually delivers
+__global__ void __launch_bounds__( 256 ) fp32_peak_kernel( float *out, int iters, float a, float b )
+{
+   float acc[16];
+#pragma unroll
+   for ( int i = 0; i < 16; ++i ) acc[i] = (float)( threadIdx.x + i );
+   for ( int it = 0; it < iters; ++it )
+   {
+#pragma unroll
+      for ( int i = 0; i < 16; ++i ) acc[i] = fmaf( acc[i], a, b );
+   }
+   float s = 0.0f;
+#pragma unroll
+   for ( int i = 0; i < 16; ++i ) s += acc[i];
+   if ( s == 123.456f ) out[0] = s; // never true; keeps the chains alive
+}
+
+extern "C" int silero_b200_measure_fp32_peak( silero_b200 *h, float *tflops )
+{
+   if ( !h || !tflops ) return set_err( SILERO_B200_ERR_ARG, "null argument" );
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+   DevBuf o;
+   if ( o.alloc( 4 ) ) return SILERO_B200_ERR_CUDA;
+   const int iters = 1 << 15, blocks = h->sm_count * 8, threads = 256;
+   float best = 0.0f;
+   for ( int rep = 0; rep < 5; ++rep )
+   {
+      CU( cudaEventRecord( h->ev_stage[0], h->stream ) );
+      fp32_peak_kernel<<<blocks, threads, 0, h->stream>>>( o.p, iters, 0.999f, 0.001f );
+      CU( cudaEventRecord( h->ev_stage[1], h->stream ) );
+      CU( cudaEventSynchronize( h->ev_stage[1] ) );
+      float ms = 0.0f;
+      CU( cudaEventElapsedTime( &ms, h->ev_stage[0], h->ev_stage[1] ) );
+      float tf = 2.0f * 16.0f * (float)iters * (float)blocks * (float)threads / ( ms * 1e-3f ) / 1e12f;
+      if ( rep > 0 && tf > best ) best = tf;
+   }
+   *tflops = best;
+   return SILERO_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// parity taps (test-facing; layouts converted on the host, compute on the device)
+// ---------------------------------------------------------------------------------------------
 
 static int up( silero_b200 *h, float *d, const float *src, size_t n )
 {
