@@ -353,7 +353,7 @@ def main():
 
 
 # dram bytes per chunk of the STFT kernel from the committed ncu capture (profiles/); None until measured
-TRAFFIC_STFT_BYTES_PER_CHUNK = None
+TRAFFIC_STFT_BYTES_PER_CHUNK = 15118  # profiles/ncu_summary_r01.md: (154.4 MB read + 588.7 MB written) / 49152 chunks
 
 if __name__ == "__main__":
     sys.exit(main())
