@@ -49,12 +49,21 @@ enum
 
 typedef struct silero_b200 silero_b200; /* opaque engine handle */
 
+/* STFT evaluation. HYBRID: fp32 FFT everywhere + the reference's exact rounding
+   sequence (stft.c:108-184) for every bin whose magnitude is below stft_k_rel * ||windowed frame||_2;
+   EXACT: the reference's sequence for every bin (bit-identical magnitudes, ~7x slower STFT). */
+#define SILERO_B200_STFT_HYBRID 0
+#define SILERO_B200_STFT_EXACT 1
+#define SILERO_B200_STFT_K_REL_DEFAULT 0.004f
+
 typedef struct silero_b200_opts
 {
    int device;          /* CUDA device ordinal (default 0) */
    int max_streams;     /* number of independent streams whose LSTM state is kept on device (default 1) */
    int window_chunks;   /* chunks per stream processed per internal pass; 0 = choose from memory budget */
-   int reserved[5];
+   int stft_mode;       /* SILERO_B200_STFT_HYBRID (default) or SILERO_B200_STFT_EXACT */
+   float stft_k_rel;    /* hybrid threshold; 0 = SILERO_B200_STFT_K_REL_DEFAULT */
+   int reserved[3];
 } silero_b200_opts;
 
 void silero_b200_default_opts( silero_b200_opts *opts );
@@ -116,6 +125,8 @@ int silero_b200_host_free_pinned( void *ptr );
    ms[0]=total, [1]=stft, [2]=layer1, [3]=layer2, [4]=layer3, [5]=layer4, [6]=lstm0, [7]=lstm1+decoder;
    kernel_launches = number of kernels launched by that call. Valid after silero_b200_sync. */
 int silero_b200_last_timing( silero_b200 *h, float ms[8], long long *kernel_launches );
+/* hybrid STFT statistics since the last reset: spectrogram bins produced and bins that took the exact path */
+int silero_b200_stft_stats( silero_b200 *h, unsigned long long *bins_total, unsigned long long *bins_exact, int reset );
 /* enable (1) / disable (0) per-stage CUDA-event timing (adds events between kernels) */
 int silero_b200_set_profiling( silero_b200 *h, int enabled );
 

@@ -11,14 +11,16 @@ def md(a, b): return float(np.abs(a - b).max())
 def main():
     S = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
     N = int(sys.argv[2]) if len(sys.argv) > 2 else 64
-    e = vadc_b200.Engine(max_streams=max(S, 64))
+    mode = int(os.environ.get("STFT_MODE", "0"))
+    e = vadc_b200.Engine(max_streams=max(S, 64), stft_mode=mode, stft_k_rel=float(os.environ.get("K_REL", "0")))
     print(e.info())
     o = Oracle()
     pcm = vadc_b200.synth_pcm(3, 1536 * 40)
     x = (pcm.astype(np.float32) / np.float32(32768)).reshape(-1, 1536)
     st = o.run_stages(x)
     mag = e.stage_stft_magnitude(x)
-    print("stft magnitude max diff", md(mag, st["stft"]), "bit-exact", np.array_equal(mag, st["stft"]))
+    print("stft magnitude max diff", md(mag, st["stft"]), "bit-exact", np.array_equal(mag, st["stft"]), "max rel diff", float((np.abs(mag - st["stft"]) / np.maximum(st["stft"], 1e-30)).max()))
+    print("stft stats (total, exact)", e.stft_stats(reset=True))
     norm, logmag = e.stage_stft_norm(x)
     print("norm max diff", md(norm, st["norm"]))
     print("stage_norm(mag) diff", md(e.stage_norm(st["stft"]), st["norm"]))
@@ -49,6 +51,8 @@ def main():
         ref = o.run_pcm(pcm2[s])
         worst = max(worst, md(out2[s], ref))
     print("multi-stream vs oracle max diff", worst)
+    tot, ex = e.stft_stats(reset=True)
+    print("hybrid stft: %d bins, %d exact (%.3f %%)" % (tot, ex, 100.0 * ex / max(tot, 1)))
     # device-resident timing with per-stage profile
     d_pcm = e.device_alloc(pcm2.nbytes); d_probs = e.device_alloc(S * N * 4)
     e.h2d(d_pcm, pcm2)

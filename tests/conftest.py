@@ -25,3 +25,12 @@ def engine():
     e = vadc_b200.Engine(max_streams=64)
     yield e
     e.close()
+
+
+@pytest.fixture(scope="session")
+def engine_exact():
+    """Engine with the bit-faithful STFT for every bin (SILERO_B200_STFT_EXACT)."""
+    import vadc_b200
+    e = vadc_b200.Engine(max_streams=8, stft_mode=vadc_b200.api.STFT_EXACT)
+    yield e
+    e.close()

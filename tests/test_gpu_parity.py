@@ -13,6 +13,7 @@ from oracle_lib import ROOT, Oracle, have_ref, ref_cli
 
 pytestmark = pytest.mark.gpu
 PTOL = 1e-4
+HYB_REL = 3e-4   # hybrid STFT: bins above the fix-up threshold carry <= c*eps/k_rel relative error (measured 7e-5)
 CASES = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "e2e_*.npz")))
 
 
@@ -26,7 +27,7 @@ def margins(p):
 
 
 @pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p) for p in CASES])
-def test_golden_reference_vectors(engine, path):
+def test_golden_reference_vectors(engine, engine_exact, path):
     g = np.load(path)
     pcm = g["pcm"]
     engine.reset()
@@ -39,27 +40,76 @@ def test_golden_reference_vectors(engine, path):
     assert vadc_b200.segments_text(probs[0], vadc_b200.seg_params(centiseconds=1)) == str(g["stdout_centi"])
     # per-stage tensors of the first 8 chunks
     x = f32(pcm[: 8 * 1536])
-    assert np.array_equal(engine.stage_stft_magnitude(x), g["stages_stft"])          # bit-exact
-    norm, logmag = engine.stage_stft_norm(x)
+    assert np.array_equal(engine_exact.stage_stft_magnitude(x), g["stages_stft"])    # exact mode: bit-exact
+    norm, logmag = engine_exact.stage_stft_norm(x)
     assert np.abs(norm - g["stages_norm"]).max() < 5e-6
+    mag = engine.stage_stft_magnitude(x)                                              # hybrid mode (default)
+    assert (np.abs(mag - g["stages_stft"]) <= HYB_REL * g["stages_stft"]).all()
+    norm, logmag = engine.stage_stft_norm(x)
+    assert np.abs(norm - g["stages_norm"]).max() < 2 * HYB_REL
+    engine_exact.reset()
+    assert np.abs(engine_exact.run_streams(pcm[None, :], want_out2=True)[1][0] - g["out2"]).max() <= PTOL
     for got, k in zip(engine.stage_pipeline(x), ("l1", "l2", "l3", "l4")):
         ref = g["stages_" + k]
         assert np.abs(got - ref).max() <= 2e-4 * max(1.0, float(np.abs(ref).max())), k
 
 
-def test_stft_bit_exact_on_edge_signals(engine, oracle):
+def _edge_signals():
     rng = np.random.default_rng(0)
-    x = np.zeros((6, 1536), np.float32)
+    x = np.zeros((8, 1536), np.float32)
     x[1] = 1.0 - 2.0 ** -15                      # full-scale DC
     x[2] = rng.uniform(-1, 1, 1536)              # white
     x[3, ::2] = 0.999; x[3, 1::2] = -1.0         # Nyquist
     x[4, 700] = 1.0                              # impulse
     x[5] = (rng.integers(-3, 4, 1536) / 32768.0) # near-silent LSB noise (worst case for log1p)
+    x[6] = 0.5 * np.sin(2 * np.pi * 1000.0 * np.arange(1536) / 16000.0)   # pure tone on a bin centre: almost every bin is "small"
+    x[7] = np.round(3000 * np.sin(2 * np.pi * 440.0 * np.arange(1536) / 16000.0)) / 32768.0 + x[5]
+    return x
+
+
+def test_stft_bit_exact_on_edge_signals(engine_exact, oracle):
+    x = _edge_signals()
     oracle.reset()
     st = oracle.run_stages(x)
-    assert np.array_equal(engine.stage_stft_magnitude(x), st["stft"])
-    norm, _ = engine.stage_stft_norm(x)
+    assert np.array_equal(engine_exact.stage_stft_magnitude(x), st["stft"])
+    norm, _ = engine_exact.stage_stft_norm(x)
     assert np.abs(norm - st["norm"]).max() < 5e-6
+
+
+def test_hybrid_stft_on_edge_signals(engine, oracle):
+    """Hybrid mode: bins below the threshold are bit-identical to the reference (exact tree), the
+    others within HYB_REL; degenerate signals push most bins onto the exact path."""
+    x = _edge_signals()
+    oracle.reset()
+    st = oracle.run_stages(x)
+    engine.stft_stats(reset=True)
+    mag = engine.stage_stft_magnitude(x)
+    total, exact = engine.stft_stats(reset=True)
+    assert total == 8 * 129 * 25 and exact > 0.3 * total
+    assert (np.abs(mag - st["stft"]) <= HYB_REL * st["stft"]).all()
+    norm, _ = engine.stage_stft_norm(x)
+    assert np.abs(norm - st["norm"]).max() < 2 * HYB_REL
+    engine.reset()
+    assert np.abs(engine.run_chunks(x) - st["out"]).max() <= PTOL
+
+
+def test_hybrid_exact_path_alone_is_bit_exact(oracle):
+    """k_rel = huge sends every bin through the warp-cooperative exact tree of the hybrid kernel."""
+    e = vadc_b200.Engine(stft_k_rel=1e30)
+    x = np.concatenate([_edge_signals(), f32(vadc_b200.synth_pcm(8, 1536 * 8))])
+    oracle.reset()
+    assert np.array_equal(e.stage_stft_magnitude(x), oracle.run_stages(x)["stft"])
+    total, exact = e.stft_stats()
+    assert exact > 0.85 * total   # all-zero frames have threshold 0 and are already exact (FFT of zeros)
+    e.close()
+
+
+def test_hybrid_fix_fraction_on_speech_like_audio(engine):
+    pcm = np.stack([vadc_b200.synth_pcm(60 + s, 1536 * 100) for s in range(8)])
+    engine.reset(); engine.stft_stats(reset=True)
+    engine.run_streams(pcm)
+    total, exact = engine.stft_stats(reset=True)
+    assert total == 8 * 100 * 3225 and 0 < exact < 0.02 * total, (total, exact)
 
 
 @pytest.mark.parametrize("S,N,window", [(1, 1, 0), (3, 7, 0), (37, 70, 16), (130, 33, 5), (64, 96, 0)])

@@ -15,6 +15,7 @@ WEIGHTS_PATH = os.path.join(_HERE, "weights", "silero_v31_16k.testtensor")
 
 CHUNK = 1536
 SAMPLE_RATE = 16000
+STFT_HYBRID, STFT_EXACT = 0, 1
 
 
 class EngineError(RuntimeError):
@@ -22,7 +23,8 @@ class EngineError(RuntimeError):
 
 
 class Opts(C.Structure):
-    _fields_ = [("device", C.c_int), ("max_streams", C.c_int), ("window_chunks", C.c_int), ("reserved", C.c_int * 5)]
+    _fields_ = [("device", C.c_int), ("max_streams", C.c_int), ("window_chunks", C.c_int), ("stft_mode", C.c_int),
+                ("stft_k_rel", C.c_float), ("reserved", C.c_int * 3)]
 
 
 class Info(C.Structure):
@@ -76,11 +78,12 @@ def _f32(a):
 class Engine:
     """One engine per GPU (silero_b200 handle)."""
 
-    def __init__(self, weights=None, device=0, max_streams=1, window_chunks=0):
+    def __init__(self, weights=None, device=0, max_streams=1, window_chunks=0, stft_mode=0, stft_k_rel=0.0):
         L = lib()
         opts = Opts()
         L.silero_b200_default_opts(C.byref(opts))
         opts.device, opts.max_streams, opts.window_chunks = device, max_streams, window_chunks
+        opts.stft_mode, opts.stft_k_rel = stft_mode, stft_k_rel
         self._h = C.c_void_p()
         if weights is None:
             weights = WEIGHTS_PATH
@@ -172,6 +175,11 @@ class Engine:
     def d2h(self, arr, d_ptr):
         assert arr.flags["C_CONTIGUOUS"]
         self._check(lib().silero_b200_memcpy_d2h(self._h, _p(arr), C.c_void_p(d_ptr), C.c_size_t(arr.nbytes)))
+
+    def stft_stats(self, reset=False):
+        tot, ex = C.c_ulonglong(), C.c_ulonglong()
+        self._check(lib().silero_b200_stft_stats(self._h, C.byref(tot), C.byref(ex), 1 if reset else 0))
+        return int(tot.value), int(ex.value)
 
     def set_profiling(self, on):
         self._check(lib().silero_b200_set_profiling(self._h, 1 if on else 0))

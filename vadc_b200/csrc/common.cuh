@@ -72,6 +72,7 @@ struct LayerPack
 struct DeviceWeights
 {
    const float *basis_pack; // [2 halves][64 kquads][128 rows][4]  (stft_kernel.cuh)
+   const float *basis_raw;  // [258][256] as stored in the container (stft_hybrid_kernel.cuh)
    const float *layer[4];   // LayerPack<L> blobs
    const float *lstm_w;     // [2 layers][32 kquads][256 rows][4]
    const float *lstm_b;     // [2][256]

@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "layer_kernel.cuh"
 #include "lstm_kernel.cuh"
+#include "stft_hybrid_kernel.cuh"
 #include "stft_kernel.cuh"
 #include "testtensor.h"
 
@@ -54,6 +55,10 @@ struct silero_b200
    int sm_count;
    int max_streams;
    int window_chunks_opt;
+   int stft_mode;            // SILERO_B200_STFT_HYBRID / _EXACT
+   float stft_k_rel;         // hybrid: exact re-evaluation below k_rel * ||frame||
+   unsigned long long *d_flagged; // bins that took the exact path (device counter)
+   unsigned long long bins_total;
    cudaStream_t stream;      // compute
    cudaStream_t copy_stream; // H2D of the next window
    float *d_weights;         // one allocation holding every packed weight
@@ -203,6 +208,8 @@ extern "C" void silero_b200_default_opts( silero_b200_opts *o )
    o->device = 0;
    o->max_streams = 1;
    o->window_chunks = 0;
+   o->stft_mode = SILERO_B200_STFT_HYBRID;
+   o->stft_k_rel = 0.0f; /* 0 = default (SILERO_B200_STFT_K_REL_DEFAULT) */
 }
 
 template <typename K>
@@ -215,6 +222,8 @@ static int configure_kernels()
 {
    CU( allow_smem( stft_logmag_kernel<false>, STFT_SMEM_BYTES ) );
    CU( allow_smem( stft_logmag_kernel<true>, STFT_SMEM_BYTES ) );
+   CU( allow_smem( stft_hybrid_kernel<false>, HYB_SMEM_BYTES ) );
+   CU( allow_smem( stft_hybrid_kernel<true>, HYB_SMEM_BYTES ) );
    CU( allow_smem( layer_kernel<0, true>, LayerCfg<0>::SMEM_BYTES ) );
    CU( allow_smem( layer_kernel<0, false>, LayerCfg<0>::SMEM_BYTES ) );
    CU( allow_smem( layer_kernel<1, false>, LayerCfg<1>::SMEM_BYTES ) );
@@ -245,6 +254,7 @@ extern "C" void silero_b200_destroy( silero_b200 *h )
    cudaFree( h->d_probs );
    cudaFree( h->d_out2 );
    cudaFree( h->d_f32 );
+   cudaFree( h->d_flagged );
    for ( int i = 0; i < 2; ++i )
    {
       cudaFree( h->pcm_stage[i] );
@@ -296,6 +306,8 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    h->device = opts.device;
    h->max_streams = opts.max_streams;
    h->window_chunks_opt = opts.window_chunks;
+   h->stft_mode = opts.stft_mode == SILERO_B200_STFT_EXACT ? SILERO_B200_STFT_EXACT : SILERO_B200_STFT_HYBRID;
+   h->stft_k_rel = opts.stft_k_rel > 0.0f ? opts.stft_k_rel : SILERO_B200_STFT_K_REL_DEFAULT;
 
 #define CU_H( call )                                                                                   \
    do                                                                                                  \
@@ -342,7 +354,8 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    const size_t n_basis = 2 * STFT_BS_FLOATS;
    const size_t n_l0 = LayerPack<0>::TOTAL, n_l1 = LayerPack<1>::TOTAL, n_l2 = LayerPack<2>::TOTAL, n_l3 = LayerPack<3>::TOTAL;
    const size_t n_lstm = 2 * LSTM_WS_FLOATS, n_lb = 512, n_dw = 128, n_db = 4;
-   const size_t total = n_basis + n_l0 + n_l1 + n_l2 + n_l3 + n_lstm + n_lb + n_dw + n_db;
+   const size_t n_raw = 258 * 256;
+   const size_t total = n_basis + n_l0 + n_l1 + n_l2 + n_l3 + n_lstm + n_lb + n_dw + n_db + n_raw;
    float *host = (float *)calloc( total, sizeof( float ) );
    if ( !host )
    {
@@ -360,6 +373,7 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    size_t o_lb = off; off += n_lb;
    size_t o_dw = off; off += n_dw;
    size_t o_db = off; off += n_db;
+   size_t o_raw = off; off += n_raw;
    pack_basis( tf.tensors[0].data, host + o_basis );
    pack_layer<0>( tf.tensors + 1, host + o_l0 );
    pack_layer<1>( tf.tensors + 25, host + o_l1 );
@@ -369,6 +383,7 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    memcpy( host + o_lb, tf.tensors[96].data, sizeof( float ) * 512 );
    memcpy( host + o_dw, tf.tensors[97].data, sizeof( float ) * 128 );
    memcpy( host + o_db, tf.tensors[98].data, sizeof( float ) * 2 );
+   memcpy( host + o_raw, tf.tensors[0].data, sizeof( float ) * n_raw );
    vb_testtensor_free( &tf );
    memset( &tf, 0, sizeof( tf ) );
 
@@ -385,6 +400,9 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    h->w.lstm_b = h->d_weights + o_lb;
    h->w.dec_w = h->d_weights + o_dw;
    h->w.dec_b = h->d_weights + o_db;
+   h->w.basis_raw = h->d_weights + o_raw;
+   CU_H( cudaMalloc( &h->d_flagged, sizeof( unsigned long long ) ) );
+   CU_H( cudaMemset( h->d_flagged, 0, sizeof( unsigned long long ) ) );
 
    size_t sbytes = (size_t)h->max_streams * SILERO_B200_STATE_FLOATS * sizeof( float );
    CU_H( cudaMalloc( &h->state_h, sbytes ) );
@@ -487,12 +505,30 @@ static inline int imin( int a, int b ) { return a < b ? a : b; }
 
 static int launch_stft( silero_b200 *h, const void *d_in, int in_f32, long long stream_stride, int nw, int nchunks, float *spec, int out_mode )
 {
-   int npairs = imin( h->sm_count / 2, ( nchunks + 1 ) / 2 );
-   if ( npairs < 1 ) npairs = 1;
-   if ( in_f32 )
-      stft_logmag_kernel<true><<<npairs * 2, STFT_THREADS, STFT_SMEM_BYTES, h->stream>>>( d_in, stream_stride, nw, nchunks, h->w.basis_pack, spec, out_mode );
+   if ( h->stft_mode == SILERO_B200_STFT_EXACT )
+   {
+      int npairs = imin( h->sm_count / 2, ( nchunks + STFT_GROUPS - 1 ) / STFT_GROUPS );
+      if ( npairs < 1 ) npairs = 1;
+      if ( in_f32 )
+         stft_logmag_kernel<true><<<npairs * 2, STFT_THREADS, STFT_SMEM_BYTES, h->stream>>>( d_in, stream_stride, nw, nchunks, h->w.basis_pack, spec, out_mode );
+      else
+         stft_logmag_kernel<false><<<npairs * 2, STFT_THREADS, STFT_SMEM_BYTES, h->stream>>>( d_in, stream_stride, nw, nchunks, h->w.basis_pack, spec, out_mode );
+   }
    else
-      stft_logmag_kernel<false><<<npairs * 2, STFT_THREADS, STFT_SMEM_BYTES, h->stream>>>( d_in, stream_stride, nw, nchunks, h->w.basis_pack, spec, out_mode );
+   {
+      static int per_sm = 0;
+      if ( !per_sm )
+      {
+         CU( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm, stft_hybrid_kernel<false>, HYB_THREADS, HYB_SMEM_BYTES ) );
+         if ( per_sm < 1 ) per_sm = 1;
+      }
+      int grid = imin( nchunks, h->sm_count * per_sm );
+      if ( in_f32 )
+         stft_hybrid_kernel<true><<<grid, HYB_THREADS, HYB_SMEM_BYTES, h->stream>>>( d_in, stream_stride, nw, nchunks, h->w.basis_raw, spec, h->stft_k_rel, out_mode, h->d_flagged );
+      else
+         stft_hybrid_kernel<false><<<grid, HYB_THREADS, HYB_SMEM_BYTES, h->stream>>>( d_in, stream_stride, nw, nchunks, h->w.basis_raw, spec, h->stft_k_rel, out_mode, h->d_flagged );
+      h->bins_total += (unsigned long long)nchunks * VB_BINS * VB_FRAMES;
+   }
    h->launches++;
    CU( cudaGetLastError() );
    return 0;
@@ -792,6 +828,23 @@ extern "C" int silero_b200_host_alloc_pinned( size_t nbytes, void **ptr )
 extern "C" int silero_b200_host_free_pinned( void *ptr )
 {
    CU( cudaFreeHost( ptr ) );
+   return SILERO_B200_OK;
+}
+
+extern "C" int silero_b200_stft_stats( silero_b200 *h, unsigned long long *bins_total, unsigned long long *bins_exact, int reset )
+{
+   if ( !h ) return set_err( SILERO_B200_ERR_ARG, "null handle" );
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+   CU( cudaStreamSynchronize( h->stream ) );
+   unsigned long long n = 0;
+   CU( cudaMemcpy( &n, h->d_flagged, sizeof( n ), cudaMemcpyDeviceToHost ) );
+   if ( bins_total ) *bins_total = h->bins_total;
+   if ( bins_exact ) *bins_exact = n;
+   if ( reset )
+   {
+      CU( cudaMemset( h->d_flagged, 0, sizeof( n ) ) );
+      h->bins_total = 0;
+   }
    return SILERO_B200_OK;
 }
 

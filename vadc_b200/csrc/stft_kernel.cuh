@@ -21,34 +21,48 @@
 // whole launch in a [k-quad][row][4] layout so that lanes (= bins) read consecutive 16-byte words;
 // the padded audio of a chunk lives in shared memory as X[r][l][v] (r = 64-sample row, l = k%8,
 // v = (k/8)%8) so that the 8 taps of one tree leaf are two float4 broadcasts. A thread owns
-// 2 bins (re+im = 4 rows) x 5 frames; 160 threads cover a chunk-half, a CTA runs 2 chunks at once.
+// 1 bin (re+im rows) x 5 frames with its tree state in registers (<=102, no spills); 320 threads
+// cover a chunk-half, a CTA runs 2 chunks at once (20 warps per SM).
 #pragma once
 #include "common.cuh"
 
-#define STFT_THREADS 320
-#define STFT_GROUP 160
+// thread = 1 bin (re + im row) x 5 frames; 64 bins x 5 frame groups = 320 threads per chunk-half;
+// a CTA runs STFT_GROUPS chunks at once
+#define STFT_GROUP 320
+#define STFT_GROUPS 2
+#define STFT_THREADS ( STFT_GROUP * STFT_GROUPS )
 #define STFT_BS_FLOATS ( 64 * 128 * 4 )
 #define STFT_XS_FLOATS ( 28 * 64 )
-#define STFT_SMEM_BYTES ( ( STFT_BS_FLOATS + 2 * 2 * STFT_XS_FLOATS ) * 4 )
+#define STFT_SMEM_BYTES ( ( STFT_BS_FLOATS + 2 * STFT_GROUPS * STFT_XS_FLOATS ) * 4 )
 
-__device__ __forceinline__ float stft_tree8( const float x[8], const float4 b0, const float4 b1 )
+__device__ __forceinline__ float stft_tree8( const float4 xa, const float4 xb, const float4 b0, const float4 b1 )
 {
-   float p0 = __fmul_rn( x[0], b0.x ), p1 = __fmul_rn( x[1], b0.y );
-   float p2 = __fmul_rn( x[2], b0.z ), p3 = __fmul_rn( x[3], b0.w );
-   float p4 = __fmul_rn( x[4], b1.x ), p5 = __fmul_rn( x[5], b1.y );
-   float p6 = __fmul_rn( x[6], b1.z ), p7 = __fmul_rn( x[7], b1.w );
+   float p0 = __fmul_rn( xa.x, b0.x ), p1 = __fmul_rn( xa.y, b0.y );
+   float p2 = __fmul_rn( xa.z, b0.z ), p3 = __fmul_rn( xa.w, b0.w );
+   float p4 = __fmul_rn( xb.x, b1.x ), p5 = __fmul_rn( xb.y, b1.y );
+   float p6 = __fmul_rn( xb.z, b1.z ), p7 = __fmul_rn( xb.w, b1.w );
    float s01 = __fadd_rn( p0, p1 ), s23 = __fadd_rn( p2, p3 );
    float s45 = __fadd_rn( p4, p5 ), s67 = __fadd_rn( p6, p7 );
    return __fadd_rn( __fadd_rn( s01, s23 ), __fadd_rn( s45, s67 ) );
 }
 
-// position of padded sample j (0..1791) inside the permuted chunk tile
+// position of padded sample j (0..1791) inside the permuted chunk tile X[r][l][v]
 __device__ __forceinline__ int stft_xidx( int j ) { return ( j >> 6 ) * 64 + ( j & 7 ) * 8 + ( ( j >> 3 ) & 7 ); }
+
+// sample m (0..1535) of the chunk -> tile, including its mirror images in the reflect padding
+// (tensor.h:942-953, edge sample not repeated): xp[128+m] = x[m]; xp[128-m] = x[m] for 1<=m<=128;
+// xp[3198-m] = x[m] for 1407<=m<=1534
+__device__ __forceinline__ void stft_put( float *xs, int m, float v )
+{
+   xs[stft_xidx( 128 + m )] = v;
+   if ( m >= 1 && m <= 128 ) xs[stft_xidx( 128 - m )] = v;
+   if ( m >= 1407 && m <= 1534 ) xs[stft_xidx( 3198 - m )] = v;
+}
 
 template <bool F32>
 struct StftRaw
 {
-   int4 v[F32 ? 3 : 2];
+   int4 v[F32 ? 2 : 1];
 };
 
 // chunk ci of the window -> first sample. Window layout: ci = s * nw + n.
@@ -64,7 +78,7 @@ template <bool F32>
 __device__ __forceinline__ void stft_load_raw( StftRaw<F32> &raw, const void *chunk, int t )
 {
    constexpr int NV = F32 ? 384 : 192; // 16-byte vectors per chunk
-   constexpr int PER = F32 ? 3 : 2;
+   constexpr int PER = F32 ? 2 : 1;
 #pragma unroll
    for ( int i = 0; i < PER; ++i )
    {
@@ -77,7 +91,7 @@ template <bool F32>
 __device__ __forceinline__ void stft_store_x( float *xs, const StftRaw<F32> &raw, int t )
 {
    constexpr int NV = F32 ? 384 : 192;
-   constexpr int PER = F32 ? 3 : 2;
+   constexpr int PER = F32 ? 2 : 1;
 #pragma unroll
    for ( int i = 0; i < PER; ++i )
    {
@@ -88,27 +102,16 @@ __device__ __forceinline__ void stft_store_x( float *xs, const StftRaw<F32> &raw
          {
             const float *f = reinterpret_cast<const float *>( &raw.v[i] );
 #pragma unroll
-            for ( int e = 0; e < 4; ++e ) xs[stft_xidx( 128 + 4 * q + e )] = f[e];
+            for ( int e = 0; e < 4; ++e ) stft_put( xs, 4 * q + e, f[e] );
          }
          else
          {
             const short *h = reinterpret_cast<const short *>( &raw.v[i] );
             // (float)s16 / 32768.0f (vadc.c:884,898); the division by a power of two is exact
 #pragma unroll
-            for ( int e = 0; e < 8; ++e ) xs[stft_xidx( 128 + 8 * q + e )] = (float)h[e] * ( 1.0f / 32768.0f );
+            for ( int e = 0; e < 8; ++e ) stft_put( xs, 8 * q + e, (float)h[e] * ( 1.0f / 32768.0f ) );
          }
       }
-   }
-}
-
-// reflect padding without repeating the edge sample (tensor.h:942-953): xp[j] = xp[256-j] for j<128,
-// xp[1664+j] = xp[1662-j] for j<128
-__device__ __forceinline__ void stft_pad_x( float *xs, int t )
-{
-   if ( t < 128 )
-   {
-      xs[stft_xidx( t )] = xs[stft_xidx( 256 - t )];
-      xs[stft_xidx( 1664 + t )] = xs[stft_xidx( 1662 - t )];
    }
 }
 
@@ -120,16 +123,17 @@ stft_logmag_kernel( const void *__restrict__ in, long long stream_stride, int nw
 {
    extern __shared__ __align__( 16 ) float smem[];
    float *Bs = smem;
-   float *Xs_all = smem + STFT_BS_FLOATS; // [2 buffers][2 groups][1792]
+   float *Xs_all = smem + STFT_BS_FLOATS; // [2 buffers][groups][1792]
 
    const int tid = threadIdx.x;
    const int half = blockIdx.x & 1;
    const int pair = blockIdx.x >> 1;
    const int npairs = gridDim.x >> 1;
-   const int cg = tid / STFT_GROUP;      // chunk group 0/1
+   const int cg = tid / STFT_GROUP;      // chunk group
    const int t = tid - cg * STFT_GROUP;  // thread within group
-   const int tg = t >> 5;                // frame group: frames 5*tg .. 5*tg+4
-   const int fl = t & 31;                // bin lane
+   const int tg = t >> 6;                // frame group: frames 5*tg .. 5*tg+4
+   const int fl = t & 63;                // bin lane: basis rows fl (re) and 64+fl (im)
+   const int stride_chunks = npairs * STFT_GROUPS;
 
    // resident half basis
    {
@@ -139,106 +143,97 @@ stft_logmag_kernel( const void *__restrict__ in, long long stream_stride, int nw
    }
 
    StftRaw<F32> raw;
-   int ci = pair * 2 + cg;
+   int ci = pair * STFT_GROUPS + cg;
    if ( ci < nchunks ) stft_load_raw<F32>( raw, stft_chunk_ptr<F32>( in, stream_stride, nw, ci ), t );
    __syncthreads();
 
    int buf = 0;
-   for ( ; ci < nchunks; ci += npairs * 2, buf ^= 1 )
+   for ( ; ci < nchunks; ci += stride_chunks, buf ^= 1 )
    {
-      float *xs = Xs_all + ( buf * 2 + cg ) * STFT_XS_FLOATS;
+      // double-buffered tile: the previous chunk of this group may still be read by slower warps
+      float *xs = Xs_all + ( buf * STFT_GROUPS + cg ) * STFT_XS_FLOATS;
       stft_store_x<F32>( xs, raw, t );
-      bar_sync( 1 + cg, STFT_GROUP );
-      stft_pad_x( xs, t );
       bar_sync( 1 + cg, STFT_GROUP );
 
       // prefetch the next chunk of this group while computing this one
-      int cn = ci + npairs * 2;
+      int cn = ci + stride_chunks;
       if ( cn < nchunks ) stft_load_raw<F32>( raw, stft_chunk_ptr<F32>( in, stream_stride, nw, cn ), t );
 
-      float S0[4][5], S1[4][5], TL[4][5];
+      float S0[2][5], S1[2][5];
 #pragma unroll
-      for ( int a = 0; a < 4; ++a )
+      for ( int a = 0; a < 2; ++a )
 #pragma unroll
-         for ( int i = 0; i < 5; ++i ) S0[a][i] = S1[a][i] = TL[a][i] = 0.0f;
+         for ( int i = 0; i < 5; ++i ) S0[a][i] = S1[a][i] = 0.0f;
 
 #pragma unroll 1
-      for ( int l = 0; l < 8; ++l )
+      for ( int lp = 0; lp < 4; ++lp )
       {
-         float A[4][5], Bv[4][5];
+         float TL[2][5];
 #pragma unroll
-         for ( int g = 0; g < 4; ++g )
+         for ( int lo = 0; lo < 2; ++lo )
          {
-            float xr[5][8];
+            const int l = lp * 2 + lo;
+            float A[2][5], Bv[2][5];
 #pragma unroll
-            for ( int i = 0; i < 5; ++i )
+            for ( int g = 0; g < 4; ++g )
             {
-               const float *xp = xs + ( 5 * tg + i + g ) * 64 + l * 8;
-               float4 a = ld4( xp ), b = ld4( xp + 4 );
-               xr[i][0] = a.x; xr[i][1] = a.y; xr[i][2] = a.z; xr[i][3] = a.w;
-               xr[i][4] = b.x; xr[i][5] = b.y; xr[i][6] = b.z; xr[i][7] = b.w;
-            }
-            const float *bq = Bs + ( ( l * 8 + g * 2 ) * 128 + fl ) * 4;
-#pragma unroll
-            for ( int fr = 0; fr < 4; ++fr )
-            {
-               float4 b0 = ld4( bq + fr * 32 * 4 );
-               float4 b1 = ld4( bq + fr * 32 * 4 + 128 * 4 );
+               const float *bq = Bs + ( ( l * 8 + g * 2 ) * 128 + fl ) * 4;
+               const float4 re0 = ld4( bq ), re1 = ld4( bq + 128 * 4 );
+               const float4 im0 = ld4( bq + 64 * 4 ), im1 = ld4( bq + 64 * 4 + 128 * 4 );
 #pragma unroll
                for ( int i = 0; i < 5; ++i )
                {
-                  float r = stft_tree8( xr[i], b0, b1 );
-                  if ( g == 0 ) A[fr][i] = r;
-                  else if ( g == 1 ) A[fr][i] = __fadd_rn( A[fr][i], r );
-                  else if ( g == 2 ) Bv[fr][i] = r;
-                  else Bv[fr][i] = __fadd_rn( Bv[fr][i], r );
+                  const float *xp = xs + ( 5 * tg + i + g ) * 64 + l * 8;
+                  const float4 xa = ld4( xp ), xb = ld4( xp + 4 );
+                  float rr = stft_tree8( xa, xb, re0, re1 );
+                  float ri = stft_tree8( xa, xb, im0, im1 );
+                  if ( g == 0 ) { A[0][i] = rr; A[1][i] = ri; }
+                  else if ( g == 1 ) { A[0][i] = __fadd_rn( A[0][i], rr ); A[1][i] = __fadd_rn( A[1][i], ri ); }
+                  else if ( g == 2 ) { Bv[0][i] = rr; Bv[1][i] = ri; }
+                  else { Bv[0][i] = __fadd_rn( Bv[0][i], rr ); Bv[1][i] = __fadd_rn( Bv[1][i], ri ); }
                }
             }
-         }
 #pragma unroll
-         for ( int fr = 0; fr < 4; ++fr )
+            for ( int a = 0; a < 2; ++a )
 #pragma unroll
-            for ( int i = 0; i < 5; ++i )
-            {
-               float R = __fadd_rn( A[fr][i], Bv[fr][i] );
-               if ( ( l & 1 ) == 0 )
-                  TL[fr][i] = R;
-               else
+               for ( int i = 0; i < 5; ++i )
                {
-                  float pr = __fadd_rn( TL[fr][i], R );
-                  if ( l == 1 ) S0[fr][i] = pr;
-                  else if ( l == 3 ) S0[fr][i] = __fadd_rn( S0[fr][i], pr );
-                  else if ( l == 5 ) S1[fr][i] = pr;
-                  else S1[fr][i] = __fadd_rn( S1[fr][i], pr );
+                  float R = __fadd_rn( A[a][i], Bv[a][i] );
+                  if ( lo == 0 )
+                     TL[a][i] = R;
+                  else
+                  {
+                     float pr = __fadd_rn( TL[a][i], R );       // lanes (2lp, 2lp+1)
+                     if ( lp == 0 ) S0[a][i] = pr;               // s01
+                     else if ( lp == 1 ) S0[a][i] = __fadd_rn( S0[a][i], pr ); // s0123
+                     else if ( lp == 2 ) S1[a][i] = pr;          // s45
+                     else S1[a][i] = __fadd_rn( S1[a][i], pr );  // s4567
+                  }
                }
-            }
+         }
       }
 
       // magnitude (stft.c:194-213) and log1p(m * 2^20) (misc.c:40-46)
       float *o = spec + (size_t)ci * ( VB_BINS * VB_FRAMES );
       const bool special = ( half == 0 && fl == 0 ); // im slot of bin 0 carries re of bin 128
+      const int f = half * 64 + fl;
 #pragma unroll
-      for ( int a = 0; a < 2; ++a )
+      for ( int i = 0; i < 5; ++i )
       {
-         int f = half * 64 + fl + a * 32;
-#pragma unroll
-         for ( int i = 0; i < 5; ++i )
+         float re = __fadd_rn( S0[0][i], S1[0][i] );
+         float im = __fadd_rn( S0[1][i], S1[1][i] );
+         float extra = 0.0f;
+         if ( special )
          {
-            float re = __fadd_rn( S0[a][i], S1[a][i] );
-            float im = __fadd_rn( S0[a + 2][i], S1[a + 2][i] );
-            float extra = 0.0f;
-            if ( a == 0 && special )
-            {
-               extra = im;
-               im = 0.0f;
-            }
-            float m = sqrtf( __fadd_rn( __fmul_rn( re, re ), __fmul_rn( im, im ) ) );
-            o[f * VB_FRAMES + 5 * tg + i] = out_mode ? m : log1pf( __fmul_rn( m, 1048576.0f ) );
-            if ( a == 0 && special )
-            {
-               float m2 = sqrtf( __fadd_rn( __fmul_rn( extra, extra ), 0.0f ) );
-               o[128 * VB_FRAMES + 5 * tg + i] = out_mode ? m2 : log1pf( __fmul_rn( m2, 1048576.0f ) );
-            }
+            extra = im;
+            im = 0.0f;
+         }
+         float m = sqrtf( __fadd_rn( __fmul_rn( re, re ), __fmul_rn( im, im ) ) );
+         o[f * VB_FRAMES + 5 * tg + i] = out_mode ? m : log1pf( __fmul_rn( m, 1048576.0f ) );
+         if ( special )
+         {
+            float m2 = sqrtf( __fadd_rn( __fmul_rn( extra, extra ), 0.0f ) );
+            o[128 * VB_FRAMES + 5 * tg + i] = out_mode ? m2 : log1pf( __fmul_rn( m2, 1048576.0f ) );
          }
       }
    }
