@@ -158,8 +158,7 @@ int silero_b200_stage_encoder( silero_b200 *h, const float *norm, int batch,
 int silero_b200_stage_layer( silero_b200 *h, int layer, const float *in, int batch, float *out );
 /* sub-stage taps of one layer for the reference's op/block-level fixtures (conv_block conv.c:761,
    dual_head_attention transformer.c:13, layer_norm misc.c:143, transformer_block transformer.c:160,
-   conv+batch_norm1d transformer.c:280-290). layer 0..3, or 4 = first-layer shapes at T=64 (the size of
-   the dw_conv_129 / pw_conv_129_16 / first_layer_conv_block fixtures).
+   conv+batch_norm1d transformer.c:280-290). layer 0..3.
    entry: 0 layer input in the reference layout [B,cin,T]; 1 conv_block output [B,T,C]; 2 transformer_block output [B,T,C]
    tap:   0 layer output [B,C,TOUT]; 1 conv_block output; 2 attention output; 3 after norm1; 4 transformer_block output (all [B,T,C]) */
 int silero_b200_stage_layer_tap( silero_b200 *h, int layer, int entry, int tap, const float *in, int batch, float *out );

@@ -94,11 +94,25 @@ def test_decoder():
 
 
 # ---- op / block level fixtures through the sub-stage taps of the production layer kernel ---------
+def conv_block_t64(e, x):
+    """The reference's conv fixtures are 64 frames long; the production first-layer kernel handles 25
+    frames per chunk. The depthwise conv needs a +-2 halo, so three overlapping 25-frame windows
+    (starting at 0, 21, 39) replayed as a batch of 3 chunks cover all 64 frames: the true sequence
+    ends coincide with window ends (zero padding there), interior frames come from window interiors."""
+    starts = (0, 21, 39)
+    batch = np.stack([x[:, s:s + 25] for s in starts])          # [3,129,25]
+    y = e.stage_layer_tap(0, 0, 1, batch)                        # [3,25,16] token-major
+    out = np.zeros((16, 64), np.float32)
+    out[:, 0:23] = y[0, 0:23].T
+    out[:, 23:44] = y[1, 2:23].T
+    out[:, 41:64] = y[2, 2:25].T
+    return out
+
+
 def test_first_layer_conv_block():
     dw_w, dw_b, pw_w, pw_b, pr_w, pr_b, x, exp = fx("first_layer_conv_block")
     e = engine({1: dw_w, 2: dw_b, 3: pw_w, 4: pw_b, 5: pr_w, 6: pr_b})
-    y = e.stage_layer_tap(4, 0, 1, x.reshape(1, 129, 64))  # [1,64,16]
-    assert np.abs(y[0].T - exp).max() < ATOL
+    assert np.abs(conv_block_t64(e, x) - exp).max() < ATOL
 
 
 def test_pw_conv_129_16():
@@ -109,7 +123,7 @@ def test_pw_conv_129_16():
     parts = []
     for sign in (1.0, -1.0):
         e = engine({1: zero_dw, 2: np.zeros(129), 3: np.zeros((16, 129)), 4: np.zeros(16), 5: sign * w, 6: sign * b})
-        parts.append(e.stage_layer_tap(4, 0, 1, x.reshape(1, 129, 64))[0].T)
+        parts.append(conv_block_t64(e, x))
     assert np.abs((parts[0] - parts[1]) - exp).max() < ATOL
 
 
@@ -125,7 +139,7 @@ def test_dw_conv_129():
         parts = []
         for sign in (1.0, -1.0):
             e = engine({1: sign * w, 2: sign * b, 3: sel, 4: np.zeros(16), 5: np.zeros((16, 129)), 6: np.zeros(16)})
-            parts.append(e.stage_layer_tap(4, 0, 1, x.reshape(1, 129, 64))[0].T)
+            parts.append(conv_block_t64(e, x))
         got[c0:c0 + n] = (parts[0] - parts[1])[:n]
     assert np.abs(got - exp).max() < ATOL
 

@@ -246,7 +246,7 @@ class Engine:
         return out
 
     def stage_layer_tap(self, layer, entry, tap, x):
-        cin, c, t, stride = ((129, 16, 25, 2), (16, 32, 13, 2), (32, 32, 7, 1), (32, 64, 7, 1), (129, 16, 64, 2))[layer]
+        cin, c, t, stride = ((129, 16, 25, 2), (16, 32, 13, 2), (32, 32, 7, 1), (32, 64, 7, 1))[layer]
         x = _f32(x).reshape((-1, cin, t) if entry == 0 else (-1, t, c))
         out = np.zeros((x.shape[0], c, 1 + (t - 1) // stride) if tap == 0 else (x.shape[0], t, c), np.float32)
         self._check(lib().silero_b200_stage_layer_tap(self._h, layer, entry, tap, _p(x), x.shape[0], _p(out)))

@@ -229,7 +229,6 @@ static int configure_kernels()
    CU( allow_smem( layer_kernel<1, false>, LayerCfg<1>::SMEM_BYTES ) );
    CU( allow_smem( layer_kernel<2, false>, LayerCfg<2>::SMEM_BYTES ) );
    CU( allow_smem( layer_kernel<3, false>, LayerCfg<3>::SMEM_BYTES ) );
-   CU( allow_smem( layer_kernel<4, false>, LayerCfg<4>::SMEM_BYTES ) );
    CU( allow_smem( lstm_layer_kernel<0, 4>, LstmSmem<4>::BYTES ) );
    CU( allow_smem( lstm_layer_kernel<1, 4>, LstmSmem<4>::BYTES ) );
    CU( allow_smem( lstm_layer_kernel<0, 1>, LstmSmem<1>::BYTES ) );
@@ -543,7 +542,7 @@ static int launch_layer( silero_b200 *h, const float *in, float *out, int nchunk
    if ( per_sm < 1 ) per_sm = 1;
    if ( per_sm > 8 ) per_sm = 8;
    int grid = imin( ntiles, h->sm_count * per_sm );
-   layer_kernel<L, NORM><<<grid, LAYER_THREADS, Cfg::SMEM_BYTES, h->stream>>>( in, out, h->w.layer[L == 4 ? 0 : L], nchunks, entry, tap );
+   layer_kernel<L, NORM><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, h->stream>>>( in, out, h->w.layer[L], nchunks, entry, tap );
    h->launches++;
    CU( cudaGetLastError() );
    return 0;
@@ -1153,11 +1152,11 @@ extern "C" int silero_b200_stage_layer( silero_b200 *h, int layer, const float *
 }
 
 // Sub-stage taps of one layer for the reference's op/block-level fixtures (layer_kernel.cuh).
-// layer 0..3, or 4 = the first layer's weights at T=64. in: entry 0 -> reference layout [B,cin,T];
+// layer 0..3. in: entry 0 -> reference layout [B,cin,T];
 // entry 1/2 -> token-major [B,T,C]. out: tap 0 -> reference layout [B,C,TOUT]; else token-major [B,T,C].
 extern "C" int silero_b200_stage_layer_tap( silero_b200 *h, int layer, int entry, int tap, const float *in, int batch, float *out )
 {
-   if ( !h || !in || !out || batch <= 0 || layer < 0 || layer > 4 || entry < 0 || entry > 2 || tap < 0 || tap > 4 ) return set_err( SILERO_B200_ERR_ARG, "bad argument" );
+   if ( !h || !in || !out || batch <= 0 || layer < 0 || layer > 3 || entry < 0 || entry > 2 || tap < 0 || tap > 4 ) return set_err( SILERO_B200_ERR_ARG, "bad argument" );
    if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
    const LayerDims d = layer_dims( layer );
    const int tout = 1 + ( d.t - 1 ) / d.stride;
@@ -1183,8 +1182,7 @@ extern "C" int silero_b200_stage_layer_tap( silero_b200 *h, int layer, int entry
          case 0: rc = launch_layer<0, false>( h, din.p, dout.p, batch, entry, tap ); break;
          case 1: rc = launch_layer<1, false>( h, din.p, dout.p, batch, entry, tap ); break;
          case 2: rc = launch_layer<2, false>( h, din.p, dout.p, batch, entry, tap ); break;
-         case 3: rc = launch_layer<3, false>( h, din.p, dout.p, batch, entry, tap ); break;
-         default: rc = launch_layer<4, false>( h, din.p, dout.p, batch, entry, tap ); break;
+         default: rc = launch_layer<3, false>( h, din.p, dout.p, batch, entry, tap ); break;
       }
    }
    if ( !rc && tap == TAP_LAYER )

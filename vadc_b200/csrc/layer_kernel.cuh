@@ -6,21 +6,24 @@
 // -> conv 1x1 with stride (conv.c:715) -> batch_norm1d (misc.c:221-258) -> ReLU, and, for the first
 // layer, the mean part of adaptive_audio_normalization_inplace (misc.c:48-121).
 //
-// Mapping ("thread = token row"): a CTA of 128 threads owns a tile of G = 128/T chunks; thread r
-// owns token (chunk g, frame t) and carries its activation row through the whole layer in a
-// private shared-memory row of RS floats (RS*4 is an odd multiple of 16 bytes, so float4 row
-// accesses of a warp are bank-conflict free). Every linear layer is an in-thread GEMV whose weight
-// operand is a warp-wide shared-memory broadcast (all lanes read the same float4), so the FP32
-// pipe sees K*N FMAs per (K/4)*(N+1) shared loads. Attention reads the other rows of the same
-// chunk from shared memory; layer norm and softmax are sequential in-thread, in the reference's
-// order. Tiny irregular dims (T = 25/13/7, C = 16..64) make this CUDA-core work, not tensor-core
-// work: the layer is 0.3..8.8 % of the model's FLOPs each.
+// Mapping ("lane = token"): the T frames of a chunk are padded to TP = 32/16/8 lanes so that a
+// chunk never straddles a warp: 1, 2 or 4 chunks per warp. A lane owns token (chunk, frame) and
+// carries its activation row through the whole layer in a private shared-memory row of RS floats
+// (RS*4 B = odd multiple of 16 B, so float4 row accesses of a warp are bank-conflict free). All
+// cross-token traffic (depthwise taps, attention) stays inside the warp, so the only barriers are
+// __syncwarp (layer 4 additionally stages its 134 KB of weights through shared memory per sub-step).
+// Every linear layer is an in-lane GEMV whose weight operand is a warp-wide shared-memory
+// broadcast; because a broadcast float4 costs a shared-memory wavefront per 4 FMAs, each lane
+// processes U = 2 tokens (two different chunks) so every weight load feeds 8 FMAs. The first layer
+// reads the spectrogram straight from global memory (one coalesced load per bin and chunk) and gets
+// its +-2 depthwise taps by warp shuffle. Attention, layer norm and softmax are sequential in-lane,
+// in the reference's order. Tiny irregular dims (T = 25/13/7, C = 16..64) make this CUDA-core work:
+// the layers are 6.7 / 4.2 / 2.3 / 8.8 % of the model's FLOPs.
 //
 // Activations between layers are token-major: [chunk][T][C].
 #pragma once
 #include "common.cuh"
 
-#define LAYER_THREADS 128
 
 template <int L>
 struct LayerCfg
@@ -28,37 +31,72 @@ struct LayerCfg
    using P = LayerPack<L>;
    static constexpr int CIN = P::CIN, C = P::C, T = P::T, D = P::D, STRIDE = P::STRIDE, TOUT = P::TOUT;
    static constexpr bool PROJ = P::PROJ != 0;
-   static constexpr int G = LAYER_THREADS / T; // chunks per tile
-   static constexpr int R = G * T;             // live rows
-   // row: U[C] | Q[3*D] | O[C]   (O doubles as the input row X for L>0: CIN <= C)
-   static constexpr int OFF_U = 0, OFF_Q = C, OFF_O = C + 3 * D;
-   static constexpr int RS_RAW = 2 * C + 3 * D;
+   static constexpr int TP = T <= 8 ? 8 : ( T <= 16 ? 16 : 32 ); // lanes per chunk
+   static constexpr int CPW = 32 / TP;                            // chunks per warp (per token set)
+   static constexpr int U = ( C < 64 ) ? 2 : 1;                   // tokens per lane
+   // warps per CTA: sized so that rows + weights fill the SM with 8..12 warps
+   static constexpr int NWARPS = ( C == 16 ) ? 4 : ( C == 32 ? 8 : 4 );
+   static constexpr int THREADS = NWARPS * 32;
+   static constexpr int G = NWARPS * CPW * U;                     // chunks per CTA tile
+   static constexpr int TOK = THREADS * U;                        // token rows in shared memory
+   // row: U[C] | Q[3*D]. U carries y -> u1 -> u2; Q holds the block input X (CIN <= 3*D), then q|k|v of
+   // one head, then the FFN hidden row (C <= 3*D). The attention output stays in registers.
+   static constexpr int OFF_U = 0, OFF_Q = C;
+   static constexpr int RS_RAW = C + 3 * D;
    // smallest RS >= RS_RAW with RS % 8 == 4 (RS*4 bytes = odd multiple of 16)
    static constexpr int RS = RS_RAW + ( ( 4 - ( RS_RAW % 8 ) + 8 ) % 8 );
+   static constexpr bool FIRST = ( CIN == VB_BINS ); // consumes the [chunk][129][T] spectrogram layout
    static constexpr bool RESIDENT = ( C < 64 );
    static constexpr int WS = RESIDENT ? P::TOTAL : ( 3 * D * C + 3 * D ); // staged: largest stage (one QKV head)
-   static constexpr bool FIRST = ( CIN == VB_BINS ); // consumes the [chunk][129][T] spectrogram layout
-   static constexpr int SPEC = FIRST ? G * VB_BINS * T + 2 * LAYER_THREADS : 0;
-   static constexpr int SMEM_FLOATS = LAYER_THREADS * RS + WS + SPEC;
+   static constexpr int SMEM_FLOATS = TOK * RS + WS;
    static constexpr int SMEM_BYTES = SMEM_FLOATS * 4;
 };
 
-// acc[o] += sum_k W[o*ldw + k] * x[k], k < K (K % 4 == 0); x: own row (float4 aligned), W: broadcast
-template <int K, int NB>
-__device__ __forceinline__ void lin_acc( const float *__restrict__ x, const float *__restrict__ W, int ldw, float ( &acc )[NB] )
+// acc[u][o] += sum_k W[o*ldw + k] * x[u][k], k < K (K % 4 == 0); x[u]: own rows, W: warp broadcast
+template <int K, int NB, int U>
+__device__ __forceinline__ void lin_acc( const float *const ( &x )[U], const float *__restrict__ W, int ldw, float ( &acc )[U][NB] )
 {
-#pragma unroll 4
+#pragma unroll 2
    for ( int k = 0; k < K; k += 4 )
    {
-      float4 xv = ld4( x + k );
+      float4 xv[U];
+#pragma unroll
+      for ( int u = 0; u < U; ++u ) xv[u] = ld4( x[u] + k );
 #pragma unroll
       for ( int o = 0; o < NB; ++o )
       {
          float4 w = ld4( W + o * ldw + k );
-         acc[o] = fmaf( w.x, xv.x, acc[o] );
-         acc[o] = fmaf( w.y, xv.y, acc[o] );
-         acc[o] = fmaf( w.z, xv.z, acc[o] );
-         acc[o] = fmaf( w.w, xv.w, acc[o] );
+#pragma unroll
+         for ( int u = 0; u < U; ++u )
+         {
+            acc[u][o] = fmaf( w.x, xv[u].x, acc[u][o] );
+            acc[u][o] = fmaf( w.y, xv[u].y, acc[u][o] );
+            acc[u][o] = fmaf( w.z, xv[u].z, acc[u][o] );
+            acc[u][o] = fmaf( w.w, xv[u].w, acc[u][o] );
+         }
+      }
+   }
+}
+
+// same with the input rows held in registers
+template <int K, int NB, int U>
+__device__ __forceinline__ void lin_acc_reg( const float ( &x )[U][K], const float *__restrict__ W, int ldw, float ( &acc )[U][NB] )
+{
+#pragma unroll
+   for ( int k = 0; k < K; k += 4 )
+   {
+#pragma unroll
+      for ( int o = 0; o < NB; ++o )
+      {
+         float4 w = ld4( W + o * ldw + k );
+#pragma unroll
+         for ( int u = 0; u < U; ++u )
+         {
+            acc[u][o] = fmaf( w.x, x[u][k], acc[u][o] );
+            acc[u][o] = fmaf( w.y, x[u][k + 1], acc[u][o] );
+            acc[u][o] = fmaf( w.z, x[u][k + 2], acc[u][o] );
+            acc[u][o] = fmaf( w.w, x[u][k + 3], acc[u][o] );
+         }
       }
    }
 }
@@ -102,7 +140,7 @@ __device__ __forceinline__ void layer_norm_row( float *x, const float *__restric
 // one head of dual_head_attention (transformer.c:72-143) for token (chunk rows at crows, frame t):
 // A = softmax_rows((K Q^T) / sqrt(D)) with rows = K positions; O = A V.
 template <int T, int D, int RS, int OFF_Q>
-__device__ __forceinline__ void attention_head( const float *__restrict__ crows, int t, float *__restrict__ o_out )
+__device__ __forceinline__ void attention_head( const float *__restrict__ crows, int t, float *o_out )
 {
    const float *mine = crows + t * RS + OFF_Q;
    float kreg[D];
@@ -160,7 +198,7 @@ __device__ __forceinline__ void attention_head( const float *__restrict__ crows,
       }
    }
 #pragma unroll
-   for ( int j = 0; j < D; j += 4 ) st4( o_out + j, make_float4( o[j], o[j + 1], o[j + 2], o[j + 3] ) );
+   for ( int j = 0; j < D; ++j ) o_out[j] = o[j];
 }
 
 // NORM (first layer only): input is log1p(mag*2^20) and the adaptive-normalization mean is computed
@@ -176,25 +214,36 @@ enum { TAP_LAYER = 0, TAP_CONV_BLOCK = 1, TAP_ATTENTION = 2, TAP_NORM1 = 3, TAP_
 enum { ENTRY_LAYER = 0, ENTRY_BLOCK = 1, ENTRY_CONV = 2 };
 
 template <int L, bool NORM>
-__global__ void __launch_bounds__( LAYER_THREADS )
+__global__ void __launch_bounds__( LayerCfg<L>::THREADS )
 layer_kernel( const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ wblob, int nchunks, int entry, int tap )
 {
    using Cfg = LayerCfg<L>;
    using P = LayerPack<L>;
-   constexpr int CIN = Cfg::CIN, C = Cfg::C, T = Cfg::T, D = Cfg::D, G = Cfg::G, R = Cfg::R, RS = Cfg::RS;
-   constexpr int OFF_U = Cfg::OFF_U, OFF_Q = Cfg::OFF_Q, OFF_O = Cfg::OFF_O;
+   constexpr int CIN = Cfg::CIN, C = Cfg::C, T = Cfg::T, D = Cfg::D, G = Cfg::G, RS = Cfg::RS;
+   constexpr int TP = Cfg::TP, CPW = Cfg::CPW, U = Cfg::U;
+   constexpr int OFF_U = Cfg::OFF_U, OFF_Q = Cfg::OFF_Q;
+   constexpr int LAYER_THREADS = Cfg::THREADS;
    constexpr bool RES = Cfg::RESIDENT;
    constexpr bool FIRST = Cfg::FIRST;
+   constexpr unsigned FULL = 0xffffffffu;
 
    extern __shared__ __align__( 16 ) float smem[];
    float *rows = smem;
-   float *wbuf = smem + LAYER_THREADS * RS;
-   float *spec = wbuf + Cfg::WS; // first layer only
+   float *wbuf = smem + Cfg::TOK * RS;
 
-   const int tid = threadIdx.x;
-   const int g = tid / T, t = tid - g * T;
-   float *myrow = rows + tid * RS;
-   const float *crows = rows + g * T * RS; // rows of my chunk
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   const int slot = lane / TP, t = lane - slot * TP;
+   float *myrow[U];
+   const float *crows[U];
+   int gidx[U];
+#pragma unroll
+   for ( int u = 0; u < U; ++u )
+   {
+      const int set = warp * U + u; // token set: 32 rows
+      myrow[u] = rows + ( set * 32 + lane ) * RS;
+      crows[u] = rows + ( set * 32 + slot * TP ) * RS;
+      gidx[u] = set * CPW + slot;
+   }
 
    // weight staging: resident layers load the whole blob once; layer 4 stages per sub-step
    auto stage = [&]( int base, int n ) -> const float * {
@@ -207,191 +256,221 @@ layer_kernel( const float *__restrict__ in, float *__restrict__ out, const float
    if ( RES )
    {
       for ( int i = tid * 4; i < P::TOTAL; i += LAYER_THREADS * 4 ) st4( wbuf + i, __ldg( reinterpret_cast<const float4 *>( wblob + i ) ) );
+      __syncthreads();
    }
+
+   // warp-level copy of this warp's chunks, token-major [chunk][T][W] in global -> row slot `off`
+   auto load_rows = [&]( int chunk0, int width, int off ) {
+#pragma unroll
+      for ( int u = 0; u < U; ++u )
+      {
+         const int cb = chunk0 + ( warp * U + u ) * CPW;
+         const int nvalid = max( 0, min( CPW, nchunks - cb ) );
+         const int total = nvalid * T * width;
+         const float *src = in + (size_t)cb * ( T * width );
+         float *dst = rows + ( ( warp * U + u ) * 32 ) * RS + off;
+         for ( int i = lane * 4; i < total; i += 128 )
+         {
+            int cs = i / ( T * width ), rem = i - cs * ( T * width );
+            int tt = rem / width, c = rem - tt * width;
+            st4( dst + ( cs * TP + tt ) * RS + c, __ldg( reinterpret_cast<const float4 *>( src + i ) ) );
+         }
+      }
+      __syncwarp();
+   };
 
    const int ntiles = ( nchunks + G - 1 ) / G;
    for ( int tile = blockIdx.x; tile < ntiles; tile += gridDim.x )
    {
       const int chunk0 = tile * G;
-      const int gvalid = min( G, nchunks - chunk0 );
-      const bool live = ( tid < R ) && ( g < gvalid );
-      __syncthreads(); // previous tile fully consumed (and resident weights visible)
-
-      // copies row-private values [chunk][T][C] <-> the U slots (taps and alternate entries)
-      auto load_rows_u = [&]() {
-         const float *src = in + (size_t)chunk0 * ( T * C );
-         const int n = gvalid * T * C;
-         for ( int i = tid * 4; i < n; i += LAYER_THREADS * 4 )
-         {
-            int r = i / C, c = i - r * C;
-            st4( rows + r * RS + OFF_U + c, __ldg( reinterpret_cast<const float4 *>( src + i ) ) );
-         }
-      };
-      auto tap_row = [&]( const float *v ) {
-         if ( live )
-         {
-            float *dst = out + ( (size_t)( chunk0 + g ) * T + t ) * C;
+      bool live[U];
 #pragma unroll
-            for ( int c = 0; c < C; c += 4 ) st4( dst + c, ld4( v + c ) );
-         }
+      for ( int u = 0; u < U; ++u ) live[u] = ( t < T ) && ( chunk0 + gidx[u] < nchunks );
+      __syncwarp(); // this warp is done with the rows of its previous tile
+
+      auto tap_row = [&]( int off ) {
+#pragma unroll
+         for ( int u = 0; u < U; ++u )
+            if ( live[u] )
+            {
+               float *dst = out + ( (size_t)( chunk0 + gidx[u] ) * T + t ) * C;
+#pragma unroll
+               for ( int c = 0; c < C; c += 4 ) st4( dst + c, ld4( myrow[u] + off + c ) );
+            }
       };
 
-      if ( entry != ENTRY_LAYER )
-      {
-         load_rows_u();
-         __syncthreads();
-      }
+      if ( entry != ENTRY_LAYER ) load_rows( chunk0, C, OFF_U );
       if ( entry == ENTRY_LAYER )
       {
-      // ---- 1. input tile -> shared ---------------------------------------------------------
-      if ( FIRST )
-      {
-         const float *src = in + (size_t)chunk0 * ( VB_BINS * T );
-         const int n = gvalid * VB_BINS * T;
-         for ( int i = tid; i < n; i += LAYER_THREADS ) spec[i] = __ldg( src + i );
-      }
-      else
-      {
-         const float *src = in + (size_t)chunk0 * ( T * CIN );
-         const int n = gvalid * T * CIN;
-         for ( int i = tid * 4; i < n; i += LAYER_THREADS * 4 )
+         // ---- 1+2. input -> conv_block -> U ---------------------------------------------------
+         const float *wa = RES ? wbuf : ( stage( P::DW, P::QKV - P::DW ) - P::DW );
+         if ( FIRST )
          {
-            int r = i / CIN, c = i - r * CIN;
-            st4( rows + r * RS + OFF_O + c, __ldg( reinterpret_cast<const float4 *>( src + i ) ) );
-         }
-      }
-      __syncthreads();
-
-      // ---- 2. conv_block -> U ---------------------------------------------------------------
-      const float *wa = RES ? wbuf : ( stage( P::DW, P::QKV - P::DW ) - P::DW );
-      if ( FIRST )
-      {
-         float *mbuf = spec + G * VB_BINS * T;
-         float *sbuf = mbuf + LAYER_THREADS;
-         const float *sp = spec + g * ( VB_BINS * T );
-         float mu = 0.0f;
-         if ( NORM )
-         {
-            // misc.c:48-62: per-frame mean over the 129 bins, sequential
-            if ( live )
-            {
-               float s = 0.0f;
-               for ( int f = 0; f < VB_BINS; ++f ) s = __fadd_rn( s, sp[f * T + t] );
-               mbuf[tid] = s / (float)VB_BINS;
-            }
-            __syncthreads();
-            // misc.c:64-66: reflect pad 3 + 7-tap smoothing (generic conv path: 0 + left-to-right)
-            if ( live )
+            // one chunk per warp per token set: lane = frame; the spectrogram is read from global
+            const float *sp[U];
+#pragma unroll
+            for ( int u = 0; u < U; ++u ) sp[u] = in + (size_t)min( chunk0 + gidx[u], nchunks - 1 ) * ( VB_BINS * T ) + min( t, T - 1 );
+            float mu[U];
+#pragma unroll
+            for ( int u = 0; u < U; ++u ) mu[u] = 0.0f;
+            if ( NORM )
             {
                const float gk[7] = { 0.03663284704089164733887f, 0.11128076165914535522461f,
                                      0.21674531698226928710938f, 0.27068215608596801757812f,
                                      0.21674531698226928710938f, 0.11128076165914535522461f,
                                      0.03663284704089164733887f };
-               float v = 0.0f;
 #pragma unroll
-               for ( int k = 0; k < 7; ++k )
+               for ( int u = 0; u < U; ++u )
                {
-                  int idx = t + k - 3;
-                  if ( idx < 0 ) idx = -idx;
-                  if ( idx >= T ) idx = 2 * ( T - 1 ) - idx;
-                  v = __fadd_rn( v, __fmul_rn( mbuf[g * T + idx], gk[k] ) );
-               }
-               sbuf[tid] = v;
-            }
-            __syncthreads();
-            // misc.c:68-82: mean over the 25 smoothed values
-            if ( live )
-            {
-               float s = 0.0f;
-               for ( int i = 0; i < T; ++i ) s = __fadd_rn( s, sbuf[g * T + i] );
-               mu = s / (float)T;
-            }
-         }
-         if ( live )
-         {
-            float acc[2 * C];
+                  // misc.c:48-62: per-frame mean over the 129 bins, sequential
+                  float s = 0.0f;
+#pragma unroll 8
+                  for ( int f = 0; f < VB_BINS; ++f ) s = __fadd_rn( s, __ldg( sp[u] + f * T ) );
+                  const float m = s / (float)VB_BINS;
+                  // misc.c:64-66: reflect pad 3 + 7-tap smoothing (generic conv path: 0 + left-to-right)
+                  float v = 0.0f;
 #pragma unroll
-            for ( int o = 0; o < 2 * C; ++o ) acc[o] = 0.0f;
+                  for ( int k = 0; k < 7; ++k )
+                  {
+                     int idx = t + k - 3;
+                     if ( idx < 0 ) idx = -idx;
+                     if ( idx >= T ) idx = 2 * ( T - 1 ) - idx;
+                     v = __fadd_rn( v, __fmul_rn( __shfl_sync( FULL, m, idx & 31 ), gk[k] ) );
+                  }
+                  // misc.c:68-82: mean over the 25 smoothed values, sequential
+                  float a = 0.0f;
+                  for ( int i = 0; i < T; ++i ) a = __fadd_rn( a, __shfl_sync( FULL, v, i ) );
+                  mu[u] = a / (float)T;
+               }
+            }
+            float acc[U][2 * C];
+#pragma unroll
+            for ( int u = 0; u < U; ++u )
+#pragma unroll
+               for ( int o = 0; o < 2 * C; ++o ) acc[u][o] = 0.0f;
             const float *dw = wa + P::DW;
             const float *pw = wa + P::PW;
-            for ( int f = 0; f < VB_BINS; ++f )
+            constexpr int FB = 4; // bins per batch of loads
+#pragma unroll 1
+            for ( int f0 = 0; f0 < VB_BINS; f0 += FB )
             {
-               const float *xf = sp + f * T;
-               float4 w0 = ld4( dw + f * 8 ), w1 = ld4( dw + f * 8 + 4 );
-               // zero padding applies to the normalized signal: absent taps contribute nothing
-               float xm2 = ( t >= 2 ) ? xf[t - 2] - mu : 0.0f;
-               float xm1 = ( t >= 1 ) ? xf[t - 1] - mu : 0.0f;
-               float x0 = xf[t] - mu;
-               float xp1 = ( t + 1 < T ) ? xf[t + 1] - mu : 0.0f;
-               float xp2 = ( t + 2 < T ) ? xf[t + 2] - mu : 0.0f;
-               float dv = w1.y; // bias
-               dv = fmaf( xm2, w0.x, dv );
-               dv = fmaf( xm1, w0.y, dv );
-               dv = fmaf( x0, w0.z, dv );
-               dv = fmaf( xp1, w0.w, dv );
-               dv = fmaf( xp2, w1.x, dv );
-               dv = fmaxf( dv, 0.0f );
-               const float *wf = pw + f * ( 2 * C );
+               float xin[FB][U];
 #pragma unroll
-               for ( int o = 0; o < C; o += 4 )
+               for ( int k = 0; k < FB; ++k )
+#pragma unroll
+                  for ( int u = 0; u < U; ++u ) xin[k][u] = ( f0 + k < VB_BINS ) ? __ldg( sp[u] + ( f0 + k ) * T ) : 0.0f;
+#pragma unroll
+               for ( int k = 0; k < FB; ++k )
                {
-                  float4 a = ld4( wf + o ), b = ld4( wf + C + o );
-                  acc[o] = fmaf( a.x, dv, acc[o] );
-                  acc[o + 1] = fmaf( a.y, dv, acc[o + 1] );
-                  acc[o + 2] = fmaf( a.z, dv, acc[o + 2] );
-                  acc[o + 3] = fmaf( a.w, dv, acc[o + 3] );
-                  acc[C + o] = fmaf( b.x, x0, acc[C + o] );
-                  acc[C + o + 1] = fmaf( b.y, x0, acc[C + o + 1] );
-                  acc[C + o + 2] = fmaf( b.z, x0, acc[C + o + 2] );
-                  acc[C + o + 3] = fmaf( b.w, x0, acc[C + o + 3] );
+                  const int f = f0 + k;
+                  if ( f < VB_BINS )
+                  {
+                     const float4 w0 = ld4( dw + f * 8 ), w1 = ld4( dw + f * 8 + 4 );
+                     float dv[U], x0[U];
+#pragma unroll
+                     for ( int u = 0; u < U; ++u )
+                     {
+                        // zero padding applies to the normalized signal: absent taps contribute nothing
+                        x0[u] = live[u] ? xin[k][u] - mu[u] : 0.0f;
+                        float xm1 = __shfl_up_sync( FULL, x0[u], 1 ), xm2 = __shfl_up_sync( FULL, x0[u], 2 );
+                        float xp1 = __shfl_down_sync( FULL, x0[u], 1 ), xp2 = __shfl_down_sync( FULL, x0[u], 2 );
+                        if ( t < 1 ) xm1 = 0.0f;
+                        if ( t < 2 ) xm2 = 0.0f;
+                        if ( t + 1 >= T ) xp1 = 0.0f;
+                        if ( t + 2 >= T ) xp2 = 0.0f;
+                        float d = w1.y; // bias
+                        d = fmaf( xm2, w0.x, d );
+                        d = fmaf( xm1, w0.y, d );
+                        d = fmaf( x0[u], w0.z, d );
+                        d = fmaf( xp1, w0.w, d );
+                        d = fmaf( xp2, w1.x, d );
+                        dv[u] = fmaxf( d, 0.0f );
+                     }
+                     const float *wf = pw + f * ( 2 * C );
+#pragma unroll
+                     for ( int o = 0; o < C; o += 4 )
+                     {
+                        const float4 a = ld4( wf + o ), b = ld4( wf + C + o );
+#pragma unroll
+                        for ( int u = 0; u < U; ++u )
+                        {
+                           acc[u][o] = fmaf( a.x, dv[u], acc[u][o] );
+                           acc[u][o + 1] = fmaf( a.y, dv[u], acc[u][o + 1] );
+                           acc[u][o + 2] = fmaf( a.z, dv[u], acc[u][o + 2] );
+                           acc[u][o + 3] = fmaf( a.w, dv[u], acc[u][o + 3] );
+                           acc[u][C + o] = fmaf( b.x, x0[u], acc[u][C + o] );
+                           acc[u][C + o + 1] = fmaf( b.y, x0[u], acc[u][C + o + 1] );
+                           acc[u][C + o + 2] = fmaf( b.z, x0[u], acc[u][C + o + 2] );
+                           acc[u][C + o + 3] = fmaf( b.w, x0[u], acc[u][C + o + 3] );
+                        }
+                     }
+                  }
                }
             }
             const float *pb = wa + P::PWB;
 #pragma unroll
-            for ( int o = 0; o < C; ++o ) myrow[OFF_U + o] = fmaxf( acc[o] + acc[C + o] + pb[o], 0.0f );
+            for ( int u = 0; u < U; ++u )
+#pragma unroll
+               for ( int o = 0; o < C; o += 4 )
+                  st4( myrow[u] + OFF_U + o, make_float4( fmaxf( acc[u][o] + acc[u][C + o] + pb[o], 0.0f ),
+                                                          fmaxf( acc[u][o + 1] + acc[u][C + o + 1] + pb[o + 1], 0.0f ),
+                                                          fmaxf( acc[u][o + 2] + acc[u][C + o + 2] + pb[o + 2], 0.0f ),
+                                                          fmaxf( acc[u][o + 3] + acc[u][C + o + 3] + pb[o + 3], 0.0f ) ) );
          }
-      }
-      else
-      {
-         if ( live )
+         else
          {
+            load_rows( chunk0, CIN, OFF_Q );
             // depthwise k=5 zero-pad 2 + bias + ReLU, 4 channels at a time, into registers
-            float dreg[CIN];
+            float dreg[U][CIN];
             const float *dw = wa + P::DW;
 #pragma unroll
-            for ( int c = 0; c < CIN; c += 4 )
-            {
-               float4 x[5];
-#pragma unroll
-               for ( int k = 0; k < 5; ++k )
+            for ( int u = 0; u < U; ++u )
+               if ( live[u] )
                {
-                  int tt = t + k - 2;
-                  x[k] = ( tt >= 0 && tt < T ) ? ld4( crows + tt * RS + OFF_O + c ) : make_float4( 0.f, 0.f, 0.f, 0.f );
-               }
 #pragma unroll
-               for ( int e = 0; e < 4; ++e )
-               {
-                  float4 w0 = ld4( dw + ( c + e ) * 8 ), w1 = ld4( dw + ( c + e ) * 8 + 4 );
-                  float dv = w1.y;
-                  dv = fmaf( reinterpret_cast<const float *>( &x[0] )[e], w0.x, dv );
-                  dv = fmaf( reinterpret_cast<const float *>( &x[1] )[e], w0.y, dv );
-                  dv = fmaf( reinterpret_cast<const float *>( &x[2] )[e], w0.z, dv );
-                  dv = fmaf( reinterpret_cast<const float *>( &x[3] )[e], w0.w, dv );
-                  dv = fmaf( reinterpret_cast<const float *>( &x[4] )[e], w1.x, dv );
-                  dreg[c + e] = fmaxf( dv, 0.0f );
+                  for ( int c = 0; c < CIN; c += 4 )
+                  {
+                     float4 x[5];
+#pragma unroll
+                     for ( int k = 0; k < 5; ++k )
+                     {
+                        int tt = t + k - 2;
+                        x[k] = ( tt >= 0 && tt < T ) ? ld4( crows[u] + tt * RS + OFF_Q + c ) : make_float4( 0.f, 0.f, 0.f, 0.f );
+                     }
+#pragma unroll
+                     for ( int e = 0; e < 4; ++e )
+                     {
+                        float4 w0 = ld4( dw + ( c + e ) * 8 ), w1 = ld4( dw + ( c + e ) * 8 + 4 );
+                        float dv = w1.y;
+                        dv = fmaf( reinterpret_cast<const float *>( &x[0] )[e], w0.x, dv );
+                        dv = fmaf( reinterpret_cast<const float *>( &x[1] )[e], w0.y, dv );
+                        dv = fmaf( reinterpret_cast<const float *>( &x[2] )[e], w0.z, dv );
+                        dv = fmaf( reinterpret_cast<const float *>( &x[3] )[e], w0.w, dv );
+                        dv = fmaf( reinterpret_cast<const float *>( &x[4] )[e], w1.x, dv );
+                        dreg[u][c + e] = fmaxf( dv, 0.0f );
+                     }
+                  }
                }
-            }
+               else
+               {
+#pragma unroll
+                  for ( int c = 0; c < CIN; ++c ) dreg[u][c] = 0.0f;
+               }
             // pointwise (+ projection of the block input, or identity residual) + ReLU
             const float *pw = wa + P::PW;
             const float *pb = wa + P::PWB;
-            const float *xrow = myrow + OFF_O;
+            const float *xrow[U];
+#pragma unroll
+            for ( int u = 0; u < U; ++u ) xrow[u] = myrow[u] + OFF_Q;
             constexpr int NB = 16;
 #pragma unroll 1
             for ( int ob = 0; ob < C; ob += NB )
             {
-               float acc[NB];
+               float acc[U][NB];
 #pragma unroll
-               for ( int o = 0; o < NB; ++o ) acc[o] = pb[ob + o];
+               for ( int u = 0; u < U; ++u )
+#pragma unroll
+                  for ( int o = 0; o < NB; ++o ) acc[u][o] = pb[ob + o];
 #pragma unroll
                for ( int k = 0; k < CIN; k += 4 )
                {
@@ -399,159 +478,192 @@ layer_kernel( const float *__restrict__ in, float *__restrict__ out, const float
                   for ( int o = 0; o < NB; ++o )
                   {
                      float4 w = ld4( pw + ( ob + o ) * P::KP + k );
-                     acc[o] = fmaf( w.x, dreg[k], acc[o] );
-                     acc[o] = fmaf( w.y, dreg[k + 1], acc[o] );
-                     acc[o] = fmaf( w.z, dreg[k + 2], acc[o] );
-                     acc[o] = fmaf( w.w, dreg[k + 3], acc[o] );
+#pragma unroll
+                     for ( int u = 0; u < U; ++u )
+                     {
+                        acc[u][o] = fmaf( w.x, dreg[u][k], acc[u][o] );
+                        acc[u][o] = fmaf( w.y, dreg[u][k + 1], acc[u][o] );
+                        acc[u][o] = fmaf( w.z, dreg[u][k + 2], acc[u][o] );
+                        acc[u][o] = fmaf( w.w, dreg[u][k + 3], acc[u][o] );
+                     }
                   }
                }
                if ( Cfg::PROJ )
-                  lin_acc<CIN, NB>( xrow, pw + ob * P::KP + CIN, P::KP, acc );
+                  lin_acc<CIN, NB, U>( xrow, pw + ob * P::KP + CIN, P::KP, acc );
                else
                {
 #pragma unroll
-                  for ( int o = 0; o < NB; ++o ) acc[o] += xrow[ob + o];
+                  for ( int u = 0; u < U; ++u )
+#pragma unroll
+                     for ( int o = 0; o < NB; ++o ) acc[u][o] += xrow[u][ob + o];
                }
 #pragma unroll
-               for ( int o = 0; o < NB; o += 4 )
-                  st4( myrow + OFF_U + ob + o, make_float4( fmaxf( acc[o], 0.f ), fmaxf( acc[o + 1], 0.f ),
-                                                            fmaxf( acc[o + 2], 0.f ), fmaxf( acc[o + 3], 0.f ) ) );
+               for ( int u = 0; u < U; ++u )
+#pragma unroll
+                  for ( int o = 0; o < NB; o += 4 )
+                     st4( myrow[u] + OFF_U + ob + o, make_float4( fmaxf( acc[u][o], 0.f ), fmaxf( acc[u][o + 1], 0.f ),
+                                                                  fmaxf( acc[u][o + 2], 0.f ), fmaxf( acc[u][o + 3], 0.f ) ) );
             }
          }
-      }
-
       } // entry == ENTRY_LAYER
       if ( tap == TAP_CONV_BLOCK )
       {
-         tap_row( myrow + OFF_U );
+         tap_row( OFF_U );
          continue;
+      }
+
+      const float *urow[U], *hrow[U];
+#pragma unroll
+      for ( int u = 0; u < U; ++u )
+      {
+         urow[u] = myrow[u] + OFF_U;
+         hrow[u] = myrow[u] + OFF_Q; // FFN hidden row
       }
 
       if ( entry != ENTRY_CONV )
       {
-      // ---- 3. attention, one head at a time: QKV_h -> Q, then A V -> O[h*D..] -----------------
-#pragma unroll 1
-      for ( int h = 0; h < 2; ++h )
-      {
-         const float *wq = RES ? ( wbuf + P::QKV + h * P::QH ) : stage( P::QKV + h * P::QH, P::QH );
-         if ( RES ) __syncthreads(); // Q of the previous head / X of this tile no longer read by others
-         if ( live )
+         // ---- 3. attention, one head at a time: QKV_h -> Q, then A V -> registers ------------------
+         float att[U][C];
+#pragma unroll
+         for ( int u = 0; u < U; ++u )
+#pragma unroll
+            for ( int c = 0; c < C; ++c ) att[u][c] = 0.0f;
+#pragma unroll
+         for ( int h = 0; h < 2; ++h )
          {
-            constexpr int NB = 12;
-#pragma unroll 1
-            for ( int ob = 0; ob < 3 * D; ob += NB )
+            const float *wq = RES ? ( wbuf + P::QKV + h * P::QH ) : stage( P::QKV + h * P::QH, P::QH );
+            __syncwarp(); // Q of the previous head / X of this tile no longer read by other lanes
             {
-               float acc[NB];
+               constexpr int NB = 12;
+#pragma unroll 1
+               for ( int ob = 0; ob < 3 * D; ob += NB )
+               {
+                  float acc[U][NB];
 #pragma unroll
-               for ( int o = 0; o < NB; ++o ) acc[o] = wq[3 * D * C + ob + o];
-               lin_acc<C, NB>( myrow + OFF_U, wq + ob * C, C, acc );
+                  for ( int u = 0; u < U; ++u )
 #pragma unroll
-               for ( int o = 0; o < NB; o += 4 ) st4( myrow + OFF_Q + ob + o, make_float4( acc[o], acc[o + 1], acc[o + 2], acc[o + 3] ) );
+                     for ( int o = 0; o < NB; ++o ) acc[u][o] = wq[3 * D * C + ob + o];
+                  lin_acc<C, NB, U>( urow, wq + ob * C, C, acc );
+#pragma unroll
+                  for ( int u = 0; u < U; ++u )
+#pragma unroll
+                     for ( int o = 0; o < NB; o += 4 )
+                        st4( myrow[u] + OFF_Q + ob + o, make_float4( acc[u][o], acc[u][o + 1], acc[u][o + 2], acc[u][o + 3] ) );
+               }
             }
+            __syncwarp();
+#pragma unroll
+            for ( int u = 0; u < U; ++u )
+               if ( live[u] ) attention_head<T, D, RS, OFF_Q>( crows[u], t, &att[u][h * D] );
          }
-         __syncthreads();
-         if ( live ) attention_head<T, D, RS, OFF_Q>( crows, t, myrow + OFF_O + h * D );
-      }
 
-      // ---- 4. out-proj + residual + LayerNorm1 -> U -------------------------------------------
-      {
-         const float *w = RES ? wbuf : ( stage( P::AO, P::F1 - P::AO ) - P::AO );
-         if ( live )
+         // ---- 4. out-proj + residual + LayerNorm1 -> U -------------------------------------------
          {
+            const float *w = RES ? wbuf : ( stage( P::AO, P::F1 - P::AO ) - P::AO );
             constexpr int NB = 16;
 #pragma unroll 1
             for ( int ob = 0; ob < C; ob += NB )
             {
-               float acc[NB];
+               float acc[U][NB];
 #pragma unroll
-               for ( int o = 0; o < NB; ++o ) acc[o] = w[P::AOB + ob + o];
-               lin_acc<C, NB>( myrow + OFF_O, w + P::AO + ob * C, C, acc );
-               if ( tap == TAP_ATTENTION )
-               {
+               for ( int u = 0; u < U; ++u )
 #pragma unroll
-                  for ( int o = 0; o < NB; ++o ) myrow[OFF_U + ob + o] = acc[o];
-               }
-               else
-               {
+                  for ( int o = 0; o < NB; ++o ) acc[u][o] = w[P::AOB + ob + o];
+               lin_acc_reg<C, NB, U>( att, w + P::AO + ob * C, C, acc );
 #pragma unroll
-                  for ( int o = 0; o < NB; ++o ) myrow[OFF_U + ob + o] += acc[o];
-               }
+               for ( int u = 0; u < U; ++u )
+#pragma unroll
+                  for ( int o = 0; o < NB; ++o )
+                     myrow[u][OFF_U + ob + o] = ( tap == TAP_ATTENTION ) ? acc[u][o] : myrow[u][OFF_U + ob + o] + acc[u][o];
             }
-            if ( tap != TAP_ATTENTION ) layer_norm_row<C>( myrow + OFF_U, w + P::LN1W, w + P::LN1B );
+            if ( tap != TAP_ATTENTION )
+            {
+#pragma unroll
+               for ( int u = 0; u < U; ++u ) layer_norm_row<C>( myrow[u] + OFF_U, w + P::LN1W, w + P::LN1B );
+            }
          }
-      }
-      if ( tap == TAP_ATTENTION || tap == TAP_NORM1 )
-      {
-         tap_row( myrow + OFF_U );
-         continue;
-      }
-      // ---- 5. FFN: linear1 + ReLU -> O ; linear2 + residual + LayerNorm2 -> U ------------------
-      {
-         const float *w = RES ? wbuf : ( stage( P::F1, P::F2 - P::F1 ) - P::F1 );
-         if ( live )
+         if ( tap == TAP_ATTENTION || tap == TAP_NORM1 )
          {
+            tap_row( OFF_U );
+            continue;
+         }
+         // ---- 5. FFN: linear1 + ReLU -> Q slot ; linear2 + residual + LayerNorm2 -> U -------------
+         {
+            const float *w = RES ? wbuf : ( stage( P::F1, P::F2 - P::F1 ) - P::F1 );
+            __syncwarp(); // the other lanes are done reading this row's q|k|v
             constexpr int NB = 16;
 #pragma unroll 1
             for ( int ob = 0; ob < C; ob += NB )
             {
-               float acc[NB];
+               float acc[U][NB];
 #pragma unroll
-               for ( int o = 0; o < NB; ++o ) acc[o] = w[P::F1B + ob + o];
-               lin_acc<C, NB>( myrow + OFF_U, w + P::F1 + ob * C, C, acc );
+               for ( int u = 0; u < U; ++u )
 #pragma unroll
-               for ( int o = 0; o < NB; ++o ) myrow[OFF_O + ob + o] = fmaxf( acc[o], 0.0f );
+                  for ( int o = 0; o < NB; ++o ) acc[u][o] = w[P::F1B + ob + o];
+               lin_acc<C, NB, U>( urow, w + P::F1 + ob * C, C, acc );
+#pragma unroll
+               for ( int u = 0; u < U; ++u )
+#pragma unroll
+                  for ( int o = 0; o < NB; o += 4 )
+                     st4( myrow[u] + OFF_Q + ob + o, make_float4( fmaxf( acc[u][o], 0.f ), fmaxf( acc[u][o + 1], 0.f ),
+                                                                  fmaxf( acc[u][o + 2], 0.f ), fmaxf( acc[u][o + 3], 0.f ) ) );
             }
          }
-      }
-      {
-         const float *w = RES ? wbuf : ( stage( P::F2, P::CV - P::F2 ) - P::F2 );
-         if ( live )
          {
+            const float *w = RES ? wbuf : ( stage( P::F2, P::CV - P::F2 ) - P::F2 );
             constexpr int NB = 16;
 #pragma unroll 1
             for ( int ob = 0; ob < C; ob += NB )
             {
-               float acc[NB];
+               float acc[U][NB];
 #pragma unroll
-               for ( int o = 0; o < NB; ++o ) acc[o] = w[P::F2B + ob + o];
-               lin_acc<C, NB>( myrow + OFF_O, w + P::F2 + ob * C, C, acc );
+               for ( int u = 0; u < U; ++u )
 #pragma unroll
-               for ( int o = 0; o < NB; ++o ) myrow[OFF_U + ob + o] += acc[o];
+                  for ( int o = 0; o < NB; ++o ) acc[u][o] = w[P::F2B + ob + o];
+               lin_acc<C, NB, U>( hrow, w + P::F2 + ob * C, C, acc );
+#pragma unroll
+               for ( int u = 0; u < U; ++u )
+#pragma unroll
+                  for ( int o = 0; o < NB; ++o ) myrow[u][OFF_U + ob + o] += acc[u][o];
             }
-            layer_norm_row<C>( myrow + OFF_U, w + P::LN2W, w + P::LN2B );
+#pragma unroll
+            for ( int u = 0; u < U; ++u ) layer_norm_row<C>( myrow[u] + OFF_U, w + P::LN2W, w + P::LN2B );
          }
-      }
       } // entry != ENTRY_CONV
       if ( tap == TAP_BLOCK )
       {
-         tap_row( myrow + OFF_U );
+         tap_row( OFF_U );
          continue;
       }
       // ---- 6. conv 1x1 (stride) + BatchNorm(eval) + ReLU -> global -----------------------------
       {
          const float *w = RES ? wbuf : ( stage( P::CV, P::TOTAL - P::CV ) - P::CV );
-         if ( live && ( t % Cfg::STRIDE ) == 0 )
-         {
-            float *o_row = out + ( (size_t)( chunk0 + g ) * Cfg::TOUT + t / Cfg::STRIDE ) * C;
-            constexpr int NB = 16;
+         constexpr int NB = 16;
 #pragma unroll 1
-            for ( int ob = 0; ob < C; ob += NB )
-            {
-               float acc[NB];
+         for ( int ob = 0; ob < C; ob += NB )
+         {
+            float acc[U][NB];
 #pragma unroll
-               for ( int o = 0; o < NB; ++o ) acc[o] = 0.0f;
-               lin_acc<C, NB>( myrow + OFF_U, w + P::CV + ob * C, C, acc );
-               float r[NB];
+            for ( int u = 0; u < U; ++u )
 #pragma unroll
-               for ( int o = 0; o < NB; ++o )
+               for ( int o = 0; o < NB; ++o ) acc[u][o] = 0.0f;
+            lin_acc<C, NB, U>( urow, w + P::CV + ob * C, C, acc );
+#pragma unroll
+            for ( int u = 0; u < U; ++u )
+               if ( live[u] && ( t % Cfg::STRIDE ) == 0 )
                {
-                  float z = acc[o] + w[P::CVB + ob + o];
-                  float nv = ( z - w[P::BNM + ob + o] ) / w[P::BNS + ob + o]; // misc.c:251 true division
-                  r[o] = fmaxf( nv * w[P::BNW + ob + o] + w[P::BNB + ob + o], 0.0f );
-               }
+                  float *o_row = out + ( (size_t)( chunk0 + gidx[u] ) * Cfg::TOUT + t / Cfg::STRIDE ) * C;
+                  float r[NB];
 #pragma unroll
-               for ( int o = 0; o < NB; o += 4 ) st4( o_row + ob + o, make_float4( r[o], r[o + 1], r[o + 2], r[o + 3] ) );
-            }
+                  for ( int o = 0; o < NB; ++o )
+                  {
+                     float z = acc[u][o] + w[P::CVB + ob + o];
+                     float nv = ( z - w[P::BNM + ob + o] ) / w[P::BNS + ob + o]; // misc.c:251 true division
+                     r[o] = fmaxf( nv * w[P::BNW + ob + o] + w[P::BNB + ob + o], 0.0f );
+                  }
+#pragma unroll
+                  for ( int o = 0; o < NB; o += 4 ) st4( o_row + ob + o, make_float4( r[o], r[o + 1], r[o + 2], r[o + 3] ) );
+               }
          }
       }
    }
