@@ -139,10 +139,14 @@ __device__ __forceinline__ void layer_norm_row( float *x, const float *__restric
 
 // one head of dual_head_attention (transformer.c:72-143) for token (chunk rows at crows, frame t):
 // A = softmax_rows((K Q^T) / sqrt(D)) with rows = K positions; O = A V.
+// Not inlined: the fully unrolled body (T x D) is the largest piece of code in the layer and is
+// called 2*U times per tile; one copy keeps the kernel inside the instruction cache. The result is
+// written over the lane's own k (consumed into registers first; no other lane reads it).
 template <int T, int D, int RS, int OFF_Q>
-__device__ __forceinline__ void attention_head( const float *__restrict__ crows, int t, float *o_out )
+__device__ __noinline__ void attention_head( const float *crows, int t )
 {
    const float *mine = crows + t * RS + OFF_Q;
+   float *o_out = const_cast<float *>( mine ) + D;
    float kreg[D];
 #pragma unroll
    for ( int j = 0; j < D; j += 4 )
@@ -198,7 +202,7 @@ __device__ __forceinline__ void attention_head( const float *__restrict__ crows,
       }
    }
 #pragma unroll
-   for ( int j = 0; j < D; ++j ) o_out[j] = o[j];
+   for ( int j = 0; j < D; j += 4 ) st4( o_out + j, make_float4( o[j], o[j + 1], o[j + 2], o[j + 3] ) );
 }
 
 // NORM (first layer only): input is log1p(mag*2^20) and the adaptive-normalization mean is computed
@@ -350,7 +354,12 @@ layer_kernel( const float *__restrict__ in, float *__restrict__ out, const float
                for ( int o = 0; o < 2 * C; ++o ) acc[u][o] = 0.0f;
             const float *dw = wa + P::DW;
             const float *pw = wa + P::PW;
-            constexpr int FB = 4; // bins per batch of loads
+            constexpr int FB = 4; // bins per batch of loads; the next batch is in flight while this one is used
+            float xnext[FB][U];
+#pragma unroll
+            for ( int k = 0; k < FB; ++k )
+#pragma unroll
+               for ( int u = 0; u < U; ++u ) xnext[k][u] = __ldg( sp[u] + k * T );
 #pragma unroll 1
             for ( int f0 = 0; f0 < VB_BINS; f0 += FB )
             {
@@ -358,7 +367,11 @@ layer_kernel( const float *__restrict__ in, float *__restrict__ out, const float
 #pragma unroll
                for ( int k = 0; k < FB; ++k )
 #pragma unroll
-                  for ( int u = 0; u < U; ++u ) xin[k][u] = ( f0 + k < VB_BINS ) ? __ldg( sp[u] + ( f0 + k ) * T ) : 0.0f;
+                  for ( int u = 0; u < U; ++u )
+                  {
+                     xin[k][u] = xnext[k][u];
+                     xnext[k][u] = ( f0 + FB + k < VB_BINS ) ? __ldg( sp[u] + ( f0 + FB + k ) * T ) : 0.0f;
+                  }
 #pragma unroll
                for ( int k = 0; k < FB; ++k )
                {
@@ -462,7 +475,7 @@ layer_kernel( const float *__restrict__ in, float *__restrict__ out, const float
             const float *xrow[U];
 #pragma unroll
             for ( int u = 0; u < U; ++u ) xrow[u] = myrow[u] + OFF_Q;
-            constexpr int NB = 16;
+            constexpr int NB = 8;
 #pragma unroll 1
             for ( int ob = 0; ob < C; ob += NB )
             {
@@ -554,13 +567,22 @@ layer_kernel( const float *__restrict__ in, float *__restrict__ out, const float
             __syncwarp();
 #pragma unroll
             for ( int u = 0; u < U; ++u )
-               if ( live[u] ) attention_head<T, D, RS, OFF_Q>( crows[u], t, &att[u][h * D] );
+               if ( live[u] )
+               {
+                  attention_head<T, D, RS, OFF_Q>( crows[u], t );
+#pragma unroll
+                  for ( int jj = 0; jj < D; jj += 4 )
+                  {
+                     float4 v = ld4( myrow[u] + OFF_Q + D + jj );
+                     att[u][h * D + jj] = v.x; att[u][h * D + jj + 1] = v.y; att[u][h * D + jj + 2] = v.z; att[u][h * D + jj + 3] = v.w;
+                  }
+               }
          }
 
          // ---- 4. out-proj + residual + LayerNorm1 -> U -------------------------------------------
          {
             const float *w = RES ? wbuf : ( stage( P::AO, P::F1 - P::AO ) - P::AO );
-            constexpr int NB = 16;
+            constexpr int NB = 8;
 #pragma unroll 1
             for ( int ob = 0; ob < C; ob += NB )
             {
