@@ -32,6 +32,11 @@ CHUNK = 1536
 CHUNK_SECONDS = CHUNK / 16000.0
 FLOP_PER_CHUNK = 5404954          # 2 x 2 702 477 MAC, reference's dense formulation
 STFT_FLOP_PER_CHUNK = 2 * 1651200 # K1: 258 x 25 x 256 MAC
+# algorithmic MACs per chunk of every stage on the reference's formulation (sums to 2 702 477)
+STAGE_MAC = {"stft": 1651200, "layer1": 181053, "layer2": 112208, "layer3": 61600, "layer4": 236768,
+             "lstm0": 229376, "lstm1_decoder": 229376 + 896}
+STAGE_KERNEL = {"stft": "stft_hybrid_kernel<s16>", "layer1": "layer_kernel<0,NORM>", "layer2": "layer_kernel<1>", "layer3": "layer_kernel<2>",
+                "layer4": "layer_kernel<3>", "lstm0": "lstm_layer_kernel<0>", "lstm1_decoder": "lstm_layer_kernel<1> (+decoder)"}
 STREAMS_PER_GPU = 4096
 STEP_CHUNKS = 125
 N_BASE = 32                       # distinct synthetic base streams
@@ -281,21 +286,26 @@ def main():
         stage_ms, n_launch = eng.last_timing()
     eng.set_profiling(False)
     windows = n_launch // 7
-    stft_ms_per_launch = stage_ms["stft"] / windows
     chunks_per_launch = S * C / windows
     fp32_peak = eng.measure_fp32_peak()
-    stft_tflops = STFT_FLOP_PER_CHUNK * chunks_per_launch / (stft_ms_per_launch * 1e-3) / 1e12
     kernel_sum = sum(v for k, v in stage_ms.items() if k != "total")
+    top = max((k for k in stage_ms if k != "total"), key=lambda k: stage_ms[k])
+    top_ms_per_launch = stage_ms[top] / windows
+    top_tflops = 2 * STAGE_MAC[top] * chunks_per_launch / (top_ms_per_launch * 1e-3) / 1e12
+    per_stage = {k: {"ms_per_launch": stage_ms[k] / windows, "share": stage_ms[k] / kernel_sum,
+                     "algorithmic_tflops": 2 * STAGE_MAC[k] * chunks_per_launch / (stage_ms[k] / windows * 1e-3) / 1e12}
+                 for k in stage_ms if k != "total"}
+    bins_total, bins_exact = eng.stft_stats()
     roofline = {
-        "kernel": "stft_logmag_kernel<s16>", "bound": "fp32",
-        "achieved": stft_tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": stft_tflops / fp32_peak,
+        "kernel": STAGE_KERNEL[top], "bound": "fp32",
+        "achieved": top_tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": top_tflops / fp32_peak,
         "peak_source": "FP32 FMA pipe measured live by silero_b200_measure_fp32_peak (independent FFMA chains); MEASURED_PEAKS.json has no FP32 figure "
-                       "(its bf16 tensor peak does not bound this kernel: the reference's rounding sequence must be reproduced, see DESIGN.md)",
-        "algorithmic_flop_per_launch": STFT_FLOP_PER_CHUNK * chunks_per_launch, "ms_per_launch": stft_ms_per_launch,
-        "share_of_step": stage_ms["stft"] / kernel_sum,
-        "executed_fp32_ops_frac": (511.0 / 512.0) * 2 * stft_tflops / fp32_peak,  # mul+add issued separately: 511 pipe ops per 256-MAC output
-        "traffic": TRAFFIC_STFT_BYTES_PER_CHUNK * chunks_per_launch if TRAFFIC_STFT_BYTES_PER_CHUNK else None,
-        "stage_ms": stage_ms,
+                       "and its HBM / bf16-tensor peaks do not bound these kernels (DESIGN.md sections 2, 4)",
+        "algorithmic_flop_per_launch": 2 * STAGE_MAC[top] * chunks_per_launch, "ms_per_launch": top_ms_per_launch,
+        "share_of_step": stage_ms[top] / kernel_sum,
+        "traffic": TRAFFIC_BYTES_PER_CHUNK.get(top, 0) * chunks_per_launch if TRAFFIC_BYTES_PER_CHUNK.get(top) else None,
+        "stages": per_stage,
+        "stft_exact_bin_fraction": bins_exact / max(bins_total, 1),
         "pipeline_algorithmic_tflops": FLOP_PER_CHUNK * (value / world / CHUNK_SECONDS) / 1e12,
         "pipeline_frac_of_fp32_peak": FLOP_PER_CHUNK * (value / world / CHUNK_SECONDS) / 1e12 / fp32_peak,
     }
@@ -352,8 +362,8 @@ def main():
     return 0
 
 
-# dram bytes per chunk of the STFT kernel from the committed ncu capture (profiles/); None until measured
-TRAFFIC_STFT_BYTES_PER_CHUNK = 15118  # profiles/ncu_summary_r01.md: (154.4 MB read + 588.7 MB written) / 49152 chunks
+# dram bytes per chunk of each kernel from the committed ncu captures (profiles/); absent until measured
+TRAFFIC_BYTES_PER_CHUNK = {}
 
 if __name__ == "__main__":
     sys.exit(main())

@@ -66,7 +66,7 @@ struct silero_b200
    float *state_h, *state_c; // [max_streams][2][64]
    // window scratch (grow-only)
    size_t cap_chunks;
-   float *spec, *a1, *a2, *a3, *a4, *h0;
+   float *spec, *a1, *a2, *a3, *a4, *h0, *mu;
    // host-call staging
    int16_t *pcm_stage[2];
    size_t pcm_stage_cap; // samples per buffer
@@ -245,6 +245,7 @@ extern "C" void silero_b200_destroy( silero_b200 *h )
    cudaFree( h->state_h );
    cudaFree( h->state_c );
    cudaFree( h->spec );
+   cudaFree( h->mu );
    cudaFree( h->a1 );
    cudaFree( h->a2 );
    cudaFree( h->a3 );
@@ -470,8 +471,8 @@ static int ensure_scratch( silero_b200 *h, size_t chunks )
 {
    if ( chunks <= h->cap_chunks ) return 0;
    CU( cudaStreamSynchronize( h->stream ) );
-   cudaFree( h->spec ); cudaFree( h->a1 ); cudaFree( h->a2 ); cudaFree( h->a3 ); cudaFree( h->a4 ); cudaFree( h->h0 );
-   h->spec = h->a1 = h->a2 = h->a3 = h->a4 = h->h0 = 0;
+   cudaFree( h->spec ); cudaFree( h->a1 ); cudaFree( h->a2 ); cudaFree( h->a3 ); cudaFree( h->a4 ); cudaFree( h->h0 ); cudaFree( h->mu );
+   h->spec = h->a1 = h->a2 = h->a3 = h->a4 = h->h0 = h->mu = 0;
    h->cap_chunks = 0;
    CU( cudaMalloc( &h->spec, chunks * VB_BINS * VB_FRAMES * sizeof( float ) ) );
    CU( cudaMalloc( &h->a1, chunks * 13 * 16 * sizeof( float ) ) );
@@ -479,6 +480,7 @@ static int ensure_scratch( silero_b200 *h, size_t chunks )
    CU( cudaMalloc( &h->a3, chunks * 7 * 32 * sizeof( float ) ) );
    CU( cudaMalloc( &h->a4, chunks * 7 * 64 * sizeof( float ) ) );
    CU( cudaMalloc( &h->h0, chunks * 7 * 64 * sizeof( float ) ) );
+   CU( cudaMalloc( &h->mu, chunks * sizeof( float ) ) );
    h->cap_chunks = chunks;
    return 0;
 }
@@ -502,7 +504,7 @@ static int pick_window( const silero_b200 *h, int nstreams, int nchunks )
 // ---------------------------------------------------------------------------------------------
 static inline int imin( int a, int b ) { return a < b ? a : b; }
 
-static int launch_stft( silero_b200 *h, const void *d_in, int in_f32, long long stream_stride, int nw, int nchunks, float *spec, int out_mode )
+static int launch_stft( silero_b200 *h, const void *d_in, int in_f32, long long stream_stride, int nw, int nchunks, float *spec, int out_mode, float *mu = 0 )
 {
    if ( h->stft_mode == SILERO_B200_STFT_EXACT )
    {
@@ -523,9 +525,9 @@ static int launch_stft( silero_b200 *h, const void *d_in, int in_f32, long long 
       }
       int grid = imin( nchunks, h->sm_count * per_sm );
       if ( in_f32 )
-         stft_hybrid_kernel<true><<<grid, HYB_THREADS, HYB_SMEM_BYTES, h->stream>>>( d_in, stream_stride, nw, nchunks, h->w.basis_raw, spec, h->stft_k_rel, out_mode, h->d_flagged );
+         stft_hybrid_kernel<true><<<grid, HYB_THREADS, HYB_SMEM_BYTES, h->stream>>>( d_in, stream_stride, nw, nchunks, h->w.basis_raw, spec, mu, h->stft_k_rel, out_mode, h->d_flagged );
       else
-         stft_hybrid_kernel<false><<<grid, HYB_THREADS, HYB_SMEM_BYTES, h->stream>>>( d_in, stream_stride, nw, nchunks, h->w.basis_raw, spec, h->stft_k_rel, out_mode, h->d_flagged );
+         stft_hybrid_kernel<false><<<grid, HYB_THREADS, HYB_SMEM_BYTES, h->stream>>>( d_in, stream_stride, nw, nchunks, h->w.basis_raw, spec, mu, h->stft_k_rel, out_mode, h->d_flagged );
       h->bins_total += (unsigned long long)nchunks * VB_BINS * VB_FRAMES;
    }
    h->launches++;
@@ -534,7 +536,7 @@ static int launch_stft( silero_b200 *h, const void *d_in, int in_f32, long long 
 }
 
 template <int L, bool NORM>
-static int launch_layer( silero_b200 *h, const float *in, float *out, int nchunks, int entry = ENTRY_LAYER, int tap = TAP_LAYER )
+static int launch_layer( silero_b200 *h, const float *in, float *out, int nchunks, int entry = ENTRY_LAYER, int tap = TAP_LAYER, const float *mu = 0 )
 {
    using Cfg = LayerCfg<L>;
    int ntiles = ( nchunks + Cfg::G - 1 ) / Cfg::G;
@@ -542,7 +544,7 @@ static int launch_layer( silero_b200 *h, const float *in, float *out, int nchunk
    if ( per_sm < 1 ) per_sm = 1;
    if ( per_sm > 8 ) per_sm = 8;
    int grid = imin( ntiles, h->sm_count * per_sm );
-   layer_kernel<L, NORM><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, h->stream>>>( in, out, h->w.layer[L], nchunks, entry, tap );
+   layer_kernel<L, NORM><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, h->stream>>>( in, out, h->w.layer[L], nchunks, entry, tap, mu );
    h->launches++;
    CU( cudaGetLastError() );
    return 0;
@@ -584,9 +586,12 @@ static int run_window( silero_b200 *h, const void *d_in, int in_f32, long long s
    const int nchunks = nstreams * nw;
    if ( ensure_scratch( h, (size_t)nchunks ) ) return SILERO_B200_ERR_CUDA;
    stage_mark( h, 0 );
-   if ( launch_stft( h, d_in, in_f32, stream_stride, nw, nchunks, h->spec, 0 ) ) return SILERO_B200_ERR_CUDA;
+   const bool hybrid = h->stft_mode != SILERO_B200_STFT_EXACT;
+   if ( launch_stft( h, d_in, in_f32, stream_stride, nw, nchunks, h->spec, 0, hybrid ? h->mu : 0 ) ) return SILERO_B200_ERR_CUDA;
    stage_mark( h, 1 );
-   if ( launch_layer<0, true>( h, h->spec, h->a1, nchunks ) ) return SILERO_B200_ERR_CUDA;
+   // the hybrid STFT kernel also produces the normalization scalar; the exact one leaves it to the first layer
+   if ( hybrid ? launch_layer<0, false>( h, h->spec, h->a1, nchunks, ENTRY_LAYER, TAP_LAYER, h->mu ) : launch_layer<0, true>( h, h->spec, h->a1, nchunks ) )
+      return SILERO_B200_ERR_CUDA;
    stage_mark( h, 2 );
    if ( launch_layer<1, false>( h, h->a1, h->a2, nchunks ) ) return SILERO_B200_ERR_CUDA;
    stage_mark( h, 3 );
@@ -1070,8 +1075,12 @@ extern "C" int silero_b200_stage_pipeline( silero_b200 *h, const float *samples,
    if ( in.alloc( B * VB_CHUNK ) || sp.alloc( B * 3225 ) || d1.alloc( B * 208 ) || d2.alloc( B * 224 ) || d3.alloc( B * 224 ) || d4.alloc( B * 448 ) )
       return SILERO_B200_ERR_CUDA;
    if ( up( h, in.p, samples, B * VB_CHUNK ) ) return SILERO_B200_ERR_CUDA;
-   if ( launch_stft( h, in.p, 1, 0, batch, batch, sp.p, 0 ) ) return SILERO_B200_ERR_CUDA;
-   if ( launch_layer<0, true>( h, sp.p, d1.p, batch ) ) return SILERO_B200_ERR_CUDA;
+   const bool hybrid = h->stft_mode != SILERO_B200_STFT_EXACT;
+   DevBuf mu;
+   if ( mu.alloc( B ) ) return SILERO_B200_ERR_CUDA;
+   if ( launch_stft( h, in.p, 1, 0, batch, batch, sp.p, 0, hybrid ? mu.p : 0 ) ) return SILERO_B200_ERR_CUDA;
+   if ( hybrid ? launch_layer<0, false>( h, sp.p, d1.p, batch, ENTRY_LAYER, TAP_LAYER, mu.p ) : launch_layer<0, true>( h, sp.p, d1.p, batch ) )
+      return SILERO_B200_ERR_CUDA;
    if ( launch_layer<1, false>( h, d1.p, d2.p, batch ) ) return SILERO_B200_ERR_CUDA;
    if ( launch_layer<2, false>( h, d2.p, d3.p, batch ) ) return SILERO_B200_ERR_CUDA;
    if ( launch_layer<3, false>( h, d3.p, d4.p, batch ) ) return SILERO_B200_ERR_CUDA;

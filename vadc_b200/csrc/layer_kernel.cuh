@@ -206,7 +206,8 @@ __device__ __noinline__ void attention_head( const float *crows, int t )
 }
 
 // NORM (first layer only): input is log1p(mag*2^20) and the adaptive-normalization mean is computed
-// and subtracted here; otherwise the input is taken as already normalized (parity tap).
+// and subtracted here; otherwise the per-chunk mean comes from mu_in (computed by the STFT kernel),
+// or the input is taken as already normalized when mu_in is NULL (parity tap).
 //
 // Parity taps for the reference's op/block-level fixtures (production launches pass 0, 0):
 //   entry 0: `in` is the layer input.  1: `in` is the conv_block output y [chunk][T][C] (skips the
@@ -219,7 +220,8 @@ enum { ENTRY_LAYER = 0, ENTRY_BLOCK = 1, ENTRY_CONV = 2 };
 
 template <int L, bool NORM>
 __global__ void __launch_bounds__( LayerCfg<L>::THREADS )
-layer_kernel( const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ wblob, int nchunks, int entry, int tap )
+layer_kernel( const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ wblob, int nchunks, int entry, int tap,
+              const float *__restrict__ mu_in )
 {
    using Cfg = LayerCfg<L>;
    using P = LayerPack<L>;
@@ -316,7 +318,7 @@ layer_kernel( const float *__restrict__ in, float *__restrict__ out, const float
             for ( int u = 0; u < U; ++u ) sp[u] = in + (size_t)min( chunk0 + gidx[u], nchunks - 1 ) * ( VB_BINS * T ) + min( t, T - 1 );
             float mu[U];
 #pragma unroll
-            for ( int u = 0; u < U; ++u ) mu[u] = 0.0f;
+            for ( int u = 0; u < U; ++u ) mu[u] = ( !NORM && mu_in ) ? __ldg( mu_in + min( chunk0 + gidx[u], nchunks - 1 ) ) : 0.0f;
             if ( NORM )
             {
                const float gk[7] = { 0.03663284704089164733887f, 0.11128076165914535522461f,

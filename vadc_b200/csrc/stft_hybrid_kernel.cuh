@@ -130,7 +130,7 @@ __device__ __forceinline__ const void *hyb_chunk_ptr( const void *in, long long 
 template <bool F32>
 __global__ void __launch_bounds__( HYB_THREADS )
 stft_hybrid_kernel( const void *__restrict__ in, long long stream_stride, int nw, int nchunks, const float *__restrict__ basis,
-                    float *__restrict__ spec, float k_rel, int out_mode, unsigned long long *__restrict__ flagged )
+                    float *__restrict__ spec, float *__restrict__ mu_out, float k_rel, int out_mode, unsigned long long *__restrict__ flagged )
 {
    extern __shared__ __align__( 16 ) float smem[];
    float *Xs = smem;                         // [2][1792]
@@ -284,6 +284,30 @@ stft_hybrid_kernel( const void *__restrict__ in, long long stream_stride, int nw
          if ( j == 0 ) Os[128 * VB_FRAMES + t] = out_mode ? nyq : log1pf( __fmul_rn( nyq, 1048576.0f ) );
       }
       __syncthreads();
+      if ( warp == 0 && mu_out )
+      {
+         // the scalar of adaptive_audio_normalization_inplace (misc.c:48-82), in the reference's order:
+         // per-frame mean over the 129 bins, reflect-pad 3 + 7-tap smoothing, mean over the 25 frames
+         const float gk[7] = { 0.03663284704089164733887f, 0.11128076165914535522461f, 0.21674531698226928710938f, 0.27068215608596801757812f,
+                               0.21674531698226928710938f, 0.11128076165914535522461f, 0.03663284704089164733887f };
+         const int tt = lane < VB_FRAMES ? lane : VB_FRAMES - 1;
+         float sacc = 0.0f;
+#pragma unroll 8
+         for ( int f = 0; f < VB_BINS; ++f ) sacc = __fadd_rn( sacc, Os[f * VB_FRAMES + tt] );
+         const float m = sacc / (float)VB_BINS;
+         float v = 0.0f;
+#pragma unroll
+         for ( int k = 0; k < 7; ++k )
+         {
+            int idx = tt + k - 3;
+            if ( idx < 0 ) idx = -idx;
+            if ( idx >= VB_FRAMES ) idx = 2 * ( VB_FRAMES - 1 ) - idx;
+            v = __fadd_rn( v, __fmul_rn( __shfl_sync( 0xffffffffu, m, idx ), gk[k] ) );
+         }
+         float a = 0.0f;
+         for ( int i = 0; i < VB_FRAMES; ++i ) a = __fadd_rn( a, __shfl_sync( 0xffffffffu, v, i ) );
+         if ( lane == 0 ) mu_out[ci] = a / (float)VB_FRAMES;
+      }
       float *o = spec + (size_t)ci * HYB_OUT_FLOATS;
       for ( int i = tid; i < HYB_OUT_FLOATS; i += HYB_THREADS ) o[i] = Os[i];
    }
