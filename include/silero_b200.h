@@ -56,6 +56,14 @@ typedef struct silero_b200 silero_b200; /* opaque engine handle */
 #define SILERO_B200_STFT_EXACT 1
 #define SILERO_B200_STFT_K_REL_DEFAULT 0.004f
 
+/* Decoder LSTM evaluation. FP32: gate contractions as fp32 FMA chains on the CUDA cores
+   (any stream count). TENSOR: tcgen05 tensor-core GEMM over tiles of 32 streams with the bf16x2 split
+   (3 partial products, fp32 accumulation). AUTO picks TENSOR from SILERO_B200_LSTM_TENSOR_MIN_STREAMS streams up. */
+#define SILERO_B200_LSTM_AUTO 0
+#define SILERO_B200_LSTM_FP32 1
+#define SILERO_B200_LSTM_TENSOR 2
+#define SILERO_B200_LSTM_TENSOR_MIN_STREAMS 1024
+
 typedef struct silero_b200_opts
 {
    int device;          /* CUDA device ordinal (default 0) */
@@ -63,7 +71,8 @@ typedef struct silero_b200_opts
    int window_chunks;   /* chunks per stream processed per internal pass; 0 = choose from memory budget */
    int stft_mode;       /* SILERO_B200_STFT_HYBRID (default) or SILERO_B200_STFT_EXACT */
    float stft_k_rel;    /* hybrid threshold; 0 = SILERO_B200_STFT_K_REL_DEFAULT */
-   int reserved[3];
+   int lstm_mode;       /* SILERO_B200_LSTM_AUTO (default), _FP32 (CUDA-core kernel) or _TENSOR (tcgen05 kernel) */
+   int reserved[2];
 } silero_b200_opts;
 
 void silero_b200_default_opts( silero_b200_opts *opts );
@@ -168,6 +177,10 @@ int silero_b200_stage_lstm( silero_b200 *h, const float *x, int batch, const flo
                             float *out, float *hn, float *cn );
 /* decoder_tensor (silero_v3.c:305): in [B,64,7] -> out [B,2] */
 int silero_b200_stage_decoder( silero_b200 *h, const float *in, int batch, float *out );
+/* tensor-core plumbing tap (vadc_b200/csrc/tc_probe.cuh): D[128][N] = A[128][K] * B[N][K]^T evaluated by
+ * tcgen05.mma with the bf16 x nsplit scheme (1: plain bf16, 2: 3 partial products, 3: 6 partial products).
+ * reps > 1 repeats the MMA phase; *cycles (optional) receives the SM cycles spent in it. */
+int silero_b200_stage_tc_gemm( silero_b200 *h, const float *A, const float *B, int N, int K, int nsplit, int reps, float *D, long long *cycles );
 
 #ifdef __cplusplus
 }

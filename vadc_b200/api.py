@@ -16,6 +16,7 @@ WEIGHTS_PATH = os.path.join(_HERE, "weights", "silero_v31_16k.testtensor")
 CHUNK = 1536
 SAMPLE_RATE = 16000
 STFT_HYBRID, STFT_EXACT = 0, 1
+LSTM_AUTO, LSTM_FP32, LSTM_TENSOR = 0, 1, 2
 
 
 class EngineError(RuntimeError):
@@ -24,7 +25,7 @@ class EngineError(RuntimeError):
 
 class Opts(C.Structure):
     _fields_ = [("device", C.c_int), ("max_streams", C.c_int), ("window_chunks", C.c_int), ("stft_mode", C.c_int),
-                ("stft_k_rel", C.c_float), ("reserved", C.c_int * 3)]
+                ("stft_k_rel", C.c_float), ("lstm_mode", C.c_int), ("reserved", C.c_int * 2)]
 
 
 class Info(C.Structure):
@@ -78,12 +79,12 @@ def _f32(a):
 class Engine:
     """One engine per GPU (silero_b200 handle)."""
 
-    def __init__(self, weights=None, device=0, max_streams=1, window_chunks=0, stft_mode=0, stft_k_rel=0.0):
+    def __init__(self, weights=None, device=0, max_streams=1, window_chunks=0, stft_mode=0, stft_k_rel=0.0, lstm_mode=0):
         L = lib()
         opts = Opts()
         L.silero_b200_default_opts(C.byref(opts))
         opts.device, opts.max_streams, opts.window_chunks = device, max_streams, window_chunks
-        opts.stft_mode, opts.stft_k_rel = stft_mode, stft_k_rel
+        opts.stft_mode, opts.stft_k_rel, opts.lstm_mode = stft_mode, stft_k_rel, lstm_mode
         self._h = C.c_void_p()
         if weights is None:
             weights = WEIGHTS_PATH
@@ -267,6 +268,15 @@ class Engine:
         out = np.zeros((x.shape[0], 2), np.float32)
         self._check(lib().silero_b200_stage_decoder(self._h, _p(x), x.shape[0], _p(out)))
         return out
+
+    def stage_tc_gemm(self, a, b, nsplit=2, reps=1):
+        """D[128,N] = A[128,K] @ B[N,K]^T on tcgen05 (bf16 x nsplit). Returns (D, cycles of the MMA phase)."""
+        a, b = _f32(a), _f32(b)
+        assert a.shape[0] == 128 and a.shape[1] == b.shape[1]
+        d = np.zeros((128, b.shape[0]), np.float32)
+        cyc = C.c_longlong(0)
+        self._check(lib().silero_b200_stage_tc_gemm(self._h, _p(a), _p(b), b.shape[0], a.shape[1], nsplit, reps, _p(d), C.byref(cyc)))
+        return d, cyc.value
 
 
 def pinned_empty(shape, dtype):

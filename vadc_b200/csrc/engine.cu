@@ -16,8 +16,10 @@
 #include "common.cuh"
 #include "layer_kernel.cuh"
 #include "lstm_kernel.cuh"
+#include "lstm_tc_kernel.cuh"
 #include "stft_hybrid_kernel.cuh"
 #include "stft_kernel.cuh"
+#include "tc_probe.cuh"
 #include "testtensor.h"
 
 // ---------------------------------------------------------------------------------------------
@@ -57,6 +59,9 @@ struct silero_b200
    int window_chunks_opt;
    int stft_mode;            // SILERO_B200_STFT_HYBRID / _EXACT
    float stft_k_rel;         // hybrid: exact re-evaluation below k_rel * ||frame||
+   int lstm_mode;            // SILERO_B200_LSTM_*
+   unsigned char *d_lstm_tc; // [2 layers][LTC_W_BYTES] bf16 hi/lo weight images (lstm_tc_kernel.cuh)
+   size_t cap_h0_floats;
    unsigned long long *d_flagged; // bins that took the exact path (device counter)
    unsigned long long bins_total;
    cudaStream_t stream;      // compute
@@ -199,6 +204,28 @@ static void pack_lstm( const float *w /*[2][256][128]*/, float *out /*[2][32][25
          for ( int k = 0; k < 128; ++k ) out[( ( (size_t)l * 32 + ( k >> 2 ) ) * 256 + r ) * 4 + ( k & 3 )] = w[( (size_t)l * 256 + r ) * 128 + k];
 }
 
+// bf16 hi/lo image of one LSTM layer in the shared-memory order of lstm_tc_kernel.cuh:
+// [split][K chunk of 8][row'][8], rows permuted so that a warp's 32 TMEM lanes hold (i|f) resp. (g|o) of 16 units
+static void pack_lstm_tc( const float *w /*[2][256][128]*/, unsigned char *img /*[2][LTC_W_BYTES]*/ )
+{
+   for ( int l = 0; l < 2; ++l )
+      for ( int rp = 0; rp < 256; ++rp )
+      {
+         const int m = rp >> 7, L = rp & 127, wq = L >> 5, q = L & 31;
+         const int u = 16 * wq + ( q & 15 );
+         const int gate = m == 0 ? ( q < 16 ? 0 : 1 ) : ( q < 16 ? 2 : 3 );
+         const float *src = w + ( (size_t)l * 256 + gate * 64 + u ) * 128;
+         for ( int k = 0; k < 128; ++k )
+         {
+            const __nv_bfloat16 hi = __float2bfloat16_rn( src[k] );
+            const __nv_bfloat16 lo = __float2bfloat16_rn( src[k] - __bfloat162float( hi ) );
+            const size_t off = (size_t)l * LTC_W_BYTES + (size_t)( k >> 3 ) * LTC_W_LBO + (size_t)rp * 16 + (size_t)( k & 7 ) * 2;
+            memcpy( img + off, &hi, 2 );
+            memcpy( img + off + LTC_W_SPLIT_BYTES, &lo, 2 );
+         }
+      }
+}
+
 // ---------------------------------------------------------------------------------------------
 // create / destroy
 // ---------------------------------------------------------------------------------------------
@@ -210,6 +237,7 @@ extern "C" void silero_b200_default_opts( silero_b200_opts *o )
    o->window_chunks = 0;
    o->stft_mode = SILERO_B200_STFT_HYBRID;
    o->stft_k_rel = 0.0f; /* 0 = default (SILERO_B200_STFT_K_REL_DEFAULT) */
+   o->lstm_mode = SILERO_B200_LSTM_AUTO;
 }
 
 template <typename K>
@@ -233,6 +261,9 @@ static int configure_kernels()
    CU( allow_smem( lstm_layer_kernel<1, 4>, LstmSmem<4>::BYTES ) );
    CU( allow_smem( lstm_layer_kernel<0, 1>, LstmSmem<1>::BYTES ) );
    CU( allow_smem( lstm_layer_kernel<1, 1>, LstmSmem<1>::BYTES ) );
+   CU( allow_smem( tc_probe_kernel, 200 * 1024 ) );
+   CU( allow_smem( lstm_tc_kernel<0>, LTC_SMEM_BYTES ) );
+   CU( allow_smem( lstm_tc_kernel<1>, LTC_SMEM_BYTES ) );
    return 0;
 }
 
@@ -255,6 +286,7 @@ extern "C" void silero_b200_destroy( silero_b200 *h )
    cudaFree( h->d_out2 );
    cudaFree( h->d_f32 );
    cudaFree( h->d_flagged );
+   cudaFree( h->d_lstm_tc );
    for ( int i = 0; i < 2; ++i )
    {
       cudaFree( h->pcm_stage[i] );
@@ -308,6 +340,7 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    h->window_chunks_opt = opts.window_chunks;
    h->stft_mode = opts.stft_mode == SILERO_B200_STFT_EXACT ? SILERO_B200_STFT_EXACT : SILERO_B200_STFT_HYBRID;
    h->stft_k_rel = opts.stft_k_rel > 0.0f ? opts.stft_k_rel : SILERO_B200_STFT_K_REL_DEFAULT;
+   h->lstm_mode = ( opts.lstm_mode == SILERO_B200_LSTM_FP32 || opts.lstm_mode == SILERO_B200_LSTM_TENSOR ) ? opts.lstm_mode : SILERO_B200_LSTM_AUTO;
 
 #define CU_H( call )                                                                                   \
    do                                                                                                  \
@@ -380,6 +413,8 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    pack_layer<2>( tf.tensors + 49, host + o_l2 );
    pack_layer<3>( tf.tensors + 71, host + o_l3 );
    pack_lstm( tf.tensors[95].data, host + o_lstm );
+   unsigned char *tc_img = (unsigned char *)calloc( 2, LTC_W_BYTES );
+   if ( tc_img ) pack_lstm_tc( tf.tensors[95].data, tc_img );
    memcpy( host + o_lb, tf.tensors[96].data, sizeof( float ) * 512 );
    memcpy( host + o_dw, tf.tensors[97].data, sizeof( float ) * 128 );
    memcpy( host + o_db, tf.tensors[98].data, sizeof( float ) * 2 );
@@ -390,6 +425,10 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    cudaError_t ce = cudaMalloc( &h->d_weights, total * sizeof( float ) );
    if ( ce == cudaSuccess ) ce = cudaMemcpy( h->d_weights, host, total * sizeof( float ), cudaMemcpyHostToDevice );
    free( host );
+   if ( ce == cudaSuccess && !tc_img ) ce = cudaErrorMemoryAllocation;
+   if ( ce == cudaSuccess ) ce = cudaMalloc( &h->d_lstm_tc, 2 * LTC_W_BYTES );
+   if ( ce == cudaSuccess ) ce = cudaMemcpy( h->d_lstm_tc, tc_img, 2 * LTC_W_BYTES, cudaMemcpyHostToDevice );
+   free( tc_img );
    CU_H( ce );
    h->w.basis_pack = h->d_weights + o_basis;
    h->w.layer[0] = h->d_weights + o_l0;
@@ -467,19 +506,27 @@ static int grow( T **p, size_t *cap, size_t need )
    return 0;
 }
 
-static int ensure_scratch( silero_b200 *h, size_t chunks )
+static int ensure_scratch( silero_b200 *h, size_t chunks, size_t h0_floats )
 {
+   if ( h0_floats > h->cap_h0_floats )
+   {
+      CU( cudaStreamSynchronize( h->stream ) );
+      cudaFree( h->h0 );
+      h->h0 = 0;
+      h->cap_h0_floats = 0;
+      CU( cudaMalloc( &h->h0, h0_floats * sizeof( float ) ) );
+      h->cap_h0_floats = h0_floats;
+   }
    if ( chunks <= h->cap_chunks ) return 0;
    CU( cudaStreamSynchronize( h->stream ) );
-   cudaFree( h->spec ); cudaFree( h->a1 ); cudaFree( h->a2 ); cudaFree( h->a3 ); cudaFree( h->a4 ); cudaFree( h->h0 ); cudaFree( h->mu );
-   h->spec = h->a1 = h->a2 = h->a3 = h->a4 = h->h0 = h->mu = 0;
+   cudaFree( h->spec ); cudaFree( h->a1 ); cudaFree( h->a2 ); cudaFree( h->a3 ); cudaFree( h->a4 ); cudaFree( h->mu );
+   h->spec = h->a1 = h->a2 = h->a3 = h->a4 = h->mu = 0;
    h->cap_chunks = 0;
    CU( cudaMalloc( &h->spec, chunks * VB_BINS * VB_FRAMES * sizeof( float ) ) );
    CU( cudaMalloc( &h->a1, chunks * 13 * 16 * sizeof( float ) ) );
    CU( cudaMalloc( &h->a2, chunks * 7 * 32 * sizeof( float ) ) );
    CU( cudaMalloc( &h->a3, chunks * 7 * 32 * sizeof( float ) ) );
    CU( cudaMalloc( &h->a4, chunks * 7 * 64 * sizeof( float ) ) );
-   CU( cudaMalloc( &h->h0, chunks * 7 * 64 * sizeof( float ) ) );
    CU( cudaMalloc( &h->mu, chunks * sizeof( float ) ) );
    h->cap_chunks = chunks;
    return 0;
@@ -574,6 +621,30 @@ static int launch_lstm( silero_b200 *h, const float *x, float *hseq, int first_s
    return 0;
 }
 
+static bool lstm_use_tensor( const silero_b200 *h, int nstreams )
+{
+   if ( h->lstm_mode == SILERO_B200_LSTM_TENSOR ) return true;
+   if ( h->lstm_mode == SILERO_B200_LSTM_FP32 ) return false;
+   return nstreams >= SILERO_B200_LSTM_TENSOR_MIN_STREAMS;
+}
+
+// tensor-core LSTM (lstm_tc_kernel.cuh): layer 0 consumes a4 and leaves its packed h sequence in h->h0
+template <int LAYER>
+static int launch_lstm_tc( silero_b200 *h, const float *a4, int first_stream, int nstreams, int nw, float *d_out2, float *d_probs, long long out_stride,
+                           long long out_off )
+{
+   float *sh = h->state_h + (size_t)first_stream * SILERO_B200_STATE_FLOATS;
+   float *sc = h->state_c + (size_t)first_stream * SILERO_B200_STATE_FLOATS;
+   const int ntiles = ( nstreams + LTC_N - 1 ) / LTC_N;
+   const int grid = imin( ntiles, h->sm_count );
+   unsigned char *hp = reinterpret_cast<unsigned char *>( h->h0 );
+   lstm_tc_kernel<LAYER><<<grid, LTC_THREADS, LTC_SMEM_BYTES, h->stream>>>( a4, hp, hp, sh, sc, h->d_lstm_tc, h->w.lstm_b, h->w.dec_w, h->w.dec_b, nstreams, nw,
+                                                                            d_out2, d_probs, out_stride, out_off );
+   h->launches++;
+   CU( cudaGetLastError() );
+   return 0;
+}
+
 static void stage_mark( silero_b200 *h, int i )
 {
    if ( h->profiling ) cudaEventRecord( h->ev_stage[i], h->stream );
@@ -584,7 +655,8 @@ static int run_window( silero_b200 *h, const void *d_in, int in_f32, long long s
                        float *d_probs, long long out_stride, long long out_off, int accumulate_timing )
 {
    const int nchunks = nstreams * nw;
-   if ( ensure_scratch( h, (size_t)nchunks ) ) return SILERO_B200_ERR_CUDA;
+   const size_t h0_floats = (size_t)( ( nstreams + LTC_N - 1 ) / LTC_N ) * LTC_N * nw * 7 * 64;
+   if ( ensure_scratch( h, (size_t)nchunks, h0_floats ) ) return SILERO_B200_ERR_CUDA;
    stage_mark( h, 0 );
    const bool hybrid = h->stft_mode != SILERO_B200_STFT_EXACT;
    if ( launch_stft( h, d_in, in_f32, stream_stride, nw, nchunks, h->spec, 0, hybrid ? h->mu : 0 ) ) return SILERO_B200_ERR_CUDA;
@@ -599,9 +671,13 @@ static int run_window( silero_b200 *h, const void *d_in, int in_f32, long long s
    stage_mark( h, 4 );
    if ( launch_layer<3, false>( h, h->a3, h->a4, nchunks ) ) return SILERO_B200_ERR_CUDA;
    stage_mark( h, 5 );
-   if ( launch_lstm<0>( h, h->a4, h->h0, first_stream, nstreams, nw, 0, 0, 0, 0 ) ) return SILERO_B200_ERR_CUDA;
+   const bool tensor = lstm_use_tensor( h, nstreams );
+   if ( tensor ? launch_lstm_tc<0>( h, h->a4, first_stream, nstreams, nw, 0, 0, 0, 0 ) : launch_lstm<0>( h, h->a4, h->h0, first_stream, nstreams, nw, 0, 0, 0, 0 ) )
+      return SILERO_B200_ERR_CUDA;
    stage_mark( h, 6 );
-   if ( launch_lstm<1>( h, h->h0, 0, first_stream, nstreams, nw, d_out2, d_probs, out_stride, out_off ) ) return SILERO_B200_ERR_CUDA;
+   if ( tensor ? launch_lstm_tc<1>( h, 0, first_stream, nstreams, nw, d_out2, d_probs, out_stride, out_off )
+               : launch_lstm<1>( h, h->h0, 0, first_stream, nstreams, nw, d_out2, d_probs, out_stride, out_off ) )
+      return SILERO_B200_ERR_CUDA;
    stage_mark( h, 7 );
    if ( h->profiling && accumulate_timing )
    {
@@ -1259,4 +1335,25 @@ extern "C" int silero_b200_stage_decoder( silero_b200 *h, const float *in, int b
    decoder_kernel<<<( batch * 2 + 127 ) / 128, 128, 0, h->stream>>>( din.p, h->w.dec_w, h->w.dec_b, dout.p, batch );
    CU( cudaGetLastError() );
    return down( h, out, dout.p, (size_t)batch * 2 ) ? SILERO_B200_ERR_CUDA : SILERO_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tensor-core plumbing tap: D[128][N] = A[128][K] * B[N][K]^T on tcgen05 with the bf16xS split
+// ---------------------------------------------------------------------------------------------
+extern "C" int silero_b200_stage_tc_gemm( silero_b200 *h, const float *A, const float *B, int N, int K, int nsplit, int reps, float *D, long long *cycles )
+{
+   if ( !h || !A || !B || !D ) return set_err( SILERO_B200_ERR_ARG, "null argument" );
+   if ( N < 16 || N > 256 || ( N % 16 ) || K < 16 || K > 128 || ( K % 16 ) || nsplit < 1 || nsplit > 3 || reps < 1 )
+      return set_err( SILERO_B200_ERR_ARG, "tc_gemm: need N in 16..256 step 16, K in 16..128 step 16, nsplit 1..3" );
+   const size_t smem = (size_t)nsplit * ( K / 8 ) * ( 128 + N ) * 16;
+   if ( smem > 200 * 1024 ) return set_err( SILERO_B200_ERR_ARG, "tc_gemm: tile does not fit in shared memory" );
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+   DevBuf a, b, d, c;
+   if ( a.alloc( (size_t)128 * K ) || b.alloc( (size_t)N * K ) || d.alloc( (size_t)128 * N ) || c.alloc( 2 ) ) return SILERO_B200_ERR_CUDA;
+   if ( up( h, a.p, A, (size_t)128 * K ) || up( h, b.p, B, (size_t)N * K ) ) return SILERO_B200_ERR_CUDA;
+   tc_probe_kernel<<<1, TCP_THREADS, smem, h->stream>>>( a.p, b.p, d.p, N, K, nsplit, reps, reinterpret_cast<long long *>( c.p ) );
+   CU( cudaGetLastError() );
+   if ( down( h, D, d.p, (size_t)128 * N ) ) return SILERO_B200_ERR_CUDA;
+   if ( cycles ) CU( cudaMemcpy( cycles, c.p, sizeof( long long ), cudaMemcpyDeviceToHost ) );
+   return SILERO_B200_OK;
 }
