@@ -313,24 +313,38 @@ def main():
     # ---- end to end through the C ABI with host buffers --------------------------------------------
     h_pcm, h_pcm_ptr = vadc_b200.pinned_empty((S, C * CHUNK), np.int16)
     h_probs, h_probs_ptr = vadc_b200.pinned_empty((S, C), np.float32)
+    SEG_CAP = C // 2 + 2
+    h_segs, h_segs_ptr = vadc_b200.pinned_empty((S, SEG_CAP, 2), np.int32)
+    h_counts, h_counts_ptr = vadc_b200.pinned_empty((S,), np.int32)
     h_pcm[:] = bufs[0].cpu().numpy()
     eng.reset()
+    eng.segments_configure()
+
+    def e2e_step(last):
+        # synchronous: returns with the probabilities AND the finished speech segments (on-device segmenter) on the host
+        eng.run_streams_segments_ptr(h_pcm_ptr, C * CHUNK, S, C, last, h_segs_ptr, SEG_CAP, h_counts_ptr, h_probs_ptr)
+
     for k in range(2):
-        eng.run_streams_ptr(h_pcm_ptr, C * CHUNK, S, C, h_probs_ptr)
+        e2e_step(False)
+    eng.reset()
+    eng.segments_reset()
+    my_segments = [[] for _ in range(S)]
     barrier()
     t0 = time.perf_counter()
     for k in range(args.steps):
-        eng.run_streams_ptr(h_pcm_ptr, C * CHUNK, S, C, h_probs_ptr)   # synchronous: returns with the probabilities on the host
+        e2e_step(k == args.steps - 1)
+        if h_counts.max() > SEG_CAP:
+            raise SystemExit("segment capacity exceeded")
+        for s in np.nonzero(h_counts)[0]:                     # host side of the product: collect what the device emitted
+            my_segments[s] += [tuple(p) for p in h_segs[s, :h_counts[s]].tolist()]
     e2e_ms = (time.perf_counter() - t0) * 1e3
     barrier()
     e2e_ms = max_over_ranks(e2e_ms)
     e2e_value = audio_s / (e2e_ms / 1e3)
-    # the "final gather of per-stream segments": segment a few streams per rank, gather counts on rank 0
-    seg_count = sum(vadc_b200.segments_text(h_probs[s]).count("\n") for s in range(0, S, 512))
-    if world > 1:
-        counts = [None] * world
-        dist.all_gather_object(counts, seg_count)
-        seg_count = sum(counts)
+    # the "final gather of per-stream segments" (not timed): rank 0 receives every stream's (start, end) pairs
+    from vadc_b200 import shard
+    gathered = shard.gather_segments(my_segments, rank * S, world * S)
+    seg_count = sum(len(x) for x in gathered) if rank == 0 else 0
 
     # ---- CPU baseline (rank 0, N=1 only) --------------------------------------------------------------
     cpu = None
@@ -349,13 +363,16 @@ def main():
                        "streams_per_gpu": S, "chunks_per_step": C, "l2_policy": "inputs larger than L2 (1.57 GB PCM per step, rotating step buffers)",
                        "parity_max_abs_err_vs_oracle": parity, "segments_gathered": seg_count, "sharding": "streams across ranks, no collective on the data path"},
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": "audio-seconds/sec", "h2d_bytes_per_step": S * C * CHUNK * 2, "d2h_bytes_per_step": S * C * 4,
-                    "ms_per_step": e2e_ms / args.steps},
+            "e2e": {"value": e2e_value, "unit": "audio-seconds/sec", "h2d_bytes_per_step": S * C * CHUNK * 2, "d2h_bytes_per_step": S * C * 4 + S * SEG_CAP * 8 + S * 4,
+                    "ms_per_step": e2e_ms / args.steps,
+                    "call": "silero_b200_run_streams_segments: pinned host s16 PCM in; probabilities + on-device-segmenter (start,end) pairs out"},
             "gpu_launches": launches,
         }
         print(json.dumps(line))
     vadc_b200.pinned_free(h_pcm_ptr)
     vadc_b200.pinned_free(h_probs_ptr)
+    vadc_b200.pinned_free(h_segs_ptr)
+    vadc_b200.pinned_free(h_counts_ptr)
     eng.close()
     if world > 1:
         dist.destroy_process_group()

@@ -12,7 +12,8 @@
  *   silero_run_one_batch_with_context   silero_v3.c:72-215   silero_b200_run_chunks
  *   Silero_Context.state_lstm_h/c       tensor.h:89-95       per-stream device state + get/set/reset
  *   run_inference s16->f32 + process_chunks vadc.c:56-103,873-909   silero_b200_run_streams
- *   feed_probability / combine / emit   vadc.c:165-299,1005-1027    vadc_segments_* (vadc_segmenter.h)
+ *   feed_probability / combine / emit   vadc.c:165-299,1005-1027    vadc_segments_* (vadc_segmenter.h, host) and
+ *                                                            silero_b200_run_streams_segments* (same state machine on the device)
  *   load_testtensor(_from_bytes)        tensor.h:201-325     the .testtensor blob passed to create
  *   my_stft, adaptive_audio_normalization_inplace, transformer_layer, lstm_tensor_minibatched,
  *   decoder_tensor (stft.c:226, misc.c:1, transformer.c:237, lstm.c:228, silero_v3.c:305)
@@ -29,6 +30,8 @@
 
 #include <stddef.h>
 #include <stdint.h>
+
+#include "vadc_segmenter.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -117,6 +120,28 @@ int silero_b200_run_streams( silero_b200 *h, const int16_t *pcm, long long strea
 int silero_b200_run_streams_device( silero_b200 *h, const int16_t *d_pcm, long long stream_stride,
                                     int first_stream, int nstreams, int nchunks, float *d_probs, float *d_out2 );
 int silero_b200_sync( silero_b200 *h );
+
+/* ---- on-device segmenter: feed_probability / combine_or_emit_speech_segment / end-of-stream logic
+   (vadc.c:165-299, 1005-1027) as a per-stream scan on the GPU (vadc_b200/csrc/segment_kernel.cuh). Each of the
+   handle's streams carries its own FeedState + buffered candidate across calls, like its LSTM state, so only
+   finished (start_chunk, end_chunk) pairs leave the device instead of the [streams][chunks] probabilities.
+   Pairs are bit-identical to vadc_segmenter_feed/finish on the same probabilities; format them with
+   vadc_segment_format. configure(NULL) = the reference's option defaults; configure resets every stream's
+   segmenter state (not its LSTM state). */
+int silero_b200_segments_configure( silero_b200 *h, const vadc_seg_params *params );
+int silero_b200_segments_reset( silero_b200 *h, int first_stream, int nstreams );
+/* run_streams + segmentation. segs: host [nstreams][cap] pairs finished by THIS call, counts: host [nstreams]
+   (a count above cap means the excess pairs were dropped; nchunks/(min_speech+min_silence chunks)+2 always suffices).
+   end_of_stream != 0 additionally closes an open segment and flushes the buffered one (nchunks may then be 0).
+   probs (optional, may be NULL): host f32 [nstreams][nchunks]. */
+int silero_b200_run_streams_segments( silero_b200 *h, const int16_t *pcm, long long stream_stride, int first_stream, int nstreams, int nchunks,
+                                      int end_of_stream, vadc_segment *segs, int cap, int *counts, float *probs );
+/* same with every buffer in DEVICE memory; asynchronous (silero_b200_sync). d_probs may be NULL (internal scratch). */
+int silero_b200_run_streams_segments_device( silero_b200 *h, const int16_t *d_pcm, long long stream_stride, int first_stream, int nstreams, int nchunks,
+                                             int end_of_stream, float *d_probs, vadc_segment *d_segs, int cap, int *d_counts );
+/* the segmenter alone on device-resident probabilities: stream s, chunk n at d_probs[s*stride + n] */
+int silero_b200_segment_probs_device( silero_b200 *h, const float *d_probs, long long stride, int first_stream, int nstreams, int nchunks,
+                                      int end_of_stream, vadc_segment *d_segs, int cap, int *d_counts );
 
 /* per-stream LSTM state (zero after create / reset); h_out,c_out: host f32 [128] = [2][64] */
 int silero_b200_reset( silero_b200 *h, int first_stream, int nstreams );

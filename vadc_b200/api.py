@@ -147,6 +147,50 @@ class Engine:
     def sync(self):
         self._check(lib().silero_b200_sync(self._h))
 
+    # ---- on-device segmenter --------------------------------------------------------------------
+    def segments_configure(self, params=None):
+        self._check(lib().silero_b200_segments_configure(self._h, C.byref(params) if params is not None else None))
+
+    def segments_reset(self, first_stream=0, nstreams=None):
+        self._check(lib().silero_b200_segments_reset(self._h, first_stream, self.max_streams - first_stream if nstreams is None else nstreams))
+
+    def run_streams_segments(self, pcm, nchunks=None, end_of_stream=False, cap=None, first_stream=0, want_probs=False):
+        """pcm: int16 [S, nsamples] host array (or None with end_of_stream to only flush). Returns a list of
+        [(start_chunk, end_chunk), ...] per stream (pairs finished by this call), plus probs if asked."""
+        if pcm is None:
+            S, nchunks = self.max_streams - first_stream, 0
+            ptr, stride = None, 0
+        else:
+            assert pcm.dtype == np.int16 and pcm.ndim == 2 and pcm.strides[1] == 2
+            S = pcm.shape[0]
+            if nchunks is None:
+                nchunks = pcm.shape[1] // CHUNK
+            ptr, stride = _p(pcm), pcm.strides[0] // 2
+        if cap is None:
+            cap = nchunks // 2 + 2
+        segs = np.zeros((S, cap, 2), np.int32)
+        counts = np.zeros(S, np.int32)
+        probs = np.zeros((S, nchunks), np.float32) if want_probs else None
+        self._check(lib().silero_b200_run_streams_segments(self._h, ptr, C.c_longlong(stride), first_stream, S, nchunks,
+                                                           1 if end_of_stream else 0, _p(segs), cap, _p(counts), _p(probs)))
+        out = [[(int(a), int(b)) for a, b in segs[s, :min(int(counts[s]), cap)]] for s in range(S)]
+        return (out, counts, probs) if want_probs else (out, counts)
+
+    def run_streams_segments_ptr(self, pcm_ptr, stream_stride, nstreams, nchunks, end_of_stream, segs_ptr, cap, counts_ptr, probs_ptr=None, first_stream=0):
+        """Raw-pointer form (pinned host buffers): segs int32 [nstreams][cap][2], counts int32 [nstreams]."""
+        self._check(lib().silero_b200_run_streams_segments(self._h, C.c_void_p(pcm_ptr) if pcm_ptr else None, C.c_longlong(stream_stride), first_stream,
+                                                           nstreams, nchunks, 1 if end_of_stream else 0, C.c_void_p(segs_ptr), cap,
+                                                           C.c_void_p(counts_ptr), C.c_void_p(probs_ptr) if probs_ptr else None))
+
+    def run_streams_segments_device(self, d_pcm, stream_stride, nstreams, nchunks, end_of_stream, d_segs, cap, d_counts, d_probs=None, first_stream=0):
+        self._check(lib().silero_b200_run_streams_segments_device(self._h, C.c_void_p(d_pcm) if d_pcm else None, C.c_longlong(stream_stride), first_stream,
+                                                                  nstreams, nchunks, 1 if end_of_stream else 0,
+                                                                  C.c_void_p(d_probs) if d_probs else None, C.c_void_p(d_segs), cap, C.c_void_p(d_counts)))
+
+    def segment_probs_device(self, d_probs, stride, nstreams, nchunks, end_of_stream, d_segs, cap, d_counts, first_stream=0):
+        self._check(lib().silero_b200_segment_probs_device(self._h, C.c_void_p(d_probs) if d_probs else None, C.c_longlong(stride), first_stream, nstreams,
+                                                           nchunks, 1 if end_of_stream else 0, C.c_void_p(d_segs), cap, C.c_void_p(d_counts)))
+
     def reset(self, first_stream=0, nstreams=None):
         self._check(lib().silero_b200_reset(self._h, first_stream, self.max_streams - first_stream if nstreams is None else nstreams))
 

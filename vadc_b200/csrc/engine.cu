@@ -17,10 +17,12 @@
 #include "layer_kernel.cuh"
 #include "lstm_kernel.cuh"
 #include "lstm_tc_kernel.cuh"
+#include "segment_kernel.cuh"
 #include "stft_hybrid_kernel.cuh"
 #include "stft_kernel.cuh"
 #include "tc_probe.cuh"
 #include "testtensor.h"
+#include "vadc_segmenter.h"
 
 // ---------------------------------------------------------------------------------------------
 // errors
@@ -82,6 +84,13 @@ struct silero_b200
    size_t d_out2_cap;
    float *d_f32;
    size_t d_f32_cap;
+   // on-device segmenter (segment_kernel.cuh): per-stream FeedState + buffered candidate, output staging
+   SegStateDev *d_seg_state; // [max_streams]
+   SegParamsDev seg_params;
+   SegPair *d_segs;
+   size_t d_segs_cap;
+   int *d_counts;
+   size_t d_counts_cap;
    // timing
    int profiling;
    cudaEvent_t ev_begin, ev_end;
@@ -287,6 +296,9 @@ extern "C" void silero_b200_destroy( silero_b200 *h )
    cudaFree( h->d_f32 );
    cudaFree( h->d_flagged );
    cudaFree( h->d_lstm_tc );
+   cudaFree( h->d_seg_state );
+   cudaFree( h->d_segs );
+   cudaFree( h->d_counts );
    for ( int i = 0; i < 2; ++i )
    {
       cudaFree( h->pcm_stage[i] );
@@ -300,6 +312,25 @@ extern "C" void silero_b200_destroy( silero_b200 *h )
    if ( h->stream ) cudaStreamDestroy( h->stream );
    if ( h->copy_stream ) cudaStreamDestroy( h->copy_stream );
    free( h );
+}
+
+// derived segmenter constants exactly as the host state machine computes them (segmenter.c: vadc_segmenter_init)
+static void set_seg_params( silero_b200 *h, const vadc_seg_params *p_in )
+{
+   vadc_seg_params p;
+   if ( p_in )
+      p = *p_in;
+   else
+      vadc_seg_params_default( &p );
+   vadc_segmenter s;
+   vadc_segmenter_init( &s, &p );
+   h->seg_params.threshold = p.threshold;
+   h->seg_params.neg_threshold = s.neg_threshold;
+   h->seg_params.seconds_per_chunk = s.seconds_per_chunk;
+   h->seg_params.pad_seconds = p.speech_pad_ms / 1000.0f; // vadc.c:231
+   h->seg_params.min_speech_chunks = s.min_speech_chunks;
+   h->seg_params.min_silence_chunks = s.min_silence_chunks;
+   h->seg_params.chunk_samples = p.chunk_samples;
 }
 
 static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts *opts_in, silero_b200 **out )
@@ -448,6 +479,9 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    CU_H( cudaMalloc( &h->state_c, sbytes ) );
    CU_H( cudaMemset( h->state_h, 0, sbytes ) );
    CU_H( cudaMemset( h->state_c, 0, sbytes ) );
+   CU_H( cudaMalloc( &h->d_seg_state, (size_t)h->max_streams * sizeof( SegStateDev ) ) );
+   CU_H( cudaMemset( h->d_seg_state, 0, (size_t)h->max_streams * sizeof( SegStateDev ) ) );
+   set_seg_params( h, 0 );
 #undef CU_H
    *out = h;
    return SILERO_B200_OK;
@@ -745,59 +779,166 @@ extern "C" int silero_b200_sync( silero_b200 *h )
    return SILERO_B200_OK;
 }
 
-extern "C" int silero_b200_run_streams( silero_b200 *h, const int16_t *pcm, long long stream_stride, int first_stream, int nstreams, int nchunks,
-                                        float *probs, float *out2 )
+// ---- on-device segmenter launches -------------------------------------------------------------
+static int launch_segments( silero_b200 *h, const float *d_probs, long long stride, long long off, int first_stream, int nstreams, int nchunks, int finish,
+                            SegPair *d_segs, int cap, int *d_counts )
+{
+   const int threads = 128;
+   segment_scan_kernel<<<( nstreams + threads - 1 ) / threads, threads, 0, h->stream>>>( d_probs, stride, off, nchunks, h->d_seg_state + first_stream, nstreams,
+                                                                                        h->seg_params, finish, d_segs, cap, d_counts );
+   h->launches++;
+   CU( cudaGetLastError() );
+   return 0;
+}
+
+struct SegRequest
+{
+   int finish, cap;
+   vadc_segment *segs; // host [nstreams][cap]
+   int *counts;        // host [nstreams]
+};
+
+static int run_streams_host( silero_b200 *h, const int16_t *pcm, long long stream_stride, int first_stream, int nstreams, int nchunks, float *probs, float *out2,
+                             const SegRequest *seg )
 {
    int rc = check_streams( h, first_stream, nstreams, nchunks );
    if ( rc ) return rc;
-   if ( nstreams == 0 || nchunks == 0 ) return SILERO_B200_OK;
-   if ( !pcm ) return set_err( SILERO_B200_ERR_ARG, "null pcm" );
+   if ( nstreams == 0 ) return SILERO_B200_OK;
+   if ( nchunks == 0 && !( seg && seg->finish ) ) return SILERO_B200_OK;
+   if ( nchunks > 0 && !pcm ) return set_err( SILERO_B200_ERR_ARG, "null pcm" );
+   if ( seg && ( !seg->segs || !seg->counts || seg->cap < 1 ) ) return set_err( SILERO_B200_ERR_ARG, "segments: null output or cap < 1" );
    if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
 
-   const int nw_max = pick_window( h, nstreams, nchunks );
-   const size_t win_samples = (size_t)nstreams * nw_max * VB_CHUNK;
-   if ( win_samples > h->pcm_stage_cap )
-   {
-      CU( cudaStreamSynchronize( h->stream ) );
-      CU( cudaStreamSynchronize( h->copy_stream ) );
-      for ( int i = 0; i < 2; ++i )
-      {
-         if ( h->pcm_stage[i] ) CU( cudaFree( h->pcm_stage[i] ) );
-         h->pcm_stage[i] = 0;
-      }
-      h->pcm_stage_cap = 0;
-      for ( int i = 0; i < 2; ++i ) CU( cudaMalloc( &h->pcm_stage[i], win_samples * sizeof( int16_t ) ) );
-      h->pcm_stage_cap = win_samples;
-   }
    const size_t nout = (size_t)nstreams * nchunks;
-   if ( probs && grow( &h->d_probs, &h->d_probs_cap, nout ) ) return SILERO_B200_ERR_CUDA;
+   if ( ( probs || seg ) && grow( &h->d_probs, &h->d_probs_cap, nout ? nout : 1 ) ) return SILERO_B200_ERR_CUDA;
    if ( out2 && grow( &h->d_out2, &h->d_out2_cap, nout * 2 ) ) return SILERO_B200_ERR_CUDA;
+   if ( seg )
+   {
+      if ( grow( &h->d_segs, &h->d_segs_cap, (size_t)nstreams * seg->cap ) ) return SILERO_B200_ERR_CUDA;
+      if ( grow( &h->d_counts, &h->d_counts_cap, (size_t)nstreams ) ) return SILERO_B200_ERR_CUDA;
+   }
 
    timing_begin( h );
-   const int nwin = ( nchunks + nw_max - 1 ) / nw_max;
-   // window w is copied on copy_stream into stage[w&1] while window w-1 computes
-   auto issue_copy = [&]( int w ) -> int {
-      int n0 = w * nw_max, nw = imin( nw_max, nchunks - n0 ), b = w & 1;
-      if ( w >= 2 ) CU( cudaStreamWaitEvent( h->copy_stream, h->pcm_free[b], 0 ) );
-      CU( cudaMemcpy2DAsync( h->pcm_stage[b], (size_t)nw * VB_CHUNK * sizeof( int16_t ), pcm + (long long)n0 * VB_CHUNK,
-                             (size_t)stream_stride * sizeof( int16_t ), (size_t)nw * VB_CHUNK * sizeof( int16_t ), (size_t)nstreams,
-                             cudaMemcpyHostToDevice, h->copy_stream ) );
-      CU( cudaEventRecord( h->pcm_ready[b], h->copy_stream ) );
-      return 0;
-   };
-   if ( issue_copy( 0 ) ) return SILERO_B200_ERR_CUDA;
-   for ( int w = 0; w < nwin; ++w )
+   if ( nchunks > 0 )
    {
-      int n0 = w * nw_max, nw = imin( nw_max, nchunks - n0 ), b = w & 1;
-      if ( w + 1 < nwin && issue_copy( w + 1 ) ) return SILERO_B200_ERR_CUDA;
-      CU( cudaStreamWaitEvent( h->stream, h->pcm_ready[b], 0 ) );
-      rc = run_window( h, h->pcm_stage[b], 0, (long long)nw * VB_CHUNK, first_stream, nstreams, nw, out2 ? h->d_out2 : 0, probs ? h->d_probs : 0, nchunks, n0, 1 );
-      if ( rc ) return rc;
-      CU( cudaEventRecord( h->pcm_free[b], h->stream ) );
+      const int nw_max = pick_window( h, nstreams, nchunks );
+      const size_t win_samples = (size_t)nstreams * nw_max * VB_CHUNK;
+      if ( win_samples > h->pcm_stage_cap )
+      {
+         CU( cudaStreamSynchronize( h->stream ) );
+         CU( cudaStreamSynchronize( h->copy_stream ) );
+         for ( int i = 0; i < 2; ++i )
+         {
+            if ( h->pcm_stage[i] ) CU( cudaFree( h->pcm_stage[i] ) );
+            h->pcm_stage[i] = 0;
+         }
+         h->pcm_stage_cap = 0;
+         for ( int i = 0; i < 2; ++i ) CU( cudaMalloc( &h->pcm_stage[i], win_samples * sizeof( int16_t ) ) );
+         h->pcm_stage_cap = win_samples;
+         cudaEventRecord( h->ev_begin, h->stream );
+      }
+      const int nwin = ( nchunks + nw_max - 1 ) / nw_max;
+      // window w is copied on copy_stream into stage[w&1] while window w-1 computes
+      auto issue_copy = [&]( int w ) -> int {
+         int n0 = w * nw_max, nw = imin( nw_max, nchunks - n0 ), b = w & 1;
+         if ( w >= 2 ) CU( cudaStreamWaitEvent( h->copy_stream, h->pcm_free[b], 0 ) );
+         CU( cudaMemcpy2DAsync( h->pcm_stage[b], (size_t)nw * VB_CHUNK * sizeof( int16_t ), pcm + (long long)n0 * VB_CHUNK,
+                                (size_t)stream_stride * sizeof( int16_t ), (size_t)nw * VB_CHUNK * sizeof( int16_t ), (size_t)nstreams,
+                                cudaMemcpyHostToDevice, h->copy_stream ) );
+         CU( cudaEventRecord( h->pcm_ready[b], h->copy_stream ) );
+         return 0;
+      };
+      if ( issue_copy( 0 ) ) return SILERO_B200_ERR_CUDA;
+      const bool need_probs = probs || seg;
+      for ( int w = 0; w < nwin; ++w )
+      {
+         int n0 = w * nw_max, nw = imin( nw_max, nchunks - n0 ), b = w & 1;
+         if ( w + 1 < nwin && issue_copy( w + 1 ) ) return SILERO_B200_ERR_CUDA;
+         CU( cudaStreamWaitEvent( h->stream, h->pcm_ready[b], 0 ) );
+         rc = run_window( h, h->pcm_stage[b], 0, (long long)nw * VB_CHUNK, first_stream, nstreams, nw, out2 ? h->d_out2 : 0, need_probs ? h->d_probs : 0, nchunks, n0, 1 );
+         if ( rc ) return rc;
+         CU( cudaEventRecord( h->pcm_free[b], h->stream ) );
+      }
    }
-   if ( probs ) CU( cudaMemcpyAsync( probs, h->d_probs, nout * sizeof( float ), cudaMemcpyDeviceToHost, h->stream ) );
-   if ( out2 ) CU( cudaMemcpyAsync( out2, h->d_out2, nout * 2 * sizeof( float ), cudaMemcpyDeviceToHost, h->stream ) );
+   if ( seg )
+   {
+      if ( launch_segments( h, h->d_probs, nchunks, 0, first_stream, nstreams, nchunks, seg->finish, h->d_segs, seg->cap, h->d_counts ) ) return SILERO_B200_ERR_CUDA;
+      CU( cudaMemcpyAsync( seg->counts, h->d_counts, (size_t)nstreams * sizeof( int ), cudaMemcpyDeviceToHost, h->stream ) );
+      CU( cudaMemcpyAsync( seg->segs, h->d_segs, (size_t)nstreams * seg->cap * sizeof( SegPair ), cudaMemcpyDeviceToHost, h->stream ) );
+   }
+   if ( probs && nout ) CU( cudaMemcpyAsync( probs, h->d_probs, nout * sizeof( float ), cudaMemcpyDeviceToHost, h->stream ) );
+   if ( out2 && nout ) CU( cudaMemcpyAsync( out2, h->d_out2, nout * 2 * sizeof( float ), cudaMemcpyDeviceToHost, h->stream ) );
    timing_end( h );
+   CU( cudaStreamSynchronize( h->stream ) );
+   return SILERO_B200_OK;
+}
+
+extern "C" int silero_b200_run_streams( silero_b200 *h, const int16_t *pcm, long long stream_stride, int first_stream, int nstreams, int nchunks,
+                                        float *probs, float *out2 )
+{
+   return run_streams_host( h, pcm, stream_stride, first_stream, nstreams, nchunks, probs, out2, 0 );
+}
+
+static_assert( sizeof( SegPair ) == sizeof( vadc_segment ), "device and host segment records must have the same layout" );
+
+extern "C" int silero_b200_run_streams_segments( silero_b200 *h, const int16_t *pcm, long long stream_stride, int first_stream, int nstreams, int nchunks,
+                                                 int end_of_stream, vadc_segment *segs, int cap, int *counts, float *probs )
+{
+   SegRequest rq = { end_of_stream, cap, segs, counts };
+   return run_streams_host( h, pcm, stream_stride, first_stream, nstreams, nchunks, probs, 0, &rq );
+}
+
+extern "C" int silero_b200_segment_probs_device( silero_b200 *h, const float *d_probs, long long stride, int first_stream, int nstreams, int nchunks,
+                                                 int end_of_stream, vadc_segment *d_segs, int cap, int *d_counts )
+{
+   int rc = check_streams( h, first_stream, nstreams, nchunks );
+   if ( rc ) return rc;
+   if ( nstreams == 0 ) return SILERO_B200_OK;
+   if ( ( nchunks > 0 && !d_probs ) || !d_segs || !d_counts || cap < 1 ) return set_err( SILERO_B200_ERR_ARG, "segments: null buffer or cap < 1" );
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+   return launch_segments( h, d_probs, stride, 0, first_stream, nstreams, nchunks, end_of_stream, reinterpret_cast<SegPair *>( d_segs ), cap, d_counts );
+}
+
+extern "C" int silero_b200_run_streams_segments_device( silero_b200 *h, const int16_t *d_pcm, long long stream_stride, int first_stream, int nstreams, int nchunks,
+                                                        int end_of_stream, float *d_probs, vadc_segment *d_segs, int cap, int *d_counts )
+{
+   int rc = check_streams( h, first_stream, nstreams, nchunks );
+   if ( rc ) return rc;
+   if ( nstreams == 0 ) return SILERO_B200_OK;
+   if ( !d_segs || !d_counts || cap < 1 ) return set_err( SILERO_B200_ERR_ARG, "segments: null buffer or cap < 1" );
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+   if ( !d_probs )
+   {
+      if ( grow( &h->d_probs, &h->d_probs_cap, (size_t)nstreams * ( nchunks ? nchunks : 1 ) ) ) return SILERO_B200_ERR_CUDA;
+      d_probs = h->d_probs;
+   }
+   if ( nchunks > 0 )
+   {
+      rc = silero_b200_run_streams_device( h, d_pcm, stream_stride, first_stream, nstreams, nchunks, d_probs, 0 );
+      if ( rc ) return rc;
+   }
+   if ( launch_segments( h, d_probs, nchunks, 0, first_stream, nstreams, nchunks, end_of_stream, reinterpret_cast<SegPair *>( d_segs ), cap, d_counts ) )
+      return SILERO_B200_ERR_CUDA;
+   timing_end( h );
+   return SILERO_B200_OK;
+}
+
+extern "C" int silero_b200_segments_configure( silero_b200 *h, const vadc_seg_params *params )
+{
+   if ( !h ) return set_err( SILERO_B200_ERR_ARG, "null handle" );
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+   set_seg_params( h, params );
+   CU( cudaMemsetAsync( h->d_seg_state, 0, (size_t)h->max_streams * sizeof( SegStateDev ), h->stream ) );
+   CU( cudaStreamSynchronize( h->stream ) );
+   return SILERO_B200_OK;
+}
+
+extern "C" int silero_b200_segments_reset( silero_b200 *h, int first_stream, int nstreams )
+{
+   int rc = check_streams( h, first_stream, nstreams, 0 );
+   if ( rc ) return rc;
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+   CU( cudaMemsetAsync( h->d_seg_state + first_stream, 0, (size_t)nstreams * sizeof( SegStateDev ), h->stream ) );
    CU( cudaStreamSynchronize( h->stream ) );
    return SILERO_B200_OK;
 }
