@@ -67,6 +67,16 @@ typedef struct silero_b200 silero_b200; /* opaque engine handle */
 #define SILERO_B200_LSTM_TENSOR 2
 #define SILERO_B200_LSTM_TENSOR_MIN_STREAMS 1024
 
+/* Encoder layers 2..4. FP32: every contraction as in-thread fp32 FMA chains on the CUDA cores.
+   TENSOR: the six dense contractions of a layer as tcgen05 tensor-core GEMMs over tiles of 128 tokens with the fp16x2
+   split (hi/lo, 3 partial products, 22 significant bits per operand, fp32 accumulation); depthwise conv, attention core,
+   layer/batch norm stay fp32 on the CUDA cores. AUTO picks TENSOR from SILERO_B200_LAYERS_TENSOR_MIN_CHUNKS chunks per
+   pass up. The first layer (129 -> 16 channels) always runs on the CUDA cores. */
+#define SILERO_B200_LAYERS_AUTO 0
+#define SILERO_B200_LAYERS_FP32 1
+#define SILERO_B200_LAYERS_TENSOR 2
+#define SILERO_B200_LAYERS_TENSOR_MIN_CHUNKS 2048
+
 typedef struct silero_b200_opts
 {
    int device;          /* CUDA device ordinal (default 0) */
@@ -75,7 +85,8 @@ typedef struct silero_b200_opts
    int stft_mode;       /* SILERO_B200_STFT_HYBRID (default) or SILERO_B200_STFT_EXACT */
    float stft_k_rel;    /* hybrid threshold; 0 = SILERO_B200_STFT_K_REL_DEFAULT */
    int lstm_mode;       /* SILERO_B200_LSTM_AUTO (default), _FP32 (CUDA-core kernel) or _TENSOR (tcgen05 kernel) */
-   int reserved[2];
+   int layer_mode;      /* SILERO_B200_LAYERS_AUTO (default), _FP32 (CUDA-core kernels) or _TENSOR (tcgen05 kernel) */
+   int reserved[1];
 } silero_b200_opts;
 
 void silero_b200_default_opts( silero_b200_opts *opts );

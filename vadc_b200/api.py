@@ -17,6 +17,7 @@ CHUNK = 1536
 SAMPLE_RATE = 16000
 STFT_HYBRID, STFT_EXACT = 0, 1
 LSTM_AUTO, LSTM_FP32, LSTM_TENSOR = 0, 1, 2
+LAYERS_AUTO, LAYERS_FP32, LAYERS_TENSOR = 0, 1, 2
 
 
 class EngineError(RuntimeError):
@@ -25,7 +26,7 @@ class EngineError(RuntimeError):
 
 class Opts(C.Structure):
     _fields_ = [("device", C.c_int), ("max_streams", C.c_int), ("window_chunks", C.c_int), ("stft_mode", C.c_int),
-                ("stft_k_rel", C.c_float), ("lstm_mode", C.c_int), ("reserved", C.c_int * 2)]
+                ("stft_k_rel", C.c_float), ("lstm_mode", C.c_int), ("layer_mode", C.c_int), ("reserved", C.c_int * 1)]
 
 
 class Info(C.Structure):
@@ -79,12 +80,12 @@ def _f32(a):
 class Engine:
     """One engine per GPU (silero_b200 handle)."""
 
-    def __init__(self, weights=None, device=0, max_streams=1, window_chunks=0, stft_mode=0, stft_k_rel=0.0, lstm_mode=0):
+    def __init__(self, weights=None, device=0, max_streams=1, window_chunks=0, stft_mode=0, stft_k_rel=0.0, lstm_mode=0, layer_mode=0):
         L = lib()
         opts = Opts()
         L.silero_b200_default_opts(C.byref(opts))
         opts.device, opts.max_streams, opts.window_chunks = device, max_streams, window_chunks
-        opts.stft_mode, opts.stft_k_rel, opts.lstm_mode = stft_mode, stft_k_rel, lstm_mode
+        opts.stft_mode, opts.stft_k_rel, opts.lstm_mode, opts.layer_mode = stft_mode, stft_k_rel, lstm_mode, layer_mode
         self._h = C.c_void_p()
         if weights is None:
             weights = WEIGHTS_PATH

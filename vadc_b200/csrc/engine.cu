@@ -15,6 +15,7 @@
 
 #include "common.cuh"
 #include "layer_kernel.cuh"
+#include "layer_tc_kernel.cuh"
 #include "lstm_kernel.cuh"
 #include "lstm_tc_kernel.cuh"
 #include "segment_kernel.cuh"
@@ -63,6 +64,8 @@ struct silero_b200
    float stft_k_rel;         // hybrid: exact re-evaluation below k_rel * ||frame||
    int lstm_mode;            // SILERO_B200_LSTM_*
    unsigned char *d_lstm_tc; // [2 layers][LTC_W_BYTES] bf16 hi/lo weight images (lstm_tc_kernel.cuh)
+   int layer_mode;           // SILERO_B200_LAYERS_*
+   unsigned char *d_layer_tc[4]; // fp16 hi/lo weight images + fp32 parameters of layers 2..4 (layer_tc_kernel.cuh); [0] unused
    size_t cap_h0_floats;
    unsigned long long *d_flagged; // bins that took the exact path (device counter)
    unsigned long long bins_total;
@@ -235,6 +238,60 @@ static void pack_lstm_tc( const float *w /*[2][256][128]*/, unsigned char *img /
       }
 }
 
+// fp16 hi/lo image of one [N][K] weight matrix in the operand order of tc_common.cuh: [split][K/8][N][8]
+static void pack_f16_split( const float *w, int ldw, int N, int K, unsigned char *img )
+{
+   const size_t split_bytes = (size_t)( K / 8 ) * N * 16;
+   for ( int n = 0; n < N; ++n )
+      for ( int k = 0; k < K; ++k )
+      {
+         const float v = w[(size_t)n * ldw + k];
+         const __half hi = __float2half_rn( v );
+         const __half lo = __float2half_rn( v - __half2float( hi ) );
+         const size_t off = (size_t)( k >> 3 ) * N * 16 + (size_t)n * 16 + (size_t)( k & 7 ) * 2;
+         memcpy( img + off, &hi, 2 );
+         memcpy( img + split_bytes + off, &lo, 2 );
+      }
+}
+
+// image of one layer for layer_tc_kernel<L>, built from the validated fp32 LayerPack<L> blob
+template <int L>
+static void pack_layer_tc( const float *blob, unsigned char *img )
+{
+   using P = LayerPack<L>;
+   using Cfg = LtcCfg<L>;
+   constexpr int C = P::C, D = P::D, CIN = P::CIN;
+   memset( img, 0, Cfg::IMG_BYTES );
+   pack_f16_split( blob + P::PW, P::KP, C, P::KP, img + Cfg::W_PW ); // row o = [pw_w[o][:], proj_w[o][:]]
+   // fused QKV: rows in head-major order [h][q(D) k(D) v(D)], exactly the blob's per-head blocks
+   {
+      float *tmp = (float *)malloc( sizeof( float ) * 3 * C * C );
+      for ( int h = 0; h < 2; ++h ) memcpy( tmp + (size_t)h * 3 * D * C, blob + P::QKV + h * P::QH, sizeof( float ) * 3 * D * C );
+      pack_f16_split( tmp, C, 3 * C, C, img + Cfg::W_QKV );
+      free( tmp );
+   }
+   pack_f16_split( blob + P::AO, C, C, C, img + Cfg::W_AO );
+   pack_f16_split( blob + P::F1, C, C, C, img + Cfg::W_F1 );
+   pack_f16_split( blob + P::F2, C, C, C, img + Cfg::W_F2 );
+   pack_f16_split( blob + P::CV, C, C, C, img + Cfg::W_CV );
+   float *f = reinterpret_cast<float *>( img + Cfg::W_END );
+   memcpy( f + Cfg::F_DW, blob + P::DW, sizeof( float ) * CIN * 8 );
+   memcpy( f + Cfg::F_PWB, blob + P::PWB, sizeof( float ) * C );
+   for ( int h = 0; h < 2; ++h ) memcpy( f + Cfg::F_QKVB + h * 3 * D, blob + P::QKV + h * P::QH + 3 * D * C, sizeof( float ) * 3 * D );
+   memcpy( f + Cfg::F_AOB, blob + P::AOB, sizeof( float ) * C );
+   memcpy( f + Cfg::F_LN1W, blob + P::LN1W, sizeof( float ) * C );
+   memcpy( f + Cfg::F_LN1B, blob + P::LN1B, sizeof( float ) * C );
+   memcpy( f + Cfg::F_F1B, blob + P::F1B, sizeof( float ) * C );
+   memcpy( f + Cfg::F_F2B, blob + P::F2B, sizeof( float ) * C );
+   memcpy( f + Cfg::F_LN2W, blob + P::LN2W, sizeof( float ) * C );
+   memcpy( f + Cfg::F_LN2B, blob + P::LN2B, sizeof( float ) * C );
+   memcpy( f + Cfg::F_CVB, blob + P::CVB, sizeof( float ) * C );
+   memcpy( f + Cfg::F_BNM, blob + P::BNM, sizeof( float ) * C );
+   memcpy( f + Cfg::F_BNS, blob + P::BNS, sizeof( float ) * C );
+   memcpy( f + Cfg::F_BNW, blob + P::BNW, sizeof( float ) * C );
+   memcpy( f + Cfg::F_BNB, blob + P::BNB, sizeof( float ) * C );
+}
+
 // ---------------------------------------------------------------------------------------------
 // create / destroy
 // ---------------------------------------------------------------------------------------------
@@ -247,6 +304,7 @@ extern "C" void silero_b200_default_opts( silero_b200_opts *o )
    o->stft_mode = SILERO_B200_STFT_HYBRID;
    o->stft_k_rel = 0.0f; /* 0 = default (SILERO_B200_STFT_K_REL_DEFAULT) */
    o->lstm_mode = SILERO_B200_LSTM_AUTO;
+   o->layer_mode = SILERO_B200_LAYERS_AUTO;
 }
 
 template <typename K>
@@ -273,6 +331,9 @@ static int configure_kernels()
    CU( allow_smem( tc_probe_kernel, 200 * 1024 ) );
    CU( allow_smem( lstm_tc_kernel<0>, LTC_SMEM_BYTES ) );
    CU( allow_smem( lstm_tc_kernel<1>, LTC_SMEM_BYTES ) );
+   CU( allow_smem( layer_tc_kernel<1>, LtcCfg<1>::SMEM_BYTES ) );
+   CU( allow_smem( layer_tc_kernel<2>, LtcCfg<2>::SMEM_BYTES ) );
+   CU( allow_smem( layer_tc_kernel<3>, LtcCfg<3>::SMEM_BYTES ) );
    return 0;
 }
 
@@ -296,6 +357,7 @@ extern "C" void silero_b200_destroy( silero_b200 *h )
    cudaFree( h->d_f32 );
    cudaFree( h->d_flagged );
    cudaFree( h->d_lstm_tc );
+   for ( int i = 0; i < 4; ++i ) cudaFree( h->d_layer_tc[i] );
    cudaFree( h->d_seg_state );
    cudaFree( h->d_segs );
    cudaFree( h->d_counts );
@@ -372,6 +434,7 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    h->stft_mode = opts.stft_mode == SILERO_B200_STFT_EXACT ? SILERO_B200_STFT_EXACT : SILERO_B200_STFT_HYBRID;
    h->stft_k_rel = opts.stft_k_rel > 0.0f ? opts.stft_k_rel : SILERO_B200_STFT_K_REL_DEFAULT;
    h->lstm_mode = ( opts.lstm_mode == SILERO_B200_LSTM_FP32 || opts.lstm_mode == SILERO_B200_LSTM_TENSOR ) ? opts.lstm_mode : SILERO_B200_LSTM_AUTO;
+   h->layer_mode = ( opts.layer_mode == SILERO_B200_LAYERS_FP32 || opts.layer_mode == SILERO_B200_LAYERS_TENSOR ) ? opts.layer_mode : SILERO_B200_LAYERS_AUTO;
 
 #define CU_H( call )                                                                                   \
    do                                                                                                  \
@@ -446,6 +509,12 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    pack_lstm( tf.tensors[95].data, host + o_lstm );
    unsigned char *tc_img = (unsigned char *)calloc( 2, LTC_W_BYTES );
    if ( tc_img ) pack_lstm_tc( tf.tensors[95].data, tc_img );
+   unsigned char *ltc_img[4] = { 0, (unsigned char *)malloc( LtcCfg<1>::IMG_BYTES ), (unsigned char *)malloc( LtcCfg<2>::IMG_BYTES ),
+                                 (unsigned char *)malloc( LtcCfg<3>::IMG_BYTES ) };
+   const size_t ltc_bytes[4] = { 0, LtcCfg<1>::IMG_BYTES, LtcCfg<2>::IMG_BYTES, LtcCfg<3>::IMG_BYTES };
+   if ( ltc_img[1] ) pack_layer_tc<1>( host + o_l1, ltc_img[1] );
+   if ( ltc_img[2] ) pack_layer_tc<2>( host + o_l2, ltc_img[2] );
+   if ( ltc_img[3] ) pack_layer_tc<3>( host + o_l3, ltc_img[3] );
    memcpy( host + o_lb, tf.tensors[96].data, sizeof( float ) * 512 );
    memcpy( host + o_dw, tf.tensors[97].data, sizeof( float ) * 128 );
    memcpy( host + o_db, tf.tensors[98].data, sizeof( float ) * 2 );
@@ -460,6 +529,13 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    if ( ce == cudaSuccess ) ce = cudaMalloc( &h->d_lstm_tc, 2 * LTC_W_BYTES );
    if ( ce == cudaSuccess ) ce = cudaMemcpy( h->d_lstm_tc, tc_img, 2 * LTC_W_BYTES, cudaMemcpyHostToDevice );
    free( tc_img );
+   for ( int l = 1; l < 4; ++l )
+   {
+      if ( ce == cudaSuccess && !ltc_img[l] ) ce = cudaErrorMemoryAllocation;
+      if ( ce == cudaSuccess ) ce = cudaMalloc( &h->d_layer_tc[l], ltc_bytes[l] );
+      if ( ce == cudaSuccess ) ce = cudaMemcpy( h->d_layer_tc[l], ltc_img[l], ltc_bytes[l], cudaMemcpyHostToDevice );
+      free( ltc_img[l] );
+   }
    CU_H( ce );
    h->w.basis_pack = h->d_weights + o_basis;
    h->w.layer[0] = h->d_weights + o_l0;
@@ -631,6 +707,33 @@ static int launch_layer( silero_b200 *h, const float *in, float *out, int nchunk
    return 0;
 }
 
+// tensor-core layer (layer_tc_kernel.cuh), layers 2..4 (L = 1..3); same in/out layouts as launch_layer
+template <int L>
+static int launch_layer_tc( silero_b200 *h, const float *in, float *out, int nchunks )
+{
+   using Cfg = LtcCfg<L>;
+   const int ntiles = ( nchunks + Cfg::CPT - 1 ) / Cfg::CPT;
+   const int grid = imin( ( ntiles + Cfg::NGROUPS - 1 ) / Cfg::NGROUPS, h->sm_count );
+   layer_tc_kernel<L><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, h->stream>>>( in, out, h->d_layer_tc[L], nchunks );
+   h->launches++;
+   CU( cudaGetLastError() );
+   return 0;
+}
+
+static bool layers_use_tensor( const silero_b200 *h, int nchunks )
+{
+   if ( h->layer_mode == SILERO_B200_LAYERS_TENSOR ) return true;
+   if ( h->layer_mode == SILERO_B200_LAYERS_FP32 ) return false;
+   return nchunks >= SILERO_B200_LAYERS_TENSOR_MIN_CHUNKS;
+}
+
+// layers 2..4 of the encoder on whichever kernel family the engine is configured for
+template <int L>
+static int launch_layer_any( silero_b200 *h, const float *in, float *out, int nchunks )
+{
+   return layers_use_tensor( h, nchunks ) ? launch_layer_tc<L>( h, in, out, nchunks ) : launch_layer<L, false>( h, in, out, nchunks );
+}
+
 template <int LAYER>
 static int launch_lstm( silero_b200 *h, const float *x, float *hseq, int first_stream, int nstreams, int nw, float *d_out2, float *d_probs,
                         long long out_stride, long long out_off )
@@ -699,11 +802,11 @@ static int run_window( silero_b200 *h, const void *d_in, int in_f32, long long s
    if ( hybrid ? launch_layer<0, false>( h, h->spec, h->a1, nchunks, ENTRY_LAYER, TAP_LAYER, h->mu ) : launch_layer<0, true>( h, h->spec, h->a1, nchunks ) )
       return SILERO_B200_ERR_CUDA;
    stage_mark( h, 2 );
-   if ( launch_layer<1, false>( h, h->a1, h->a2, nchunks ) ) return SILERO_B200_ERR_CUDA;
+   if ( launch_layer_any<1>( h, h->a1, h->a2, nchunks ) ) return SILERO_B200_ERR_CUDA;
    stage_mark( h, 3 );
-   if ( launch_layer<2, false>( h, h->a2, h->a3, nchunks ) ) return SILERO_B200_ERR_CUDA;
+   if ( launch_layer_any<2>( h, h->a2, h->a3, nchunks ) ) return SILERO_B200_ERR_CUDA;
    stage_mark( h, 4 );
-   if ( launch_layer<3, false>( h, h->a3, h->a4, nchunks ) ) return SILERO_B200_ERR_CUDA;
+   if ( launch_layer_any<3>( h, h->a3, h->a4, nchunks ) ) return SILERO_B200_ERR_CUDA;
    stage_mark( h, 5 );
    const bool tensor = lstm_use_tensor( h, nstreams );
    if ( tensor ? launch_lstm_tc<0>( h, h->a4, first_stream, nstreams, nw, 0, 0, 0, 0 ) : launch_lstm<0>( h, h->a4, h->h0, first_stream, nstreams, nw, 0, 0, 0, 0 ) )
@@ -1298,9 +1401,9 @@ extern "C" int silero_b200_stage_pipeline( silero_b200 *h, const float *samples,
    if ( launch_stft( h, in.p, 1, 0, batch, batch, sp.p, 0, hybrid ? mu.p : 0 ) ) return SILERO_B200_ERR_CUDA;
    if ( hybrid ? launch_layer<0, false>( h, sp.p, d1.p, batch, ENTRY_LAYER, TAP_LAYER, mu.p ) : launch_layer<0, true>( h, sp.p, d1.p, batch ) )
       return SILERO_B200_ERR_CUDA;
-   if ( launch_layer<1, false>( h, d1.p, d2.p, batch ) ) return SILERO_B200_ERR_CUDA;
-   if ( launch_layer<2, false>( h, d2.p, d3.p, batch ) ) return SILERO_B200_ERR_CUDA;
-   if ( launch_layer<3, false>( h, d3.p, d4.p, batch ) ) return SILERO_B200_ERR_CUDA;
+   if ( launch_layer_any<1>( h, d1.p, d2.p, batch ) ) return SILERO_B200_ERR_CUDA;
+   if ( launch_layer_any<2>( h, d2.p, d3.p, batch ) ) return SILERO_B200_ERR_CUDA;
+   if ( launch_layer_any<3>( h, d3.p, d4.p, batch ) ) return SILERO_B200_ERR_CUDA;
    float *tmp = (float *)malloc( B * 448 * sizeof( float ) );
    if ( !tmp ) return set_err( SILERO_B200_ERR_NOMEM, "out of host memory" );
    int rc = 0;
@@ -1315,9 +1418,9 @@ extern "C" int silero_b200_stage_pipeline( silero_b200 *h, const float *samples,
 static int run_encoder_from( silero_b200 *h, int first_layer, const float *d_in, int batch, float *d1, float *d2, float *d3, float *d4 )
 {
    if ( first_layer <= 0 && launch_layer<0, false>( h, d_in, d1, batch ) ) return SILERO_B200_ERR_CUDA;
-   if ( first_layer <= 1 && launch_layer<1, false>( h, first_layer == 1 ? d_in : d1, d2, batch ) ) return SILERO_B200_ERR_CUDA;
-   if ( first_layer <= 2 && launch_layer<2, false>( h, first_layer == 2 ? d_in : d2, d3, batch ) ) return SILERO_B200_ERR_CUDA;
-   if ( first_layer <= 3 && launch_layer<3, false>( h, first_layer == 3 ? d_in : d3, d4, batch ) ) return SILERO_B200_ERR_CUDA;
+   if ( first_layer <= 1 && launch_layer_any<1>( h, first_layer == 1 ? d_in : d1, d2, batch ) ) return SILERO_B200_ERR_CUDA;
+   if ( first_layer <= 2 && launch_layer_any<2>( h, first_layer == 2 ? d_in : d2, d3, batch ) ) return SILERO_B200_ERR_CUDA;
+   if ( first_layer <= 3 && launch_layer_any<3>( h, first_layer == 3 ? d_in : d3, d4, batch ) ) return SILERO_B200_ERR_CUDA;
    return 0;
 }
 
@@ -1366,9 +1469,9 @@ extern "C" int silero_b200_stage_layer( silero_b200 *h, int layer, const float *
       switch ( layer )
       {
          case 0: rc = launch_layer<0, false>( h, din.p, dout.p, batch ); break;
-         case 1: rc = launch_layer<1, false>( h, din.p, dout.p, batch ); break;
-         case 2: rc = launch_layer<2, false>( h, din.p, dout.p, batch ); break;
-         default: rc = launch_layer<3, false>( h, din.p, dout.p, batch ); break;
+         case 1: rc = launch_layer_any<1>( h, din.p, dout.p, batch ); break;
+         case 2: rc = launch_layer_any<2>( h, din.p, dout.p, batch ); break;
+         default: rc = launch_layer_any<3>( h, din.p, dout.p, batch ); break;
       }
    }
    if ( !rc ) rc = down( h, tmp, dout.p, nout );

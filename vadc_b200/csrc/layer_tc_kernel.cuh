@@ -1,0 +1,422 @@
+// vadc_b200/csrc/layer_tc_kernel.cuh -- encoder transformer_layer 2..4 on the 5th-gen tensor cores.
+//
+// Same function as layer_kernel.cuh (transformer_layer, transformer.c:237-295: conv_block conv.c:761-814,
+// dual_head_attention transformer.c:13-153, layer_norm misc.c:143-210, tensor_linear tensor.h:675-723,
+// conv 1x1 + batch_norm1d transformer.c:280-290), used once the chunk batch makes the six dense
+// contractions of a layer (pointwise (+) projection conv, fused QKV, attention out-proj, FFN linear1/2,
+// strided 1x1 conv) GEMMs with M = tokens. Everything else (depthwise taps, softmax attention core,
+// layer norm, batch norm, ReLU) stays on the CUDA cores in fp32, in the thread that owns the token.
+//
+// Tile = 128 token rows = 128 TMEM lanes: the T frames of a chunk are padded to TP = 8 / 16 rows so a
+// chunk never straddles a warp (16 / 8 chunks per tile). A "group" of 4 warps owns one tile at a time;
+// thread r of the group owns token row r for the whole layer and keeps its activation row in registers.
+// Per contraction: every thread writes its row as the A operand (K-major [K/8][128][8] fp16, hi and lo
+// split -> tc::split_store8_f16), group barrier, one elected thread issues
+//     D[128][N] = A_hi*W_hi + A_lo*W_hi + A_hi*W_lo      (tcgen05.mma kind::f16, fp32 accumulation in TMEM)
+// and commits to the group's mbarrier; all threads wait, read their row back with tcgen05.ld and run the
+// fp32 epilogue. The fp16x2 split carries 22 significant bits per operand: measured effect on the speech
+// probability 1-2e-6, the same as plain fp32 reordering (scripts/experiments/bf16_split_encoder_sensitivity.py);
+// a bf16 split (16 bits) costs 2-4e-5 and single bf16 3e-2.
+// The phases of a tile are strictly sequential, so there is no dedicated MMA warp; instead 2 (C = 64)
+// or 4 (C = 32) independent groups per CTA overlap one group's MMA wait with the others' epilogues.
+// All fp16 weight images of the layer (<= 128 KB) stay resident in shared memory; TMEM: 512 columns
+// per CTA split evenly between the groups (one CTA per SM).
+#pragma once
+#include "common.cuh"
+#include "tc_common.cuh"
+
+template <int L>
+struct LtcCfg
+{
+   using P = LayerPack<L>;
+   static constexpr int CIN = P::CIN, C = P::C, T = P::T, D = P::D, STRIDE = P::STRIDE, TOUT = P::TOUT, KP = P::KP;
+   static constexpr bool PROJ = P::PROJ != 0;
+   static_assert( KP == C, "layers 2..4: the conv-block contraction length equals C" );
+   static constexpr int TP = T <= 8 ? 8 : 16; // rows per chunk
+   static constexpr int CPT = 128 / TP;       // chunks per tile
+   static constexpr int NGROUPS = C == 64 ? 2 : 4;
+   static constexpr int THREADS = NGROUPS * 128;
+   static constexpr int TMEM_COLS = 512 / NGROUPS;
+   static_assert( TMEM_COLS >= 3 * C, "accumulator columns" );
+   // fp16 weight images, each [split hi|lo][K/8][N][8]
+   static constexpr int wbytes( int N, int K ) { return 2 * N * K * 2; }
+   static constexpr int W_PW = 0;
+   static constexpr int W_QKV = W_PW + wbytes( C, C );
+   static constexpr int W_AO = W_QKV + wbytes( 3 * C, C );
+   static constexpr int W_F1 = W_AO + wbytes( C, C );
+   static constexpr int W_F2 = W_F1 + wbytes( C, C );
+   static constexpr int W_CV = W_F2 + wbytes( C, C );
+   static constexpr int W_END = W_CV + wbytes( C, C );
+   // fp32 parameters behind the images (offsets in floats)
+   static constexpr int F_DW = 0; // [CIN][8]: w0..w4, bias, 0, 0
+   static constexpr int F_PWB = F_DW + CIN * 8;
+   static constexpr int F_QKVB = F_PWB + C; // [2 heads][q(D) k(D) v(D)]
+   static constexpr int F_AOB = F_QKVB + 3 * C;
+   static constexpr int F_LN1W = F_AOB + C;
+   static constexpr int F_LN1B = F_LN1W + C;
+   static constexpr int F_F1B = F_LN1B + C;
+   static constexpr int F_F2B = F_F1B + C;
+   static constexpr int F_LN2W = F_F2B + C;
+   static constexpr int F_LN2B = F_LN2W + C;
+   static constexpr int F_CVB = F_LN2B + C;
+   static constexpr int F_BNM = F_CVB + C;
+   static constexpr int F_BNS = F_BNM + C;
+   static constexpr int F_BNW = F_BNS + C;
+   static constexpr int F_BNB = F_BNW + C;
+   static constexpr int F_TOTAL = F_BNB + C;
+   static constexpr int IMG_BYTES = W_END + F_TOTAL * 4; // multiple of 16
+   // per-group buffer: the A operand, aliased with the attention staging rows [q_h | v_h]
+   static constexpr int A_LBO = 128 * 16;
+   static constexpr int A_SPLIT = ( C / 8 ) * A_LBO;
+   static constexpr int A_BYTES = 2 * A_SPLIT;
+   static constexpr int SS = 2 * D + 4; // staging row stride in floats (odd multiple of 16 B)
+   static constexpr int STG_BYTES = 128 * SS * 4;
+   static constexpr int GBUF = A_BYTES > STG_BYTES ? A_BYTES : STG_BYTES;
+   static constexpr int SMEM_NEED = IMG_BYTES + NGROUPS * GBUF + 128;
+   // every CTA allocates all 512 TMEM columns: ask for more than half an SM's shared memory so that two CTAs can never be co-resident
+   static constexpr int SMEM_BYTES = SMEM_NEED > 120 * 1024 ? SMEM_NEED : 120 * 1024;
+};
+
+// D[128][N] (TMEM) = A[128][K] * W[N][K]^T with the fp16x2 split; issued by one thread, completion on `bar`
+template <int N, int K>
+__device__ __forceinline__ void ltc_issue_gemm( uint32_t d_tmem, uint32_t a_saddr, uint32_t w_saddr, uint64_t *bar )
+{
+   constexpr uint32_t A_LBO = 128 * 16, A_SPLIT = ( K / 8 ) * A_LBO;
+   constexpr uint32_t W_LBO = N * 16, W_SPLIT = ( K / 8 ) * W_LBO;
+   constexpr uint32_t idesc = tc::idesc_f16_f32( 128, N );
+   const uint64_t dA = tc::smem_desc( a_saddr, A_LBO, 128 ), dW = tc::smem_desc( w_saddr, W_LBO, 128 );
+#pragma unroll
+   for ( int p = 0; p < 3; ++p ) // (A split, W split): (hi,hi) (lo,hi) (hi,lo)
+   {
+      const uint64_t da = dA + (uint64_t)( ( p == 1 ? A_SPLIT : 0u ) >> 4 );
+      const uint64_t dw = dW + (uint64_t)( ( p == 2 ? W_SPLIT : 0u ) >> 4 );
+#pragma unroll
+      for ( int kk = 0; kk < K / 16; ++kk )
+         tc::mma_bf16( d_tmem, da + (uint64_t)( ( kk * 2 * A_LBO ) >> 4 ), dw + (uint64_t)( ( kk * 2 * W_LBO ) >> 4 ), idesc, ( p | kk ) ? 1u : 0u );
+   }
+   tc::mma_commit( bar );
+}
+
+template <int L>
+__global__ void __launch_bounds__( LtcCfg<L>::THREADS, 1 )
+layer_tc_kernel( const float *__restrict__ in /*[chunk][T][CIN]*/, float *__restrict__ out /*[chunk][TOUT][C]*/, const unsigned char *__restrict__ img, int nchunks )
+{
+   using Cfg = LtcCfg<L>;
+   constexpr int CIN = Cfg::CIN, C = Cfg::C, T = Cfg::T, D = Cfg::D, TP = Cfg::TP, CPT = Cfg::CPT, SS = Cfg::SS;
+   constexpr int NGROUPS = Cfg::NGROUPS, THREADS = Cfg::THREADS;
+   constexpr unsigned FULL = 0xffffffffu;
+
+   extern __shared__ __align__( 128 ) unsigned char ltc_layer_smem[];
+   unsigned char *smem = ltc_layer_smem;
+   const float *sF = reinterpret_cast<const float *>( smem + Cfg::W_END );
+   uint64_t *bars = reinterpret_cast<uint64_t *>( smem + Cfg::IMG_BYTES + NGROUPS * Cfg::GBUF );
+   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>( bars + NGROUPS );
+
+   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+   const int g = warp >> 2, wq = warp & 3, r = tid & 127;
+
+   // ---- one-time setup: weight images -> shared memory, TMEM, barriers ------------------------------------
+   for ( int i = tid; i < Cfg::IMG_BYTES / 16; i += THREADS ) reinterpret_cast<int4 *>( smem )[i] = __ldg( reinterpret_cast<const int4 *>( img ) + i );
+   if ( warp == 0 )
+   {
+      tc::tmem_alloc( tmem_slot, 512 );
+      if ( lane == 0 )
+      {
+         for ( int i = 0; i < NGROUPS; ++i ) tc::mbar_init( &bars[i], 1 );
+         tc::mbar_fence_init();
+      }
+   }
+   tc::fence_async_smem(); // the images were written with generic stores
+   tc::fence_before_sync();
+   __syncthreads();
+   tc::fence_after_sync();
+
+   const uint32_t tmem = *tmem_slot + (uint32_t)( g * Cfg::TMEM_COLS );
+   const uint32_t trow = tmem + ( (uint32_t)( wq * 32 ) << 16 ); // this warp's lane quarter
+   unsigned char *abuf = smem + Cfg::IMG_BYTES + g * Cfg::GBUF;
+   float *stg = reinterpret_cast<float *>( abuf );
+   uint64_t *bar = &bars[g];
+   const uint32_t a_saddr = tc::smem_u32( abuf ), w_saddr = tc::smem_u32( smem );
+   uint32_t nph = 0; // contractions issued by this group so far (mbarrier phase parity)
+
+   const int slot = r / TP, t = r - slot * TP;
+
+   // write this thread's activation row as the A operand (both splits)
+   auto put_row = [&]( const float *v ) {
+#pragma unroll
+      for ( int kc = 0; kc < C / 8; ++kc )
+         tc::split_store8_f16( v + 8 * kc, abuf + kc * Cfg::A_LBO + r * 16, abuf + Cfg::A_SPLIT + kc * Cfg::A_LBO + r * 16 );
+   };
+   // operand rows complete -> issue -> wait for the accumulator
+#define LTC_GEMM( N_, W_OFF_ )                                                                    \
+   do                                                                                             \
+   {                                                                                              \
+      tc::fence_async_smem();                                                                     \
+      tc::fence_before_sync();                                                                    \
+      bar_sync( 1 + g, 128 );                                                                     \
+      if ( wq == 0 )                                                                              \
+      {                                                                                           \
+         tc::fence_after_sync();                                                                  \
+         if ( tc::elect_one() ) ltc_issue_gemm<N_, C>( tmem, a_saddr, w_saddr + ( W_OFF_ ), bar ); \
+         __syncwarp();                                                                            \
+      }                                                                                           \
+      tc::mbar_wait( bar, nph & 1u );                                                             \
+      ++nph;                                                                                      \
+      tc::fence_after_sync();                                                                     \
+   } while ( 0 )
+
+   auto layer_norm = [&]( float( &u )[C], const float *w, const float *b ) {
+      // misc.c:143-210: two-pass mean / biased variance, eps 1e-5, (x*rstd - mean*rstd)*w + b
+      float sum = 0.0f;
+#pragma unroll
+      for ( int i = 0; i < C; ++i ) sum += u[i];
+      const float mean = sum * ( 1.0f / C );
+      float vs = 0.0f;
+#pragma unroll
+      for ( int i = 0; i < C; ++i )
+      {
+         const float d = u[i] - mean;
+         vs = fmaf( d, d, vs );
+      }
+      const float rstd = 1.0f / sqrtf( vs * ( 1.0f / C ) + 1e-5f );
+      const float mr = mean * rstd;
+#pragma unroll
+      for ( int i = 0; i < C; i += 4 )
+      {
+         const float4 ww = ld4( w + i ), bb = ld4( b + i );
+         u[i] = ( u[i] * rstd - mr ) * ww.x + bb.x;
+         u[i + 1] = ( u[i + 1] * rstd - mr ) * ww.y + bb.y;
+         u[i + 2] = ( u[i + 2] * rstd - mr ) * ww.z + bb.z;
+         u[i + 3] = ( u[i + 3] * rstd - mr ) * ww.w + bb.w;
+      }
+   };
+
+   const int ntiles = ( nchunks + CPT - 1 ) / CPT;
+   for ( int tile = blockIdx.x * NGROUPS + g; tile < ntiles; tile += gridDim.x * NGROUPS )
+   {
+      const int chunk = tile * CPT + slot;
+      const bool live = ( t < T ) && ( chunk < nchunks );
+
+      // ---- 1. conv_block: depthwise k=5 (+bias, ReLU) by warp shuffle; A = [d | x]; y = relu(Wpw d + Wproj x + b) ----
+      float u[C];
+      {
+         float x[CIN];
+         if ( live )
+         {
+            const float4 *p = reinterpret_cast<const float4 *>( in + ( (size_t)chunk * T + t ) * CIN );
+#pragma unroll
+            for ( int i = 0; i < CIN / 4; ++i )
+            {
+               const float4 v = __ldg( p + i );
+               x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+            }
+         }
+         else
+         {
+#pragma unroll
+            for ( int i = 0; i < CIN; ++i ) x[i] = 0.0f;
+         }
+         float a[C];
+         const float *dw = sF + Cfg::F_DW;
+#pragma unroll
+         for ( int c = 0; c < CIN; ++c )
+         {
+            float xm1 = __shfl_up_sync( FULL, x[c], 1 ), xm2 = __shfl_up_sync( FULL, x[c], 2 );
+            float xp1 = __shfl_down_sync( FULL, x[c], 1 ), xp2 = __shfl_down_sync( FULL, x[c], 2 );
+            if ( t < 1 ) xm1 = 0.0f;
+            if ( t < 2 ) xm2 = 0.0f;
+            if ( t + 1 >= T ) xp1 = 0.0f;
+            if ( t + 2 >= T ) xp2 = 0.0f;
+            const float4 w0 = ld4( dw + c * 8 ), w1 = ld4( dw + c * 8 + 4 );
+            float d = w1.y;
+            d = fmaf( xm2, w0.x, d );
+            d = fmaf( xm1, w0.y, d );
+            d = fmaf( x[c], w0.z, d );
+            d = fmaf( xp1, w0.w, d );
+            d = fmaf( xp2, w1.x, d );
+            a[c] = fmaxf( d, 0.0f );
+            if ( Cfg::PROJ ) a[CIN + c] = x[c];
+         }
+         put_row( a );
+         LTC_GEMM( C, Cfg::W_PW );
+         tc::tmem_ld_cols<C>( trow, u );
+         tc::tmem_wait_ld();
+         const float *pb = sF + Cfg::F_PWB;
+#pragma unroll
+         for ( int c = 0; c < C; c += 4 )
+         {
+            const float4 b4 = ld4( pb + c );
+            const float bv[4] = { b4.x, b4.y, b4.z, b4.w };
+#pragma unroll
+            for ( int e = 0; e < 4; ++e )
+            {
+               float y = u[c + e] + bv[e];
+               if ( !Cfg::PROJ ) y += x[( c + e ) % CIN]; // identity residual (CIN == C)
+               u[c + e] = fmaxf( y, 0.0f );
+            }
+         }
+      }
+
+      // ---- 2. fused QKV, then dual-head attention in fp32 (rows of a chunk live in one warp) ------------------
+      put_row( u );
+      LTC_GEMM( 3 * C, Cfg::W_QKV );
+      float o[C];
+      {
+         const float scale = 1.0f / sqrtf( (float)D );
+         float *mine = stg + r * SS;
+         const float *crow = stg + ( r - t ) * SS;
+#pragma unroll
+         for ( int h = 0; h < 2; ++h )
+         {
+            const float *qb = sF + Cfg::F_QKVB + h * 3 * D;
+            float k[D];
+            {
+               float q[D], v[D];
+               tc::tmem_ld_cols<D>( trow + h * 3 * D, q );
+               tc::tmem_ld_cols<D>( trow + h * 3 * D + D, k );
+               tc::tmem_ld_cols<D>( trow + h * 3 * D + 2 * D, v );
+               tc::tmem_wait_ld();
+#pragma unroll
+               for ( int j = 0; j < D; j += 4 )
+               {
+                  const float4 bq = ld4( qb + j ), bk = ld4( qb + D + j ), bv = ld4( qb + 2 * D + j );
+                  st4( mine + j, make_float4( q[j] + bq.x, q[j + 1] + bq.y, q[j + 2] + bq.z, q[j + 3] + bq.w ) );
+                  st4( mine + D + j, make_float4( v[j] + bv.x, v[j + 1] + bv.y, v[j + 2] + bv.z, v[j + 3] + bv.w ) );
+                  k[j] += bk.x; k[j + 1] += bk.y; k[j + 2] += bk.z; k[j + 3] += bk.w;
+               }
+            }
+            __syncwarp();
+            // transformer.c:101-143: rows = K positions, softmax over Q positions; O = A V
+            float s[T];
+#pragma unroll
+            for ( int tq = 0; tq < T; ++tq )
+            {
+               const float *q = crow + tq * SS;
+               float acc = 0.0f;
+#pragma unroll
+               for ( int j = 0; j < D; j += 4 )
+               {
+                  const float4 qv = ld4( q + j );
+                  acc = fmaf( k[j], qv.x, acc );
+                  acc = fmaf( k[j + 1], qv.y, acc );
+                  acc = fmaf( k[j + 2], qv.z, acc );
+                  acc = fmaf( k[j + 3], qv.w, acc );
+               }
+               s[tq] = acc * scale;
+            }
+            float mx = s[0];
+#pragma unroll
+            for ( int tq = 1; tq < T; ++tq ) mx = fmaxf( mx, s[tq] );
+            float sum = 0.0f;
+#pragma unroll
+            for ( int tq = 0; tq < T; ++tq )
+            {
+               s[tq] = expf( s[tq] - mx );
+               sum += s[tq];
+            }
+            const float inv = 1.0f / sum;
+#pragma unroll
+            for ( int j = 0; j < D; ++j ) o[h * D + j] = 0.0f;
+#pragma unroll
+            for ( int tq = 0; tq < T; ++tq )
+            {
+               const float *v = crow + tq * SS + D;
+               const float aw = s[tq] * inv;
+#pragma unroll
+               for ( int j = 0; j < D; j += 4 )
+               {
+                  const float4 vv = ld4( v + j );
+                  o[h * D + j] = fmaf( aw, vv.x, o[h * D + j] );
+                  o[h * D + j + 1] = fmaf( aw, vv.y, o[h * D + j + 1] );
+                  o[h * D + j + 2] = fmaf( aw, vv.z, o[h * D + j + 2] );
+                  o[h * D + j + 3] = fmaf( aw, vv.w, o[h * D + j + 3] );
+               }
+            }
+            __syncwarp(); // the staging rows are rewritten by the next head
+         }
+      }
+      // the staging rows alias the A operand: every warp of the group must be done reading them
+      bar_sync( 1 + g, 128 );
+
+      // ---- 3. attention out-proj + residual + LayerNorm1 ----------------------------------------------------
+      put_row( o );
+      LTC_GEMM( C, Cfg::W_AO );
+      {
+         float acc[C];
+         tc::tmem_ld_cols<C>( trow, acc );
+         tc::tmem_wait_ld();
+         const float *b = sF + Cfg::F_AOB;
+#pragma unroll
+         for ( int c = 0; c < C; c += 4 )
+         {
+            const float4 b4 = ld4( b + c );
+            u[c] += acc[c] + b4.x; u[c + 1] += acc[c + 1] + b4.y; u[c + 2] += acc[c + 2] + b4.z; u[c + 3] += acc[c + 3] + b4.w;
+         }
+         layer_norm( u, sF + Cfg::F_LN1W, sF + Cfg::F_LN1B );
+      }
+
+      // ---- 4. FFN linear1 + ReLU, linear2 + residual + LayerNorm2 ---------------------------------------------
+      put_row( u );
+      LTC_GEMM( C, Cfg::W_F1 );
+      {
+         float hdn[C];
+         tc::tmem_ld_cols<C>( trow, hdn );
+         tc::tmem_wait_ld();
+         const float *b = sF + Cfg::F_F1B;
+#pragma unroll
+         for ( int c = 0; c < C; c += 4 )
+         {
+            const float4 b4 = ld4( b + c );
+            hdn[c] = fmaxf( hdn[c] + b4.x, 0.0f ); hdn[c + 1] = fmaxf( hdn[c + 1] + b4.y, 0.0f );
+            hdn[c + 2] = fmaxf( hdn[c + 2] + b4.z, 0.0f ); hdn[c + 3] = fmaxf( hdn[c + 3] + b4.w, 0.0f );
+         }
+         put_row( hdn );
+      }
+      LTC_GEMM( C, Cfg::W_F2 );
+      {
+         float acc[C];
+         tc::tmem_ld_cols<C>( trow, acc );
+         tc::tmem_wait_ld();
+         const float *b = sF + Cfg::F_F2B;
+#pragma unroll
+         for ( int c = 0; c < C; c += 4 )
+         {
+            const float4 b4 = ld4( b + c );
+            u[c] += acc[c] + b4.x; u[c + 1] += acc[c + 1] + b4.y; u[c + 2] += acc[c + 2] + b4.z; u[c + 3] += acc[c + 3] + b4.w;
+         }
+         layer_norm( u, sF + Cfg::F_LN2W, sF + Cfg::F_LN2B );
+      }
+
+      // ---- 5. conv 1x1 (stride) + BatchNorm(eval) + ReLU -> global ----------------------------------------------
+      put_row( u );
+      LTC_GEMM( C, Cfg::W_CV );
+      {
+         float z[C];
+         tc::tmem_ld_cols<C>( trow, z );
+         tc::tmem_wait_ld();
+         if ( live && ( t % Cfg::STRIDE ) == 0 )
+         {
+            float *o_row = out + ( (size_t)chunk * Cfg::TOUT + t / Cfg::STRIDE ) * C;
+            const float *cb = sF + Cfg::F_CVB, *bm = sF + Cfg::F_BNM, *bs = sF + Cfg::F_BNS, *bw = sF + Cfg::F_BNW, *bb = sF + Cfg::F_BNB;
+#pragma unroll
+            for ( int c = 0; c < C; c += 4 )
+            {
+               const float4 cb4 = ld4( cb + c ), bm4 = ld4( bm + c ), bs4 = ld4( bs + c ), bw4 = ld4( bw + c ), bb4 = ld4( bb + c );
+               float4 rr;
+               // misc.c:251 true division
+               rr.x = fmaxf( ( ( z[c] + cb4.x ) - bm4.x ) / bs4.x * bw4.x + bb4.x, 0.0f );
+               rr.y = fmaxf( ( ( z[c + 1] + cb4.y ) - bm4.y ) / bs4.y * bw4.y + bb4.y, 0.0f );
+               rr.z = fmaxf( ( ( z[c + 2] + cb4.z ) - bm4.z ) / bs4.z * bw4.z + bb4.z, 0.0f );
+               rr.w = fmaxf( ( ( z[c + 3] + cb4.w ) - bm4.w ) / bs4.w * bw4.w + bb4.w, 0.0f );
+               st4( o_row + c, rr );
+            }
+         }
+      }
+      // the next tile's first operand write must not overtake another warp's TMEM read of this tile: the group
+      // barrier inside LTC_GEMM orders them (every thread passes tmem_wait_ld before it arrives there)
+   }
+#undef LTC_GEMM
+   tc::fence_before_sync();
+   __syncthreads();
+   if ( warp == 0 ) tc::tmem_dealloc( *tmem_slot, 512 );
+}

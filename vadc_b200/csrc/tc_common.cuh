@@ -14,6 +14,7 @@
 // and one MMA (K = 16) consumes two consecutive chunks; advancing K by 16 adds 2*LBO to the address.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace tc
@@ -86,6 +87,34 @@ __device__ __forceinline__ void tmem_ld8( uint32_t taddr, float ( &v )[8] )
    for ( int i = 0; i < 8; ++i ) v[i] = __uint_as_float( r[i] );
 }
 
+__device__ __forceinline__ void tmem_ld32( uint32_t taddr, float ( &v )[32] )
+{
+   uint32_t r[32];
+   asm volatile( "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"( r[0] ), "=r"( r[1] ), "=r"( r[2] ), "=r"( r[3] ), "=r"( r[4] ), "=r"( r[5] ), "=r"( r[6] ), "=r"( r[7] ), "=r"( r[8] ),
+                   "=r"( r[9] ), "=r"( r[10] ), "=r"( r[11] ), "=r"( r[12] ), "=r"( r[13] ), "=r"( r[14] ), "=r"( r[15] ), "=r"( r[16] ), "=r"( r[17] ),
+                   "=r"( r[18] ), "=r"( r[19] ), "=r"( r[20] ), "=r"( r[21] ), "=r"( r[22] ), "=r"( r[23] ), "=r"( r[24] ), "=r"( r[25] ), "=r"( r[26] ),
+                   "=r"( r[27] ), "=r"( r[28] ), "=r"( r[29] ), "=r"( r[30] ), "=r"( r[31] )
+                 : "r"( taddr )
+                 : "memory" );
+#pragma unroll
+   for ( int i = 0; i < 32; ++i ) v[i] = __uint_as_float( r[i] );
+}
+// NC consecutive columns (NC = 16 or a multiple of 32) of this thread's TMEM lane; the caller waits (tmem_wait_ld)
+template <int NC>
+__device__ __forceinline__ void tmem_ld_cols( uint32_t taddr, float ( &v )[NC] )
+{
+   static_assert( NC == 16 || NC % 32 == 0, "column count" );
+   if constexpr ( NC == 16 )
+      tmem_ld16( taddr, v );
+   else
+   {
+#pragma unroll
+      for ( int c = 0; c < NC; c += 32 ) tmem_ld32( taddr + c, *reinterpret_cast<float( * )[32]>( &v[c] ) );
+   }
+}
+
 // ---- descriptors ---------------------------------------------------------------------------------
 // shared-memory matrix descriptor, K-major, SWIZZLE_NONE, version 1 (sm_100)
 __device__ __forceinline__ uint64_t smem_desc( uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes )
@@ -97,6 +126,12 @@ __device__ __forceinline__ uint64_t smem_desc( uint32_t saddr, uint32_t lbo_byte
 __host__ __device__ constexpr uint32_t idesc_bf16_f32( int M, int N )
 {
    return ( 1u << 4 ) | ( 1u << 7 ) | ( 1u << 10 ) | ( (uint32_t)( N >> 3 ) << 17 ) | ( (uint32_t)( M >> 4 ) << 24 );
+}
+
+// same for A, B = fp16
+__host__ __device__ constexpr uint32_t idesc_f16_f32( int M, int N )
+{
+   return ( 1u << 4 ) | ( (uint32_t)( N >> 3 ) << 17 ) | ( (uint32_t)( M >> 4 ) << 24 );
 }
 
 // one lane of a converged warp (keeps the surrounding code warp-uniform, so descriptors stay in
@@ -132,6 +167,22 @@ __device__ __forceinline__ Split2 split2( float v )
    s.hi = __float2bfloat16_rn( v );
    s.lo = __float2bfloat16_rn( v - __bfloat162float( s.hi ) );
    return s;
+}
+
+// fp16x2 split of 8 consecutive K elements of one operand row: hi = fp16(v), lo = fp16(v - hi) (22 significant
+// bits together; products hi*hi + lo*hi + hi*lo). One 16-byte store per split into the [K/8][R][8] layout.
+__device__ __forceinline__ void split_store8_f16( const float *v, unsigned char *hi_ptr, unsigned char *lo_ptr )
+{
+   __half2 hi[4], lo[4];
+#pragma unroll
+   for ( int i = 0; i < 4; ++i )
+   {
+      hi[i] = __floats2half2_rn( v[2 * i], v[2 * i + 1] );
+      const float2 f = __half22float2( hi[i] );
+      lo[i] = __floats2half2_rn( v[2 * i] - f.x, v[2 * i + 1] - f.y );
+   }
+   *reinterpret_cast<int4 *>( hi_ptr ) = *reinterpret_cast<const int4 *>( hi );
+   *reinterpret_cast<int4 *>( lo_ptr ) = *reinterpret_cast<const int4 *>( lo );
 }
 
 // byte offset of element (row r, k) in the [K/8][R][8] bf16 operand layout with chunk stride `lbo` bytes
