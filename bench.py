@@ -328,17 +328,21 @@ def main():
         e2e_step(False)
     eng.reset()
     eng.segments_reset()
-    my_segments = [[] for _ in range(S)]
+    seg_log = []
     barrier()
     t0 = time.perf_counter()
     for k in range(args.steps):
         e2e_step(k == args.steps - 1)
-        if h_counts.max() > SEG_CAP:
-            raise SystemExit("segment capacity exceeded")
-        for s in np.nonzero(h_counts)[0]:                     # host side of the product: collect what the device emitted
-            my_segments[s] += [tuple(p) for p in h_segs[s, :h_counts[s]].tolist()]
+        m = int(h_counts.max())                               # host side of the product: keep what the device emitted this step
+        seg_log.append((h_counts.copy(), h_segs[:, :m].copy()))
     e2e_ms = (time.perf_counter() - t0) * 1e3
     barrier()
+    my_segments = [[] for _ in range(S)]
+    for counts, segs in seg_log:
+        if counts.max() > SEG_CAP:
+            raise SystemExit("segment capacity exceeded")
+        for s in np.nonzero(counts)[0]:
+            my_segments[s] += [tuple(p) for p in segs[s, :counts[s]].tolist()]
     e2e_ms = max_over_ranks(e2e_ms)
     e2e_value = audio_s / (e2e_ms / 1e3)
     # the "final gather of per-stream segments" (not timed): rank 0 receives every stream's (start, end) pairs

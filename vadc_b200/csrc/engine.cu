@@ -940,10 +940,36 @@ static int run_streams_host( silero_b200 *h, const int16_t *pcm, long long strea
          h->pcm_stage_cap = win_samples;
          cudaEventRecord( h->ev_begin, h->stream );
       }
-      const int nwin = ( nchunks + nw_max - 1 ) / nw_max;
+      // Window plan: short windows at both ends so that neither the first copy (nothing to overlap with) nor the
+      // last compute pass (no copy left to hide behind) costs a full window; full-size windows in between.
+      int wsize[64 + 8], nwin = 0;
+      {
+         const int q = nw_max / 4 > 0 ? nw_max / 4 : 1, hh = nw_max / 2 > 0 ? nw_max / 2 : 1;
+         const long long mid = (long long)nchunks - 2ll * ( q + hh );
+         if ( mid < nw_max || ( mid + nw_max - 1 ) / nw_max > 64 )
+            nwin = -1; // short call (or very long one): uniform windows
+         else
+         {
+            const int nmid = (int)( ( mid + nw_max - 1 ) / nw_max );
+            wsize[nwin++] = q;
+            wsize[nwin++] = hh;
+            for ( int i = 0; i < nmid; ++i ) wsize[nwin++] = (int)( mid / nmid ) + ( i < mid % nmid ? 1 : 0 );
+            wsize[nwin++] = hh;
+            wsize[nwin++] = q;
+         }
+      }
+      const bool planned = nwin > 0;
+      if ( !planned ) nwin = ( nchunks + nw_max - 1 ) / nw_max;
+      auto win_begin = [&]( int w ) -> int {
+         if ( !planned ) return w * nw_max;
+         int n0 = 0;
+         for ( int i = 0; i < w; ++i ) n0 += wsize[i];
+         return n0;
+      };
+      auto win_size = [&]( int w ) -> int { return planned ? wsize[w] : imin( nw_max, nchunks - w * nw_max ); };
       // window w is copied on copy_stream into stage[w&1] while window w-1 computes
       auto issue_copy = [&]( int w ) -> int {
-         int n0 = w * nw_max, nw = imin( nw_max, nchunks - n0 ), b = w & 1;
+         int n0 = win_begin( w ), nw = win_size( w ), b = w & 1;
          if ( w >= 2 ) CU( cudaStreamWaitEvent( h->copy_stream, h->pcm_free[b], 0 ) );
          CU( cudaMemcpy2DAsync( h->pcm_stage[b], (size_t)nw * VB_CHUNK * sizeof( int16_t ), pcm + (long long)n0 * VB_CHUNK,
                                 (size_t)stream_stride * sizeof( int16_t ), (size_t)nw * VB_CHUNK * sizeof( int16_t ), (size_t)nstreams,
@@ -955,7 +981,7 @@ static int run_streams_host( silero_b200 *h, const int16_t *pcm, long long strea
       const bool need_probs = probs || seg;
       for ( int w = 0; w < nwin; ++w )
       {
-         int n0 = w * nw_max, nw = imin( nw_max, nchunks - n0 ), b = w & 1;
+         int n0 = win_begin( w ), nw = win_size( w ), b = w & 1;
          if ( w + 1 < nwin && issue_copy( w + 1 ) ) return SILERO_B200_ERR_CUDA;
          CU( cudaStreamWaitEvent( h->stream, h->pcm_ready[b], 0 ) );
          rc = run_window( h, h->pcm_stage[b], 0, (long long)nw * VB_CHUNK, first_stream, nstreams, nw, out2 ? h->d_out2 : 0, need_probs ? h->d_probs : 0, nchunks, n0, 1 );
