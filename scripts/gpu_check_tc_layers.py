@@ -14,7 +14,7 @@ def main():
     st = o.run_stages(x)
     et = vadc_b200.Engine(max_streams=4096, layer_mode=vadc_b200.LAYERS_TENSOR)
     ef = vadc_b200.Engine(max_streams=4096, layer_mode=vadc_b200.LAYERS_FP32)
-    for layer, (ki, ko) in enumerate((("l1", "l2"), ("l2", "l3"), ("l3", "l4")), start=1):
+    for layer, (ki, ko) in enumerate((("norm", "l1"), ("l1", "l2"), ("l2", "l3"), ("l3", "l4"))):
         gt, gf = et.stage_layer(layer, st[ki]), ef.stage_layer(layer, st[ko if False else ki])
         print("layer", layer, "tensor err %.3e  fp32 err %.3e  scale %.2f" % (np.abs(gt - st[ko]).max(), np.abs(gf - st[ko]).max(), np.abs(st[ko]).max()), flush=True)
     S, N = 4096, 20

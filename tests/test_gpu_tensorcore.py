@@ -66,7 +66,7 @@ def test_tensor_core_lstm_vs_oracle_and_fp32_path(S, N, window):
     ef.close()
 
 
-# ---- tensor-core encoder layers 2..4 (vadc_b200/csrc/layer_tc_kernel.cuh) ------------------------------------
+# ---- tensor-core encoder layers (vadc_b200/csrc/layer0_tc_kernel.cuh, layer_tc_kernel.cuh) ------------------------------------
 def _fixture_engine(overrides, **kw):
     from test_gpu_fixtures import blob
     return vadc_b200.Engine(weights=blob(overrides), max_streams=1, layer_mode=vadc_b200.LAYERS_TENSOR, **kw)
@@ -75,6 +75,10 @@ def _fixture_engine(overrides, **kw):
 def test_tc_layers_on_the_reference_fixtures():
     """The checked-in layer fixtures (test.c atol 1e-4) through the tcgen05 layer kernel."""
     from test_gpu_fixtures import fx
+    v = fx("transformer_first_layer")
+    e = _fixture_engine({1 + i: v[i] for i in range(24)})
+    assert np.abs(e.stage_layer(0, v[24]) - v[25]).max() < 1e-4
+    e.close()
     v = fx("transformer_layers_3")
     e = _fixture_engine({49 + i: v[i] for i in range(22)})
     assert np.abs(e.stage_layer(2, v[22]) - v[23]).max() < 1e-4
@@ -94,7 +98,7 @@ def test_tc_layers_on_the_reference_fixtures():
 
 @pytest.mark.parametrize("batch", [1, 5, 16, 17, 37, 300])
 def test_tc_layers_vs_oracle_stage_tensors(batch):
-    """Each of layers 2..4 alone from the oracle's exact input of that layer, partial tiles included:
+    """Each encoder layer alone from the oracle's exact input of that layer, partial tiles included:
     within 2e-5 * scale of the oracle (the fp16x2 split keeps 22 bits; the FP32 kernels land at the same distance)."""
     from oracle_lib import Oracle
     o = Oracle()
@@ -103,7 +107,7 @@ def test_tc_layers_vs_oracle_stage_tensors(batch):
     st = o.run_stages(x)
     et = vadc_b200.Engine(max_streams=1, layer_mode=vadc_b200.LAYERS_TENSOR)
     ef = vadc_b200.Engine(max_streams=1, layer_mode=vadc_b200.LAYERS_FP32)
-    for layer, (k_in, k_out) in enumerate((("l1", "l2"), ("l2", "l3"), ("l3", "l4")), start=1):
+    for layer, (k_in, k_out) in enumerate((("norm", "l1"), ("l1", "l2"), ("l2", "l3"), ("l3", "l4"))):
         ref = st[k_out]
         got = et.stage_layer(layer, st[k_in])
         scale = max(1.0, float(np.abs(ref).max()))

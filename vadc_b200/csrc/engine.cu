@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "layer_kernel.cuh"
 #include "layer_tc_kernel.cuh"
+#include "layer0_tc_kernel.cuh"
 #include "lstm_kernel.cuh"
 #include "lstm_tc_kernel.cuh"
 #include "segment_kernel.cuh"
@@ -65,7 +66,7 @@ struct silero_b200
    int lstm_mode;            // SILERO_B200_LSTM_*
    unsigned char *d_lstm_tc; // [2 layers][LTC_W_BYTES] bf16 hi/lo weight images (lstm_tc_kernel.cuh)
    int layer_mode;           // SILERO_B200_LAYERS_*
-   unsigned char *d_layer_tc[4]; // fp16 hi/lo weight images + fp32 parameters of layers 2..4 (layer_tc_kernel.cuh); [0] unused
+   unsigned char *d_layer_tc[4]; // fp16 hi/lo weight images + fp32 parameters per layer (layer0_tc_kernel.cuh, layer_tc_kernel.cuh)
    size_t cap_h0_floats;
    unsigned long long *d_flagged; // bins that took the exact path (device counter)
    unsigned long long bins_total;
@@ -292,6 +293,51 @@ static void pack_layer_tc( const float *blob, unsigned char *img )
    memcpy( f + Cfg::F_BNB, blob + P::BNB, sizeof( float ) * C );
 }
 
+// image of the first layer for layer0_tc_kernel, from the LayerPack<0> blob
+static void pack_layer0_tc( const float *blob, unsigned char *img )
+{
+   using P = LayerPack<0>;
+   using Cfg = L0tc;
+   constexpr int C = 16, D = 8;
+   memset( img, 0, Cfg::IMG_BYTES );
+   float tmp[48 * 16 > 16 * 256 ? 48 * 16 : 16 * 256];
+   // conv block: k = 2*f + {0: pw_w[o][f] (applied to relu(dw(x))), 1: proj_w[o][f] (applied to x)}, f < 128
+   for ( int o = 0; o < C; ++o )
+      for ( int f = 0; f < 128; ++f )
+      {
+         tmp[o * 256 + 2 * f] = blob[P::PW + f * 2 * C + o];
+         tmp[o * 256 + 2 * f + 1] = blob[P::PW + f * 2 * C + C + o];
+      }
+   pack_f16_split( tmp, 256, C, 256, img + Cfg::W_PW );
+   for ( int h = 0; h < 2; ++h ) memcpy( tmp + (size_t)h * 3 * D * C, blob + P::QKV + h * P::QH, sizeof( float ) * 3 * D * C );
+   pack_f16_split( tmp, C, 3 * C, C, img + Cfg::W_QKV );
+   pack_f16_split( blob + P::AO, C, C, C, img + Cfg::W_AO );
+   pack_f16_split( blob + P::F1, C, C, C, img + Cfg::W_F1 );
+   pack_f16_split( blob + P::F2, C, C, C, img + Cfg::W_F2 );
+   pack_f16_split( blob + P::CV, C, C, C, img + Cfg::W_CV );
+   float *f = reinterpret_cast<float *>( img + Cfg::W_END );
+   memcpy( f + Cfg::F_DW, blob + P::DW, sizeof( float ) * 129 * 8 );
+   for ( int o = 0; o < C; ++o )
+   {
+      f[Cfg::F_WL + o] = blob[P::PW + 128 * 2 * C + o];
+      f[Cfg::F_WL + C + o] = blob[P::PW + 128 * 2 * C + C + o];
+   }
+   memcpy( f + Cfg::F_PWB, blob + P::PWB, sizeof( float ) * C );
+   for ( int h = 0; h < 2; ++h ) memcpy( f + Cfg::F_QKVB + h * 3 * D, blob + P::QKV + h * P::QH + 3 * D * C, sizeof( float ) * 3 * D );
+   memcpy( f + Cfg::F_AOB, blob + P::AOB, sizeof( float ) * C );
+   memcpy( f + Cfg::F_LN1W, blob + P::LN1W, sizeof( float ) * C );
+   memcpy( f + Cfg::F_LN1B, blob + P::LN1B, sizeof( float ) * C );
+   memcpy( f + Cfg::F_F1B, blob + P::F1B, sizeof( float ) * C );
+   memcpy( f + Cfg::F_F2B, blob + P::F2B, sizeof( float ) * C );
+   memcpy( f + Cfg::F_LN2W, blob + P::LN2W, sizeof( float ) * C );
+   memcpy( f + Cfg::F_LN2B, blob + P::LN2B, sizeof( float ) * C );
+   memcpy( f + Cfg::F_CVB, blob + P::CVB, sizeof( float ) * C );
+   memcpy( f + Cfg::F_BNM, blob + P::BNM, sizeof( float ) * C );
+   memcpy( f + Cfg::F_BNS, blob + P::BNS, sizeof( float ) * C );
+   memcpy( f + Cfg::F_BNW, blob + P::BNW, sizeof( float ) * C );
+   memcpy( f + Cfg::F_BNB, blob + P::BNB, sizeof( float ) * C );
+}
+
 // ---------------------------------------------------------------------------------------------
 // create / destroy
 // ---------------------------------------------------------------------------------------------
@@ -331,6 +377,7 @@ static int configure_kernels()
    CU( allow_smem( tc_probe_kernel, 200 * 1024 ) );
    CU( allow_smem( lstm_tc_kernel<0>, LTC_SMEM_BYTES ) );
    CU( allow_smem( lstm_tc_kernel<1>, LTC_SMEM_BYTES ) );
+   CU( allow_smem( layer0_tc_kernel, L0tc::SMEM_BYTES ) );
    CU( allow_smem( layer_tc_kernel<1>, LtcCfg<1>::SMEM_BYTES ) );
    CU( allow_smem( layer_tc_kernel<2>, LtcCfg<2>::SMEM_BYTES ) );
    CU( allow_smem( layer_tc_kernel<3>, LtcCfg<3>::SMEM_BYTES ) );
@@ -509,9 +556,10 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    pack_lstm( tf.tensors[95].data, host + o_lstm );
    unsigned char *tc_img = (unsigned char *)calloc( 2, LTC_W_BYTES );
    if ( tc_img ) pack_lstm_tc( tf.tensors[95].data, tc_img );
-   unsigned char *ltc_img[4] = { 0, (unsigned char *)malloc( LtcCfg<1>::IMG_BYTES ), (unsigned char *)malloc( LtcCfg<2>::IMG_BYTES ),
+   unsigned char *ltc_img[4] = { (unsigned char *)malloc( L0tc::IMG_BYTES ), (unsigned char *)malloc( LtcCfg<1>::IMG_BYTES ), (unsigned char *)malloc( LtcCfg<2>::IMG_BYTES ),
                                  (unsigned char *)malloc( LtcCfg<3>::IMG_BYTES ) };
-   const size_t ltc_bytes[4] = { 0, LtcCfg<1>::IMG_BYTES, LtcCfg<2>::IMG_BYTES, LtcCfg<3>::IMG_BYTES };
+   const size_t ltc_bytes[4] = { L0tc::IMG_BYTES, LtcCfg<1>::IMG_BYTES, LtcCfg<2>::IMG_BYTES, LtcCfg<3>::IMG_BYTES };
+   if ( ltc_img[0] ) pack_layer0_tc( host + o_l0, ltc_img[0] );
    if ( ltc_img[1] ) pack_layer_tc<1>( host + o_l1, ltc_img[1] );
    if ( ltc_img[2] ) pack_layer_tc<2>( host + o_l2, ltc_img[2] );
    if ( ltc_img[3] ) pack_layer_tc<3>( host + o_l3, ltc_img[3] );
@@ -529,7 +577,7 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    if ( ce == cudaSuccess ) ce = cudaMalloc( &h->d_lstm_tc, 2 * LTC_W_BYTES );
    if ( ce == cudaSuccess ) ce = cudaMemcpy( h->d_lstm_tc, tc_img, 2 * LTC_W_BYTES, cudaMemcpyHostToDevice );
    free( tc_img );
-   for ( int l = 1; l < 4; ++l )
+   for ( int l = 0; l < 4; ++l )
    {
       if ( ce == cudaSuccess && !ltc_img[l] ) ce = cudaErrorMemoryAllocation;
       if ( ce == cudaSuccess ) ce = cudaMalloc( &h->d_layer_tc[l], ltc_bytes[l] );
@@ -720,6 +768,17 @@ static int launch_layer_tc( silero_b200 *h, const float *in, float *out, int nch
    return 0;
 }
 
+// first layer on the tensor cores; in: log spectrogram [chunk][129][25], mu: per-chunk normalization scalar (NULL: input already normalized)
+static int launch_layer0_tc( silero_b200 *h, const float *in, float *out, int nchunks, const float *mu )
+{
+   const int ntiles = ( nchunks + 3 ) / 4;
+   const int grid = imin( ( ntiles + L0tc::NGROUPS - 1 ) / L0tc::NGROUPS, h->sm_count );
+   layer0_tc_kernel<<<grid, L0tc::THREADS, L0tc::SMEM_BYTES, h->stream>>>( in, out, h->d_layer_tc[0], nchunks, mu );
+   h->launches++;
+   CU( cudaGetLastError() );
+   return 0;
+}
+
 static bool layers_use_tensor( const silero_b200 *h, int nchunks )
 {
    if ( h->layer_mode == SILERO_B200_LAYERS_TENSOR ) return true;
@@ -799,7 +858,9 @@ static int run_window( silero_b200 *h, const void *d_in, int in_f32, long long s
    if ( launch_stft( h, d_in, in_f32, stream_stride, nw, nchunks, h->spec, 0, hybrid ? h->mu : 0 ) ) return SILERO_B200_ERR_CUDA;
    stage_mark( h, 1 );
    // the hybrid STFT kernel also produces the normalization scalar; the exact one leaves it to the first layer
-   if ( hybrid ? launch_layer<0, false>( h, h->spec, h->a1, nchunks, ENTRY_LAYER, TAP_LAYER, h->mu ) : launch_layer<0, true>( h, h->spec, h->a1, nchunks ) )
+   if ( hybrid ? ( layers_use_tensor( h, nchunks ) ? launch_layer0_tc( h, h->spec, h->a1, nchunks, h->mu )
+                                                   : launch_layer<0, false>( h, h->spec, h->a1, nchunks, ENTRY_LAYER, TAP_LAYER, h->mu ) )
+               : launch_layer<0, true>( h, h->spec, h->a1, nchunks ) )
       return SILERO_B200_ERR_CUDA;
    stage_mark( h, 2 );
    if ( launch_layer_any<1>( h, h->a1, h->a2, nchunks ) ) return SILERO_B200_ERR_CUDA;
@@ -1425,7 +1486,8 @@ extern "C" int silero_b200_stage_pipeline( silero_b200 *h, const float *samples,
    DevBuf mu;
    if ( mu.alloc( B ) ) return SILERO_B200_ERR_CUDA;
    if ( launch_stft( h, in.p, 1, 0, batch, batch, sp.p, 0, hybrid ? mu.p : 0 ) ) return SILERO_B200_ERR_CUDA;
-   if ( hybrid ? launch_layer<0, false>( h, sp.p, d1.p, batch, ENTRY_LAYER, TAP_LAYER, mu.p ) : launch_layer<0, true>( h, sp.p, d1.p, batch ) )
+   if ( hybrid ? ( layers_use_tensor( h, batch ) ? launch_layer0_tc( h, sp.p, d1.p, batch, mu.p ) : launch_layer<0, false>( h, sp.p, d1.p, batch, ENTRY_LAYER, TAP_LAYER, mu.p ) )
+               : launch_layer<0, true>( h, sp.p, d1.p, batch ) )
       return SILERO_B200_ERR_CUDA;
    if ( launch_layer_any<1>( h, d1.p, d2.p, batch ) ) return SILERO_B200_ERR_CUDA;
    if ( launch_layer_any<2>( h, d2.p, d3.p, batch ) ) return SILERO_B200_ERR_CUDA;
@@ -1443,7 +1505,8 @@ extern "C" int silero_b200_stage_pipeline( silero_b200 *h, const float *samples,
 
 static int run_encoder_from( silero_b200 *h, int first_layer, const float *d_in, int batch, float *d1, float *d2, float *d3, float *d4 )
 {
-   if ( first_layer <= 0 && launch_layer<0, false>( h, d_in, d1, batch ) ) return SILERO_B200_ERR_CUDA;
+   if ( first_layer <= 0 && ( layers_use_tensor( h, batch ) ? launch_layer0_tc( h, d_in, d1, batch, 0 ) : launch_layer<0, false>( h, d_in, d1, batch ) ) )
+      return SILERO_B200_ERR_CUDA;
    if ( first_layer <= 1 && launch_layer_any<1>( h, first_layer == 1 ? d_in : d1, d2, batch ) ) return SILERO_B200_ERR_CUDA;
    if ( first_layer <= 2 && launch_layer_any<2>( h, first_layer == 2 ? d_in : d2, d3, batch ) ) return SILERO_B200_ERR_CUDA;
    if ( first_layer <= 3 && launch_layer_any<3>( h, first_layer == 3 ? d_in : d3, d4, batch ) ) return SILERO_B200_ERR_CUDA;
@@ -1494,7 +1557,7 @@ extern "C" int silero_b200_stage_layer( silero_b200 *h, int layer, const float *
    {
       switch ( layer )
       {
-         case 0: rc = launch_layer<0, false>( h, din.p, dout.p, batch ); break;
+         case 0: rc = layers_use_tensor( h, batch ) ? launch_layer0_tc( h, din.p, dout.p, batch, 0 ) : launch_layer<0, false>( h, din.p, dout.p, batch ); break;
          case 1: rc = launch_layer_any<1>( h, din.p, dout.p, batch ); break;
          case 2: rc = launch_layer_any<2>( h, din.p, dout.p, batch ); break;
          default: rc = launch_layer_any<3>( h, din.p, dout.p, batch ); break;

@@ -1,0 +1,393 @@
+// vadc_b200/csrc/layer0_tc_kernel.cuh -- the FIRST encoder transformer_layer (129 -> 16 channels, 25 -> 13
+// frames) on the 5th-gen tensor cores.
+//
+// Same function as layer_kernel<0,false> (transformer_layer transformer.c:237-295 on the normalized
+// spectrogram: conv_block conv.c:761-814 with dw_conv_tensor :60 / pw_conv_tensor :726, dual_head_attention
+// transformer.c:13-153, layer_norm misc.c:143-210, conv 1x1 stride 2 + batch_norm1d transformer.c:280-290, and
+// the subtraction of the adaptive-normalization scalar misc.c:84-121 whose value the STFT kernel produced).
+// Scheme as in layer_tc_kernel.cuh (thread = token row = TMEM lane, groups of 4 warps, fp16x2 split, fp32
+// everything outside the dense contractions) with one difference: the conv-block contraction is long
+// (K = 2 x 129: relu(dw(x)) and x of every bin against [Wpw | Wproj]) and thin (N = 16), so its A operand is
+// produced and consumed in 8 slices of 16 bins (K = 32: k = 2*(f mod 16) + {0: d, 1: x}) through a double
+// buffer: while the tensor core accumulates slice s into TMEM the threads already convert slice s+1
+// (spectrogram loads from global, depthwise taps by warp shuffle, split to fp16 hi/lo). Bin 128 does not
+// fill a slice and is added in fp32 in the epilogue. Tile = 4 chunks (warp = chunk, lane = frame, 25 of 32
+// lanes live). 4 groups per CTA, 128 TMEM columns each.
+#pragma once
+#include "common.cuh"
+#include "tc_common.cuh"
+
+struct L0tc
+{
+   using P = LayerPack<0>;
+   static constexpr int CIN = 129, C = 16, T = 25, D = 8, TOUT = 13;
+   static constexpr int NGROUPS = 4, THREADS = NGROUPS * 128, TMEM_COLS = 128;
+   static constexpr int NSLICE = 8, SLICE_BINS = 16;
+   static constexpr int A_LBO = 128 * 16;
+   static constexpr int SLICE_SPLIT = 4 * A_LBO;       // K = 32 per slice: 4 chunks of 8
+   static constexpr int SLICE_BYTES = 2 * SLICE_SPLIT; // hi, lo
+   // fp16 weight images [split][K/8][N][8]
+   static constexpr int PW_LBO = 16 * 16, PW_SPLIT = 32 * PW_LBO;
+   static constexpr int W_PW = 0;
+   static constexpr int W_QKV = W_PW + 2 * PW_SPLIT; // N = 48, K = 16
+   static constexpr int W_AO = W_QKV + 2 * 48 * 16 * 2;
+   static constexpr int W_F1 = W_AO + 2 * 16 * 16 * 2;
+   static constexpr int W_F2 = W_F1 + 2 * 16 * 16 * 2;
+   static constexpr int W_CV = W_F2 + 2 * 16 * 16 * 2;
+   static constexpr int W_END = W_CV + 2 * 16 * 16 * 2;
+   // fp32 parameters (float offsets)
+   static constexpr int F_DW = 0;              // [129][8]: w0..w4, bias, 0, 0
+   static constexpr int F_WL = F_DW + CIN * 8; // bin 128: pw_w[o][128] (16), proj_w[o][128] (16)
+   static constexpr int F_PWB = F_WL + 32;
+   static constexpr int F_QKVB = F_PWB + C;    // [2 heads][q(8) k(8) v(8)]
+   static constexpr int F_AOB = F_QKVB + 3 * C;
+   static constexpr int F_LN1W = F_AOB + C;
+   static constexpr int F_LN1B = F_LN1W + C;
+   static constexpr int F_F1B = F_LN1B + C;
+   static constexpr int F_F2B = F_F1B + C;
+   static constexpr int F_LN2W = F_F2B + C;
+   static constexpr int F_LN2B = F_LN2W + C;
+   static constexpr int F_CVB = F_LN2B + C;
+   static constexpr int F_BNM = F_CVB + C;
+   static constexpr int F_BNS = F_BNM + C;
+   static constexpr int F_BNW = F_BNS + C;
+   static constexpr int F_BNB = F_BNW + C;
+   static constexpr int F_TOTAL = F_BNB + C;
+   static constexpr int IMG_BYTES = ( W_END + F_TOTAL * 4 + 127 ) / 128 * 128;
+   static constexpr int SS = 2 * D + 4; // attention staging row stride (floats)
+   static constexpr int GBUF = 2 * SLICE_BYTES;
+   static_assert( 128 * SS * 4 <= GBUF, "staging fits the slice buffers" );
+   static constexpr int SMEM_BYTES = IMG_BYTES + NGROUPS * GBUF + 256;
+   static_assert( SMEM_BYTES > 120 * 1024, "one CTA per SM (every CTA allocates all 512 TMEM columns)" );
+};
+
+__global__ void __launch_bounds__( L0tc::THREADS, 1 )
+layer0_tc_kernel( const float *__restrict__ in /*[chunk][129][25] log spectrogram*/, float *__restrict__ out /*[chunk][13][16]*/,
+                  const unsigned char *__restrict__ img, int nchunks, const float *__restrict__ mu_in )
+{
+   using Cfg = L0tc;
+   constexpr int CIN = Cfg::CIN, C = Cfg::C, T = Cfg::T, D = Cfg::D, SS = Cfg::SS, NGROUPS = Cfg::NGROUPS;
+   constexpr unsigned FULL = 0xffffffffu;
+
+   extern __shared__ __align__( 128 ) unsigned char l0tc_smem[];
+   unsigned char *smem = l0tc_smem;
+   const float *sF = reinterpret_cast<const float *>( smem + Cfg::W_END );
+   uint64_t *bars = reinterpret_cast<uint64_t *>( smem + Cfg::IMG_BYTES + NGROUPS * Cfg::GBUF ); // [group][3]: slice buffer 0, 1, main
+   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>( bars + 3 * NGROUPS );
+
+   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+   const int g = warp >> 2, wq = warp & 3, r = tid & 127, t = lane;
+
+   for ( int i = tid; i < Cfg::IMG_BYTES / 16; i += Cfg::THREADS ) reinterpret_cast<int4 *>( smem )[i] = __ldg( reinterpret_cast<const int4 *>( img ) + i );
+   if ( warp == 0 )
+   {
+      tc::tmem_alloc( tmem_slot, 512 );
+      if ( lane == 0 )
+      {
+         for ( int i = 0; i < 3 * NGROUPS; ++i ) tc::mbar_init( &bars[i], 1 );
+         tc::mbar_fence_init();
+      }
+   }
+   tc::fence_async_smem();
+   tc::fence_before_sync();
+   __syncthreads();
+   tc::fence_after_sync();
+
+   const uint32_t tmem = *tmem_slot + (uint32_t)( g * Cfg::TMEM_COLS );
+   const uint32_t trow = tmem + ( (uint32_t)( wq * 32 ) << 16 );
+   unsigned char *gbuf = smem + Cfg::IMG_BYTES + g * Cfg::GBUF;
+   float *stg = reinterpret_cast<float *>( gbuf );
+   uint64_t *bar_s = &bars[3 * g], *bar_m = &bars[3 * g + 2];
+   const uint32_t g_saddr = tc::smem_u32( gbuf ), w_saddr = tc::smem_u32( smem );
+   uint32_t n_s[2] = { 0, 0 }, n_m = 0; // commits so far on each barrier (phase parity bookkeeping, uniform in the group)
+
+   // short contractions of the transformer block: A operand K = 16 at the start of the group buffer
+   auto put_row16 = [&]( const float *v ) {
+      tc::split_store8_f16( v, gbuf + r * 16, gbuf + 2 * Cfg::A_LBO + r * 16 );
+      tc::split_store8_f16( v + 8, gbuf + Cfg::A_LBO + r * 16, gbuf + 3 * Cfg::A_LBO + r * 16 );
+   };
+#define L0_GEMM( N_, W_OFF_ )                                                                                  \
+   do                                                                                                          \
+   {                                                                                                           \
+      tc::fence_async_smem();                                                                                  \
+      tc::fence_before_sync();                                                                                 \
+      bar_sync( 1 + g, 128 );                                                                                  \
+      if ( wq == 0 )                                                                                           \
+      {                                                                                                        \
+         tc::fence_after_sync();                                                                               \
+         if ( tc::elect_one() ) ltc_issue_gemm<N_, 16>( tmem, g_saddr, w_saddr + ( W_OFF_ ), bar_m );          \
+         __syncwarp();                                                                                         \
+      }                                                                                                        \
+      tc::mbar_wait( bar_m, n_m & 1u );                                                                        \
+      ++n_m;                                                                                                   \
+      tc::fence_after_sync();                                                                                  \
+   } while ( 0 )
+
+   auto layer_norm = [&]( float( &u )[C], const float *w, const float *b ) {
+      float sum = 0.0f;
+#pragma unroll
+      for ( int i = 0; i < C; ++i ) sum += u[i];
+      const float mean = sum * ( 1.0f / C );
+      float vs = 0.0f;
+#pragma unroll
+      for ( int i = 0; i < C; ++i )
+      {
+         const float d = u[i] - mean;
+         vs = fmaf( d, d, vs );
+      }
+      const float rstd = 1.0f / sqrtf( vs * ( 1.0f / C ) + 1e-5f );
+      const float mr = mean * rstd;
+#pragma unroll
+      for ( int i = 0; i < C; i += 4 )
+      {
+         const float4 ww = ld4( w + i ), bb = ld4( b + i );
+         u[i] = ( u[i] * rstd - mr ) * ww.x + bb.x;
+         u[i + 1] = ( u[i + 1] * rstd - mr ) * ww.y + bb.y;
+         u[i + 2] = ( u[i + 2] * rstd - mr ) * ww.z + bb.z;
+         u[i + 3] = ( u[i + 3] * rstd - mr ) * ww.w + bb.w;
+      }
+   };
+
+   const float *dwp = sF + Cfg::F_DW;
+   // depthwise k=5 zero-pad 2 (+bias, ReLU) of one bin: taps come from the neighbouring lanes (frames)
+   auto dw_bin = [&]( int f, float x0 ) -> float {
+      float xm1 = __shfl_up_sync( FULL, x0, 1 ), xm2 = __shfl_up_sync( FULL, x0, 2 );
+      float xp1 = __shfl_down_sync( FULL, x0, 1 ), xp2 = __shfl_down_sync( FULL, x0, 2 );
+      if ( t < 1 ) xm1 = 0.0f;
+      if ( t < 2 ) xm2 = 0.0f;
+      if ( t + 1 >= T ) xp1 = 0.0f;
+      if ( t + 2 >= T ) xp2 = 0.0f;
+      const float4 w0 = ld4( dwp + f * 8 ), w1 = ld4( dwp + f * 8 + 4 );
+      float d = w1.y; // bias
+      d = fmaf( xm2, w0.x, d );
+      d = fmaf( xm1, w0.y, d );
+      d = fmaf( x0, w0.z, d );
+      d = fmaf( xp1, w0.w, d );
+      d = fmaf( xp2, w1.x, d );
+      return fmaxf( d, 0.0f );
+   };
+
+   const int ntiles = ( nchunks + 3 ) / 4;
+   for ( int tile = blockIdx.x * NGROUPS + g; tile < ntiles; tile += gridDim.x * NGROUPS )
+   {
+      const int chunk = tile * 4 + wq;
+      const bool live = ( t < T ) && ( chunk < nchunks );
+      const float *sp = in + (size_t)min( chunk, nchunks - 1 ) * ( VB_BINS * T ) + min( t, T - 1 );
+      const float mu = mu_in ? __ldg( mu_in + min( chunk, nchunks - 1 ) ) : 0.0f;
+
+      // ---- 1. conv_block in 8 slices of 16 bins -----------------------------------------------------------------
+      float xq[4], xn[4]; // software pipeline: the next 4 bins are in flight while these 4 are converted
+#pragma unroll
+      for ( int k = 0; k < 4; ++k ) xn[k] = __ldg( sp + k * T );
+#pragma unroll 1
+      for ( int s = 0; s < Cfg::NSLICE; ++s )
+      {
+         const int b = s & 1;
+         unsigned char *sb = gbuf + b * Cfg::SLICE_BYTES;
+         // the tensor core must be done with the slice that used this buffer two slices ago
+         if ( s >= 2 )
+         {
+            tc::mbar_wait( &bar_s[b], ( n_s[b] - 1u ) & 1u );
+         }
+#pragma unroll
+         for ( int kc = 0; kc < 4; ++kc ) // 4 bins -> 8 K elements [d0 x0 d1 x1 d2 x2 d3 x3] -> one 16-byte store per split
+         {
+            const int f0 = s * 16 + kc * 4;
+            float v[8];
+#pragma unroll
+            for ( int k = 0; k < 4; ++k )
+            {
+               xq[k] = xn[k];
+               xn[k] = __ldg( sp + min( f0 + 4 + k, VB_BINS - 1 ) * T );
+            }
+#pragma unroll
+            for ( int k = 0; k < 4; ++k )
+            {
+               const float x0 = live ? xq[k] - mu : 0.0f; // zero padding applies to the normalized signal
+               v[2 * k] = dw_bin( f0 + k, x0 );
+               v[2 * k + 1] = x0;
+            }
+            tc::split_store8_f16( v, sb + kc * Cfg::A_LBO + r * 16, sb + Cfg::SLICE_SPLIT + kc * Cfg::A_LBO + r * 16 );
+         }
+         tc::fence_async_smem();
+         tc::fence_before_sync();
+         bar_sync( 1 + g, 128 );
+         if ( wq == 0 )
+         {
+            tc::fence_after_sync();
+            if ( tc::elect_one() )
+            {
+               constexpr uint32_t idesc = tc::idesc_f16_f32( 128, 16 );
+               const uint64_t dA = tc::smem_desc( g_saddr + b * Cfg::SLICE_BYTES, Cfg::A_LBO, 128 );
+               const uint64_t dW = tc::smem_desc( w_saddr + Cfg::W_PW + s * 4 * Cfg::PW_LBO, Cfg::PW_LBO, 128 );
+#pragma unroll
+               for ( int p = 0; p < 3; ++p ) // (A split, W split): (hi,hi) (lo,hi) (hi,lo)
+               {
+                  const uint64_t da = dA + (uint64_t)( ( p == 1 ? Cfg::SLICE_SPLIT : 0 ) >> 4 );
+                  const uint64_t dw = dW + (uint64_t)( ( p == 2 ? Cfg::PW_SPLIT : 0 ) >> 4 );
+#pragma unroll
+                  for ( int kk = 0; kk < 2; ++kk )
+                     tc::mma_bf16( tmem, da + (uint64_t)( ( kk * 2 * Cfg::A_LBO ) >> 4 ), dw + (uint64_t)( ( kk * 2 * Cfg::PW_LBO ) >> 4 ), idesc,
+                                   ( s | p | kk ) ? 1u : 0u );
+               }
+               tc::mma_commit( &bar_s[b] );
+            }
+            __syncwarp();
+         }
+         ++n_s[b];
+      }
+      // bin 128 in fp32 while the last slices finish (xq/xn: xn[0] holds bin 128 after the last refill)
+      const float x128 = live ? xn[0] - mu : 0.0f;
+      const float d128 = dw_bin( 128, x128 );
+      tc::mbar_wait( &bar_s[0], ( n_s[0] - 1u ) & 1u );
+      tc::mbar_wait( &bar_s[1], ( n_s[1] - 1u ) & 1u );
+      tc::fence_after_sync();
+      float u[C];
+      {
+         tc::tmem_ld16( trow, u );
+         tc::tmem_wait_ld();
+         const float *wl = sF + Cfg::F_WL, *pb = sF + Cfg::F_PWB;
+#pragma unroll
+         for ( int c = 0; c < C; c += 4 )
+         {
+            const float4 a = ld4( wl + c ), b4 = ld4( wl + C + c ), bias = ld4( pb + c );
+            u[c] = fmaxf( fmaf( a.x, d128, fmaf( b4.x, x128, u[c] ) ) + bias.x, 0.0f );
+            u[c + 1] = fmaxf( fmaf( a.y, d128, fmaf( b4.y, x128, u[c + 1] ) ) + bias.y, 0.0f );
+            u[c + 2] = fmaxf( fmaf( a.z, d128, fmaf( b4.z, x128, u[c + 2] ) ) + bias.z, 0.0f );
+            u[c + 3] = fmaxf( fmaf( a.w, d128, fmaf( b4.w, x128, u[c + 3] ) ) + bias.w, 0.0f );
+         }
+      }
+
+      // ---- 2. fused QKV + dual-head attention (all 25 frames of a chunk are the lanes of this warp) ---------------
+      put_row16( u );
+      L0_GEMM( 48, Cfg::W_QKV );
+      float o[C];
+      {
+         const float scale = 1.0f / sqrtf( (float)D );
+         float *mine = stg + r * SS;
+         const float *crow = stg + ( r - t ) * SS;
+#pragma unroll
+         for ( int h = 0; h < 2; ++h )
+         {
+            const float *qb = sF + Cfg::F_QKVB + h * 3 * D;
+            float k[D];
+            {
+               float q[D], v[D];
+               tc::tmem_ld8( trow + h * 3 * D, q );
+               tc::tmem_ld8( trow + h * 3 * D + D, k );
+               tc::tmem_ld8( trow + h * 3 * D + 2 * D, v );
+               tc::tmem_wait_ld();
+#pragma unroll
+               for ( int j = 0; j < D; j += 4 )
+               {
+                  const float4 bq = ld4( qb + j ), bk = ld4( qb + D + j ), bv = ld4( qb + 2 * D + j );
+                  st4( mine + j, make_float4( q[j] + bq.x, q[j + 1] + bq.y, q[j + 2] + bq.z, q[j + 3] + bq.w ) );
+                  st4( mine + D + j, make_float4( v[j] + bv.x, v[j + 1] + bv.y, v[j + 2] + bv.z, v[j + 3] + bv.w ) );
+                  k[j] += bk.x; k[j + 1] += bk.y; k[j + 2] += bk.z; k[j + 3] += bk.w;
+               }
+            }
+            __syncwarp();
+            float sc[T];
+#pragma unroll
+            for ( int tq = 0; tq < T; ++tq )
+            {
+               const float4 q0 = ld4( crow + tq * SS ), q1 = ld4( crow + tq * SS + 4 );
+               float acc = k[0] * q0.x;
+               acc = fmaf( k[1], q0.y, acc ); acc = fmaf( k[2], q0.z, acc ); acc = fmaf( k[3], q0.w, acc );
+               acc = fmaf( k[4], q1.x, acc ); acc = fmaf( k[5], q1.y, acc ); acc = fmaf( k[6], q1.z, acc ); acc = fmaf( k[7], q1.w, acc );
+               sc[tq] = acc * scale;
+            }
+            float mx = sc[0];
+#pragma unroll
+            for ( int tq = 1; tq < T; ++tq ) mx = fmaxf( mx, sc[tq] );
+            float sum = 0.0f;
+#pragma unroll
+            for ( int tq = 0; tq < T; ++tq )
+            {
+               sc[tq] = expf( sc[tq] - mx );
+               sum += sc[tq];
+            }
+            const float inv = 1.0f / sum;
+#pragma unroll
+            for ( int j = 0; j < D; ++j ) o[h * D + j] = 0.0f;
+#pragma unroll
+            for ( int tq = 0; tq < T; ++tq )
+            {
+               const float4 v0 = ld4( crow + tq * SS + D ), v1 = ld4( crow + tq * SS + D + 4 );
+               const float aw = sc[tq] * inv;
+               o[h * D] = fmaf( aw, v0.x, o[h * D] ); o[h * D + 1] = fmaf( aw, v0.y, o[h * D + 1] );
+               o[h * D + 2] = fmaf( aw, v0.z, o[h * D + 2] ); o[h * D + 3] = fmaf( aw, v0.w, o[h * D + 3] );
+               o[h * D + 4] = fmaf( aw, v1.x, o[h * D + 4] ); o[h * D + 5] = fmaf( aw, v1.y, o[h * D + 5] );
+               o[h * D + 6] = fmaf( aw, v1.z, o[h * D + 6] ); o[h * D + 7] = fmaf( aw, v1.w, o[h * D + 7] );
+            }
+            __syncwarp();
+         }
+      }
+      bar_sync( 1 + g, 128 ); // staging rows alias the A operand of the other warps
+
+      // ---- 3. out-proj + residual + LayerNorm1 ----------------------------------------------------------------------
+      put_row16( o );
+      L0_GEMM( 16, Cfg::W_AO );
+      {
+         float acc[C];
+         tc::tmem_ld16( trow, acc );
+         tc::tmem_wait_ld();
+         const float *b = sF + Cfg::F_AOB;
+#pragma unroll
+         for ( int c = 0; c < C; ++c ) u[c] += acc[c] + b[c];
+         layer_norm( u, sF + Cfg::F_LN1W, sF + Cfg::F_LN1B );
+      }
+      // ---- 4. FFN ---------------------------------------------------------------------------------------------------
+      put_row16( u );
+      L0_GEMM( 16, Cfg::W_F1 );
+      {
+         float hdn[C];
+         tc::tmem_ld16( trow, hdn );
+         tc::tmem_wait_ld();
+         const float *b = sF + Cfg::F_F1B;
+#pragma unroll
+         for ( int c = 0; c < C; ++c ) hdn[c] = fmaxf( hdn[c] + b[c], 0.0f );
+         put_row16( hdn );
+      }
+      L0_GEMM( 16, Cfg::W_F2 );
+      {
+         float acc[C];
+         tc::tmem_ld16( trow, acc );
+         tc::tmem_wait_ld();
+         const float *b = sF + Cfg::F_F2B;
+#pragma unroll
+         for ( int c = 0; c < C; ++c ) u[c] += acc[c] + b[c];
+         layer_norm( u, sF + Cfg::F_LN2W, sF + Cfg::F_LN2B );
+      }
+      // ---- 5. conv 1x1 stride 2 + BatchNorm(eval) + ReLU -> global -----------------------------------------------------
+      put_row16( u );
+      L0_GEMM( 16, Cfg::W_CV );
+      {
+         float z[C];
+         tc::tmem_ld16( trow, z );
+         tc::tmem_wait_ld();
+         if ( live && ( t & 1 ) == 0 )
+         {
+            float *o_row = out + ( (size_t)chunk * Cfg::TOUT + ( t >> 1 ) ) * C;
+            const float *cb = sF + Cfg::F_CVB, *bm = sF + Cfg::F_BNM, *bs = sF + Cfg::F_BNS, *bw = sF + Cfg::F_BNW, *bb = sF + Cfg::F_BNB;
+#pragma unroll
+            for ( int c = 0; c < C; c += 4 )
+            {
+               const float4 cb4 = ld4( cb + c ), bm4 = ld4( bm + c ), bs4 = ld4( bs + c ), bw4 = ld4( bw + c ), bb4 = ld4( bb + c );
+               float4 rr;
+               rr.x = fmaxf( ( ( z[c] + cb4.x ) - bm4.x ) / bs4.x * bw4.x + bb4.x, 0.0f ); // misc.c:251 true division
+               rr.y = fmaxf( ( ( z[c + 1] + cb4.y ) - bm4.y ) / bs4.y * bw4.y + bb4.y, 0.0f );
+               rr.z = fmaxf( ( ( z[c + 2] + cb4.z ) - bm4.z ) / bs4.z * bw4.z + bb4.z, 0.0f );
+               rr.w = fmaxf( ( ( z[c + 3] + cb4.w ) - bm4.w ) / bs4.w * bw4.w + bb4.w, 0.0f );
+               st4( o_row + c, rr );
+            }
+         }
+      }
+      // the next tile's slices reuse the group buffer: every warp must be past its last read of it (the A operand of
+      // the final contraction was consumed by the tensor core before bar_m completed, which every thread waited for)
+   }
+#undef L0_GEMM
+   tc::fence_before_sync();
+   __syncthreads();
+   if ( warp == 0 ) tc::tmem_dealloc( *tmem_slot, 512 );
+}

@@ -24,7 +24,7 @@
 #define HYB_THREADS ( HYB_WARPS * 32 )
 #define HYB_XS_FLOATS 1792
 #define HYB_OUT_FLOATS ( VB_BINS * VB_FRAMES )
-#define HYB_SMEM_BYTES ( ( 2 * HYB_XS_FLOATS + HYB_OUT_FLOATS ) * 4 )
+#define HYB_SMEM_BYTES ( ( 2 * HYB_XS_FLOATS + HYB_OUT_FLOATS + 32 ) * 4 )
 
 __device__ __forceinline__ int brev5( int j ) { return (int)( __brev( (unsigned)j ) >> 27 ); }
 
@@ -135,6 +135,7 @@ stft_hybrid_kernel( const void *__restrict__ in, long long stream_stride, int nw
    extern __shared__ __align__( 16 ) float smem[];
    float *Xs = smem;                         // [2][1792]
    float *Os = smem + 2 * HYB_XS_FLOATS;     // [129][25]
+   float *Ms = Os + HYB_OUT_FLOATS;          // [25] per-frame mean of the log spectrum
 
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    const int j = lane;
@@ -278,23 +279,36 @@ stft_hybrid_kernel( const void *__restrict__ in, long long stream_stride, int nw
             ++nflag;
          }
          // ---- log1p(m * 2^20) (misc.c:40-46) into the chunk's output tile --------------------------
+         float fsum = 0.0f;
 #pragma unroll
          for ( int q = 0; q < 4; ++q )
-            Os[( 4 * kp + q ) * VB_FRAMES + t] = out_mode ? mag[q] : log1pf( __fmul_rn( mag[q], 1048576.0f ) );
-         if ( j == 0 ) Os[128 * VB_FRAMES + t] = out_mode ? nyq : log1pf( __fmul_rn( nyq, 1048576.0f ) );
+         {
+            const float lv = out_mode ? mag[q] : log1pf( __fmul_rn( mag[q], 1048576.0f ) );
+            Os[( 4 * kp + q ) * VB_FRAMES + t] = lv;
+            fsum += lv;
+         }
+         if ( j == 0 )
+         {
+            const float lv = out_mode ? nyq : log1pf( __fmul_rn( nyq, 1048576.0f ) );
+            Os[128 * VB_FRAMES + t] = lv;
+            fsum += lv;
+         }
+         // per-frame mean over the 129 bins (misc.c:48-62) as a warp reduction: the values are already in registers.
+         // (The summation order differs from the reference's sequential loop by ~1e-7 relative, far inside the budget
+         // of everything downstream of the log)
+#pragma unroll
+         for ( int off = 16; off > 0; off >>= 1 ) fsum += __shfl_xor_sync( 0xffffffffu, fsum, off );
+         if ( j == 0 ) Ms[t] = fsum / (float)VB_BINS;
       }
       __syncthreads();
       if ( warp == 0 && mu_out )
       {
-         // the scalar of adaptive_audio_normalization_inplace (misc.c:48-82), in the reference's order:
-         // per-frame mean over the 129 bins, reflect-pad 3 + 7-tap smoothing, mean over the 25 frames
+         // the scalar of adaptive_audio_normalization_inplace (misc.c:48-82): per-frame means (computed by the frame
+         // warps above), reflect-pad 3 + 7-tap smoothing, mean over the 25 frames
          const float gk[7] = { 0.03663284704089164733887f, 0.11128076165914535522461f, 0.21674531698226928710938f, 0.27068215608596801757812f,
                                0.21674531698226928710938f, 0.11128076165914535522461f, 0.03663284704089164733887f };
          const int tt = lane < VB_FRAMES ? lane : VB_FRAMES - 1;
-         float sacc = 0.0f;
-#pragma unroll 8
-         for ( int f = 0; f < VB_BINS; ++f ) sacc = __fadd_rn( sacc, Os[f * VB_FRAMES + tt] );
-         const float m = sacc / (float)VB_BINS;
+         const float m = Ms[tt];
          float v = 0.0f;
 #pragma unroll
          for ( int k = 0; k < 7; ++k )
