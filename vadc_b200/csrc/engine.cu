@@ -66,6 +66,7 @@ struct silero_b200
    int lstm_mode;            // SILERO_B200_LSTM_*
    unsigned char *d_lstm_tc; // [2 layers][LTC_W_BYTES] bf16 hi/lo weight images (lstm_tc_kernel.cuh)
    int layer_mode;           // SILERO_B200_LAYERS_*
+   L0DwParams l0_dw;         // first layer's depthwise taps, passed to layer0_tc_kernel by value
    unsigned char *d_layer_tc[4]; // fp16 hi/lo weight images + fp32 parameters per layer (layer0_tc_kernel.cuh, layer_tc_kernel.cuh)
    size_t cap_h0_floats;
    unsigned long long *d_flagged; // bins that took the exact path (device counter)
@@ -560,6 +561,8 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
                                  (unsigned char *)malloc( LtcCfg<3>::IMG_BYTES ) };
    const size_t ltc_bytes[4] = { L0tc::IMG_BYTES, LtcCfg<1>::IMG_BYTES, LtcCfg<2>::IMG_BYTES, LtcCfg<3>::IMG_BYTES };
    if ( ltc_img[0] ) pack_layer0_tc( host + o_l0, ltc_img[0] );
+   for ( int f = 0; f < 129; ++f )
+      for ( int k = 0; k < 6; ++k ) h->l0_dw.w[f][k] = host[o_l0 + LayerPack<0>::DW + f * 8 + k];
    if ( ltc_img[1] ) pack_layer_tc<1>( host + o_l1, ltc_img[1] );
    if ( ltc_img[2] ) pack_layer_tc<2>( host + o_l2, ltc_img[2] );
    if ( ltc_img[3] ) pack_layer_tc<3>( host + o_l3, ltc_img[3] );
@@ -773,7 +776,7 @@ static int launch_layer0_tc( silero_b200 *h, const float *in, float *out, int nc
 {
    const int ntiles = ( nchunks + 3 ) / 4;
    const int grid = imin( ( ntiles + L0tc::NGROUPS - 1 ) / L0tc::NGROUPS, h->sm_count );
-   layer0_tc_kernel<<<grid, L0tc::THREADS, L0tc::SMEM_BYTES, h->stream>>>( in, out, h->d_layer_tc[0], nchunks, mu );
+   layer0_tc_kernel<<<grid, L0tc::THREADS, L0tc::SMEM_BYTES, h->stream>>>( in, out, h->d_layer_tc[0], nchunks, mu, h->l0_dw );
    h->launches++;
    CU( cudaGetLastError() );
    return 0;

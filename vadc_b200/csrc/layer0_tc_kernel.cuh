@@ -61,9 +61,16 @@ struct L0tc
    static_assert( SMEM_BYTES > 120 * 1024, "one CTA per SM (every CTA allocates all 512 TMEM columns)" );
 };
 
+// depthwise weights travel as a kernel parameter: parameters live in the constant bank, and the bin index is warp-uniform,
+// so the taps are read through the uniform datapath instead of costing two shared-memory wavefronts per bin and warp
+struct L0DwParams
+{
+   float w[129][6]; // w0..w4, bias
+};
+
 __global__ void __launch_bounds__( L0tc::THREADS, 1 )
 layer0_tc_kernel( const float *__restrict__ in /*[chunk][129][25] log spectrogram*/, float *__restrict__ out /*[chunk][13][16]*/,
-                  const unsigned char *__restrict__ img, int nchunks, const float *__restrict__ mu_in )
+                  const unsigned char *__restrict__ img, int nchunks, const float *__restrict__ mu_in, const __grid_constant__ L0DwParams dwc )
 {
    using Cfg = L0tc;
    constexpr int CIN = Cfg::CIN, C = Cfg::C, T = Cfg::T, D = Cfg::D, SS = Cfg::SS, NGROUPS = Cfg::NGROUPS;
@@ -148,22 +155,18 @@ layer0_tc_kernel( const float *__restrict__ in /*[chunk][129][25] log spectrogra
       }
    };
 
-   const float *dwp = sF + Cfg::F_DW;
-   // depthwise k=5 zero-pad 2 (+bias, ReLU) of one bin: taps come from the neighbouring lanes (frames)
+   // depthwise k=5 zero-pad 2 (+bias, ReLU) of one bin: taps come from the neighbouring lanes (frames). Lanes 25..31
+   // carry x0 = 0, so rotating shuffles deliver the zero padding on both sides without any masking.
+   const int lm1 = ( lane + 31 ) & 31, lm2 = ( lane + 30 ) & 31, lp1 = ( lane + 1 ) & 31, lp2 = ( lane + 2 ) & 31;
    auto dw_bin = [&]( int f, float x0 ) -> float {
-      float xm1 = __shfl_up_sync( FULL, x0, 1 ), xm2 = __shfl_up_sync( FULL, x0, 2 );
-      float xp1 = __shfl_down_sync( FULL, x0, 1 ), xp2 = __shfl_down_sync( FULL, x0, 2 );
-      if ( t < 1 ) xm1 = 0.0f;
-      if ( t < 2 ) xm2 = 0.0f;
-      if ( t + 1 >= T ) xp1 = 0.0f;
-      if ( t + 2 >= T ) xp2 = 0.0f;
-      const float4 w0 = ld4( dwp + f * 8 ), w1 = ld4( dwp + f * 8 + 4 );
-      float d = w1.y; // bias
-      d = fmaf( xm2, w0.x, d );
-      d = fmaf( xm1, w0.y, d );
-      d = fmaf( x0, w0.z, d );
-      d = fmaf( xp1, w0.w, d );
-      d = fmaf( xp2, w1.x, d );
+      const float xm1 = __shfl_sync( FULL, x0, lm1 ), xm2 = __shfl_sync( FULL, x0, lm2 );
+      const float xp1 = __shfl_sync( FULL, x0, lp1 ), xp2 = __shfl_sync( FULL, x0, lp2 );
+      float d = dwc.w[f][5]; // bias
+      d = fmaf( xm2, dwc.w[f][0], d );
+      d = fmaf( xm1, dwc.w[f][1], d );
+      d = fmaf( x0, dwc.w[f][2], d );
+      d = fmaf( xp1, dwc.w[f][3], d );
+      d = fmaf( xp2, dwc.w[f][4], d );
       return fmaxf( d, 0.0f );
    };
 

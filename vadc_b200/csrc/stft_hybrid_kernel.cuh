@@ -26,6 +26,19 @@
 #define HYB_OUT_FLOATS ( VB_BINS * VB_FRAMES )
 #define HYB_SMEM_BYTES ( ( 2 * HYB_XS_FLOATS + HYB_OUT_FLOATS + 32 ) * 4 )
 
+// fast paths for the bins that are NOT re-evaluated exactly: their magnitude already carries ~1e-4 relative error
+// (eps * ||frame|| / m), so a 1-ulp square root and a 2^-22-relative logarithm change nothing measurable.
+__device__ __forceinline__ float hyb_sqrt_fast( float v )
+{
+   float r;
+   asm( "sqrt.approx.ftz.f32 %0, %1;" : "=f"( r ) : "f"( v ) );
+   return r;
+}
+// log1p(m * 2^20) (misc.c:40-46) as log(1 + x): the absolute error of forming 1 + x (<= 6e-8 * (1 + x)) is what the
+// network sees (the value enters linearly), and the bins where log1p's relative accuracy at tiny x would matter are
+// exactly zero or ~1e-6, i.e. 1e-6 absolute either way
+__device__ __forceinline__ float hyb_log1p_scaled( float m ) { return __logf( fmaf( m, 1048576.0f, 1.0f ) ); }
+
 __device__ __forceinline__ int brev5( int j ) { return (int)( __brev( (unsigned)j ) >> 27 ); }
 
 struct cpx
@@ -254,7 +267,7 @@ stft_hybrid_kernel( const void *__restrict__ in, long long stream_stride, int nw
                float orr = 0.5f * ( a[q].re - zp[q].re ), oi = 0.5f * ( a[q].im + zp[q].im );
                float yr = er - ps[q] * orr + pc[q] * oi;
                float yi = ei - ps[q] * oi - pc[q] * orr;
-               mag[q] = sqrtf( fmaf( yr, yr, yi * yi ) );
+               mag[q] = hyb_sqrt_fast( fmaf( yr, yr, yi * yi ) );
             }
             if ( j == 0 ) nyq = fabsf( a[0].re - a[0].im ); // Y[128] = Re Z0 - Im Z0
          }
@@ -283,13 +296,13 @@ stft_hybrid_kernel( const void *__restrict__ in, long long stream_stride, int nw
 #pragma unroll
          for ( int q = 0; q < 4; ++q )
          {
-            const float lv = out_mode ? mag[q] : log1pf( __fmul_rn( mag[q], 1048576.0f ) );
+            const float lv = out_mode ? mag[q] : hyb_log1p_scaled( mag[q] );
             Os[( 4 * kp + q ) * VB_FRAMES + t] = lv;
             fsum += lv;
          }
          if ( j == 0 )
          {
-            const float lv = out_mode ? nyq : log1pf( __fmul_rn( nyq, 1048576.0f ) );
+            const float lv = out_mode ? nyq : hyb_log1p_scaled( nyq );
             Os[128 * VB_FRAMES + t] = lv;
             fsum += lv;
          }
