@@ -45,7 +45,15 @@
 // host-side image of one layer's weights in shared-memory order: [split][chunk][row'][8] bf16
 // (engine.cu: pack_lstm_tc)
 
-__device__ __forceinline__ float ltc_sigmoid( float v ) { return 1.0f / ( 1.0f + expf( -v ) ); }
+// Gate nonlinearities on the special-function unit (ex2.approx + rcp.approx, ~2^-22 relative each): the pre-activations
+// they are applied to already carry the ~1e-5 relative error of the bf16x2 contraction, so libm-accurate expf/tanhf
+// (3x the instructions) buy nothing here. The FP32 kernel (lstm_kernel.cuh) keeps the accurate forms.
+__device__ __forceinline__ float ltc_sigmoid( float v ) { return __fdividef( 1.0f, 1.0f + __expf( -v ) ); }
+__device__ __forceinline__ float ltc_tanh( float v )
+{
+   // 1 - 2/(1 + e^{2v}); saturates correctly for large |v| (e^{2v} -> inf gives 1, -> 0 gives -1)
+   return 1.0f - __fdividef( 2.0f, 1.0f + __expf( 2.0f * v ) );
+}
 
 template <int LAYER>
 __global__ void __launch_bounds__( LTC_THREADS, 1 )
@@ -255,10 +263,10 @@ lstm_tc_kernel( const float *__restrict__ x_f32,            // LAYER 0: a4 [S][s
                const float zf = ( up ? a[8 + j] : ra ) + bf;
                const float zg = ( up ? rb : b[j] ) + bg;
                const float zo = ( up ? b[8 + j] : rb ) + bo;
-               const float ig = ltc_sigmoid( zi ), fg = ltc_sigmoid( zf ), gg = tanhf( zg ), og = ltc_sigmoid( zo );
+               const float ig = ltc_sigmoid( zi ), fg = ltc_sigmoid( zf ), gg = ltc_tanh( zg ), og = ltc_sigmoid( zo );
                const float cn = fg * c[j] + ig * gg;
                c[j] = cn;
-               const float hn = tanhf( cn ) * og;
+               const float hn = ltc_tanh( cn ) * og;
                hlast[j] = hn;
                tc::Split2 sp = tc::split2( hn );
                *reinterpret_cast<__nv_bfloat16 *>( xnext + hoff + ( sl0 + j ) * 16 ) = sp.hi;
