@@ -307,7 +307,7 @@ layer0_tc_kernel( const float *__restrict__ in /*[chunk][129][25] log spectrogra
 #pragma unroll
             for ( int tq = 0; tq < T; ++tq )
             {
-               sc[tq] = expf( sc[tq] - mx );
+               sc[tq] = __expf( sc[tq] - mx ); // ex2.approx: 2^-22 relative, far inside the budget
                sum += sc[tq];
             }
             const float inv = 1.0f / sum;

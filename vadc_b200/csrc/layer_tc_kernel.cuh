@@ -311,7 +311,7 @@ layer_tc_kernel( const float *__restrict__ in /*[chunk][T][CIN]*/, float *__rest
 #pragma unroll
             for ( int tq = 0; tq < T; ++tq )
             {
-               s[tq] = expf( s[tq] - mx );
+               s[tq] = __expf( s[tq] - mx ); // ex2.approx: 2^-22 relative, far inside the budget
                sum += s[tq];
             }
             const float inv = 1.0f / sum;
