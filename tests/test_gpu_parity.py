@@ -255,3 +255,55 @@ def test_timestamps_bit_exact_vs_reference_cli(engine):
     assert np.abs(raw - p).max() <= PTOL + 1e-6
     m = margins(p)
     print("threshold margins: min|p-0.5|=%.2e min|p-0.35|=%.2e" % m)
+
+
+def test_cfg4_single_long_stream(oracle):
+    """BASELINE cfg4, shortened in time: ONE stream, thousands of chunks. The stateless front end runs
+    chunk-parallel over each window (tensor-core layers: >= 2048 chunks per pass), the LSTM is one serial
+    scan with its state carried across windows (warm-up-overlap segmentation cannot be exact,
+    so the engine does not segment the stream). Probabilities within 1e-4, timestamps identical."""
+    N = 4500                                   # 7.2 minutes
+    pcm = vadc_b200.synth_pcm(31337, N * 1536)
+    e = vadc_b200.Engine(max_streams=1, window_chunks=2100)   # 3 windows: 2100 + 2100 + 300
+    p, out2 = e.run_streams(pcm[None, :], want_out2=True)
+    oracle.reset()
+    ref = oracle.run_pcm(pcm)
+    assert np.abs(out2[0] - ref).max() <= PTOL
+    assert vadc_b200.segments_text(p[0]) == oracle.segments_text(ref[:, 1])
+    # the same stream through the device segmenter, fed in two calls
+    e.reset()
+    e.segments_configure()
+    s1, _ = e.run_streams_segments(pcm[None, : 3000 * 1536])
+    s2, _ = e.run_streams_segments(pcm[None, 3000 * 1536:], end_of_stream=True)
+    seg = vadc_b200.StreamSegmenter()
+    assert "".join(seg.format(x) for x in s1[0] + s2[0]) == oracle.segments_text(ref[:, 1])
+    e.close()
+
+
+def test_cfg5_many_streams_sharded_like_ranks(oracle):
+    """BASELINE cfg5, shortened in time: 16384 streams. Two engines each own one block of streams (what two
+    ranks do, vadc_b200/shard.py); together they must reproduce one engine owning all streams bit for bit
+    (no cross-stream coupling, tile composition is irrelevant), and the gathered segments must agree."""
+    from vadc_b200 import shard
+    S, N, nb = 16384, 6, 8
+    base = [vadc_b200.synth_pcm(8100 + i, N * 1536) for i in range(nb)]
+    pcm = np.stack([np.roll(base[s % nb].reshape(N, 1536), (s // nb) % N, 0).reshape(-1) for s in range(S)])
+    whole = vadc_b200.Engine(max_streams=S)
+    p_all = whole.run_streams(pcm)
+    whole.close()
+    parts, segs = [], []
+    for rank in range(2):
+        first, count = shard.stream_range(S, 2, rank)
+        e = vadc_b200.Engine(max_streams=count)
+        e.segments_configure()
+        s, _, p = e.run_streams_segments(pcm[first:first + count], end_of_stream=True, want_probs=True)
+        parts.append(p)
+        segs += s
+        e.close()
+    assert np.array_equal(np.concatenate(parts, 0), p_all)
+    for s in (0, 8191, 8192, 16383):
+        oracle.reset()
+        ref = oracle.run_pcm(pcm[s])[:, 1]
+        assert np.abs(p_all[s] - ref).max() <= PTOL
+        seg = vadc_b200.StreamSegmenter()
+        assert "".join(seg.format(x) for x in segs[s]) == oracle.segments_text(ref)
