@@ -1,0 +1,65 @@
+"""GPU: the native Linux CLI (vadc_b200/vadc_b200_cli) against the unmodified
+reference CLI built for Linux (oracle/_ref/vadc_linux): same stdin contract, same options, same stdout bytes."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import vadc_b200
+from oracle_lib import ROOT, have_ref, ref_cli
+
+pytestmark = pytest.mark.gpu
+CLI = os.path.join(ROOT, "vadc_b200", "vadc_b200_cli")
+
+
+def cli(pcm, *args, files=()):
+    data = np.ascontiguousarray(pcm, np.int16).tobytes() if pcm is not None else b""
+    r = subprocess.run([CLI, *args, *files], input=data, capture_output=True, timeout=300)
+    assert r.returncode == 0, r.stderr.decode()
+    return r.stdout.decode()
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not present")
+@pytest.mark.parametrize("args", [(), ("--output_centi_seconds",), ("--batch", "32"), ("--batch", "1"),
+                                  ("--threshold", "0.6", "--min_silence", "300", "--speech_pad", "100"),
+                                  ("--min_speech", "-5", "--neg_threshold_relative", "0.3")])
+def test_stdin_mode_reproduces_reference_cli_stdout(args):
+    pcm = vadc_b200.synth_pcm(515, 16000 * 45 + 700)      # 45 s + a partial trailing chunk (dropped, vadc.c:964)
+    want = ref_cli(pcm, *args)
+    assert want.count("\n") >= 5
+    assert cli(pcm, *args) == want
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not present")
+def test_raw_probabilities_and_edge_inputs():
+    pcm = vadc_b200.synth_pcm(99, 16000 * 20)
+    got = np.array([float(v) for v in cli(pcm, "--raw_probabilities").split()])
+    ref = np.array([float(v) for v in ref_cli(pcm, "--raw_probabilities").split()])
+    assert got.shape == ref.shape and np.abs(got - ref).max() <= 1e-4 + 1e-6
+    assert cli(np.zeros(0, np.int16)) == ref_cli(np.zeros(0, np.int16)) == ""
+    assert cli(np.zeros(1000, np.int16)) == ""               # less than one chunk
+    loud = vadc_b200.synth_pcm(5, 16000 * 10, kind=2)        # full-scale white noise
+    assert cli(loud) == ref_cli(loud)
+
+
+def test_files_are_concurrent_streams(tmp_path):
+    """Each file = one stream on the multi-stream scheduler + device segmenter; ragged lengths, one empty file, one
+    whose length is an exact multiple of the call size (closed by the end-of-stream flush)."""
+    lengths = [64, 50, 7, 0, 32, 50]                        # chunks; --batch 2 -> 32 chunks per call
+    paths, pcms = [], []
+    for i, n in enumerate(lengths):
+        pcm = vadc_b200.synth_pcm(900 + i, n * 1536 + (300 if i == 1 else 0))
+        p = tmp_path / ("s%d.s16le" % i)
+        p.write_bytes(pcm.tobytes())
+        paths.append(str(p))
+        pcms.append(pcm)
+    out = cli(None, "--batch", "2", files=paths)
+    want = "".join("# %s\n%s" % (p, cli(pcm)) for p, pcm in zip(paths, pcms))
+    assert out == want
+    assert want.count(",") >= 4
+    one = cli(None, files=paths[:1])                        # a single file prints no header
+    assert one == cli(pcms[0])
+    raw = cli(None, "--raw_probabilities", "--batch", "2", files=paths[1:3])
+    vals = [l for l in raw.splitlines() if not l.startswith("#")]
+    assert len(vals) == 50 + 7

@@ -1,0 +1,389 @@
+/* vadc_b200/csrc/vadc_b200_cli.c -- native Linux command line over libsilero_b200.so.
+ *
+ * Keeps the reference CLI's contract (README.md:62-84, vadc.c:1084-1276): s16le 16 kHz mono PCM on
+ * stdin, one "start,end" line per speech segment on stdout (flushed as soon as it is final), all
+ * diagnostics on stderr; same option names, defaults and "a value <= 0 is ignored" rule
+ * (vadc.c:1110-1124, 1215); --raw_probabilities prints "%f\n" per chunk (vadc.c:992-997);
+ * --output_centi_seconds (vadc.c:251-256); --stats line on stderr (vadc.c:1069-1075).
+ * What replaces the Win32 shell (vadc.c:401-667): plain read(2) on stdin instead of ReadFile /
+ * an ffmpeg child (feed decoded audio with `ffmpeg -i in -f s16le -ac 1 -ar 16000 - | vadc_b200`).
+ *
+ * New: any number of raw s16le FILES may be given; each file is an independent stream, all of them
+ * are pushed through the multi-stream scheduler at once (per-stream LSTM and segmenter state on the
+ * GPU, segments produced by the on-device segmenter) and the per-file results are printed in
+ * argument order ("# path" header lines when there is more than one file).
+ */
+#define _POSIX_C_SOURCE 200809L
+#include <errno.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <unistd.h>
+
+#include "silero_b200.h"
+
+typedef struct cli_opts
+{
+   vadc_seg_params seg;
+   int batch;
+   float start_seconds;
+   int raw_probabilities, stats, device;
+   const char *model;
+   const char **files;
+   int nfiles;
+} cli_opts;
+
+static double now_s( void )
+{
+   struct timespec ts;
+   clock_gettime( CLOCK_MONOTONIC, &ts );
+   return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+static int parse_args( int argc, char **argv, cli_opts *o )
+{
+   vadc_seg_params_default( &o->seg );
+   o->batch = 96; /* vadc.c:1116 */
+   o->files = (const char **)calloc( (size_t)argc + 1, sizeof( char * ) );
+   if ( !o->files ) return -1;
+   for ( int i = 1; i < argc; ++i )
+   {
+      const char *a = argv[i];
+      float *fdst = 0;
+      if ( !strcmp( a, "--raw_probabilities" ) ) o->raw_probabilities = 1;
+      else if ( !strcmp( a, "--stats" ) ) o->stats = 1;
+      else if ( !strcmp( a, "--output_centi_seconds" ) ) o->seg.centiseconds = 1;
+      else if ( !strcmp( a, "--model" ) ) { if ( i + 1 < argc ) o->model = argv[++i]; }
+      else if ( !strcmp( a, "--min_silence" ) ) fdst = &o->seg.min_silence_ms;
+      else if ( !strcmp( a, "--min_speech" ) ) fdst = &o->seg.min_speech_ms;
+      else if ( !strcmp( a, "--threshold" ) ) fdst = &o->seg.threshold;
+      else if ( !strcmp( a, "--neg_threshold_relative" ) ) fdst = &o->seg.neg_threshold_relative;
+      else if ( !strcmp( a, "--speech_pad" ) ) fdst = &o->seg.speech_pad_ms;
+      else if ( !strcmp( a, "--start_seconds" ) ) fdst = &o->start_seconds;
+      else if ( !strcmp( a, "--batch" ) || !strcmp( a, "--sequence_count" ) || !strcmp( a, "--audio_source" ) || !strcmp( a, "--device" ) )
+      {
+         /* numeric options that are not floats of the segmenter: --sequence_count is clamped to 1536 by the C backend
+            (silero.h:41-42, vadc.c:742-754); --audio_source selects an ffmpeg stream in the reference and is accepted and ignored */
+         if ( i + 1 < argc )
+         {
+            float v = (float)atof( argv[++i] );
+            if ( !strcmp( a, "--batch" ) && v > 0.0f ) o->batch = (int)v;
+            if ( !strcmp( a, "--device" ) && v >= 0.0f ) o->device = (int)v;
+         }
+      }
+      else
+         o->files[o->nfiles++] = a; /* vadc.c:1226-1229: anything else is the input */
+      if ( fdst && i + 1 < argc )
+      {
+         float v = (float)atof( argv[++i] );
+         if ( v > 0.0f ) *fdst = v; /* vadc.c:1215 */
+      }
+   }
+   if ( o->batch < 1 ) o->batch = 1;
+   return 0;
+}
+
+static void print_segment( const vadc_segmenter *s, vadc_segment seg, double *total_speech )
+{
+   char line[96];
+   float b, e;
+   vadc_segment_format( s, seg, line, sizeof( line ) );
+   fputs( line, stdout );
+   fflush( stdout ); /* vadc.c:258 */
+   vadc_segment_times( s, seg, &b, &e );
+   *total_speech += (double)e - (double)b;
+}
+
+static void print_stats( double total_speech, long long total_samples, double t0 )
+{
+   /* vadc.c:1037-1075 */
+   double total_duration = (double)total_samples / SILERO_B200_SAMPLE_RATE;
+   double elapsed = now_s() - t0;
+   int hours = (int)( total_duration / 3600.0 );
+   int minutes = (int)( ( total_duration - hours * 3600.0 ) / 60.0 );
+   int seconds = (int)( total_duration - hours * 3600.0 - minutes * 60.0 );
+   int milliseconds = (int)( ( total_duration - hours * 3600.0 - minutes * 60.0 - seconds ) * 1000.0 );
+   fprintf( stderr, "time=%02d:%02d:%02d.%04d", hours, minutes, seconds, milliseconds );
+   fprintf( stderr, " %7.2f speech (%5.1f%%), %5.1f / %5.1f (%5.1fx)\r", total_speech, total_duration > 0 ? total_speech / total_duration * 100.0 : 0.0,
+            total_duration, elapsed, elapsed > 0 ? total_duration / elapsed : 0.0 );
+}
+
+/* read exactly n bytes unless EOF comes first; returns bytes read, -1 on error */
+static long long read_full( int fd, void *buf, size_t n )
+{
+   size_t got = 0;
+   while ( got < n )
+   {
+      ssize_t r = read( fd, (char *)buf + got, n - got );
+      if ( r < 0 )
+      {
+         if ( errno == EINTR ) continue;
+         return -1;
+      }
+      if ( r == 0 ) break;
+      got += (size_t)r;
+   }
+   return (long long)got;
+}
+
+/* ---- one stream from stdin: the reference's own loop (vadc.c:852-1027) ---- */
+static int run_stdin( silero_b200 *h, const cli_opts *o )
+{
+   const size_t cap_samples = (size_t)o->batch * SILERO_B200_CHUNK_SAMPLES;
+   int16_t *pcm = (int16_t *)malloc( cap_samples * sizeof( int16_t ) );
+   float *probs = (float *)malloc( (size_t)o->batch * sizeof( float ) );
+   vadc_segment segs[64];
+   if ( !pcm || !probs ) return 1;
+   vadc_segmenter seg;
+   vadc_segmenter_init( &seg, &o->seg );
+   double total_speech = 0.0, t0 = now_s();
+   long long total_samples = 0;
+   /* --start_seconds: the reference seeks with ffmpeg -ss (vadc.c:537); on a pipe the samples are read and dropped */
+   long long skip = (long long)( (double)o->start_seconds * SILERO_B200_SAMPLE_RATE ) * 2;
+   while ( skip > 0 )
+   {
+      size_t n = skip < (long long)( cap_samples * 2 ) ? (size_t)skip : cap_samples * 2;
+      long long r = read_full( 0, pcm, n );
+      if ( r <= 0 ) break;
+      skip -= r;
+   }
+   for ( ;; )
+   {
+      long long bytes = read_full( 0, pcm, cap_samples * sizeof( int16_t ) );
+      if ( bytes < 0 )
+      {
+         fprintf( stderr, "Error: read failed: %s\n", strerror( errno ) );
+         break;
+      }
+      const long long values_read = bytes / 2;
+      const int nchunks = (int)( values_read / SILERO_B200_CHUNK_SAMPLES ); /* vadc.c:964: the trailing partial chunk is dropped */
+      if ( nchunks > 0 )
+      {
+         if ( silero_b200_run_streams( h, pcm, (long long)cap_samples, 0, 1, nchunks, probs, 0 ) )
+         {
+            fprintf( stderr, "Error: %s\n", silero_b200_last_error() );
+            return 1;
+         }
+         total_samples += (long long)nchunks * SILERO_B200_CHUNK_SAMPLES;
+         if ( o->raw_probabilities )
+            for ( int i = 0; i < nchunks; ++i ) printf( "%f\n", probs[i] ); /* vadc.c:995 */
+         else
+            for ( int i = 0; i < nchunks; i += 64 )
+            {
+               int n = nchunks - i < 64 ? nchunks - i : 64;
+               long long k = vadc_segmenter_feed( &seg, probs + i, n, segs, 64 );
+               for ( long long j = 0; j < k; ++j ) print_segment( &seg, segs[j], &total_speech );
+            }
+         if ( o->stats ) print_stats( total_speech, total_samples, t0 );
+      }
+      if ( (size_t)bytes < cap_samples * sizeof( int16_t ) ) break; /* end of stream */
+   }
+   if ( !o->raw_probabilities )
+   {
+      long long k = vadc_segmenter_finish( &seg, segs, 64 );
+      for ( long long j = 0; j < k; ++j ) print_segment( &seg, segs[j], &total_speech );
+   }
+   else
+      fflush( stdout );
+   if ( o->stats )
+   {
+      print_stats( total_speech, total_samples, t0 );
+      fputc( '\n', stderr );
+   }
+   free( pcm );
+   free( probs );
+   return 0;
+}
+
+/* ---- many files = many concurrent streams ---- */
+typedef struct file_stream
+{
+   const char *path;
+   long long nchunks;
+   int order; /* position on the command line */
+} file_stream;
+
+static int by_length_desc( const void *a, const void *b )
+{
+   const file_stream *x = (const file_stream *)a, *y = (const file_stream *)b;
+   if ( x->nchunks != y->nchunks ) return x->nchunks > y->nchunks ? -1 : 1;
+   return x->order - y->order;
+}
+
+static int run_files( silero_b200 *h, const cli_opts *o )
+{
+   const int S = o->nfiles;
+   file_stream *fs = (file_stream *)calloc( (size_t)S, sizeof( file_stream ) );
+   if ( !fs ) return 1;
+   const long long skip_samples = (long long)( (double)o->start_seconds * SILERO_B200_SAMPLE_RATE );
+   long long maxchunks = 0;
+   for ( int i = 0; i < S; ++i )
+   {
+      FILE *f = fopen( o->files[i], "rb" );
+      if ( !f )
+      {
+         fprintf( stderr, "Error: cannot open %s\n", o->files[i] );
+         return 1;
+      }
+      fseek( f, 0, SEEK_END );
+      long long samples = ftell( f ) / 2 - skip_samples;
+      fclose( f );
+      fs[i].path = o->files[i];
+      fs[i].order = i;
+      fs[i].nchunks = samples > 0 ? samples / SILERO_B200_CHUNK_SAMPLES : 0;
+      if ( fs[i].nchunks > maxchunks ) maxchunks = fs[i].nchunks;
+   }
+   /* longest first: at any time the streams that still have audio are a prefix of the stream numbering */
+   qsort( fs, (size_t)S, sizeof( file_stream ), by_length_desc );
+   const long long stride = ( maxchunks > 0 ? maxchunks : 1 ) * SILERO_B200_CHUNK_SAMPLES;
+   int16_t *pcm = 0;
+   if ( silero_b200_host_alloc_pinned( (size_t)S * (size_t)stride * sizeof( int16_t ), (void **)&pcm ) )
+   {
+      fprintf( stderr, "Error: %s\n", silero_b200_last_error() );
+      return 1;
+   }
+   for ( int s = 0; s < S; ++s )
+   {
+      FILE *f = fopen( fs[s].path, "rb" );
+      if ( !f ) return 1;
+      fseek( f, skip_samples * 2, SEEK_SET );
+      size_t want = (size_t)fs[s].nchunks * SILERO_B200_CHUNK_SAMPLES;
+      if ( fread( pcm + (size_t)s * stride, 2, want, f ) != want )
+      {
+         fprintf( stderr, "Error: short read on %s\n", fs[s].path );
+         return 1;
+      }
+      fclose( f );
+   }
+   /* results per stream */
+   const int cap = (int)( maxchunks / 2 + 2 );
+   vadc_segment *segs = (vadc_segment *)malloc( (size_t)S * cap * sizeof( vadc_segment ) );
+   int *nseg = (int *)calloc( (size_t)S, sizeof( int ) );
+   float *probs = o->raw_probabilities ? (float *)malloc( (size_t)S * ( maxchunks > 0 ? maxchunks : 1 ) * sizeof( float ) ) : 0;
+   const int B = o->batch * 16; /* chunks per stream and call: large calls keep the GPU busy */
+   vadc_segment *tmp = (vadc_segment *)malloc( (size_t)S * ( B / 2 + 2 ) * sizeof( vadc_segment ) );
+   int *cnt = (int *)malloc( (size_t)S * sizeof( int ) );
+   float *ptmp = o->raw_probabilities ? (float *)malloc( (size_t)S * B * sizeof( float ) ) : 0;
+   if ( !segs || !nseg || !tmp || !cnt || ( o->raw_probabilities && ( !probs || !ptmp ) ) ) return 1;
+   if ( silero_b200_segments_configure( h, &o->seg ) ) return 1;
+   double t0 = now_s();
+   long long total_samples = 0;
+   const int tcap = B / 2 + 2;
+   for ( long long n0 = 0; n0 < maxchunks; n0 += B )
+   {
+      /* streams [0, full) have a full slice left, [full, active) end inside this slice */
+      int active = 0, full = 0;
+      while ( active < S && fs[active].nchunks > n0 ) ++active;
+      while ( full < active && fs[full].nchunks >= n0 + B ) ++full;
+      for ( int pass = 0; pass < 2; ++pass )
+      {
+         int s_begin = pass == 0 ? 0 : full, s_end = pass == 0 ? full : active;
+         while ( s_begin < s_end )
+         {
+            /* pass 0: one call for all full streams; pass 1: runs of streams with the same remaining length, closing them */
+            int s_stop = s_end;
+            int n = B;
+            if ( pass == 1 )
+            {
+               n = (int)( fs[s_begin].nchunks - n0 );
+               s_stop = s_begin + 1;
+               while ( s_stop < s_end && fs[s_stop].nchunks == fs[s_begin].nchunks ) ++s_stop;
+            }
+            const int ns = s_stop - s_begin;
+            if ( silero_b200_run_streams_segments( h, pcm + (size_t)s_begin * stride + (size_t)n0 * SILERO_B200_CHUNK_SAMPLES, stride, s_begin, ns, n,
+                                                   pass == 1 ? 1 : 0, tmp, tcap, cnt, ptmp ) )
+            {
+               fprintf( stderr, "Error: %s\n", silero_b200_last_error() );
+               return 1;
+            }
+            for ( int i = 0; i < ns; ++i )
+            {
+               const int s = s_begin + i;
+               for ( int j = 0; j < cnt[i] && j < tcap && nseg[s] < cap; ++j ) segs[(size_t)s * cap + nseg[s]++] = tmp[(size_t)i * tcap + j];
+               if ( probs ) memcpy( probs + (size_t)s * maxchunks + n0, ptmp + (size_t)i * n, (size_t)n * sizeof( float ) );
+            }
+            total_samples += (long long)ns * n * SILERO_B200_CHUNK_SAMPLES;
+            s_begin = s_stop;
+         }
+      }
+      if ( o->stats ) print_stats( 0.0, total_samples, t0 );
+   }
+   /* streams whose length is an exact multiple of the slice were never closed: flush them (no audio, end of stream) */
+   for ( int s = 0; s < S; )
+   {
+      if ( fs[s].nchunks == 0 || fs[s].nchunks % B != 0 )
+      {
+         ++s;
+         continue;
+      }
+      int e = s + 1;
+      while ( e < S && fs[e].nchunks == fs[s].nchunks ) ++e;
+      if ( silero_b200_run_streams_segments( h, 0, 0, s, e - s, 0, 1, tmp, tcap, cnt, 0 ) ) return 1;
+      for ( int i = 0; i < e - s; ++i )
+         for ( int j = 0; j < cnt[i] && j < tcap && nseg[s + i] < cap; ++j ) segs[(size_t)( s + i ) * cap + nseg[s + i]++] = tmp[(size_t)i * tcap + j];
+      s = e;
+   }
+   /* print in argument order */
+   vadc_segmenter fmt;
+   vadc_segmenter_init( &fmt, &o->seg );
+   for ( int order = 0; order < S; ++order )
+   {
+      int s = 0;
+      while ( fs[s].order != order ) ++s;
+      if ( S > 1 ) printf( "# %s\n", fs[s].path );
+      if ( o->raw_probabilities )
+         for ( long long i = 0; i < fs[s].nchunks; ++i ) printf( "%f\n", probs[(size_t)s * maxchunks + i] );
+      else
+         for ( int j = 0; j < nseg[s]; ++j )
+         {
+            char line[96];
+            vadc_segment_format( &fmt, segs[(size_t)s * cap + j], line, sizeof( line ) );
+            fputs( line, stdout );
+         }
+   }
+   fflush( stdout );
+   if ( o->stats ) fputc( '\n', stderr );
+   silero_b200_host_free_pinned( pcm );
+   free( segs ); free( nseg ); free( probs ); free( tmp ); free( cnt ); free( ptmp ); free( fs );
+   return 0;
+}
+
+int main( int argc, char **argv )
+{
+   cli_opts o;
+   memset( &o, 0, sizeof( o ) );
+   if ( parse_args( argc, argv, &o ) ) return 1;
+   /* weights: --model, else $VADC_B200_WEIGHTS, else weights/silero_v31_16k.testtensor next to the executable
+      (the reference embeds the same file at build time, build_msvc.bat:52-54) */
+   const char *weights = o.model ? o.model : getenv( "VADC_B200_WEIGHTS" );
+   char exe[4096];
+   if ( !weights )
+   {
+      ssize_t n = readlink( "/proc/self/exe", exe, sizeof( exe ) - 64 );
+      if ( n > 0 )
+      {
+         exe[n] = 0;
+         char *slash = strrchr( exe, '/' );
+         if ( slash ) strcpy( slash + 1, "weights/silero_v31_16k.testtensor" );
+         weights = exe;
+      }
+      else
+         weights = "silero_v31_16k.testtensor";
+   }
+   silero_b200_opts eo;
+   silero_b200_default_opts( &eo );
+   eo.device = o.device;
+   eo.max_streams = o.nfiles > 1 ? o.nfiles : 1;
+   silero_b200 *h = 0;
+   if ( silero_b200_create_from_file( weights, &eo, &h ) != SILERO_B200_OK )
+   {
+      fprintf( stderr, "Error: %s\n", silero_b200_last_error() ); /* vadc.c:692-695: init failure ends the run */
+      return 1;
+   }
+   fprintf( stderr, "batch size: %d\n", o.batch ); /* vadc.c:716 */
+   int rc = o.nfiles == 0 ? run_stdin( h, &o ) : run_files( h, &o );
+   silero_b200_destroy( h );
+   free( o.files );
+   return rc;
+}
