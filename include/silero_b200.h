@@ -55,8 +55,12 @@ typedef struct silero_b200 silero_b200; /* opaque engine handle */
 /* STFT evaluation. HYBRID: fp32 FFT everywhere + the reference's exact rounding
    sequence (stft.c:108-184) for every bin whose magnitude is below stft_k_rel * ||windowed frame||_2;
    EXACT: the reference's sequence for every bin (bit-identical magnitudes, ~7x slower STFT). */
-#define SILERO_B200_STFT_HYBRID 0
+#define SILERO_B200_STFT_HYBRID 0          /* hybrid rule on the warp-per-frame fp32 FFT kernel (stft_hybrid_kernel.cuh) */
 #define SILERO_B200_STFT_EXACT 1
+#define SILERO_B200_STFT_HYBRID_FFT 2      /* same as _HYBRID */
+#define SILERO_B200_STFT_HYBRID_TENSOR 3   /* hybrid rule on the tcgen05 DFT-as-GEMM kernel (stft_tc_kernel.cuh): 25 % faster STFT, but the
+                                              tensor-core accumulator costs 10x in |dY| and probabilities reach 1.1e-4 on long streams:
+                                              opt-in, not a drop-in under the 1e-4 bar */
 #define SILERO_B200_STFT_K_REL_DEFAULT 0.004f
 
 /* Decoder LSTM evaluation. FP32: gate contractions as fp32 FMA chains on the CUDA cores
@@ -82,7 +86,7 @@ typedef struct silero_b200_opts
    int device;          /* CUDA device ordinal (default 0) */
    int max_streams;     /* number of independent streams whose LSTM state is kept on device (default 1) */
    int window_chunks;   /* chunks per stream processed per internal pass; 0 = choose from memory budget */
-   int stft_mode;       /* SILERO_B200_STFT_HYBRID (default) or SILERO_B200_STFT_EXACT */
+   int stft_mode;       /* SILERO_B200_STFT_HYBRID (default), _EXACT, _HYBRID_FFT or _HYBRID_TENSOR */
    float stft_k_rel;    /* hybrid threshold; 0 = SILERO_B200_STFT_K_REL_DEFAULT */
    int lstm_mode;       /* SILERO_B200_LSTM_AUTO (default), _FP32 (CUDA-core kernel) or _TENSOR (tcgen05 kernel) */
    int layer_mode;      /* SILERO_B200_LAYERS_AUTO (default), _FP32 (CUDA-core kernels) or _TENSOR (tcgen05 kernel) */

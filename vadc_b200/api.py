@@ -15,7 +15,7 @@ WEIGHTS_PATH = os.path.join(_HERE, "weights", "silero_v31_16k.testtensor")
 
 CHUNK = 1536
 SAMPLE_RATE = 16000
-STFT_HYBRID, STFT_EXACT = 0, 1
+STFT_HYBRID, STFT_EXACT, STFT_HYBRID_FFT, STFT_HYBRID_TENSOR = 0, 1, 2, 3
 LSTM_AUTO, LSTM_FP32, LSTM_TENSOR = 0, 1, 2
 LAYERS_AUTO, LAYERS_FP32, LAYERS_TENSOR = 0, 1, 2
 

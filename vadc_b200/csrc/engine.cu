@@ -22,6 +22,7 @@
 #include "segment_kernel.cuh"
 #include "stft_hybrid_kernel.cuh"
 #include "stft_kernel.cuh"
+#include "stft_tc_kernel.cuh"
 #include "tc_probe.cuh"
 #include "testtensor.h"
 #include "vadc_segmenter.h"
@@ -61,7 +62,11 @@ struct silero_b200
    int sm_count;
    int max_streams;
    int window_chunks_opt;
-   int stft_mode;            // SILERO_B200_STFT_HYBRID / _EXACT
+   int stft_mode;            // SILERO_B200_STFT_*
+   unsigned char *d_stft_tc; // fp16 hi/lo basis image in K slices (stft_tc_kernel.cuh)
+   unsigned long long *d_fix_list; // work list of flagged bins (stft_tc_kernel -> stft_fixup_kernel)
+   size_t fix_cap;
+   unsigned int *d_fix_count;
    float stft_k_rel;         // hybrid: exact re-evaluation below k_rel * ||frame||
    int lstm_mode;            // SILERO_B200_LSTM_*
    unsigned char *d_lstm_tc; // [2 layers][LTC_W_BYTES] bf16 hi/lo weight images (lstm_tc_kernel.cuh)
@@ -294,6 +299,26 @@ static void pack_layer_tc( const float *blob, unsigned char *img )
    memcpy( f + Cfg::F_BNB, blob + P::BNB, sizeof( float ) * C );
 }
 
+// basis image for stft_tc_kernel: [K slice (8)][split][k-chunk (4)][n (256)][8] fp16; column n = 2f -> row f (Re), 2f+1 -> row 129+f (Im),
+// n = 0 -> row 0, n = 1 -> row 128 (rows 129 and 257 are identically zero)
+static void pack_stft_tc( const float *basis /*[258][256]*/, unsigned char *img )
+{
+   for ( int n = 0; n < 256; ++n )
+   {
+      const int f = n >> 1;
+      const int row = n == 0 ? 0 : ( n == 1 ? 128 : ( ( n & 1 ) ? 129 + f : f ) );
+      for ( int k = 0; k < 256; ++k )
+      {
+         const float v = basis[(size_t)row * 256 + k];
+         const __half hi = __float2half_rn( v );
+         const __half lo = __float2half_rn( v - __half2float( hi ) );
+         const size_t off = (size_t)( k >> 5 ) * STC_B_SLICE + (size_t)( ( k >> 3 ) & 3 ) * STC_B_LBO + (size_t)n * 16 + (size_t)( k & 7 ) * 2;
+         memcpy( img + off, &hi, 2 );
+         memcpy( img + off + STC_B_SPLIT, &lo, 2 );
+      }
+   }
+}
+
 // image of the first layer for layer0_tc_kernel, from the LayerPack<0> blob
 static void pack_layer0_tc( const float *blob, unsigned char *img )
 {
@@ -378,6 +403,8 @@ static int configure_kernels()
    CU( allow_smem( tc_probe_kernel, 200 * 1024 ) );
    CU( allow_smem( lstm_tc_kernel<0>, LTC_SMEM_BYTES ) );
    CU( allow_smem( lstm_tc_kernel<1>, LTC_SMEM_BYTES ) );
+   CU( allow_smem( stft_tc_kernel<false>, STC_SMEM_BYTES ) );
+   CU( allow_smem( stft_tc_kernel<true>, STC_SMEM_BYTES ) );
    CU( allow_smem( layer0_tc_kernel, L0tc::SMEM_BYTES ) );
    CU( allow_smem( layer_tc_kernel<1>, LtcCfg<1>::SMEM_BYTES ) );
    CU( allow_smem( layer_tc_kernel<2>, LtcCfg<2>::SMEM_BYTES ) );
@@ -405,6 +432,9 @@ extern "C" void silero_b200_destroy( silero_b200 *h )
    cudaFree( h->d_f32 );
    cudaFree( h->d_flagged );
    cudaFree( h->d_lstm_tc );
+   cudaFree( h->d_stft_tc );
+   cudaFree( h->d_fix_list );
+   cudaFree( h->d_fix_count );
    for ( int i = 0; i < 4; ++i ) cudaFree( h->d_layer_tc[i] );
    cudaFree( h->d_seg_state );
    cudaFree( h->d_segs );
@@ -479,7 +509,9 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    h->device = opts.device;
    h->max_streams = opts.max_streams;
    h->window_chunks_opt = opts.window_chunks;
-   h->stft_mode = opts.stft_mode == SILERO_B200_STFT_EXACT ? SILERO_B200_STFT_EXACT : SILERO_B200_STFT_HYBRID;
+   h->stft_mode = ( opts.stft_mode == SILERO_B200_STFT_EXACT || opts.stft_mode == SILERO_B200_STFT_HYBRID_FFT || opts.stft_mode == SILERO_B200_STFT_HYBRID_TENSOR )
+                     ? opts.stft_mode
+                     : SILERO_B200_STFT_HYBRID;
    h->stft_k_rel = opts.stft_k_rel > 0.0f ? opts.stft_k_rel : SILERO_B200_STFT_K_REL_DEFAULT;
    h->lstm_mode = ( opts.lstm_mode == SILERO_B200_LSTM_FP32 || opts.lstm_mode == SILERO_B200_LSTM_TENSOR ) ? opts.lstm_mode : SILERO_B200_LSTM_AUTO;
    h->layer_mode = ( opts.layer_mode == SILERO_B200_LAYERS_FP32 || opts.layer_mode == SILERO_B200_LAYERS_TENSOR ) ? opts.layer_mode : SILERO_B200_LAYERS_AUTO;
@@ -557,6 +589,8 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    pack_lstm( tf.tensors[95].data, host + o_lstm );
    unsigned char *tc_img = (unsigned char *)calloc( 2, LTC_W_BYTES );
    if ( tc_img ) pack_lstm_tc( tf.tensors[95].data, tc_img );
+   unsigned char *stc_img = (unsigned char *)malloc( STC_B_IMAGE );
+   if ( stc_img ) pack_stft_tc( tf.tensors[0].data, stc_img );
    unsigned char *ltc_img[4] = { (unsigned char *)malloc( L0tc::IMG_BYTES ), (unsigned char *)malloc( LtcCfg<1>::IMG_BYTES ), (unsigned char *)malloc( LtcCfg<2>::IMG_BYTES ),
                                  (unsigned char *)malloc( LtcCfg<3>::IMG_BYTES ) };
    const size_t ltc_bytes[4] = { L0tc::IMG_BYTES, LtcCfg<1>::IMG_BYTES, LtcCfg<2>::IMG_BYTES, LtcCfg<3>::IMG_BYTES };
@@ -580,6 +614,10 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    if ( ce == cudaSuccess ) ce = cudaMalloc( &h->d_lstm_tc, 2 * LTC_W_BYTES );
    if ( ce == cudaSuccess ) ce = cudaMemcpy( h->d_lstm_tc, tc_img, 2 * LTC_W_BYTES, cudaMemcpyHostToDevice );
    free( tc_img );
+   if ( ce == cudaSuccess && !stc_img ) ce = cudaErrorMemoryAllocation;
+   if ( ce == cudaSuccess ) ce = cudaMalloc( &h->d_stft_tc, STC_B_IMAGE );
+   if ( ce == cudaSuccess ) ce = cudaMemcpy( h->d_stft_tc, stc_img, STC_B_IMAGE, cudaMemcpyHostToDevice );
+   free( stc_img );
    for ( int l = 0; l < 4; ++l )
    {
       if ( ce == cudaSuccess && !ltc_img[l] ) ce = cudaErrorMemoryAllocation;
@@ -712,9 +750,48 @@ static int pick_window( const silero_b200 *h, int nstreams, int nchunks )
 // ---------------------------------------------------------------------------------------------
 static inline int imin( int a, int b ) { return a < b ? a : b; }
 
+static bool stft_use_tensor( const silero_b200 *h, int nchunks )
+{
+   // opt-in only: the tensor-core accumulator truncates (measured |dY| ~ 1.3e-6 ||frame|| vs 1.3e-7 for the fp32 FFT), which
+   // leaves too little of the 1e-4 probability budget on long streams (measured 1.08e-4 on 7 minutes)
+   (void)nchunks;
+   return h->stft_mode == SILERO_B200_STFT_HYBRID_TENSOR;
+}
+
+// mu (optional): receives the adaptive-normalization scalar per chunk when the selected kernel produces it (the FFT
+// kernel); the tensor-core and exact kernels leave it to the first layer (the caller checks stft_produces_mu)
+static bool stft_produces_mu( const silero_b200 *h, int nchunks ) { return h->stft_mode != SILERO_B200_STFT_EXACT && !stft_use_tensor( h, nchunks ); }
+
 static int launch_stft( silero_b200 *h, const void *d_in, int in_f32, long long stream_stride, int nw, int nchunks, float *spec, int out_mode, float *mu = 0 )
 {
-   if ( h->stft_mode == SILERO_B200_STFT_EXACT )
+   if ( stft_use_tensor( h, nchunks ) )
+   {
+      const int ntiles = ( nchunks + 3 ) / 4;
+      const int grid = imin( ntiles, h->sm_count );
+      // work list for the flagged bins: 1/64 of all bins (4x the rate of speech-like audio); overflow is handled in-kernel
+      size_t want = (size_t)nchunks * VB_BINS * VB_FRAMES / 64 + 4096;
+      if ( want > 0xfffffff0ull ) want = 0xfffffff0ull;
+      if ( grow( &h->d_fix_list, &h->fix_cap, want ) ) return SILERO_B200_ERR_CUDA;
+      if ( !h->d_fix_count ) CU( cudaMalloc( &h->d_fix_count, sizeof( unsigned int ) ) );
+      CU( cudaMemsetAsync( h->d_fix_count, 0, sizeof( unsigned int ), h->stream ) );
+      const unsigned int cap = (unsigned int)h->fix_cap;
+      const int fgrid = h->sm_count * 8;
+      if ( in_f32 )
+      {
+         stft_tc_kernel<true><<<grid, STC_THREADS, STC_SMEM_BYTES, h->stream>>>( d_in, stream_stride, nw, nchunks, h->d_stft_tc, h->w.basis_raw, spec, h->stft_k_rel, out_mode,
+                                                                                 h->d_flagged, h->d_fix_list, h->d_fix_count, cap );
+         stft_fixup_kernel<true><<<fgrid, 256, 0, h->stream>>>( d_in, stream_stride, nw, h->w.basis_raw, spec, h->d_fix_list, h->d_fix_count, cap, out_mode, h->d_flagged );
+      }
+      else
+      {
+         stft_tc_kernel<false><<<grid, STC_THREADS, STC_SMEM_BYTES, h->stream>>>( d_in, stream_stride, nw, nchunks, h->d_stft_tc, h->w.basis_raw, spec, h->stft_k_rel, out_mode,
+                                                                                  h->d_flagged, h->d_fix_list, h->d_fix_count, cap );
+         stft_fixup_kernel<false><<<fgrid, 256, 0, h->stream>>>( d_in, stream_stride, nw, h->w.basis_raw, spec, h->d_fix_list, h->d_fix_count, cap, out_mode, h->d_flagged );
+      }
+      h->launches++;
+      h->bins_total += (unsigned long long)nchunks * VB_BINS * VB_FRAMES;
+   }
+   else if ( h->stft_mode == SILERO_B200_STFT_EXACT )
    {
       int npairs = imin( h->sm_count / 2, ( nchunks + STFT_GROUPS - 1 ) / STFT_GROUPS );
       if ( npairs < 1 ) npairs = 1;
@@ -772,11 +849,11 @@ static int launch_layer_tc( silero_b200 *h, const float *in, float *out, int nch
 }
 
 // first layer on the tensor cores; in: log spectrogram [chunk][129][25], mu: per-chunk normalization scalar (NULL: input already normalized)
-static int launch_layer0_tc( silero_b200 *h, const float *in, float *out, int nchunks, const float *mu )
+static int launch_layer0_tc( silero_b200 *h, const float *in, float *out, int nchunks, const float *mu, int compute_mu = 0 )
 {
    const int ntiles = ( nchunks + 3 ) / 4;
    const int grid = imin( ( ntiles + L0tc::NGROUPS - 1 ) / L0tc::NGROUPS, h->sm_count );
-   layer0_tc_kernel<<<grid, L0tc::THREADS, L0tc::SMEM_BYTES, h->stream>>>( in, out, h->d_layer_tc[0], nchunks, mu, h->l0_dw );
+   layer0_tc_kernel<<<grid, L0tc::THREADS, L0tc::SMEM_BYTES, h->stream>>>( in, out, h->d_layer_tc[0], nchunks, mu, compute_mu, h->l0_dw );
    h->launches++;
    CU( cudaGetLastError() );
    return 0;
@@ -844,6 +921,14 @@ static int launch_lstm_tc( silero_b200 *h, const float *a4, int first_stream, in
    return 0;
 }
 
+// first encoder layer from the log spectrogram: mu = per-chunk normalization scalar if the STFT kernel produced it, else NULL
+// (the layer computes it itself, misc.c:48-121)
+static int first_layer_from_logspec( silero_b200 *h, const float *spec, float *a1, int nchunks, const float *mu )
+{
+   if ( layers_use_tensor( h, nchunks ) ) return launch_layer0_tc( h, spec, a1, nchunks, mu, mu ? 0 : 1 );
+   return mu ? launch_layer<0, false>( h, spec, a1, nchunks, ENTRY_LAYER, TAP_LAYER, mu ) : launch_layer<0, true>( h, spec, a1, nchunks );
+}
+
 static void stage_mark( silero_b200 *h, int i )
 {
    if ( h->profiling ) cudaEventRecord( h->ev_stage[i], h->stream );
@@ -857,14 +942,11 @@ static int run_window( silero_b200 *h, const void *d_in, int in_f32, long long s
    const size_t h0_floats = (size_t)( ( nstreams + LTC_N - 1 ) / LTC_N ) * LTC_N * nw * 7 * 64;
    if ( ensure_scratch( h, (size_t)nchunks, h0_floats ) ) return SILERO_B200_ERR_CUDA;
    stage_mark( h, 0 );
-   const bool hybrid = h->stft_mode != SILERO_B200_STFT_EXACT;
-   if ( launch_stft( h, d_in, in_f32, stream_stride, nw, nchunks, h->spec, 0, hybrid ? h->mu : 0 ) ) return SILERO_B200_ERR_CUDA;
+   const bool have_mu = stft_produces_mu( h, nchunks );
+   if ( launch_stft( h, d_in, in_f32, stream_stride, nw, nchunks, h->spec, 0, have_mu ? h->mu : 0 ) ) return SILERO_B200_ERR_CUDA;
    stage_mark( h, 1 );
-   // the hybrid STFT kernel also produces the normalization scalar; the exact one leaves it to the first layer
-   if ( hybrid ? ( layers_use_tensor( h, nchunks ) ? launch_layer0_tc( h, h->spec, h->a1, nchunks, h->mu )
-                                                   : launch_layer<0, false>( h, h->spec, h->a1, nchunks, ENTRY_LAYER, TAP_LAYER, h->mu ) )
-               : launch_layer<0, true>( h, h->spec, h->a1, nchunks ) )
-      return SILERO_B200_ERR_CUDA;
+   // the FFT STFT kernel also produces the normalization scalar; the others leave it to the first layer
+   if ( first_layer_from_logspec( h, h->spec, h->a1, nchunks, have_mu ? h->mu : 0 ) ) return SILERO_B200_ERR_CUDA;
    stage_mark( h, 2 );
    if ( launch_layer_any<1>( h, h->a1, h->a2, nchunks ) ) return SILERO_B200_ERR_CUDA;
    stage_mark( h, 3 );
@@ -1485,13 +1567,11 @@ extern "C" int silero_b200_stage_pipeline( silero_b200 *h, const float *samples,
    if ( in.alloc( B * VB_CHUNK ) || sp.alloc( B * 3225 ) || d1.alloc( B * 208 ) || d2.alloc( B * 224 ) || d3.alloc( B * 224 ) || d4.alloc( B * 448 ) )
       return SILERO_B200_ERR_CUDA;
    if ( up( h, in.p, samples, B * VB_CHUNK ) ) return SILERO_B200_ERR_CUDA;
-   const bool hybrid = h->stft_mode != SILERO_B200_STFT_EXACT;
+   const bool have_mu = stft_produces_mu( h, batch );
    DevBuf mu;
    if ( mu.alloc( B ) ) return SILERO_B200_ERR_CUDA;
-   if ( launch_stft( h, in.p, 1, 0, batch, batch, sp.p, 0, hybrid ? mu.p : 0 ) ) return SILERO_B200_ERR_CUDA;
-   if ( hybrid ? ( layers_use_tensor( h, batch ) ? launch_layer0_tc( h, sp.p, d1.p, batch, mu.p ) : launch_layer<0, false>( h, sp.p, d1.p, batch, ENTRY_LAYER, TAP_LAYER, mu.p ) )
-               : launch_layer<0, true>( h, sp.p, d1.p, batch ) )
-      return SILERO_B200_ERR_CUDA;
+   if ( launch_stft( h, in.p, 1, 0, batch, batch, sp.p, 0, have_mu ? mu.p : 0 ) ) return SILERO_B200_ERR_CUDA;
+   if ( first_layer_from_logspec( h, sp.p, d1.p, batch, have_mu ? mu.p : 0 ) ) return SILERO_B200_ERR_CUDA;
    if ( launch_layer_any<1>( h, d1.p, d2.p, batch ) ) return SILERO_B200_ERR_CUDA;
    if ( launch_layer_any<2>( h, d2.p, d3.p, batch ) ) return SILERO_B200_ERR_CUDA;
    if ( launch_layer_any<3>( h, d3.p, d4.p, batch ) ) return SILERO_B200_ERR_CUDA;

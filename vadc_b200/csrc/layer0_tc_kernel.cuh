@@ -70,7 +70,8 @@ struct L0DwParams
 
 __global__ void __launch_bounds__( L0tc::THREADS, 1 )
 layer0_tc_kernel( const float *__restrict__ in /*[chunk][129][25] log spectrogram*/, float *__restrict__ out /*[chunk][13][16]*/,
-                  const unsigned char *__restrict__ img, int nchunks, const float *__restrict__ mu_in, const __grid_constant__ L0DwParams dwc )
+                  const unsigned char *__restrict__ img, int nchunks, const float *__restrict__ mu_in, int compute_mu,
+                  const __grid_constant__ L0DwParams dwc )
 {
    using Cfg = L0tc;
    constexpr int CIN = Cfg::CIN, C = Cfg::C, T = Cfg::T, D = Cfg::D, SS = Cfg::SS, NGROUPS = Cfg::NGROUPS;
@@ -170,13 +171,54 @@ layer0_tc_kernel( const float *__restrict__ in /*[chunk][129][25] log spectrogra
       return fmaxf( d, 0.0f );
    };
 
+   // per-chunk scalar from this lane's frame sum (lane = frame; all lanes of the warp return the same value)
+   auto mu_from_frame_sum = [&]( float sacc ) -> float {
+      const float gk[7] = { 0.03663284704089164733887f, 0.11128076165914535522461f, 0.21674531698226928710938f, 0.27068215608596801757812f,
+                            0.21674531698226928710938f, 0.11128076165914535522461f, 0.03663284704089164733887f };
+      const float m = sacc / (float)VB_BINS;
+      const int tt = min( t, T - 1 );
+      float v = 0.0f;
+#pragma unroll
+      for ( int k = 0; k < 7; ++k )
+      {
+         int idx = tt + k - 3;
+         if ( idx < 0 ) idx = -idx;
+         if ( idx >= T ) idx = 2 * ( T - 1 ) - idx;
+         v = __fadd_rn( v, __fmul_rn( __shfl_sync( FULL, m, idx ), gk[k] ) );
+      }
+      float a = 0.0f;
+      for ( int i = 0; i < T; ++i ) a = __fadd_rn( a, __shfl_sync( FULL, v, i ) );
+      return a / (float)T;
+   };
+   bool have_next_mu = false;
+   float next_mu = 0.0f;
+
    const int ntiles = ( nchunks + 3 ) / 4;
    for ( int tile = blockIdx.x * NGROUPS + g; tile < ntiles; tile += gridDim.x * NGROUPS )
    {
       const int chunk = tile * 4 + wq;
       const bool live = ( t < T ) && ( chunk < nchunks );
       const float *sp = in + (size_t)min( chunk, nchunks - 1 ) * ( VB_BINS * T ) + min( t, T - 1 );
-      const float mu = mu_in ? __ldg( mu_in + min( chunk, nchunks - 1 ) ) : 0.0f;
+      float mu = mu_in ? __ldg( mu_in + min( chunk, nchunks - 1 ) ) : 0.0f;
+      // compute_mu: the scalar of adaptive_audio_normalization_inplace (misc.c:48-121) in the reference's own order --
+      // per-frame mean over the 129 bins (sequential), reflect-pad 3 + 7-tap smoothing, mean over the 25 frames (sequential).
+      // The frame sums of the NEXT tile are accumulated while this tile's slices are converted (same loads pattern, no
+      // exposed latency); only a group's first tile pays for a stand-alone pass.
+      const int next_tile = tile + gridDim.x * NGROUPS;
+      const float *spn = in + (size_t)min( next_tile * 4 + wq, nchunks - 1 ) * ( VB_BINS * T ) + min( t, T - 1 );
+      if ( compute_mu )
+      {
+         if ( !have_next_mu )
+         {
+            float sacc = 0.0f;
+#pragma unroll 8
+            for ( int f = 0; f < VB_BINS; ++f ) sacc = __fadd_rn( sacc, __ldg( sp + f * T ) );
+            mu = mu_from_frame_sum( sacc );
+         }
+         else
+            mu = next_mu;
+      }
+      float nsum = 0.0f;
 
       // ---- 1. conv_block in 8 slices of 16 bins -----------------------------------------------------------------
       float xq[4], xn[4]; // software pipeline: the next 4 bins are in flight while these 4 are converted
@@ -202,6 +244,14 @@ layer0_tc_kernel( const float *__restrict__ in /*[chunk][129][25] log spectrogra
             {
                xq[k] = xn[k];
                xn[k] = __ldg( sp + min( f0 + 4 + k, VB_BINS - 1 ) * T );
+            }
+            if ( compute_mu )
+            {
+               float nx[4];
+#pragma unroll
+               for ( int k = 0; k < 4; ++k ) nx[k] = __ldg( spn + ( f0 + k ) * T );
+#pragma unroll
+               for ( int k = 0; k < 4; ++k ) nsum = __fadd_rn( nsum, nx[k] );
             }
 #pragma unroll
             for ( int k = 0; k < 4; ++k )
@@ -238,6 +288,12 @@ layer0_tc_kernel( const float *__restrict__ in /*[chunk][129][25] log spectrogra
             __syncwarp();
          }
          ++n_s[b];
+      }
+      if ( compute_mu )
+      {
+         nsum = __fadd_rn( nsum, __ldg( spn + 128 * T ) );
+         next_mu = mu_from_frame_sum( nsum );
+         have_next_mu = true;
       }
       // bin 128 in fp32 while the last slices finish (xq/xn: xn[0] holds bin 128 after the last refill)
       const float x128 = live ? xn[0] - mu : 0.0f;
