@@ -151,6 +151,13 @@ int silero_b200_segments_reset( silero_b200 *h, int first_stream, int nstreams )
    probs (optional, may be NULL): host f32 [nstreams][nchunks]. */
 int silero_b200_run_streams_segments( silero_b200 *h, const int16_t *pcm, long long stream_stride, int first_stream, int nstreams, int nchunks,
                                       int end_of_stream, vadc_segment *segs, int cap, int *counts, float *probs );
+/* Asynchronous form of silero_b200_run_streams_segments: enqueues the copies and kernels and returns a ticket; the outputs are
+   valid, and pcm may be reused, after silero_b200_wait(h, ticket). Up to 4 calls may be in flight; they execute in submission
+   order, and the H2D copies of a call overlap the compute of the previous one (this is what lets a steady stream of calls run at
+   the PCIe bound). segs/counts may be NULL (probabilities only). pcm and the outputs should be pinned host memory. */
+int silero_b200_submit_streams_segments( silero_b200 *h, const int16_t *pcm, long long stream_stride, int first_stream, int nstreams, int nchunks,
+                                         int end_of_stream, vadc_segment *segs, int cap, int *counts, float *probs, unsigned long long *ticket );
+int silero_b200_wait( silero_b200 *h, unsigned long long ticket );
 /* same with every buffer in DEVICE memory; asynchronous (silero_b200_sync). d_probs may be NULL (internal scratch). */
 int silero_b200_run_streams_segments_device( silero_b200 *h, const int16_t *d_pcm, long long stream_stride, int first_stream, int nstreams, int nchunks,
                                              int end_of_stream, float *d_probs, vadc_segment *d_segs, int cap, int *d_counts );

@@ -109,3 +109,42 @@ def test_device_segmenter_alone_matches_host_on_adversarial_probabilities(engine
         for d in (d_p, d_s, d_c):
             engine.device_free(d)
     engine.segments_configure()
+
+
+def test_async_submit_wait_equals_synchronous_calls():
+    """silero_b200_submit_streams_segments / silero_b200_wait: six calls submitted back to back (more than the four
+    tickets that may be in flight), each with its own pinned buffers; outputs identical to the blocking calls."""
+    S, n, calls = 24, 40, 6
+    pcm = np.stack([vadc_b200.synth_pcm(1300 + s, 1536 * n * calls) for s in range(S)])
+    e = vadc_b200.Engine(max_streams=S, window_chunks=16)
+    e.segments_configure()
+    want_p, want_s = [], []
+    for k in range(calls):
+        s, c, p = e.run_streams_segments(np.ascontiguousarray(pcm[:, k * n * 1536:(k + 1) * n * 1536]), end_of_stream=(k == calls - 1), want_probs=True)
+        want_p.append(p)
+        want_s.append(s)
+    e.reset()
+    e.segments_reset()
+    cap = n // 2 + 2
+    bufs, tickets = [], []
+    for k in range(calls):
+        hin, hin_ptr = vadc_b200.pinned_empty((S, n * 1536), np.int16)
+        hin[:] = pcm[:, k * n * 1536:(k + 1) * n * 1536]
+        hp, hp_ptr = vadc_b200.pinned_empty((S, n), np.float32)
+        hs, hs_ptr = vadc_b200.pinned_empty((S, cap, 2), np.int32)
+        hc, hc_ptr = vadc_b200.pinned_empty((S,), np.int32)
+        bufs.append((hin_ptr, hp, hp_ptr, hs, hs_ptr, hc, hc_ptr))
+        tickets.append(e.submit_streams_segments_ptr(hin_ptr, n * 1536, S, n, k == calls - 1, hs_ptr, cap, hc_ptr, hp_ptr))
+    for k in reversed(range(calls)):                       # waiting out of order is allowed
+        e.wait(tickets[k])
+    for k in range(calls):
+        _, hp, _, hs, _, hc, _ = bufs[k]
+        assert np.array_equal(hp, want_p[k]), k
+        got = [[(int(a), int(b)) for a, b in hs[s, :hc[s]]] for s in range(S)]
+        assert got == want_s[k], k
+    with pytest.raises(vadc_b200.EngineError):
+        e.wait(10 ** 6)
+    for b in bufs:
+        for ptr in (b[0], b[2], b[4], b[6]):
+            vadc_b200.pinned_free(ptr)
+    e.close()

@@ -183,6 +183,18 @@ class Engine:
                                                            nstreams, nchunks, 1 if end_of_stream else 0, C.c_void_p(segs_ptr), cap,
                                                            C.c_void_p(counts_ptr), C.c_void_p(probs_ptr) if probs_ptr else None))
 
+    def submit_streams_segments_ptr(self, pcm_ptr, stream_stride, nstreams, nchunks, end_of_stream, segs_ptr, cap, counts_ptr, probs_ptr=None, first_stream=0):
+        """Asynchronous run_streams_segments_ptr: returns a ticket for wait()."""
+        t = C.c_ulonglong()
+        self._check(lib().silero_b200_submit_streams_segments(self._h, C.c_void_p(pcm_ptr) if pcm_ptr else None, C.c_longlong(stream_stride), first_stream,
+                                                              nstreams, nchunks, 1 if end_of_stream else 0, C.c_void_p(segs_ptr) if segs_ptr else None, cap,
+                                                              C.c_void_p(counts_ptr) if counts_ptr else None, C.c_void_p(probs_ptr) if probs_ptr else None,
+                                                              C.byref(t)))
+        return int(t.value)
+
+    def wait(self, ticket):
+        self._check(lib().silero_b200_wait(self._h, C.c_ulonglong(ticket)))
+
     def run_streams_segments_device(self, d_pcm, stream_stride, nstreams, nchunks, end_of_stream, d_segs, cap, d_counts, d_probs=None, first_stream=0):
         self._check(lib().silero_b200_run_streams_segments_device(self._h, C.c_void_p(d_pcm) if d_pcm else None, C.c_longlong(stream_stride), first_stream,
                                                                   nstreams, nchunks, 1 if end_of_stream else 0,

@@ -88,6 +88,10 @@ struct silero_b200
    int16_t *pcm_stage[2];
    size_t pcm_stage_cap; // samples per buffer
    cudaEvent_t pcm_ready[2], pcm_free[2];
+   unsigned stage_seq;       // windows staged so far: window k of the engine's lifetime uses staging buffer k & 1
+   int stage_used[2];        // pcm_free[b] has been recorded since the staging buffers were (re)allocated
+   cudaEvent_t done_ev[4];   // completion tickets of asynchronous calls (silero_b200_submit_* / silero_b200_wait)
+   unsigned long long ticket_seq;
    float *d_probs;
    size_t d_probs_cap;
    float *d_out2;
@@ -445,6 +449,8 @@ extern "C" void silero_b200_destroy( silero_b200 *h )
       if ( h->pcm_ready[i] ) cudaEventDestroy( h->pcm_ready[i] );
       if ( h->pcm_free[i] ) cudaEventDestroy( h->pcm_free[i] );
    }
+   for ( int i = 0; i < 4; ++i )
+      if ( h->done_ev[i] ) cudaEventDestroy( h->done_ev[i] );
    if ( h->ev_begin ) cudaEventDestroy( h->ev_begin );
    if ( h->ev_end ) cudaEventDestroy( h->ev_end );
    for ( int i = 0; i < N_STAGE_EVENTS; ++i )
@@ -556,6 +562,7 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
       CU_H( cudaEventCreateWithFlags( &h->pcm_ready[i], cudaEventDisableTiming ) );
       CU_H( cudaEventCreateWithFlags( &h->pcm_free[i], cudaEventDisableTiming ) );
    }
+   for ( int i = 0; i < 4; ++i ) CU_H( cudaEventCreateWithFlags( &h->done_ev[i], cudaEventDisableTiming ) );
 
    // pack every weight into one host blob, upload once
    const size_t n_basis = 2 * STFT_BS_FLOATS;
@@ -1048,7 +1055,7 @@ struct SegRequest
 };
 
 static int run_streams_host( silero_b200 *h, const int16_t *pcm, long long stream_stride, int first_stream, int nstreams, int nchunks, float *probs, float *out2,
-                             const SegRequest *seg )
+                             const SegRequest *seg, unsigned long long *ticket = 0 )
 {
    int rc = check_streams( h, first_stream, nstreams, nchunks );
    if ( rc ) return rc;
@@ -1084,6 +1091,7 @@ static int run_streams_host( silero_b200 *h, const int16_t *pcm, long long strea
          h->pcm_stage_cap = 0;
          for ( int i = 0; i < 2; ++i ) CU( cudaMalloc( &h->pcm_stage[i], win_samples * sizeof( int16_t ) ) );
          h->pcm_stage_cap = win_samples;
+         h->stage_used[0] = h->stage_used[1] = 0;
          cudaEventRecord( h->ev_begin, h->stream );
       }
       // Window plan: short windows at both ends so that neither the first copy (nothing to overlap with) nor the
@@ -1092,7 +1100,9 @@ static int run_streams_host( silero_b200 *h, const int16_t *pcm, long long strea
       {
          const int q = nw_max / 4 > 0 ? nw_max / 4 : 1, hh = nw_max / 2 > 0 ? nw_max / 2 : 1;
          const long long mid = (long long)nchunks - 2ll * ( q + hh );
-         if ( mid < nw_max || ( mid + nw_max - 1 ) / nw_max > 64 )
+         // (asynchronous calls are pipelined against their neighbours instead: there the copy of window w+1 hides behind the
+         // compute of window w only if consecutive windows have the same size, so they keep uniform windows)
+         if ( ticket || mid < nw_max || ( mid + nw_max - 1 ) / nw_max > 64 )
             nwin = -1; // short call (or very long one): uniform windows
          else
          {
@@ -1105,18 +1115,24 @@ static int run_streams_host( silero_b200 *h, const int16_t *pcm, long long strea
          }
       }
       const bool planned = nwin > 0;
+      // otherwise: equal windows (sizes differ by at most one chunk), so that copy and compute of neighbouring windows pair up
       if ( !planned ) nwin = ( nchunks + nw_max - 1 ) / nw_max;
+      const int wbase = nchunks / nwin, wextra = nchunks % nwin;
       auto win_begin = [&]( int w ) -> int {
-         if ( !planned ) return w * nw_max;
+         if ( !planned ) return w * wbase + imin( w, wextra );
          int n0 = 0;
          for ( int i = 0; i < w; ++i ) n0 += wsize[i];
          return n0;
       };
-      auto win_size = [&]( int w ) -> int { return planned ? wsize[w] : imin( nw_max, nchunks - w * nw_max ); };
-      // window w is copied on copy_stream into stage[w&1] while window w-1 computes
+      auto win_size = [&]( int w ) -> int { return planned ? wsize[w] : wbase + ( w < wextra ? 1 : 0 ); };
+      // window w is copied on copy_stream into one staging buffer while window w-1 computes out of the other. The alternation
+      // continues across calls (stage0), so the first copy of an asynchronous call never waits for the previous call's last window.
+      const int stage0 = h->stage_seq & 1;
+      h->stage_seq += nwin;
       auto issue_copy = [&]( int w ) -> int {
-         int n0 = win_begin( w ), nw = win_size( w ), b = w & 1;
-         if ( w >= 2 ) CU( cudaStreamWaitEvent( h->copy_stream, h->pcm_free[b], 0 ) );
+         int n0 = win_begin( w ), nw = win_size( w ), b = ( w + stage0 ) & 1;
+         // the staging buffer may still be read by an earlier window -- of this call or of a previous asynchronous one
+         if ( h->stage_used[b] ) CU( cudaStreamWaitEvent( h->copy_stream, h->pcm_free[b], 0 ) );
          CU( cudaMemcpy2DAsync( h->pcm_stage[b], (size_t)nw * VB_CHUNK * sizeof( int16_t ), pcm + (long long)n0 * VB_CHUNK,
                                 (size_t)stream_stride * sizeof( int16_t ), (size_t)nw * VB_CHUNK * sizeof( int16_t ), (size_t)nstreams,
                                 cudaMemcpyHostToDevice, h->copy_stream ) );
@@ -1127,12 +1143,13 @@ static int run_streams_host( silero_b200 *h, const int16_t *pcm, long long strea
       const bool need_probs = probs || seg;
       for ( int w = 0; w < nwin; ++w )
       {
-         int n0 = win_begin( w ), nw = win_size( w ), b = w & 1;
+         int n0 = win_begin( w ), nw = win_size( w ), b = ( w + stage0 ) & 1;
          if ( w + 1 < nwin && issue_copy( w + 1 ) ) return SILERO_B200_ERR_CUDA;
          CU( cudaStreamWaitEvent( h->stream, h->pcm_ready[b], 0 ) );
          rc = run_window( h, h->pcm_stage[b], 0, (long long)nw * VB_CHUNK, first_stream, nstreams, nw, out2 ? h->d_out2 : 0, need_probs ? h->d_probs : 0, nchunks, n0, 1 );
          if ( rc ) return rc;
          CU( cudaEventRecord( h->pcm_free[b], h->stream ) );
+         h->stage_used[b] = 1;
       }
    }
    if ( seg )
@@ -1144,7 +1161,44 @@ static int run_streams_host( silero_b200 *h, const int16_t *pcm, long long strea
    if ( probs && nout ) CU( cudaMemcpyAsync( probs, h->d_probs, nout * sizeof( float ), cudaMemcpyDeviceToHost, h->stream ) );
    if ( out2 && nout ) CU( cudaMemcpyAsync( out2, h->d_out2, nout * 2 * sizeof( float ), cudaMemcpyDeviceToHost, h->stream ) );
    timing_end( h );
+   if ( ticket )
+   {
+      // asynchronous: hand out a completion ticket instead of waiting
+      CU( cudaEventRecord( h->done_ev[h->ticket_seq % 4], h->stream ) );
+      *ticket = h->ticket_seq++;
+      return SILERO_B200_OK;
+   }
    CU( cudaStreamSynchronize( h->stream ) );
+   return SILERO_B200_OK;
+}
+
+extern "C" int silero_b200_submit_streams_segments( silero_b200 *h, const int16_t *pcm, long long stream_stride, int first_stream, int nstreams, int nchunks,
+                                                    int end_of_stream, vadc_segment *segs, int cap, int *counts, float *probs, unsigned long long *ticket )
+{
+   if ( !ticket ) return set_err( SILERO_B200_ERR_ARG, "null ticket" );
+   if ( h && h->ticket_seq >= 4 )
+   {
+      // at most 4 calls in flight: the event about to be reused must have completed
+      if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+      CU( cudaEventSynchronize( h->done_ev[h->ticket_seq % 4] ) );
+   }
+   *ticket = ~0ull;
+   if ( segs )
+   {
+      SegRequest rq = { end_of_stream, cap, segs, counts };
+      return run_streams_host( h, pcm, stream_stride, first_stream, nstreams, nchunks, probs, 0, &rq, ticket );
+   }
+   return run_streams_host( h, pcm, stream_stride, first_stream, nstreams, nchunks, probs, 0, 0, ticket );
+}
+
+extern "C" int silero_b200_wait( silero_b200 *h, unsigned long long ticket )
+{
+   if ( !h ) return set_err( SILERO_B200_ERR_ARG, "null handle" );
+   if ( ticket == ~0ull ) return SILERO_B200_OK; // the submit had nothing to do
+   if ( ticket >= h->ticket_seq ) return set_err( SILERO_B200_ERR_ARG, "unknown ticket" );
+   if ( h->ticket_seq > ticket + 4 ) return SILERO_B200_OK; // its event slot has been reused, and submit waited on it before reusing it
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+   CU( cudaEventSynchronize( h->done_ev[ticket % 4] ) );
    return SILERO_B200_OK;
 }
 
