@@ -55,9 +55,11 @@ typedef struct silero_b200 silero_b200; /* opaque engine handle */
 /* STFT evaluation. HYBRID: fp32 FFT everywhere + the reference's exact rounding
    sequence (stft.c:108-184) for every bin whose magnitude is below stft_k_rel * ||windowed frame||_2;
    EXACT: the reference's sequence for every bin (bit-identical magnitudes, ~7x slower STFT). */
-#define SILERO_B200_STFT_HYBRID 0          /* hybrid rule on the warp-per-frame fp32 FFT kernel (stft_hybrid_kernel.cuh) */
+#define SILERO_B200_STFT_HYBRID 0          /* hybrid rule on the fp32 FFT kernel with 8 lanes per frame, 16 points per lane in registers
+                                              (stft_fft8_kernel.cuh) */
 #define SILERO_B200_STFT_EXACT 1
-#define SILERO_B200_STFT_HYBRID_FFT 2      /* same as _HYBRID */
+#define SILERO_B200_STFT_HYBRID_FFT 2      /* hybrid rule on the warp-per-frame fp32 FFT kernel (stft_hybrid_kernel.cuh): the first FFT kernel,
+                                              5 shuffle stages per frame, ~1.5x slower than _HYBRID */
 #define SILERO_B200_STFT_HYBRID_TENSOR 3   /* hybrid rule on the tcgen05 DFT-as-GEMM kernel (stft_tc_kernel.cuh): 25 % faster STFT, but the
                                               tensor-core accumulator costs 10x in |dY| and probabilities reach 1.1e-4 on long streams:
                                               opt-in, not a drop-in under the 1e-4 bar */

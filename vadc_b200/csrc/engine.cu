@@ -21,6 +21,7 @@
 #include "lstm_tc_kernel.cuh"
 #include "segment_kernel.cuh"
 #include "stft_hybrid_kernel.cuh"
+#include "stft_fft8_kernel.cuh"
 #include "stft_kernel.cuh"
 #include "stft_tc_kernel.cuh"
 #include "tc_probe.cuh"
@@ -395,6 +396,8 @@ static int configure_kernels()
    CU( allow_smem( stft_logmag_kernel<true>, STFT_SMEM_BYTES ) );
    CU( allow_smem( stft_hybrid_kernel<false>, HYB_SMEM_BYTES ) );
    CU( allow_smem( stft_hybrid_kernel<true>, HYB_SMEM_BYTES ) );
+   CU( allow_smem( stft_fft8_kernel<false>, F8_SMEM_BYTES ) );
+   CU( allow_smem( stft_fft8_kernel<true>, F8_SMEM_BYTES ) );
    CU( allow_smem( layer_kernel<0, true>, LayerCfg<0>::SMEM_BYTES ) );
    CU( allow_smem( layer_kernel<0, false>, LayerCfg<0>::SMEM_BYTES ) );
    CU( allow_smem( layer_kernel<1, false>, LayerCfg<1>::SMEM_BYTES ) );
@@ -787,13 +790,13 @@ static int launch_stft( silero_b200 *h, const void *d_in, int in_f32, long long 
       {
          stft_tc_kernel<true><<<grid, STC_THREADS, STC_SMEM_BYTES, h->stream>>>( d_in, stream_stride, nw, nchunks, h->d_stft_tc, h->w.basis_raw, spec, h->stft_k_rel, out_mode,
                                                                                  h->d_flagged, h->d_fix_list, h->d_fix_count, cap );
-         stft_fixup_kernel<true><<<fgrid, 256, 0, h->stream>>>( d_in, stream_stride, nw, h->w.basis_raw, spec, h->d_fix_list, h->d_fix_count, cap, out_mode, h->d_flagged );
+         stft_fixup_kernel<true><<<fgrid, 256, 0, h->stream>>>( d_in, stream_stride, nw, h->w.basis_raw, spec, h->d_fix_list, h->d_fix_count, cap, out_mode, h->d_flagged, nchunks );
       }
       else
       {
          stft_tc_kernel<false><<<grid, STC_THREADS, STC_SMEM_BYTES, h->stream>>>( d_in, stream_stride, nw, nchunks, h->d_stft_tc, h->w.basis_raw, spec, h->stft_k_rel, out_mode,
                                                                                   h->d_flagged, h->d_fix_list, h->d_fix_count, cap );
-         stft_fixup_kernel<false><<<fgrid, 256, 0, h->stream>>>( d_in, stream_stride, nw, h->w.basis_raw, spec, h->d_fix_list, h->d_fix_count, cap, out_mode, h->d_flagged );
+         stft_fixup_kernel<false><<<fgrid, 256, 0, h->stream>>>( d_in, stream_stride, nw, h->w.basis_raw, spec, h->d_fix_list, h->d_fix_count, cap, out_mode, h->d_flagged, nchunks );
       }
       h->launches++;
       h->bins_total += (unsigned long long)nchunks * VB_BINS * VB_FRAMES;
@@ -806,6 +809,21 @@ static int launch_stft( silero_b200 *h, const void *d_in, int in_f32, long long 
          stft_logmag_kernel<true><<<npairs * 2, STFT_THREADS, STFT_SMEM_BYTES, h->stream>>>( d_in, stream_stride, nw, nchunks, h->w.basis_pack, spec, out_mode );
       else
          stft_logmag_kernel<false><<<npairs * 2, STFT_THREADS, STFT_SMEM_BYTES, h->stream>>>( d_in, stream_stride, nw, nchunks, h->w.basis_pack, spec, out_mode );
+   }
+   else if ( h->stft_mode == SILERO_B200_STFT_HYBRID )
+   {
+      static int per_sm8 = 0;
+      if ( !per_sm8 )
+      {
+         CU( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm8, stft_fft8_kernel<false>, F8_THREADS, F8_SMEM_BYTES ) );
+         if ( per_sm8 < 1 ) per_sm8 = 1;
+      }
+      int grid = imin( nchunks, h->sm_count * per_sm8 );
+      if ( in_f32 )
+         stft_fft8_kernel<true><<<grid, F8_THREADS, F8_SMEM_BYTES, h->stream>>>( d_in, stream_stride, nw, nchunks, h->w.basis_raw, spec, mu, h->stft_k_rel, out_mode, h->d_flagged );
+      else
+         stft_fft8_kernel<false><<<grid, F8_THREADS, F8_SMEM_BYTES, h->stream>>>( d_in, stream_stride, nw, nchunks, h->w.basis_raw, spec, mu, h->stft_k_rel, out_mode, h->d_flagged );
+      h->bins_total += (unsigned long long)nchunks * VB_BINS * VB_FRAMES;
    }
    else
    {

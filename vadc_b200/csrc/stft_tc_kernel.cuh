@@ -462,7 +462,7 @@ template <bool F32>
 __global__ void __launch_bounds__( 256 )
 stft_fixup_kernel( const void *__restrict__ in, long long stream_stride, int nw, const float *__restrict__ basis, float *__restrict__ spec,
                    const unsigned long long *__restrict__ fix_list, const unsigned int *__restrict__ fix_count, unsigned int fix_cap, int out_mode,
-                   unsigned long long *__restrict__ flagged )
+                   unsigned long long *__restrict__ flagged, int nchunks )
 {
    const unsigned n = min( *fix_count, fix_cap );
    const int lane = threadIdx.x & 31;
@@ -470,7 +470,12 @@ stft_fixup_kernel( const void *__restrict__ in, long long stream_stride, int nw,
    for ( unsigned e = warp; e < n; e += nwarps )
    {
       const unsigned long long key = __ldg( fix_list + e );
-      const int t = (int)( key & 31ull ), f = (int)( ( key >> 5 ) & 255ull ), ci = (int)( key >> 13 );
+      const int t = (int)( key & 31ull ), f = (int)( ( key >> 5 ) & 255ull );
+      // A warp of stft_tc_kernel whose entries did not fit reserved its range without writing it (it evaluated in-kernel),
+      // so below the cap the list can hold stale entries of an earlier launch: skip anything outside this launch. A stale
+      // entry that is in range only replaces an approximate magnitude by the exact one.
+      if ( ( key >> 13 ) >= (unsigned long long)nchunks || f >= VB_BINS || t >= VB_FRAMES ) continue;
+      const int ci = (int)( key >> 13 );
       const int s = ci / nw, c = ci - s * nw;
       const long long off = (long long)s * stream_stride + (long long)c * VB_CHUNK;
       const void *cp = F32 ? (const void *)( reinterpret_cast<const float *>( in ) + off ) : (const void *)( reinterpret_cast<const int16_t *>( in ) + off );
