@@ -93,32 +93,42 @@ __device__ __forceinline__ void f8_store_x( float *xs, const F8Raw<F32> &raw, in
    }
 }
 
-// the reference's 256-tap tree for basis row `row` at frame t on the padded tile, evaluated by one warp (lane = l*4 + g);
-// same value in every lane (see hyb_exact_row)
-__device__ __forceinline__ float f8_exact_row( const float *__restrict__ xs, const float *__restrict__ basis, int row, int t, int lane )
+// The reference's 256-tap tree (stft.c:108-184) for the two basis rows of bin f (Re: row f, Im: row 129 + f) at frame t on the
+// padded tile, evaluated by one warp (lane = l*4 + g owns the 8-tap leaf {64 g + l + 8 v}; the g- and l-combines are xor
+// butterflies, the same tree because fp32 addition is commutative; see hyb_exact_row), then the magnitude (stft.c:194-213).
+// Same value in every lane. Out of line on purpose: 17 inlined copies (one per magnitude register) made the kernel 126 KB
+// of code and the instruction-cache misses showed up as the second largest stall reason.
+__device__ __noinline__ float f8_exact_mag( const float *__restrict__ xs, const float *__restrict__ basis, int f, int t, int lane )
 {
    const int l = lane >> 2, g = lane & 3;
    const float *xp = xs + 80 * ( t + g ) + l;
-   const float *bp = basis + (size_t)row * 256 + 64 * g + l;
-   float p[8];
+   const float *br = basis + (size_t)f * 256 + 64 * g + l;
+   const float *bi = br + 129 * 256;
+   float wr[8], wi[8], x[8];
 #pragma unroll
-   for ( int v = 0; v < 8; ++v ) p[v] = __fmul_rn( xp[8 * v], __ldg( bp + 8 * v ) );
-   float s01 = __fadd_rn( p[0], p[1] ), s23 = __fadd_rn( p[2], p[3] ), s45 = __fadd_rn( p[4], p[5] ), s67 = __fadd_rn( p[6], p[7] );
-   float r = __fadd_rn( __fadd_rn( s01, s23 ), __fadd_rn( s45, s67 ) );
-   r = __fadd_rn( r, __shfl_xor_sync( 0xffffffffu, r, 1 ) );
-   r = __fadd_rn( r, __shfl_xor_sync( 0xffffffffu, r, 2 ) );
-   r = __fadd_rn( r, __shfl_xor_sync( 0xffffffffu, r, 4 ) );
-   r = __fadd_rn( r, __shfl_xor_sync( 0xffffffffu, r, 8 ) );
-   r = __fadd_rn( r, __shfl_xor_sync( 0xffffffffu, r, 16 ) );
-   return r;
-}
-
-// out of line on purpose: 17 inlined copies (one per magnitude register) made the kernel 126 KB of code and the
-// instruction cache misses showed up as the second largest stall reason
-__device__ __noinline__ float f8_exact_mag( const float *xs, const float *basis, int f, int t, int lane )
-{
-   float re = f8_exact_row( xs, basis, f, t, lane );
-   float im = f8_exact_row( xs, basis, 129 + f, t, lane );
+   for ( int v = 0; v < 8; ++v )
+   {
+      wr[v] = __ldg( br + 8 * v );
+      wi[v] = __ldg( bi + 8 * v );
+   }
+#pragma unroll
+   for ( int v = 0; v < 8; ++v ) x[v] = xp[8 * v];
+   float pr[8], pi[8];
+#pragma unroll
+   for ( int v = 0; v < 8; ++v )
+   {
+      pr[v] = __fmul_rn( x[v], wr[v] );
+      pi[v] = __fmul_rn( x[v], wi[v] );
+   }
+   float re = __fadd_rn( __fadd_rn( __fadd_rn( pr[0], pr[1] ), __fadd_rn( pr[2], pr[3] ) ), __fadd_rn( __fadd_rn( pr[4], pr[5] ), __fadd_rn( pr[6], pr[7] ) ) );
+   float im = __fadd_rn( __fadd_rn( __fadd_rn( pi[0], pi[1] ), __fadd_rn( pi[2], pi[3] ) ), __fadd_rn( __fadd_rn( pi[4], pi[5] ), __fadd_rn( pi[6], pi[7] ) ) );
+#pragma unroll
+   for ( int off = 1; off < 32; off <<= 1 )
+   {
+      const float o_re = __shfl_xor_sync( 0xffffffffu, re, off ), o_im = __shfl_xor_sync( 0xffffffffu, im, off );
+      re = __fadd_rn( re, o_re );
+      im = __fadd_rn( im, o_im );
+   }
    return sqrtf( __fadd_rn( __fmul_rn( re, re ), __fmul_rn( im, im ) ) );
 }
 
@@ -249,7 +259,58 @@ stft_fft8_kernel( const void *__restrict__ in, long long stream_stride, int nw, 
       __syncwarp();
       if ( lane == 0 ) tc::mbar_arrive( &x_full[0] );
       if ( ci + (int)gridDim.x < nchunks ) f8_load_raw<F32>( raw, hyb_chunk_ptr<F32>( in, stream_stride, nw, ci + gridDim.x ), lane );
-      for ( int it = 0; ci < nchunks; ci += gridDim.x, ++it )
+      // Per iteration: first the next input tile (the compute warps need it the moment they finish the current chunk), then
+      // the output tile of the PREVIOUS chunk: both become available at the same instant (all compute warps done with chunk
+      // it-1), and the copy-out has a whole chunk of slack while a late input tile stalls 7 warps.
+      auto copy_out = [&]( int co, int ito ) {
+         const int b = ito & 1;
+         tc::mbar_wait( &o_full[b], ( ito >> 1 ) & 1 );
+         const float *os = Os + b * F8_OS_FLOATS;
+         if ( mu_out )
+         {
+            // the scalar of adaptive_audio_normalization_inplace (misc.c:48-82): reflect-pad 3 + 7-tap smoothing of the
+            // per-frame means, mean over the 25 frames (tree order; the frame means are warp reductions already)
+            const float gk[7] = { 0.03663284704089164733887f, 0.11128076165914535522461f, 0.21674531698226928710938f, 0.27068215608596801757812f,
+                                  0.21674531698226928710938f, 0.11128076165914535522461f, 0.03663284704089164733887f };
+            const int tt = lane < VB_FRAMES ? lane : VB_FRAMES - 1;
+            float v = 0.0f;
+#pragma unroll
+            for ( int k = 0; k < 7; ++k )
+            {
+               int idx = tt + k - 3;
+               if ( idx < 0 ) idx = -idx;
+               if ( idx >= VB_FRAMES ) idx = 2 * ( VB_FRAMES - 1 ) - idx;
+               v = fmaf( Ms[b * 32 + idx], gk[k], v );
+            }
+            if ( lane >= VB_FRAMES ) v = 0.0f;
+#pragma unroll
+            for ( int off = 16; off > 0; off >>= 1 ) v += __shfl_xor_sync( FULL, v, off );
+            if ( lane == 0 ) mu_out[co] = v / (float)VB_FRAMES;
+         }
+         // the tile sits at offset (co & 3) so that shared and global float indices agree modulo 4: 16-byte stores
+         // everywhere except the first and last quad
+         const int off = co & 3;
+         float *gq = spec + ( (size_t)co * HYB_OUT_FLOATS - off );
+#pragma unroll 4
+         for ( int q = lane; q < F8_OS_FLOATS / 4; q += 32 )
+         {
+            const float4 v = ld4( os + 4 * q );
+            const int s0 = 4 * q;
+            if ( s0 >= off && s0 + 3 < off + HYB_OUT_FLOATS )
+               st4( gq + s0, v );
+            else
+            {
+               if ( s0 >= off && s0 < off + HYB_OUT_FLOATS ) gq[s0] = v.x;
+               if ( s0 + 1 >= off && s0 + 1 < off + HYB_OUT_FLOATS ) gq[s0 + 1] = v.y;
+               if ( s0 + 2 >= off && s0 + 2 < off + HYB_OUT_FLOATS ) gq[s0 + 2] = v.z;
+               if ( s0 + 3 >= off && s0 + 3 < off + HYB_OUT_FLOATS ) gq[s0 + 3] = v.w;
+            }
+         }
+         __syncwarp();
+         if ( lane == 0 ) tc::mbar_arrive( &o_empty[b] );
+      };
+      int it = 0, cprev = -1;
+      for ( ; ci < nchunks; ci += gridDim.x, ++it )
       {
          const int b = it & 1;
          const int cn = ci + gridDim.x;
@@ -262,54 +323,10 @@ stft_fft8_kernel( const void *__restrict__ in, long long stream_stride, int nw, 
             if ( lane == 0 ) tc::mbar_arrive( &x_full[b ^ 1] );
             if ( cn + (int)gridDim.x < nchunks ) f8_load_raw<F32>( raw, hyb_chunk_ptr<F32>( in, stream_stride, nw, cn + gridDim.x ), lane );
          }
-         // finished output tile -> global
-         tc::mbar_wait( &o_full[b], ( it >> 1 ) & 1 );
-         const float *os = Os + b * F8_OS_FLOATS;
-         if ( mu_out )
-         {
-            // the scalar of adaptive_audio_normalization_inplace (misc.c:48-82): reflect-pad 3 + 7-tap smoothing of the
-            // per-frame means, mean over the 25 frames
-            const float gk[7] = { 0.03663284704089164733887f, 0.11128076165914535522461f, 0.21674531698226928710938f, 0.27068215608596801757812f,
-                                  0.21674531698226928710938f, 0.11128076165914535522461f, 0.03663284704089164733887f };
-            const int tt = lane < VB_FRAMES ? lane : VB_FRAMES - 1;
-            const float m = Ms[b * 32 + tt];
-            float v = 0.0f;
-#pragma unroll
-            for ( int k = 0; k < 7; ++k )
-            {
-               int idx = tt + k - 3;
-               if ( idx < 0 ) idx = -idx;
-               if ( idx >= VB_FRAMES ) idx = 2 * ( VB_FRAMES - 1 ) - idx;
-               v = __fadd_rn( v, __fmul_rn( __shfl_sync( FULL, m, idx ), gk[k] ) );
-            }
-            float a = 0.0f;
-            for ( int q = 0; q < VB_FRAMES; ++q ) a = __fadd_rn( a, __shfl_sync( FULL, v, q ) );
-            if ( lane == 0 ) mu_out[ci] = a / (float)VB_FRAMES;
-         }
-         // the tile sits at offset (ci & 3) so that shared and global float indices agree modulo 4: 16-byte stores
-         // everywhere except the first and last quad
-         {
-            const int off = ci & 3;
-            float *gq = spec + ( (size_t)ci * HYB_OUT_FLOATS - off );
-#pragma unroll 4
-            for ( int q = lane; q < F8_OS_FLOATS / 4; q += 32 )
-            {
-               const float4 v = ld4( os + 4 * q );
-               const int s0 = 4 * q;
-               if ( s0 >= off && s0 + 3 < off + HYB_OUT_FLOATS )
-                  st4( gq + s0, v );
-               else
-               {
-                  if ( s0 >= off && s0 < off + HYB_OUT_FLOATS ) gq[s0] = v.x;
-                  if ( s0 + 1 >= off && s0 + 1 < off + HYB_OUT_FLOATS ) gq[s0 + 1] = v.y;
-                  if ( s0 + 2 >= off && s0 + 2 < off + HYB_OUT_FLOATS ) gq[s0 + 2] = v.z;
-                  if ( s0 + 3 >= off && s0 + 3 < off + HYB_OUT_FLOATS ) gq[s0 + 3] = v.w;
-               }
-            }
-         }
-         __syncwarp();
-         if ( lane == 0 ) tc::mbar_arrive( &o_empty[b] );
+         if ( cprev >= 0 ) copy_out( cprev, it - 1 );
+         cprev = ci;
       }
+      copy_out( cprev, it - 1 );
       return;
    }
 
