@@ -13,6 +13,8 @@ base = [vadc_b200.synth_pcm(100 + i, 1536 * N) for i in range(nb)]
 pcm2 = np.stack([np.roll(base[s % nb].reshape(N, 1536), (s // nb) % N, axis=0).reshape(-1) for s in range(S)])
 long_pcm = vadc_b200.synth_pcm(4242, 1536 * 3000)
 o = Oracle(); ref_long = o.run_pcm(long_pcm)
+x_long = (long_pcm.astype(np.float32) / np.float32(32768)).reshape(-1, 1536)[:600]
+o.reset(); st_long = o.run_stages(x_long)
 for mode in (0, 2):
     e = vadc_b200.Engine(max_streams=S, stft_mode=mode)
     d_pcm = e.device_alloc(pcm2.nbytes); d_probs = e.device_alloc(S * N * 4)
@@ -28,6 +30,9 @@ for mode in (0, 2):
     e.reset(); e.stft_stats(reset=True)
     p, out2 = e.run_streams(long_pcm[None, :], want_out2=True)
     tot, ex = e.stft_stats(reset=True)
-    print("mode", mode, {k: round(v, 3) for k, v in tm.items()}, "unprofiled total %.3f ms -> %.2f M chunks/s" % (tm0["total"], S * N / tm0["total"] / 1e3),
+    nrm = e.stage_stft_norm(x_long)[0]; mg = e.stage_stft_magnitude(x_long)
+    print("mode", mode, "norm max|d| %.2e mean|d| %.2e, mag max rel %.2e |" % (float(np.abs(nrm - st_long["norm"]).max()), float(np.abs(nrm - st_long["norm"]).mean()),
+          float((np.abs(mg - st_long["stft"]) / np.maximum(st_long["stft"], 1e-30)).max())), end=" ")
+    print( {k: round(v, 3) for k, v in tm.items()}, "unprofiled total %.3f ms -> %.2f M chunks/s" % (tm0["total"], S * N / tm0["total"] / 1e3),
           "| long stream max|dp| %.2e, exact bins %.3f %%" % (float(np.abs(out2[0] - ref_long).max()), 100.0 * ex / tot), flush=True)
     e.close()

@@ -63,3 +63,50 @@ def test_files_are_concurrent_streams(tmp_path):
     raw = cli(None, "--raw_probabilities", "--batch", "2", files=paths[1:3])
     vals = [l for l in raw.splitlines() if not l.startswith("#")]
     assert len(vals) == 50 + 7
+
+
+def _fake_ffmpeg(tmp_path):
+    """A stand-in for ffmpeg (absent from this image): logs its argument vector, honours -ss on a raw s16le 'container'
+    and writes mono 16 kHz s16le to stdout -- what the real decoder's output contract is (vadc.c:537)."""
+    script = tmp_path / "ffmpeg"
+    script.write_text(
+        "#!/bin/bash\n"
+        "printf '%s\\n' \"$@\" > \"$FAKE_FFMPEG_LOG.$$\"\n"
+        "ss=0; inp=\n"
+        "while [ $# -gt 0 ]; do case \"$1\" in -ss) ss=$2; shift;; -i) inp=$2; shift;; esac; shift; done\n"
+        "skip=$(python3 -c \"print(int(float('$ss')*16000)*2)\")\n"
+        "tail -c +$((skip+1)) \"$inp\"\n")
+    script.chmod(0o755)
+    return str(script)
+
+
+def test_named_input_goes_through_an_ffmpeg_child(tmp_path):
+    """vadc.c:531-626: a named input is decoded by `ffmpeg ... -ss S -i FILE -map 0:a:N ... -f s16le -`; same stdout as
+    piping the decoded samples, the reference's argument vector, --start_seconds as -ss, several inputs = several streams."""
+    pcm = vadc_b200.synth_pcm(321, 16000 * 30 + 99)
+    media = tmp_path / "talk.wav"              # any name that is not *.s16le/*.raw/*.pcm takes the decoder path
+    media.write_bytes(pcm.tobytes())
+    env = dict(os.environ, VADC_FFMPEG=_fake_ffmpeg(tmp_path), FAKE_FFMPEG_LOG=str(tmp_path / "argv"))
+
+    def run(*args):
+        r = subprocess.run([CLI, *args], stdin=subprocess.DEVNULL, capture_output=True, timeout=300, env=env)
+        assert r.returncode == 0, r.stderr.decode()
+        return r.stdout.decode()
+
+    assert run(str(media)) == cli(pcm)
+    logs = sorted(p for p in os.listdir(tmp_path) if p.startswith("argv."))
+    argv = (tmp_path / logs[-1]).read_text().split("\n")[:-1]
+    assert argv == ["-hide_banner", "-loglevel", "error", "-nostats", "-ss", "0.000000", "-i", str(media), "-map", "0:a:0",
+                    "-vn", "-sn", "-dn", "-ac", "1", "-ar", "16k", "-f", "s16le", "-"]
+    assert run("--start_seconds", "7.5", "--audio_source", "2", str(media)) == cli(pcm[int(7.5 * 16000):])
+    newest = max((tmp_path / p for p in os.listdir(tmp_path) if p.startswith("argv.")), key=lambda p: p.stat().st_mtime)
+    argv = newest.read_text().split("\n")
+    assert argv[4:6] == ["-ss", "7.500000"] and argv[8:10] == ["-map", "0:a:2"]
+    # decoded and raw inputs mixed: every file is a stream of the multi-stream scheduler
+    raw = tmp_path / "other.s16le"
+    pcm2 = vadc_b200.synth_pcm(322, 16000 * 12)
+    raw.write_bytes(pcm2.tobytes())
+    assert run(str(media), str(raw)) == "# %s\n%s# %s\n%s" % (media, cli(pcm), raw, cli(pcm2))
+    # a decoder that cannot be launched: diagnostics on stderr, no segments
+    r = subprocess.run([CLI, str(media)], stdin=subprocess.DEVNULL, capture_output=True, timeout=300, env=dict(env, VADC_FFMPEG="/nonexistent/ffmpeg"))
+    assert r.stdout == b"" and b"Error launching ffmpeg" in r.stderr

@@ -75,3 +75,4 @@ def test_fft_kernels_agree_on_mu():
         outs.append(e.stage_stft_norm(x)[0])
         e.close()
     assert np.abs(outs[0] - outs[1]).max() < 1e-4
+

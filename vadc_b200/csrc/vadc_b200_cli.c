@@ -5,8 +5,11 @@
  * diagnostics on stderr; same option names, defaults and "a value <= 0 is ignored" rule
  * (vadc.c:1110-1124, 1215); --raw_probabilities prints "%f\n" per chunk (vadc.c:992-997);
  * --output_centi_seconds (vadc.c:251-256); --stats line on stderr (vadc.c:1069-1075).
- * What replaces the Win32 shell (vadc.c:401-667): plain read(2) on stdin instead of ReadFile /
- * an ffmpeg child (feed decoded audio with `ffmpeg -i in -f s16le -ac 1 -ar 16000 - | vadc_b200`).
+ * What replaces the Win32 shell (vadc.c:401-667): plain read(2) on stdin instead of ReadFile; a named input
+ * is decoded by an ffmpeg child exactly as the reference does (init_buffered_stream_ffmpeg, vadc.c:531-626:
+ * same command line, -ss from --start_seconds, -map 0:a:N from --audio_source, ffmpeg's stdin closed, its
+ * stdout on a pipe) but with fork/execvp instead of CreatePipe/CreateProcessW. Files named *.s16le, *.raw or
+ * *.pcm are taken as already-decoded PCM and read directly (no child). $VADC_FFMPEG overrides the program name.
  *
  * New: any number of raw s16le FILES may be given; each file is an independent stream, all of them
  * are pushed through the multi-stream scheduler at once (per-stream LSTM and segmenter state on the
@@ -18,6 +21,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/types.h>
+#include <sys/wait.h>
 #include <time.h>
 #include <unistd.h>
 
@@ -28,7 +33,7 @@ typedef struct cli_opts
    vadc_seg_params seg;
    int batch;
    float start_seconds;
-   int raw_probabilities, stats, device;
+   int raw_probabilities, stats, device, audio_source;
    const char *model;
    const char **files;
    int nfiles;
@@ -64,12 +69,13 @@ static int parse_args( int argc, char **argv, cli_opts *o )
       else if ( !strcmp( a, "--batch" ) || !strcmp( a, "--sequence_count" ) || !strcmp( a, "--audio_source" ) || !strcmp( a, "--device" ) )
       {
          /* numeric options that are not floats of the segmenter: --sequence_count is clamped to 1536 by the C backend
-            (silero.h:41-42, vadc.c:742-754); --audio_source selects an ffmpeg stream in the reference and is accepted and ignored */
+            (silero.h:41-42, vadc.c:742-754); --audio_source selects the ffmpeg audio stream (-map 0:a:N, vadc.c:537) */
          if ( i + 1 < argc )
          {
             float v = (float)atof( argv[++i] );
             if ( !strcmp( a, "--batch" ) && v > 0.0f ) o->batch = (int)v;
             if ( !strcmp( a, "--device" ) && v >= 0.0f ) o->device = (int)v;
+            if ( !strcmp( a, "--audio_source" ) && v > 0.0f ) o->audio_source = (int)v; /* vadc.c:1122, 1215 */
          }
       }
       else
@@ -127,8 +133,83 @@ static long long read_full( int fd, void *buf, size_t n )
    return (long long)got;
 }
 
-/* ---- one stream from stdin: the reference's own loop (vadc.c:852-1027) ---- */
-static int run_stdin( silero_b200 *h, const cli_opts *o )
+/* ---- ingest: raw PCM file or ffmpeg child (vadc.c:531-626) ---- */
+static int is_raw_pcm_name( const char *path )
+{
+   const char *dot = strrchr( path, '.' );
+   return dot && ( !strcmp( dot, ".s16le" ) || !strcmp( dot, ".raw" ) || !strcmp( dot, ".pcm" ) );
+}
+
+/* Launches `ffmpeg -hide_banner -loglevel error -nostats -ss <start> -i <path> -map 0:a:<n> -vn -sn -dn -ac 1 -ar 16k -f s16le -`
+   (the reference's command line, vadc.c:537) with stdin closed (vadc.c:560) and stdout on a pipe; returns the read end, or -1. */
+static int spawn_ffmpeg( const char *path, float start_seconds, int audio_source, pid_t *pid_out )
+{
+   int fds[2];
+   if ( pipe( fds ) )
+   {
+      fprintf( stderr, "Error creating ffmpeg pipe\n" ); /* vadc.c:552 */
+      return -1;
+   }
+   char ss[64], map[64];
+   snprintf( ss, sizeof( ss ), "%f", (double)start_seconds );
+   snprintf( map, sizeof( map ), "0:a:%d", audio_source );
+   const char *prog = getenv( "VADC_FFMPEG" );
+   if ( !prog || !*prog ) prog = "ffmpeg";
+   pid_t pid = fork();
+   if ( pid < 0 )
+   {
+      fprintf( stderr, "Error launching ffmpeg\n" ); /* vadc.c:570 */
+      close( fds[0] );
+      close( fds[1] );
+      return -1;
+   }
+   if ( pid == 0 )
+   {
+      close( fds[0] );
+      dup2( fds[1], 1 );
+      close( fds[1] );
+      close( 0 );
+      char *const argv[] = { (char *)prog, (char *)"-hide_banner", (char *)"-loglevel", (char *)"error", (char *)"-nostats", (char *)"-ss", ss,
+                             (char *)"-i", (char *)path, (char *)"-map", map, (char *)"-vn", (char *)"-sn", (char *)"-dn", (char *)"-ac", (char *)"1",
+                             (char *)"-ar", (char *)"16k", (char *)"-f", (char *)"s16le", (char *)"-", 0 };
+      execvp( prog, argv );
+      fprintf( stderr, "Error launching ffmpeg\n" );
+      _exit( 127 );
+   }
+   close( fds[1] );
+   *pid_out = pid;
+   return fds[0];
+}
+
+/* whole decoded stream into memory (multi-file mode needs every stream's length up front) */
+static int16_t *slurp_fd( int fd, long long *samples_out )
+{
+   size_t cap = 1u << 22, got = 0;
+   char *buf = (char *)malloc( cap );
+   while ( buf )
+   {
+      if ( got == cap )
+      {
+         char *nb = (char *)realloc( buf, cap * 2 );
+         if ( !nb )
+         {
+            free( buf );
+            return 0;
+         }
+         buf = nb;
+         cap *= 2;
+      }
+      ssize_t r = read( fd, buf + got, cap - got );
+      if ( r < 0 && errno == EINTR ) continue;
+      if ( r <= 0 ) break;
+      got += (size_t)r;
+   }
+   *samples_out = (long long)( got / 2 );
+   return (int16_t *)buf;
+}
+
+/* ---- one stream from a descriptor (stdin, or the ffmpeg pipe): the reference's own loop (vadc.c:852-1027) ---- */
+static int run_fd( silero_b200 *h, const cli_opts *o, int in_fd, int skip_on_read )
 {
    const size_t cap_samples = (size_t)o->batch * SILERO_B200_CHUNK_SAMPLES;
    int16_t *pcm = (int16_t *)malloc( cap_samples * sizeof( int16_t ) );
@@ -140,17 +221,17 @@ static int run_stdin( silero_b200 *h, const cli_opts *o )
    double total_speech = 0.0, t0 = now_s();
    long long total_samples = 0;
    /* --start_seconds: the reference seeks with ffmpeg -ss (vadc.c:537); on a pipe the samples are read and dropped */
-   long long skip = (long long)( (double)o->start_seconds * SILERO_B200_SAMPLE_RATE ) * 2;
+   long long skip = skip_on_read ? (long long)( (double)o->start_seconds * SILERO_B200_SAMPLE_RATE ) * 2 : 0;
    while ( skip > 0 )
    {
       size_t n = skip < (long long)( cap_samples * 2 ) ? (size_t)skip : cap_samples * 2;
-      long long r = read_full( 0, pcm, n );
+      long long r = read_full( in_fd, pcm, n );
       if ( r <= 0 ) break;
       skip -= r;
    }
    for ( ;; )
    {
-      long long bytes = read_full( 0, pcm, cap_samples * sizeof( int16_t ) );
+      long long bytes = read_full( in_fd, pcm, cap_samples * sizeof( int16_t ) );
       if ( bytes < 0 )
       {
          fprintf( stderr, "Error: read failed: %s\n", strerror( errno ) );
@@ -201,7 +282,8 @@ typedef struct file_stream
 {
    const char *path;
    long long nchunks;
-   int order; /* position on the command line */
+   int order;        /* position on the command line */
+   int16_t *decoded; /* ffmpeg inputs: the whole decoded stream; raw PCM files are read straight into the pinned buffer */
 } file_stream;
 
 static int by_length_desc( const void *a, const void *b )
@@ -220,15 +302,30 @@ static int run_files( silero_b200 *h, const cli_opts *o )
    long long maxchunks = 0;
    for ( int i = 0; i < S; ++i )
    {
-      FILE *f = fopen( o->files[i], "rb" );
-      if ( !f )
+      long long samples = 0;
+      if ( is_raw_pcm_name( o->files[i] ) )
       {
-         fprintf( stderr, "Error: cannot open %s\n", o->files[i] );
-         return 1;
+         FILE *f = fopen( o->files[i], "rb" );
+         if ( !f )
+         {
+            fprintf( stderr, "Error: cannot open %s\n", o->files[i] );
+            return 1;
+         }
+         fseek( f, 0, SEEK_END );
+         samples = ftell( f ) / 2 - skip_samples;
+         fclose( f );
       }
-      fseek( f, 0, SEEK_END );
-      long long samples = ftell( f ) / 2 - skip_samples;
-      fclose( f );
+      else
+      {
+         /* decoded by an ffmpeg child, which also does the --start_seconds seek (-ss) */
+         pid_t pid = 0;
+         int fd = spawn_ffmpeg( o->files[i], o->start_seconds, o->audio_source, &pid );
+         if ( fd < 0 ) return 1;
+         fs[i].decoded = slurp_fd( fd, &samples );
+         close( fd );
+         waitpid( pid, 0, 0 );
+         if ( !fs[i].decoded ) return 1;
+      }
       fs[i].path = o->files[i];
       fs[i].order = i;
       fs[i].nchunks = samples > 0 ? samples / SILERO_B200_CHUNK_SAMPLES : 0;
@@ -245,10 +342,17 @@ static int run_files( silero_b200 *h, const cli_opts *o )
    }
    for ( int s = 0; s < S; ++s )
    {
+      size_t want = (size_t)fs[s].nchunks * SILERO_B200_CHUNK_SAMPLES;
+      if ( fs[s].decoded )
+      {
+         memcpy( pcm + (size_t)s * stride, fs[s].decoded, want * 2 );
+         free( fs[s].decoded );
+         fs[s].decoded = 0;
+         continue;
+      }
       FILE *f = fopen( fs[s].path, "rb" );
       if ( !f ) return 1;
       fseek( f, skip_samples * 2, SEEK_SET );
-      size_t want = (size_t)fs[s].nchunks * SILERO_B200_CHUNK_SAMPLES;
       if ( fread( pcm + (size_t)s * stride, 2, want, f ) != want )
       {
          fprintf( stderr, "Error: short read on %s\n", fs[s].path );
@@ -382,7 +486,25 @@ int main( int argc, char **argv )
       return 1;
    }
    fprintf( stderr, "batch size: %d\n", o.batch ); /* vadc.c:716 */
-   int rc = o.nfiles == 0 ? run_stdin( h, &o ) : run_files( h, &o );
+   int rc;
+   if ( o.nfiles == 0 )
+      rc = run_fd( h, &o, 0, 1 );
+   else if ( o.nfiles == 1 && !is_raw_pcm_name( o.files[0] ) )
+   {
+      /* the reference's named-input mode: stream the ffmpeg child's output through the same loop as stdin */
+      pid_t pid = 0;
+      int fd = spawn_ffmpeg( o.files[0], o.start_seconds, o.audio_source, &pid );
+      if ( fd < 0 )
+         rc = 1;
+      else
+      {
+         rc = run_fd( h, &o, fd, 0 );
+         close( fd );
+         waitpid( pid, 0, 0 );
+      }
+   }
+   else
+      rc = run_files( h, &o );
    silero_b200_destroy( h );
    free( o.files );
    return rc;
