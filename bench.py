@@ -35,13 +35,13 @@ STFT_FLOP_PER_CHUNK = 2 * 1651200 # K1: 258 x 25 x 256 MAC
 # algorithmic MACs per chunk of every stage on the reference's formulation (sums to 2 702 477)
 STAGE_MAC = {"stft": 1651200, "layer1": 181053, "layer2": 112208, "layer3": 61600, "layer4": 236768,
              "lstm0": 229376, "lstm1_decoder": 229376 + 896}
-STAGE_KERNEL = {"stft": "stft_hybrid_kernel<s16>", "layer1": "layer_kernel<0> (fp32 CUDA cores)", "layer2": "layer_tc_kernel<1> (tcgen05 fp16x2)",
+STAGE_KERNEL = {"stft": "stft_fft8_kernel<s16> (fp32 FFT, 8 lanes per frame, + exact fix-up)", "layer1": "layer0_tc_kernel (tcgen05 fp16x2)", "layer2": "layer_tc_kernel<1> (tcgen05 fp16x2)",
                 "layer3": "layer_tc_kernel<2> (tcgen05 fp16x2)", "layer4": "layer_tc_kernel<3> (tcgen05 fp16x2)",
                 "lstm0": "lstm_tc_kernel<0> (tcgen05 bf16x2)", "lstm1_decoder": "lstm_tc_kernel<1> (tcgen05 bf16x2, +decoder)"}
 # FP32 operations the STFT kernel actually EXECUTES per chunk (2*FFMA + FADD + FMUL thread instructions from the committed ncu
-# capture profiles/ncu_summary_r01c.md: 8447 flop/cycle x 3.541e6 cycles / 81920 chunks): it evaluates the reference's dense
-# 258x256 correlation (3.30 MFLOP/chunk algorithmic) as a 256-point FFT plus exact re-evaluation of ~0.5 % of the bins.
-STFT_EXECUTED_FLOP_PER_CHUNK = 365e3
+# capture profiles/ncu_summary_r01h.md: 6585 flop/cycle x 2.212e6 cycles / 81920 chunks): it evaluates the reference's dense
+# 258x256 correlation (3.30 MFLOP/chunk algorithmic) as a 256-point real FFT plus exact re-evaluation of ~0.5 % of the bins.
+STFT_EXECUTED_FLOP_PER_CHUNK = 178e3
 STREAMS_PER_GPU = 4096
 STEP_CHUNKS = 125
 N_BASE = 32                       # distinct synthetic base streams
@@ -409,7 +409,10 @@ def main():
 
 
 # dram bytes per chunk of each kernel from the committed ncu captures (profiles/); absent until measured
-TRAFFIC_BYTES_PER_CHUNK = {}
+# dram__bytes_read.sum + dram__bytes_write.sum per chunk of each kernel, from the ncu --set full capture of one window of
+# 81 920 chunks (profiles/ncu_summary_r01h.md). For the STFT kernel the algorithmic bytes are 3 072 (s16 PCM) + 12 900 (log
+# spectrogram) + 4 (normalization scalar) = 15 976 per chunk: traffic == algorithmic, nothing is re-read.
+TRAFFIC_BYTES_PER_CHUNK = {"stft": 15336, "layer1": 13714, "layer2": 1128, "layer3": 1218, "layer4": 2064, "lstm0": 3117, "lstm1_decoder": 1905}
 
 if __name__ == "__main__":
     sys.exit(main())
