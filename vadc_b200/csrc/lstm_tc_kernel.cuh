@@ -11,8 +11,11 @@
 // gate pre-activations from TMEM (tcgen05.ld), apply the gate nonlinearities and the cell update
 // (lstm.c:64-88) with c in registers, write h_t as the bf16 hi/lo B operand of the next step, and
 // stage x_{t+1} next to it. mbarriers carry the two hand-offs (operand ready -> MMA, MMA done ->
-// cell update). The weights stay resident in shared memory (128 KB as bf16 hi/lo, rows permuted so
-// that the four gates of a hidden unit land in one warp).
+// cell update). The weights never change, so they are the A operand IN TENSOR MEMORY (tcgen05.mma with [a_tmem]): 256 of the
+// 512 TMEM columns hold W as bf16 hi/lo (row = lane, two K elements per 32-bit column; rows permuted so that the four gates of
+// a hidden unit land in one warp), written once per CTA with tcgen05.st. With W in shared memory every one of the 48 MMAs of a
+// step re-read 4 KB of it (32 cycles at 128 B/clk against 16 cycles of math for N = 32): ncu showed the issuing warp
+// back-pressured on every UTCHMMA and the cell-update warps waiting 41 % of the step for the contraction.
 //
 // Row permutation: M-tile m (0,1), TMEM lane L = 32*wq + q holds gate row  gate*64 + u  with
 //   u = 16*wq + (q & 15),  gate = m == 0 ? (q < 16 ? i : f) : (q < 16 ? g : o).
@@ -38,9 +41,10 @@
 #define LTC_X_SPLIT_BYTES ( 16 * LTC_X_LBO )    // 8 KB: [16 chunks][32 streams][8]
 #define LTC_X_BUF_BYTES ( 2 * LTC_X_SPLIT_BYTES )
 #define LTC_HP_BYTES ( 2 * 8 * LTC_X_LBO )      // packed h of one tile-step: [split][8 chunks][32][8] = 8 KB
-#define LTC_TMEM_COLS 128                       // 2 buffers x 2 M-tiles x 32 columns
+#define LTC_TMEM_COLS 512                       // accumulators: 2 buffers x 2 M-tiles x 32 columns; weights: see LTC_TMEM_W
+#define LTC_TMEM_W 128                          // first weight column; (M-tile m, split p) at LTC_TMEM_W + (2 m + p) * 64, K = 128 -> 64 columns
 #define LTC_DEC_FLOATS ( 2 * 4 * LTC_N * 2 )         // decoder partial sums: [chunk parity][unit quarter][stream][head]
-#define LTC_SMEM_BYTES ( LTC_W_BYTES + 2 * LTC_X_BUF_BYTES + 256 * 4 + 128 * 4 + LTC_DEC_FLOATS * 4 + 64 )
+#define LTC_SMEM_BYTES ( 2 * LTC_X_BUF_BYTES + 256 * 4 + 128 * 4 + LTC_DEC_FLOATS * 4 + 64 )
 
 // host-side image of one layer's weights in shared-memory order: [split][chunk][row'][8] bf16
 // (engine.cu: pack_lstm_tc)
@@ -66,8 +70,7 @@ lstm_tc_kernel( const float *__restrict__ x_f32,            // LAYER 0: a4 [S][s
 {
    extern __shared__ __align__( 128 ) unsigned char ltc_smem[];
    unsigned char *smem = ltc_smem;
-   unsigned char *sW = smem;
-   unsigned char *sX = smem + LTC_W_BYTES;                                  // [2 bufs][2 splits][16][32][8]
+   unsigned char *sX = smem;                                                // [2 bufs][2 splits][16][32][8]
    float *sBias = reinterpret_cast<float *>( sX + 2 * LTC_X_BUF_BYTES );    // [256]
    float *sDw = sBias + 256;                                                // [2][64]
    float *sDec = sDw + 128;                                                 // [2][4][32 streams][2 heads]
@@ -81,9 +84,6 @@ lstm_tc_kernel( const float *__restrict__ x_f32,            // LAYER 0: a4 [S][s
 
    // ---- one-time setup ---------------------------------------------------------------------------
    {
-      const int4 *src = reinterpret_cast<const int4 *>( wimg + (size_t)LAYER * LTC_W_BYTES );
-      int4 *dst = reinterpret_cast<int4 *>( sW );
-      for ( int i = tid; i < LTC_W_BYTES / 16; i += LTC_THREADS ) dst[i] = __ldg( src + i );
       for ( int i = tid; i < 256; i += LTC_THREADS ) sBias[i] = bias[LAYER * 256 + i];
       for ( int i = tid; i < 128; i += LTC_THREADS ) sDw[i] = dec_w[i];
    }
@@ -99,18 +99,36 @@ lstm_tc_kernel( const float *__restrict__ x_f32,            // LAYER 0: a4 [S][s
          tc::mbar_fence_init();
       }
    }
-   tc::fence_async_smem(); // the weight image was written with generic stores
    tc::fence_before_sync();
    __syncthreads();
    tc::fence_after_sync();
    const uint32_t tmem = *tmem_slot;
+   if ( warp < LTC_EPI_WARPS )
+   {
+      // weights -> tensor memory: warp (wq, m) writes rows 32 wq .. 32 wq + 31 of M-tile m; the host image is
+      // [split][16 K-chunks][256 rows'][8 bf16], i.e. 16 bytes = 4 columns per (chunk, row)
+      const int wq = warp & 3, m = warp >> 2;
+      const int4 *src = reinterpret_cast<const int4 *>( wimg + (size_t)LAYER * LTC_W_BYTES );
+      const uint32_t trow = tmem + ( (uint32_t)( wq * 32 ) << 16 ) + LTC_TMEM_W + m * 128;
+#pragma unroll 1
+      for ( int p = 0; p < 2; ++p )
+#pragma unroll 4
+         for ( int c = 0; c < 16; ++c )
+         {
+            const int4 v = __ldg( src + ( (size_t)p * 16 + c ) * 256 + m * 128 + wq * 32 + lane );
+            tc::tmem_st4( trow + p * 64 + c * 4, (uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w );
+         }
+      tc::tmem_wait_st();
+   }
+   tc::fence_before_sync();
+   __syncthreads();
+   tc::fence_after_sync();
 
    // `it` counts tile-steps processed by this CTA; buffer = it & 1, mbarrier phase = (it >> 1) & 1
    if ( warp == LTC_EPI_WARPS )
    {
       // ================================ MMA issuer ================================================
       const uint32_t idesc = tc::idesc_bf16_f32( 128, LTC_N );
-      const uint64_t dW = tc::smem_desc( tc::smem_u32( sW ), LTC_W_LBO, 128 );
       const uint64_t dX = tc::smem_desc( tc::smem_u32( sX ), LTC_X_LBO, 128 );
       uint32_t it = 0;
       for ( int tile = blockIdx.x; tile < ntiles; tile += gridDim.x )
@@ -126,17 +144,16 @@ lstm_tc_kernel( const float *__restrict__ x_f32,            // LAYER 0: a4 [S][s
                for ( int m = 0; m < 2; ++m )
                {
                   const uint32_t d_tmem = tmem + buf * 64 + m * 32;
-                  const uint64_t dWm = dW + (uint64_t)( m * ( 128 * 16 >> 4 ) );
+                  const uint32_t aWm = tmem + LTC_TMEM_W + m * 128;
                   // (W split, X split): (hi,hi) (lo,hi) (hi,lo)
 #pragma unroll
                   for ( int p = 0; p < 3; ++p )
                   {
-                     const uint64_t da = dWm + (uint64_t)( ( p == 1 ? 1 : 0 ) * ( LTC_W_SPLIT_BYTES >> 4 ) );
+                     const uint32_t ta = aWm + ( p == 1 ? 64 : 0 );
                      const uint64_t db = dXb + (uint64_t)( ( p == 2 ? 1 : 0 ) * ( LTC_X_SPLIT_BYTES >> 4 ) );
 #pragma unroll
                      for ( int kk = 0; kk < 8; ++kk )
-                        tc::mma_bf16( d_tmem, da + (uint64_t)( kk * ( 2 * LTC_W_LBO >> 4 ) ), db + (uint64_t)( kk * ( 2 * LTC_X_LBO >> 4 ) ), idesc,
-                                      ( p | kk ) ? 1u : 0u );
+                        tc::mma_bf16_ts( d_tmem, ta + kk * 8, db + (uint64_t)( kk * ( 2 * LTC_X_LBO >> 4 ) ), idesc, ( p | kk ) ? 1u : 0u );
                   }
                }
                tc::mma_commit( &bar_d[buf] );

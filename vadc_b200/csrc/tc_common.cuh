@@ -150,6 +150,21 @@ __device__ __forceinline__ void mma_bf16( uint32_t d_tmem, uint64_t a_desc, uint
                  "l"( a_desc ), "l"( b_desc ), "r"( idesc ), "r"( accumulate )
                  : "memory" );
 }
+// D[tmem] (+)= A[tmem] * B[smem]^T ; A sits in tensor memory (row m of the M-tile in lane m, K elements packed two per 32-bit
+// column, K-major): the operand that never changes (a weight matrix) is read from TMEM instead of 4 KB of shared memory per MMA
+__device__ __forceinline__ void mma_bf16_ts( uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate )
+{
+   asm volatile( "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"( d_tmem ),
+                 "r"( a_tmem ), "l"( b_desc ), "r"( idesc ), "r"( accumulate )
+                 : "memory" );
+}
+// four consecutive 32-bit columns of this thread's TMEM lane (warp w owns lanes 32 (w % 4) ..); the caller waits (tmem_wait_st)
+__device__ __forceinline__ void tmem_st4( uint32_t taddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3 )
+{
+   asm volatile( "tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"( taddr ), "r"( r0 ), "r"( r1 ), "r"( r2 ), "r"( r3 ) : "memory" );
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile( "tcgen05.wait::st.sync.aligned;" ::: "memory" ); }
+
 // all previously issued MMAs of this thread arrive on `bar` when complete (implies fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit( uint64_t *bar )
 {
