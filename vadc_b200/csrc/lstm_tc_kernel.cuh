@@ -23,6 +23,11 @@
 // streams; lanes q and q^16 swap halves by shuffle so that each lane ends up with all four gates of
 // one unit for 8 streams.
 //
+// Two chains per CTA. A step is a strict dependency chain (operand -> MMA -> TMEM load -> gates -> operand). The 32 streams
+// of a tile are split into two independent chains of LTC_NC = 16 streams (N = 16 MMAs), each with its own operand buffers,
+// TMEM columns, mbarriers and four cell-update warps (chain = warp >> 2): while one chain's gates are evaluated the tensor
+// core works on the other's contraction.
+//
 // Layer 0 reads the encoder output a4 (fp32 [S][steps][64]) and writes its h sequence packed as the
 // next layer's operand: hp [tile][step][split][8 chunks][32 streams][8] bf16 (8 KB per tile-step).
 // Layer 1 reads hp and folds the decoder head in (relu -> 64->2 -> mean over 7 frames -> sigmoid).
@@ -37,14 +42,17 @@
 #define LTC_W_LBO ( 256 * 16 )                  // bytes between K chunks of the weight operand
 #define LTC_W_SPLIT_BYTES ( 16 * LTC_W_LBO )    // 64 KB per split
 #define LTC_W_BYTES ( 2 * LTC_W_SPLIT_BYTES )   // hi, lo
-#define LTC_X_LBO ( LTC_N * 16 )
-#define LTC_X_SPLIT_BYTES ( 16 * LTC_X_LBO )    // 8 KB: [16 chunks][32 streams][8]
+#define LTC_NC 16                               // streams per chain (two chains per tile)
+#define LTC_CHAIN_THREADS 128
+#define LTC_X_LBO ( LTC_NC * 16 )               // operand buffers are per chain: [16 chunks][16 streams][8]
+#define LTC_X_SPLIT_BYTES ( 16 * LTC_X_LBO )    // 4 KB
 #define LTC_X_BUF_BYTES ( 2 * LTC_X_SPLIT_BYTES )
-#define LTC_HP_BYTES ( 2 * 8 * LTC_X_LBO )      // packed h of one tile-step: [split][8 chunks][32][8] = 8 KB
-#define LTC_TMEM_COLS 512                       // accumulators: 2 buffers x 2 M-tiles x 32 columns; weights: see LTC_TMEM_W
+#define LTC_HP_LBO ( LTC_N * 16 )
+#define LTC_HP_BYTES ( 2 * 8 * LTC_HP_LBO )     // packed h of one tile-step: [split][8 chunks][32 streams][8] = 8 KB
+#define LTC_TMEM_COLS 512                       // accumulators: 2 chains x 2 buffers x 2 M-tiles x 16 columns; weights: see LTC_TMEM_W
 #define LTC_TMEM_W 128                          // first weight column; (M-tile m, split p) at LTC_TMEM_W + (2 m + p) * 64, K = 128 -> 64 columns
 #define LTC_DEC_FLOATS ( 2 * 4 * LTC_N * 2 )         // decoder partial sums: [chunk parity][unit quarter][stream][head]
-#define LTC_SMEM_BYTES ( 2 * LTC_X_BUF_BYTES + 256 * 4 + 128 * 4 + LTC_DEC_FLOATS * 4 + 64 )
+#define LTC_SMEM_BYTES ( 4 * LTC_X_BUF_BYTES + 256 * 4 + 128 * 4 + LTC_DEC_FLOATS * 4 + 128 )
 
 // host-side image of one layer's weights in shared-memory order: [split][chunk][row'][8] bf16
 // (engine.cu: pack_lstm_tc)
@@ -70,13 +78,13 @@ lstm_tc_kernel( const float *__restrict__ x_f32,            // LAYER 0: a4 [S][s
 {
    extern __shared__ __align__( 128 ) unsigned char ltc_smem[];
    unsigned char *smem = ltc_smem;
-   unsigned char *sX = smem;                                                // [2 bufs][2 splits][16][32][8]
-   float *sBias = reinterpret_cast<float *>( sX + 2 * LTC_X_BUF_BYTES );    // [256]
+   unsigned char *sX = smem;                                                // [2 chains][2 bufs][2 splits][16][16][8]
+   float *sBias = reinterpret_cast<float *>( sX + 4 * LTC_X_BUF_BYTES );    // [256]
    float *sDw = sBias + 256;                                                // [2][64]
    float *sDec = sDw + 128;                                                 // [2][4][32 streams][2 heads]
-   uint64_t *bars = reinterpret_cast<uint64_t *>( sDec + LTC_DEC_FLOATS );  // xh[2], d[2]
-   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>( bars + 4 );
-   uint64_t *bar_xh = bars, *bar_d = bars + 2;
+   uint64_t *bars = reinterpret_cast<uint64_t *>( sDec + LTC_DEC_FLOATS );  // xh[chain][buf], d[chain][buf]
+   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>( bars + 8 );
+   uint64_t *bar_xh = bars, *bar_d = bars + 4;
 
    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
    const int steps = nw * 7;
@@ -92,10 +100,11 @@ lstm_tc_kernel( const float *__restrict__ x_f32,            // LAYER 0: a4 [S][s
       tc::tmem_alloc( tmem_slot, LTC_TMEM_COLS );
       if ( lane == 0 )
       {
-         tc::mbar_init( &bar_xh[0], LTC_EPI_WARPS );
-         tc::mbar_init( &bar_xh[1], LTC_EPI_WARPS );
-         tc::mbar_init( &bar_d[0], 1 );
-         tc::mbar_init( &bar_d[1], 1 );
+         for ( int i = 0; i < 4; ++i )
+         {
+            tc::mbar_init( &bar_xh[i], LTC_EPI_WARPS / 2 );
+            tc::mbar_init( &bar_d[i], 1 );
+         }
          tc::mbar_fence_init();
       }
    }
@@ -128,22 +137,24 @@ lstm_tc_kernel( const float *__restrict__ x_f32,            // LAYER 0: a4 [S][s
    if ( warp == LTC_EPI_WARPS )
    {
       // ================================ MMA issuer ================================================
-      const uint32_t idesc = tc::idesc_bf16_f32( 128, LTC_N );
+      const uint32_t idesc = tc::idesc_bf16_f32( 128, LTC_NC );
       const uint64_t dX = tc::smem_desc( tc::smem_u32( sX ), LTC_X_LBO, 128 );
       uint32_t it = 0;
       for ( int tile = blockIdx.x; tile < ntiles; tile += gridDim.x )
          for ( int step = 0; step < steps; ++step, ++it )
+#pragma unroll 1
+         for ( int chain = 0; chain < 2; ++chain )
          {
             const uint32_t buf = it & 1, ph = ( it >> 1 ) & 1;
-            tc::mbar_wait( &bar_xh[buf], ph );
+            tc::mbar_wait( &bar_xh[chain * 2 + buf], ph );
             tc::fence_after_sync();
             if ( tc::elect_one() )
             {
-               const uint64_t dXb = dX + (uint64_t)( buf * ( LTC_X_BUF_BYTES >> 4 ) );
+               const uint64_t dXb = dX + (uint64_t)( ( chain * 2 + buf ) * ( LTC_X_BUF_BYTES >> 4 ) );
 #pragma unroll
                for ( int m = 0; m < 2; ++m )
                {
-                  const uint32_t d_tmem = tmem + buf * 64 + m * 32;
+                  const uint32_t d_tmem = tmem + chain * 64 + buf * 32 + m * 16;
                   const uint32_t aWm = tmem + LTC_TMEM_W + m * 128;
                   // (W split, X split): (hi,hi) (lo,hi) (hi,lo)
 #pragma unroll
@@ -156,7 +167,7 @@ lstm_tc_kernel( const float *__restrict__ x_f32,            // LAYER 0: a4 [S][s
                         tc::mma_bf16_ts( d_tmem, ta + kk * 8, db + (uint64_t)( kk * ( 2 * LTC_X_LBO >> 4 ) ), idesc, ( p | kk ) ? 1u : 0u );
                   }
                }
-               tc::mma_commit( &bar_d[buf] );
+               tc::mma_commit( &bar_d[chain * 2 + buf] );
             }
             __syncwarp();
          }
@@ -164,17 +175,21 @@ lstm_tc_kernel( const float *__restrict__ x_f32,            // LAYER 0: a4 [S][s
    else
    {
       // ================================ cell update ===============================================
-      const int wq = warp & 3, hf = warp >> 2;
+      const int wq = warp & 3, chain = warp >> 2;
       const int q = lane & 15, up = lane >> 4; // up = 0: holds i,g and keeps streams 0..7 ; 1: holds f,o and keeps 8..15
       const int u = 16 * wq + q;
       const float bi = sBias[u], bf = sBias[64 + u], bg = sBias[128 + u], bo = sBias[192 + u];
       const float dw0 = sDw[u], dw1 = sDw[64 + u];
       const float db0 = __ldg( dec_b ), db1 = __ldg( dec_b + 1 );
-      const int sl0 = hf * 16 + up * 8; // first of this lane's 8 streams inside the tile
+      const int sl0 = chain * LTC_NC + up * 8; // first of this lane's 8 streams inside the tile
+      const int rl0 = up * 8;                  // ... and inside the chain's operand buffer
+      unsigned char *sXc = sX + chain * 2 * LTC_X_BUF_BYTES;
+      uint64_t *bar_xh_c = bar_xh + chain * 2, *bar_d_c = bar_d + chain * 2;
+      const int ctid = tid & ( LTC_CHAIN_THREADS - 1 );
       // byte offset of this lane's h element (k = 64 + u) inside one split of an X buffer, for stream row 0
       const uint32_t hoff = (uint32_t)( 8 + ( u >> 3 ) ) * LTC_X_LBO + (uint32_t)( u & 7 ) * 2u;
-      // staging role for x: thread e -> stream row e & 31, chunk e >> 5
-      const int xs = tid & 31, xc = tid >> 5;
+      // staging role for x inside the chain: thread e -> stream row e & 15, chunk e >> 4
+      const int xs = ctid & 15, xc = ctid >> 4;
 
       uint32_t it = 0;
       for ( int tile = blockIdx.x; tile < ntiles; tile += gridDim.x )
@@ -183,7 +198,7 @@ lstm_tc_kernel( const float *__restrict__ x_f32,            // LAYER 0: a4 [S][s
          float c[8], hlast[8], d0[8], d1[8];
          // ---- tile prologue: state -> registers / operand buffer, x_0 -> operand buffer -----------------
          {
-            unsigned char *xb = sX + ( it & 1 ) * LTC_X_BUF_BYTES;
+            unsigned char *xb = sXc + ( it & 1 ) * LTC_X_BUF_BYTES;
 #pragma unroll
             for ( int j = 0; j < 8; ++j )
             {
@@ -193,8 +208,8 @@ lstm_tc_kernel( const float *__restrict__ x_f32,            // LAYER 0: a4 [S][s
                hlast[j] = ok ? state_h[( (size_t)s * 2 + LAYER ) * 64 + u] : 0.0f;
                d0[j] = d1[j] = 0.0f;
                tc::Split2 sp = tc::split2( hlast[j] );
-               *reinterpret_cast<__nv_bfloat16 *>( xb + hoff + ( sl0 + j ) * 16 ) = sp.hi;
-               *reinterpret_cast<__nv_bfloat16 *>( xb + LTC_X_SPLIT_BYTES + hoff + ( sl0 + j ) * 16 ) = sp.lo;
+               *reinterpret_cast<__nv_bfloat16 *>( xb + hoff + ( rl0 + j ) * 16 ) = sp.hi;
+               *reinterpret_cast<__nv_bfloat16 *>( xb + LTC_X_SPLIT_BYTES + hoff + ( rl0 + j ) * 16 ) = sp.lo;
             }
          }
          // x of step `st` -> registers (raw), then -> operand buffer
@@ -203,7 +218,7 @@ lstm_tc_kernel( const float *__restrict__ x_f32,            // LAYER 0: a4 [S][s
          auto x_fetch = [&]( int st ) {
             if ( LAYER == 0 )
             {
-               const int s = s0 + xs;
+               const int s = s0 + chain * LTC_NC + xs;
                if ( s < nstreams && st < steps )
                {
                   const float4 *p = reinterpret_cast<const float4 *>( x_f32 + ( (size_t)s * steps + st ) * 64 + xc * 8 );
@@ -218,8 +233,8 @@ lstm_tc_kernel( const float *__restrict__ x_f32,            // LAYER 0: a4 [S][s
                if ( st < steps )
                {
                   const int4 *p = reinterpret_cast<const int4 *>( x_packed + ( (size_t)tile * steps + st ) * LTC_HP_BYTES );
-                  xp0 = __ldg( p + xc * LTC_N + xs );
-                  xp1 = __ldg( p + ( 8 + xc ) * LTC_N + xs );
+                  xp0 = __ldg( p + xc * LTC_N + chain * LTC_NC + xs );
+                  xp1 = __ldg( p + ( 8 + xc ) * LTC_N + chain * LTC_NC + xs );
                }
                else
                   xp0 = xp1 = make_int4( 0, 0, 0, 0 );
@@ -248,26 +263,26 @@ lstm_tc_kernel( const float *__restrict__ x_f32,            // LAYER 0: a4 [S][s
             *reinterpret_cast<int4 *>( xbuf + LTC_X_SPLIT_BYTES + xc * LTC_X_LBO + xs * 16 ) = lo;
          };
          x_fetch( 0 );
-         x_stage( sX + ( it & 1 ) * LTC_X_BUF_BYTES );
+         x_stage( sXc + ( it & 1 ) * LTC_X_BUF_BYTES );
          x_fetch( 1 );
          tc::fence_async_smem();
          __syncwarp();
-         if ( lane == 0 ) tc::mbar_arrive( &bar_xh[it & 1] );
+         if ( lane == 0 ) tc::mbar_arrive( &bar_xh_c[it & 1] );
 
          for ( int step = 0; step < steps; ++step, ++it )
          {
             const uint32_t buf = it & 1, ph = ( it >> 1 ) & 1;
-            unsigned char *xnext = sX + ( buf ^ 1 ) * LTC_X_BUF_BYTES;
+            unsigned char *xnext = sXc + ( buf ^ 1 ) * LTC_X_BUF_BYTES;
             // x_{t+1} can be staged while the MMAs of step t run: buffer buf^1 was last read by step t-1
             x_stage( xnext );
             x_fetch( step + 2 );
 
-            tc::mbar_wait( &bar_d[buf], ph );
+            tc::mbar_wait( &bar_d_c[buf], ph );
             tc::fence_after_sync();
             float a[16], b[16];
-            const uint32_t taddr = tmem + ( (uint32_t)( wq * 32 ) << 16 ) + buf * 64 + hf * 16;
+            const uint32_t taddr = tmem + ( (uint32_t)( wq * 32 ) << 16 ) + chain * 64 + buf * 32;
             tc::tmem_ld16( taddr, a );
-            tc::tmem_ld16( taddr + 32, b );
+            tc::tmem_ld16( taddr + 16, b );
             tc::tmem_wait_ld();
 
 #pragma unroll
@@ -286,8 +301,8 @@ lstm_tc_kernel( const float *__restrict__ x_f32,            // LAYER 0: a4 [S][s
                const float hn = ltc_tanh( cn ) * og;
                hlast[j] = hn;
                tc::Split2 sp = tc::split2( hn );
-               *reinterpret_cast<__nv_bfloat16 *>( xnext + hoff + ( sl0 + j ) * 16 ) = sp.hi;
-               *reinterpret_cast<__nv_bfloat16 *>( xnext + LTC_X_SPLIT_BYTES + hoff + ( sl0 + j ) * 16 ) = sp.lo;
+               *reinterpret_cast<__nv_bfloat16 *>( xnext + hoff + ( rl0 + j ) * 16 ) = sp.hi;
+               *reinterpret_cast<__nv_bfloat16 *>( xnext + LTC_X_SPLIT_BYTES + hoff + ( rl0 + j ) * 16 ) = sp.lo;
                if ( LAYER == 1 )
                {
                   const float r = fmaxf( hn, 0.0f );
@@ -298,18 +313,18 @@ lstm_tc_kernel( const float *__restrict__ x_f32,            // LAYER 0: a4 [S][s
             tc::fence_async_smem();
             tc::fence_before_sync();
             __syncwarp();
-            if ( lane == 0 && step + 1 < steps ) tc::mbar_arrive( &bar_xh[buf ^ 1] );
+            if ( lane == 0 && step + 1 < steps ) tc::mbar_arrive( &bar_xh_c[buf ^ 1] );
 
             if ( LAYER == 0 )
             {
-               // h_t of the whole tile is complete in xnext (chunks 8..15 of both splits) once every cell-update
-               // warp is here; write it out coalesced as the next layer's packed operand
-               bar_sync( 1, LTC_EPI_THREADS );
-               int4 *dst = reinterpret_cast<int4 *>( hp_out + ( (size_t)tile * steps + step ) * LTC_HP_BYTES );
+               // h_t of the chain's 16 streams is complete in xnext (chunks 8..15 of both splits) once its four cell-update
+               // warps are here; write it out as the next layer's packed operand ([split][8 chunks][32 streams][8])
+               bar_sync( 1 + chain, LTC_CHAIN_THREADS );
+               int4 *dst = reinterpret_cast<int4 *>( hp_out + ( (size_t)tile * steps + step ) * LTC_HP_BYTES ) + xc * LTC_N + chain * LTC_NC + xs;
                const int4 *s_hi = reinterpret_cast<const int4 *>( xnext + 8 * LTC_X_LBO );
                const int4 *s_lo = reinterpret_cast<const int4 *>( xnext + LTC_X_SPLIT_BYTES + 8 * LTC_X_LBO );
-               dst[tid] = s_hi[tid];
-               dst[256 + tid] = s_lo[tid];
+               dst[0] = s_hi[ctid];
+               dst[8 * LTC_N] = s_lo[ctid];
                // the copy must be done before step t+1's cell update overwrites... it writes the OTHER buffer; the
                // buffer read here is next written at step t+2, after the barrier of step t+1
             }
@@ -335,13 +350,13 @@ lstm_tc_kernel( const float *__restrict__ x_f32,            // LAYER 0: a4 [S][s
                   }
                   d0[j] = d1[j] = 0.0f;
                }
-               bar_sync( 1, LTC_EPI_THREADS );
-               // (the other parity is written 7 steps from now; every step in between needs all eight warps to
+               bar_sync( 1 + chain, LTC_CHAIN_THREADS );
+               // (the other parity is written 7 steps from now; every step in between needs the chain's four warps to
                // arrive before its MMAs run, so these reads are long done by then)
-               if ( tid < LTC_N * 2 )
+               if ( ctid < LTC_NC * 2 )
                {
-                  const int sl = tid >> 1, head = tid & 1, s = s0 + sl;
-                  const float sum = ( ( part[tid] + part[LTC_N * 2 + tid] ) + part[2 * LTC_N * 2 + tid] ) + part[3 * LTC_N * 2 + tid];
+                  const int sl = chain * LTC_NC + ( ctid >> 1 ), head = ctid & 1, s = s0 + sl, pi = sl * 2 + head;
+                  const float sum = ( ( part[pi] + part[LTC_N * 2 + pi] ) + part[2 * LTC_N * 2 + pi] ) + part[3 * LTC_N * 2 + pi];
                   const float mean = sum / 7.0f + ( head ? db1 : db0 );
                   if ( s < nstreams )
                   {
@@ -364,8 +379,8 @@ lstm_tc_kernel( const float *__restrict__ x_f32,            // LAYER 0: a4 [S][s
                state_h[( (size_t)s * 2 + LAYER ) * 64 + u] = hlast[j];
             }
          }
-         // all cell-update warps must be done with this tile's buffers before the next prologue writes them
-         bar_sync( 1, LTC_EPI_THREADS );
+         // the chain's cell-update warps must be done with this tile's buffers before the next prologue writes them
+         bar_sync( 1 + chain, LTC_CHAIN_THREADS );
       }
    }
    tc::fence_before_sync();
