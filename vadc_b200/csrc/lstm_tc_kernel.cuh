@@ -66,6 +66,35 @@ __device__ __forceinline__ float ltc_tanh( float v )
    // 1 - 2/(1 + e^{2v}); saturates correctly for large |v| (e^{2v} -> inf gives 1, -> 0 gives -1)
    return 1.0f - __fdividef( 2.0f, 1.0f + __expf( 2.0f * v ) );
 }
+// 2^min(x, 40) and 1/x on the special-function unit
+__device__ __forceinline__ float ltc_ex2c( float x )
+{
+   float r;
+   asm( "ex2.approx.ftz.f32 %0, %1;" : "=f"( r ) : "f"( fminf( x, 40.0f ) ) );
+   return r;
+}
+__device__ __forceinline__ float ltc_rcp( float x )
+{
+   float r;
+   asm( "rcp.approx.ftz.f32 %0, %1;" : "=f"( r ) : "f"( x ) );
+   return r;
+}
+// One LSTM cell (lstm.c:64-88) with the gate nonlinearities over common denominators: the cell-update warps are bound by the
+// special-function unit (ncu: XU pipe 63 %), and sigma(zi) tanh(zg) + sigma(zf) c = [c Di Dg + (1 - eg) Df] / (Df Di Dg) with
+// e* = 2^(-z* log2 e), D* = 1 + e* needs one reciprocal instead of three, o tanh(c') = (1 - ec) / ((1 + eo)(1 + ec)) one instead of
+// two: 7 MUFU per cell instead of 10. Exponents are clamped at 2^40 so that a product of three denominators stays finite
+// (sigma(-27.7) = 9e-13 is already below fp32 resolution next to 1).
+__device__ __forceinline__ void ltc_cell( float zi, float zf, float zg, float zo, float &c, float &h )
+{
+   constexpr float L = 1.4426950408889634f;
+   const float ei = ltc_ex2c( -L * zi ), ef = ltc_ex2c( -L * zf ), eg = ltc_ex2c( -2.0f * L * zg ), eo = ltc_ex2c( -L * zo );
+   const float di = 1.0f + ei, df = 1.0f + ef, dg = 1.0f + eg;
+   const float didg = di * dg;
+   const float cn = fmaf( c, didg, ( 1.0f - eg ) * df ) * ltc_rcp( df * didg );
+   const float ec = ltc_ex2c( -2.0f * L * cn );
+   c = cn;
+   h = ( 1.0f - ec ) * ltc_rcp( ( 1.0f + eo ) * ( 1.0f + ec ) );
+}
 
 template <int LAYER>
 __global__ void __launch_bounds__( LTC_THREADS, 1 )
@@ -295,10 +324,8 @@ lstm_tc_kernel( const float *__restrict__ x_f32,            // LAYER 0: a4 [S][s
                const float zf = ( up ? a[8 + j] : ra ) + bf;
                const float zg = ( up ? rb : b[j] ) + bg;
                const float zo = ( up ? b[8 + j] : rb ) + bo;
-               const float ig = ltc_sigmoid( zi ), fg = ltc_sigmoid( zf ), gg = ltc_tanh( zg ), og = ltc_sigmoid( zo );
-               const float cn = fg * c[j] + ig * gg;
-               c[j] = cn;
-               const float hn = ltc_tanh( cn ) * og;
+               float hn;
+               ltc_cell( zi, zf, zg, zo, c[j], hn );
                hlast[j] = hn;
                tc::Split2 sp = tc::split2( hn );
                *reinterpret_cast<__nv_bfloat16 *>( xnext + hoff + ( rl0 + j ) * 16 ) = sp.hi;
