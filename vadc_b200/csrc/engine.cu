@@ -752,6 +752,10 @@ static int pick_window( const silero_b200 *h, int nstreams, int nchunks )
    long long per_stream = (long long)( budget / kScratchPerChunk ) / ( nstreams > 0 ? nstreams : 1 );
    if ( per_stream < 1 ) per_stream = 1;
    if ( per_stream > nchunks ) per_stream = nchunks;
+   // equal windows: 125 chunks under a cap of 20 run as 7 x 18 (17) instead of 6 x 20 + 5 -- a 5-chunk window pays the same
+   // per-launch costs (weights to shared / tensor memory, partial waves) for a quarter of the work
+   const long long nwin = ( nchunks + per_stream - 1 ) / per_stream;
+   per_stream = ( nchunks + nwin - 1 ) / nwin;
    return (int)per_stream;
 }
 
