@@ -15,8 +15,8 @@ long_pcm = vadc_b200.synth_pcm(4242, 1536 * 3000)
 o = Oracle(); ref_long = o.run_pcm(long_pcm)
 x_long = (long_pcm.astype(np.float32) / np.float32(32768)).reshape(-1, 1536)[:600]
 o.reset(); st_long = o.run_stages(x_long)
-for mode in (0, 2):
-    e = vadc_b200.Engine(max_streams=S, stft_mode=mode)
+for mode in [int(m) for m in os.environ.get('MODES', '0,2').split(',')]:
+    e = vadc_b200.Engine(max_streams=S, stft_mode=mode, stft_k_rel=float(os.environ.get('K_REL', '0')))
     d_pcm = e.device_alloc(pcm2.nbytes); d_probs = e.device_alloc(S * N * 4)
     e.h2d(d_pcm, pcm2)
     e.set_profiling(1)

@@ -10,8 +10,10 @@
 // Tile = 128 token rows = 128 TMEM lanes: the T frames of a chunk are padded to TP = 8 / 16 rows so a
 // chunk never straddles a warp (16 / 8 chunks per tile). A "group" of 4 warps owns one tile at a time;
 // thread r of the group owns token row r for the whole layer and keeps its activation row in registers.
-// Per contraction: every thread writes its row as the A operand (K-major [K/8][128][8] fp16, hi and lo
-// split -> tc::split_store8_f16), group barrier, one elected thread issues
+// Per contraction: every thread writes its row as the A operand INTO TENSOR MEMORY (row = its own TMEM lane, two fp16 K
+// elements per 32-bit column, hi and lo split -> tc::split_st8_f16_tmem; the group's last K columns), group barrier, one
+// elected thread issues (tcgen05.mma with [a_tmem]: an A operand in shared memory costs a 4 KB read per MMA and a 16-byte
+// st.shared per 8 K elements and thread, on a kernel whose shared-memory pipe is the busiest unit)
 //     D[128][N] = A_hi*W_hi + A_lo*W_hi + A_hi*W_lo      (tcgen05.mma kind::f16, fp32 accumulation in TMEM)
 // and commits to the group's mbarrier; all threads wait, read their row back with tcgen05.ld and run the
 // fp32 epilogue. The fp16x2 split carries 22 significant bits per operand: measured effect on the speech
@@ -37,7 +39,8 @@ struct LtcCfg
    static constexpr int NGROUPS = C == 64 ? 2 : 4;
    static constexpr int THREADS = NGROUPS * 128;
    static constexpr int TMEM_COLS = 512 / NGROUPS;
-   static_assert( TMEM_COLS >= 3 * C, "accumulator columns" );
+   static constexpr int A_COL = TMEM_COLS - C; // A operand: K = C fp16 -> C / 2 columns hi, C / 2 columns lo
+   static_assert( A_COL >= 3 * C, "accumulator columns (widest contraction: QKV, N = 3 C) below the A operand" );
    // fp16 weight images, each [split hi|lo][K/8][N][8]
    static constexpr int wbytes( int N, int K ) { return 2 * N * K * 2; }
    static constexpr int W_PW = 0;
@@ -96,6 +99,23 @@ __device__ __forceinline__ void ltc_issue_gemm( uint32_t d_tmem, uint32_t a_sadd
    }
    tc::mma_commit( bar );
 }
+// the same with the A operand in tensor memory: hi split in columns [a_tmem, a_tmem + K/2), lo split in the next K/2
+template <int N, int K>
+__device__ __forceinline__ void ltc_issue_gemm_ts( uint32_t d_tmem, uint32_t a_tmem, uint32_t w_saddr, uint64_t *bar )
+{
+   constexpr uint32_t W_LBO = N * 16, W_SPLIT = ( K / 8 ) * W_LBO;
+   constexpr uint32_t idesc = tc::idesc_f16_f32( 128, N );
+   const uint64_t dW = tc::smem_desc( w_saddr, W_LBO, 128 );
+#pragma unroll
+   for ( int p = 0; p < 3; ++p ) // (A split, W split): (hi,hi) (lo,hi) (hi,lo)
+   {
+      const uint32_t ta = a_tmem + ( p == 1 ? K / 2 : 0 );
+      const uint64_t dw = dW + (uint64_t)( ( p == 2 ? W_SPLIT : 0u ) >> 4 );
+#pragma unroll
+      for ( int kk = 0; kk < K / 16; ++kk ) tc::mma_bf16_ts( d_tmem, ta + kk * 8, dw + (uint64_t)( ( kk * 2 * W_LBO ) >> 4 ), idesc, ( p | kk ) ? 1u : 0u );
+   }
+   tc::mma_commit( bar );
+}
 
 template <int L>
 __global__ void __launch_bounds__( LtcCfg<L>::THREADS, 1 )
@@ -144,20 +164,19 @@ layer_tc_kernel( const float *__restrict__ in /*[chunk][T][CIN]*/, float *__rest
    // write this thread's activation row as the A operand (both splits)
    auto put_row = [&]( const float *v ) {
 #pragma unroll
-      for ( int kc = 0; kc < C / 8; ++kc )
-         tc::split_store8_f16( v + 8 * kc, abuf + kc * Cfg::A_LBO + r * 16, abuf + Cfg::A_SPLIT + kc * Cfg::A_LBO + r * 16 );
+      for ( int kc = 0; kc < C / 8; ++kc ) tc::split_st8_f16_tmem( v + 8 * kc, trow + Cfg::A_COL + kc * 4, trow + Cfg::A_COL + C / 2 + kc * 4 );
    };
    // operand rows complete -> issue -> wait for the accumulator
 #define LTC_GEMM( N_, W_OFF_ )                                                                    \
    do                                                                                             \
    {                                                                                              \
-      tc::fence_async_smem();                                                                     \
+      tc::tmem_wait_st();                                                                         \
       tc::fence_before_sync();                                                                    \
       bar_sync( 1 + g, 128 );                                                                     \
       if ( wq == 0 )                                                                              \
       {                                                                                           \
          tc::fence_after_sync();                                                                  \
-         if ( tc::elect_one() ) ltc_issue_gemm<N_, C>( tmem, a_saddr, w_saddr + ( W_OFF_ ), bar ); \
+         if ( tc::elect_one() ) ltc_issue_gemm_ts<N_, C>( tmem, tmem + Cfg::A_COL, w_saddr + ( W_OFF_ ), bar ); \
          __syncwarp();                                                                            \
       }                                                                                           \
       tc::mbar_wait( bar, nph & 1u );                                                             \

@@ -200,6 +200,23 @@ __device__ __forceinline__ void split_store8_f16( const float *v, unsigned char 
    *reinterpret_cast<int4 *>( lo_ptr ) = *reinterpret_cast<const int4 *>( lo );
 }
 
+// the same split written to TENSOR memory as an A operand: 8 K elements = 4 packed 32-bit columns per split of this thread's
+// lane (row). The caller issues tmem_wait_st() before the hand-off to the MMA-issuing thread.
+__device__ __forceinline__ void split_st8_f16_tmem( const float *v, uint32_t taddr_hi, uint32_t taddr_lo )
+{
+   __half2 hi[4], lo[4];
+#pragma unroll
+   for ( int i = 0; i < 4; ++i )
+   {
+      hi[i] = __floats2half2_rn( v[2 * i], v[2 * i + 1] );
+      const float2 f = __half22float2( hi[i] );
+      lo[i] = __floats2half2_rn( v[2 * i] - f.x, v[2 * i + 1] - f.y );
+   }
+   const uint32_t *h = reinterpret_cast<const uint32_t *>( hi ), *l = reinterpret_cast<const uint32_t *>( lo );
+   tmem_st4( taddr_hi, h[0], h[1], h[2], h[3] );
+   tmem_st4( taddr_lo, l[0], l[1], l[2], l[3] );
+}
+
 // byte offset of element (row r, k) in the [K/8][R][8] bf16 operand layout with chunk stride `lbo` bytes
 __device__ __forceinline__ uint32_t op_off( int r, int k, uint32_t lbo ) { return (uint32_t)( k >> 3 ) * lbo + (uint32_t)r * 16u + (uint32_t)( k & 7 ) * 2u; }
 
