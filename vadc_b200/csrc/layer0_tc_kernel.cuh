@@ -106,24 +106,28 @@ layer0_tc_kernel( const float *__restrict__ in /*[chunk][129][25] log spectrogra
    unsigned char *gbuf = smem + Cfg::IMG_BYTES + g * Cfg::GBUF;
    float *stg = reinterpret_cast<float *>( gbuf );
    uint64_t *bar_s = &bars[3 * g], *bar_m = &bars[3 * g + 2];
-   const uint32_t g_saddr = tc::smem_u32( gbuf ), w_saddr = tc::smem_u32( smem );
+   const uint32_t w_saddr = tc::smem_u32( smem );
    uint32_t n_s[2] = { 0, 0 }, n_m = 0; // commits so far on each barrier (phase parity bookkeeping, uniform in the group)
 
    // short contractions of the transformer block: A operand K = 16 at the start of the group buffer
+   // A operands live in TENSOR memory (this thread's lane = its token row; two fp16 K elements per 32-bit column): columns
+   // [A_COL, A_COL + 64) of the group = two slice buffers of K = 32 (16 columns hi, 16 lo each); the K = 16 contractions of the
+   // transformer block reuse the first 16 of them (8 hi, 8 lo). See layer_tc_kernel.cuh for why not shared memory.
+   constexpr uint32_t A_COL = 64;
    auto put_row16 = [&]( const float *v ) {
-      tc::split_store8_f16( v, gbuf + r * 16, gbuf + 2 * Cfg::A_LBO + r * 16 );
-      tc::split_store8_f16( v + 8, gbuf + Cfg::A_LBO + r * 16, gbuf + 3 * Cfg::A_LBO + r * 16 );
+      tc::split_st8_f16_tmem( v, trow + A_COL, trow + A_COL + 8 );
+      tc::split_st8_f16_tmem( v + 8, trow + A_COL + 4, trow + A_COL + 12 );
    };
 #define L0_GEMM( N_, W_OFF_ )                                                                                  \
    do                                                                                                          \
    {                                                                                                           \
-      tc::fence_async_smem();                                                                                  \
+      tc::tmem_wait_st();                                                                                      \
       tc::fence_before_sync();                                                                                 \
       bar_sync( 1 + g, 128 );                                                                                  \
       if ( wq == 0 )                                                                                           \
       {                                                                                                        \
          tc::fence_after_sync();                                                                               \
-         if ( tc::elect_one() ) ltc_issue_gemm<N_, 16>( tmem, g_saddr, w_saddr + ( W_OFF_ ), bar_m );          \
+         if ( tc::elect_one() ) ltc_issue_gemm_ts<N_, 16>( tmem, tmem + A_COL, w_saddr + ( W_OFF_ ), bar_m );  \
          __syncwarp();                                                                                         \
       }                                                                                                        \
       tc::mbar_wait( bar_m, n_m & 1u );                                                                        \
@@ -228,7 +232,6 @@ layer0_tc_kernel( const float *__restrict__ in /*[chunk][129][25] log spectrogra
       for ( int s = 0; s < Cfg::NSLICE; ++s )
       {
          const int b = s & 1;
-         unsigned char *sb = gbuf + b * Cfg::SLICE_BYTES;
          // the tensor core must be done with the slice that used this buffer two slices ago
          if ( s >= 2 )
          {
@@ -260,9 +263,9 @@ layer0_tc_kernel( const float *__restrict__ in /*[chunk][129][25] log spectrogra
                v[2 * k] = dw_bin( f0 + k, x0 );
                v[2 * k + 1] = x0;
             }
-            tc::split_store8_f16( v, sb + kc * Cfg::A_LBO + r * 16, sb + Cfg::SLICE_SPLIT + kc * Cfg::A_LBO + r * 16 );
+            tc::split_st8_f16_tmem( v, trow + A_COL + b * 32 + kc * 4, trow + A_COL + b * 32 + 16 + kc * 4 );
          }
-         tc::fence_async_smem();
+         tc::tmem_wait_st();
          tc::fence_before_sync();
          bar_sync( 1 + g, 128 );
          if ( wq == 0 )
@@ -271,17 +274,16 @@ layer0_tc_kernel( const float *__restrict__ in /*[chunk][129][25] log spectrogra
             if ( tc::elect_one() )
             {
                constexpr uint32_t idesc = tc::idesc_f16_f32( 128, 16 );
-               const uint64_t dA = tc::smem_desc( g_saddr + b * Cfg::SLICE_BYTES, Cfg::A_LBO, 128 );
+               const uint32_t tA = tmem + A_COL + b * 32;
                const uint64_t dW = tc::smem_desc( w_saddr + Cfg::W_PW + s * 4 * Cfg::PW_LBO, Cfg::PW_LBO, 128 );
 #pragma unroll
                for ( int p = 0; p < 3; ++p ) // (A split, W split): (hi,hi) (lo,hi) (hi,lo)
                {
-                  const uint64_t da = dA + (uint64_t)( ( p == 1 ? Cfg::SLICE_SPLIT : 0 ) >> 4 );
+                  const uint32_t ta = tA + ( p == 1 ? 16 : 0 );
                   const uint64_t dw = dW + (uint64_t)( ( p == 2 ? Cfg::PW_SPLIT : 0 ) >> 4 );
 #pragma unroll
                   for ( int kk = 0; kk < 2; ++kk )
-                     tc::mma_bf16( tmem, da + (uint64_t)( ( kk * 2 * Cfg::A_LBO ) >> 4 ), dw + (uint64_t)( ( kk * 2 * Cfg::PW_LBO ) >> 4 ), idesc,
-                                   ( s | p | kk ) ? 1u : 0u );
+                     tc::mma_bf16_ts( tmem, ta + kk * 8, dw + (uint64_t)( ( kk * 2 * Cfg::PW_LBO ) >> 4 ), idesc, ( s | p | kk ) ? 1u : 0u );
                }
                tc::mma_commit( &bar_s[b] );
             }
