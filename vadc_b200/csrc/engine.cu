@@ -606,7 +606,11 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    const size_t ltc_bytes[4] = { L0tc::IMG_BYTES, LtcCfg<1>::IMG_BYTES, LtcCfg<2>::IMG_BYTES, LtcCfg<3>::IMG_BYTES };
    if ( ltc_img[0] ) pack_layer0_tc( host + o_l0, ltc_img[0] );
    for ( int f = 0; f < 129; ++f )
-      for ( int k = 0; k < 6; ++k ) h->l0_dw.w[f][k] = host[o_l0 + LayerPack<0>::DW + f * 8 + k];
+   {
+      const float *dw = host + o_l0 + LayerPack<0>::DW + f * 8;
+      h->l0_dw.w[f][0] = make_float4( dw[0], dw[1], dw[2], dw[3] );
+      h->l0_dw.w[f][1] = make_float4( dw[4], dw[5], 0.0f, 0.0f );
+   }
    if ( ltc_img[1] ) pack_layer_tc<1>( host + o_l1, ltc_img[1] );
    if ( ltc_img[2] ) pack_layer_tc<2>( host + o_l2, ltc_img[2] );
    if ( ltc_img[3] ) pack_layer_tc<3>( host + o_l3, ltc_img[3] );
