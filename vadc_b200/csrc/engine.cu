@@ -79,6 +79,8 @@ struct silero_b200
    unsigned long long bins_total;
    cudaStream_t stream;      // compute
    cudaStream_t copy_stream; // H2D of the next window
+   cudaStream_t front_stream; // STFT of window w+1 while layers 2..4 and the LSTM of window w run (run_window)
+   cudaEvent_t ev_spec_ready, ev_spec_free; // spectrogram buffer hand-offs between front_stream and stream
    float *d_weights;         // one allocation holding every packed weight
    DeviceWeights w;
    float *state_h, *state_c; // [max_streams][2][64]
@@ -460,6 +462,9 @@ extern "C" void silero_b200_destroy( silero_b200 *h )
       if ( h->ev_stage[i] ) cudaEventDestroy( h->ev_stage[i] );
    if ( h->stream ) cudaStreamDestroy( h->stream );
    if ( h->copy_stream ) cudaStreamDestroy( h->copy_stream );
+   if ( h->front_stream ) cudaStreamDestroy( h->front_stream );
+   if ( h->ev_spec_ready ) cudaEventDestroy( h->ev_spec_ready );
+   if ( h->ev_spec_free ) cudaEventDestroy( h->ev_spec_free );
    free( h );
 }
 
@@ -557,6 +562,9 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    }
    CU_H( cudaStreamCreateWithFlags( &h->stream, cudaStreamNonBlocking ) );
    CU_H( cudaStreamCreateWithFlags( &h->copy_stream, cudaStreamNonBlocking ) );
+   CU_H( cudaStreamCreateWithFlags( &h->front_stream, cudaStreamNonBlocking ) );
+   CU_H( cudaEventCreateWithFlags( &h->ev_spec_ready, cudaEventDisableTiming ) );
+   CU_H( cudaEventCreateWithFlags( &h->ev_spec_free, cudaEventDisableTiming ) );
    CU_H( cudaEventCreate( &h->ev_begin ) );
    CU_H( cudaEventCreate( &h->ev_end ) );
    for ( int i = 0; i < N_STAGE_EVENTS; ++i ) CU_H( cudaEventCreate( &h->ev_stage[i] ) );
@@ -780,8 +788,10 @@ static bool stft_use_tensor( const silero_b200 *h, int nchunks )
 // kernel); the tensor-core and exact kernels leave it to the first layer (the caller checks stft_produces_mu)
 static bool stft_produces_mu( const silero_b200 *h, int nchunks ) { return h->stft_mode != SILERO_B200_STFT_EXACT && !stft_use_tensor( h, nchunks ); }
 
-static int launch_stft( silero_b200 *h, const void *d_in, int in_f32, long long stream_stride, int nw, int nchunks, float *spec, int out_mode, float *mu = 0 )
+static int launch_stft( silero_b200 *h, const void *d_in, int in_f32, long long stream_stride, int nw, int nchunks, float *spec, int out_mode, float *mu = 0,
+                        cudaStream_t st = 0 )
 {
+   if ( !st ) st = h->stream; // (the tensor-core mode always runs on h->stream: it has a work list and a second kernel)
    if ( stft_use_tensor( h, nchunks ) )
    {
       const int ntiles = ( nchunks + 3 ) / 4;
@@ -814,9 +824,9 @@ static int launch_stft( silero_b200 *h, const void *d_in, int in_f32, long long 
       int npairs = imin( h->sm_count / 2, ( nchunks + STFT_GROUPS - 1 ) / STFT_GROUPS );
       if ( npairs < 1 ) npairs = 1;
       if ( in_f32 )
-         stft_logmag_kernel<true><<<npairs * 2, STFT_THREADS, STFT_SMEM_BYTES, h->stream>>>( d_in, stream_stride, nw, nchunks, h->w.basis_pack, spec, out_mode );
+         stft_logmag_kernel<true><<<npairs * 2, STFT_THREADS, STFT_SMEM_BYTES, st>>>( d_in, stream_stride, nw, nchunks, h->w.basis_pack, spec, out_mode );
       else
-         stft_logmag_kernel<false><<<npairs * 2, STFT_THREADS, STFT_SMEM_BYTES, h->stream>>>( d_in, stream_stride, nw, nchunks, h->w.basis_pack, spec, out_mode );
+         stft_logmag_kernel<false><<<npairs * 2, STFT_THREADS, STFT_SMEM_BYTES, st>>>( d_in, stream_stride, nw, nchunks, h->w.basis_pack, spec, out_mode );
    }
    else if ( h->stft_mode == SILERO_B200_STFT_HYBRID )
    {
@@ -828,9 +838,9 @@ static int launch_stft( silero_b200 *h, const void *d_in, int in_f32, long long 
       }
       int grid = imin( nchunks, h->sm_count * per_sm8 );
       if ( in_f32 )
-         stft_fft8_kernel<true><<<grid, F8_THREADS, F8_SMEM_BYTES, h->stream>>>( d_in, stream_stride, nw, nchunks, h->w.basis_raw, spec, mu, h->stft_k_rel, out_mode, h->d_flagged );
+         stft_fft8_kernel<true><<<grid, F8_THREADS, F8_SMEM_BYTES, st>>>( d_in, stream_stride, nw, nchunks, h->w.basis_raw, spec, mu, h->stft_k_rel, out_mode, h->d_flagged );
       else
-         stft_fft8_kernel<false><<<grid, F8_THREADS, F8_SMEM_BYTES, h->stream>>>( d_in, stream_stride, nw, nchunks, h->w.basis_raw, spec, mu, h->stft_k_rel, out_mode, h->d_flagged );
+         stft_fft8_kernel<false><<<grid, F8_THREADS, F8_SMEM_BYTES, st>>>( d_in, stream_stride, nw, nchunks, h->w.basis_raw, spec, mu, h->stft_k_rel, out_mode, h->d_flagged );
       h->bins_total += (unsigned long long)nchunks * VB_BINS * VB_FRAMES;
    }
    else
@@ -843,9 +853,9 @@ static int launch_stft( silero_b200 *h, const void *d_in, int in_f32, long long 
       }
       int grid = imin( nchunks, h->sm_count * per_sm );
       if ( in_f32 )
-         stft_hybrid_kernel<true><<<grid, HYB_THREADS, HYB_SMEM_BYTES, h->stream>>>( d_in, stream_stride, nw, nchunks, h->w.basis_raw, spec, mu, h->stft_k_rel, out_mode, h->d_flagged );
+         stft_hybrid_kernel<true><<<grid, HYB_THREADS, HYB_SMEM_BYTES, st>>>( d_in, stream_stride, nw, nchunks, h->w.basis_raw, spec, mu, h->stft_k_rel, out_mode, h->d_flagged );
       else
-         stft_hybrid_kernel<false><<<grid, HYB_THREADS, HYB_SMEM_BYTES, h->stream>>>( d_in, stream_stride, nw, nchunks, h->w.basis_raw, spec, mu, h->stft_k_rel, out_mode, h->d_flagged );
+         stft_hybrid_kernel<false><<<grid, HYB_THREADS, HYB_SMEM_BYTES, st>>>( d_in, stream_stride, nw, nchunks, h->w.basis_raw, spec, mu, h->stft_k_rel, out_mode, h->d_flagged );
       h->bins_total += (unsigned long long)nchunks * VB_BINS * VB_FRAMES;
    }
    h->launches++;
@@ -968,18 +978,44 @@ static void stage_mark( silero_b200 *h, int i )
 }
 
 // one window: nstreams x nw chunks; input chunk (s, n) at d_in + s*stream_stride + n*1536
+// in_ready (optional): event the input samples become valid on; in_free (optional): recorded once the input has been consumed.
+//
+// The STFT runs on front_stream: the spectrogram (+ normalization scalars) is the only thing it shares with the rest of the window,
+// and it is free again as soon as the first layer of the previous window has read it. Consecutive windows therefore overlap: the
+// STFT of window w+1 (CUDA-core kernel, 66 KB of shared memory and 80 registers per thread) runs beside layers 2..4 and above all
+// beside the two LSTM kernels of window w, which leave 20 SMs empty and the issue slots of the others half idle.
+// Per-stage profiling keeps everything on one stream, so that the stage times stay those of the kernels alone.
 static int run_window( silero_b200 *h, const void *d_in, int in_f32, long long stream_stride, int first_stream, int nstreams, int nw, float *d_out2,
-                       float *d_probs, long long out_stride, long long out_off, int accumulate_timing )
+                       float *d_probs, long long out_stride, long long out_off, int accumulate_timing, cudaEvent_t in_ready = 0, cudaEvent_t in_free = 0,
+                       bool input_is_ordered_on_stream = false )
 {
    const int nchunks = nstreams * nw;
    const size_t h0_floats = (size_t)( ( nstreams + LTC_N - 1 ) / LTC_N ) * LTC_N * nw * 7 * 64;
    if ( ensure_scratch( h, (size_t)nchunks, h0_floats ) ) return SILERO_B200_ERR_CUDA;
    stage_mark( h, 0 );
    const bool have_mu = stft_produces_mu( h, nchunks );
-   if ( launch_stft( h, d_in, in_f32, stream_stride, nw, nchunks, h->spec, 0, have_mu ? h->mu : 0 ) ) return SILERO_B200_ERR_CUDA;
+   // (an input that was produced by earlier work on h->stream itself, like run_chunks' own upload, keeps the STFT on that stream)
+   const bool overlap = !h->profiling && !stft_use_tensor( h, nchunks ) && !input_is_ordered_on_stream;
+   cudaStream_t fs = overlap ? h->front_stream : h->stream;
+   if ( overlap )
+   {
+      // first layer of the previous window -- of this call or of the previous one: back-to-back calls overlap the same way, so a
+      // call's own ev_begin..ev_end time can miss its first STFT; timer_start/timer_stop around several calls see all of it
+      // (a never-recorded event counts as complete)
+      CU( cudaStreamWaitEvent( fs, h->ev_spec_free, 0 ) );
+   }
+   if ( in_ready ) CU( cudaStreamWaitEvent( fs, in_ready, 0 ) );
+   if ( launch_stft( h, d_in, in_f32, stream_stride, nw, nchunks, h->spec, 0, have_mu ? h->mu : 0, fs ) ) return SILERO_B200_ERR_CUDA;
+   if ( in_free ) CU( cudaEventRecord( in_free, fs ) );
+   if ( overlap )
+   {
+      CU( cudaEventRecord( h->ev_spec_ready, fs ) );
+      CU( cudaStreamWaitEvent( h->stream, h->ev_spec_ready, 0 ) );
+   }
    stage_mark( h, 1 );
    // the FFT STFT kernel also produces the normalization scalar; the others leave it to the first layer
    if ( first_layer_from_logspec( h, h->spec, h->a1, nchunks, have_mu ? h->mu : 0 ) ) return SILERO_B200_ERR_CUDA;
+   CU( cudaEventRecord( h->ev_spec_free, h->stream ) );
    stage_mark( h, 2 );
    if ( launch_layer_any<1>( h, h->a1, h->a2, nchunks ) ) return SILERO_B200_ERR_CUDA;
    stage_mark( h, 3 );
@@ -1171,10 +1207,10 @@ static int run_streams_host( silero_b200 *h, const int16_t *pcm, long long strea
       {
          int n0 = win_begin( w ), nw = win_size( w ), b = ( w + stage0 ) & 1;
          if ( w + 1 < nwin && issue_copy( w + 1 ) ) return SILERO_B200_ERR_CUDA;
-         CU( cudaStreamWaitEvent( h->stream, h->pcm_ready[b], 0 ) );
-         rc = run_window( h, h->pcm_stage[b], 0, (long long)nw * VB_CHUNK, first_stream, nstreams, nw, out2 ? h->d_out2 : 0, need_probs ? h->d_probs : 0, nchunks, n0, 1 );
+         // the staging buffer is free again as soon as the STFT has consumed it (run_window records pcm_free there)
+         rc = run_window( h, h->pcm_stage[b], 0, (long long)nw * VB_CHUNK, first_stream, nstreams, nw, out2 ? h->d_out2 : 0, need_probs ? h->d_probs : 0, nchunks, n0, 1,
+                          h->pcm_ready[b], h->pcm_free[b] );
          if ( rc ) return rc;
-         CU( cudaEventRecord( h->pcm_free[b], h->stream ) );
          h->stage_used[b] = 1;
       }
    }
@@ -1314,7 +1350,7 @@ extern "C" int silero_b200_run_chunks( silero_b200 *h, int stream, const float *
    for ( int n0 = 0; n0 < nchunks; n0 += nw_max )
    {
       int nw = imin( nw_max, nchunks - n0 );
-      rc = run_window( h, h->d_f32 + (size_t)n0 * VB_CHUNK, 1, 0, stream, 1, nw, h->d_out2, 0, nchunks, n0, 1 );
+      rc = run_window( h, h->d_f32 + (size_t)n0 * VB_CHUNK, 1, 0, stream, 1, nw, h->d_out2, 0, nchunks, n0, 1, 0, 0, true );
       if ( rc ) return rc;
    }
    CU( cudaMemcpyAsync( out, h->d_out2, (size_t)nchunks * 2 * sizeof( float ), cudaMemcpyDeviceToHost, h->stream ) );
