@@ -29,11 +29,13 @@
 #define F8_CWARPS 7                      // compute warps
 #define F8_THREADS ( ( F8_CWARPS + 1 ) * 32 )
 #define F8_SLOTS ( F8_CWARPS * 4 )
+#define F8_EX_SLOTS ( VB_FRAMES + 1 )    // exchange slots: one per live frame + one shared by the three dead slots (their results are discarded)
+#define F8_XS_DEPTH 3                   // input tiles in flight (ring)
 #define F8_XS_FLOATS ( 1792 + 16 * 28 ) // padded chunk, 16 pad words after every 64 samples: frames of one warp start 80 words apart
 #define F8_EX_ROW 20                    // exchange row stride in words (8 complex + 4 pad): LDS.128 phases hit distinct banks
 #define F8_EX_SLOT ( 8 * F8_EX_ROW + 16 ) // 8 rows per pass (rows 0..7, then rows 8..15); slots of a half-warp 16 banks apart
 #define F8_OS_FLOATS 3228               // 3225 + up to 3 floats of alignment offset (see the copy-out)
-#define F8_SMEM_FLOATS ( 2 * F8_XS_FLOATS + F8_SLOTS * F8_EX_SLOT + 2 * F8_OS_FLOATS + 2 * 32 + 256 + 256 + 128 + 16 )
+#define F8_SMEM_FLOATS ( F8_XS_DEPTH * F8_XS_FLOATS + F8_EX_SLOTS * F8_EX_SLOT + 2 * F8_OS_FLOATS + 2 * 32 + 256 + 256 + 128 + 32 )
 #define F8_SMEM_BYTES ( F8_SMEM_FLOATS * 4 )
 
 __device__ __forceinline__ int f8_xaddr( int p ) { return p + ( ( p >> 6 ) << 4 ); }
@@ -208,15 +210,15 @@ stft_fft8_kernel( const void *__restrict__ in, long long stream_stride, int nw, 
                   float *__restrict__ spec, float *__restrict__ mu_out, float k_rel, int out_mode, unsigned long long *__restrict__ flagged )
 {
    extern __shared__ __align__( 16 ) float smem[];
-   float *Xs = smem;                                      // [2][F8_XS_FLOATS]
-   float *Ex = Xs + 2 * F8_XS_FLOATS;                     // [slot][8 rows][20]
-   float *Os = Ex + F8_SLOTS * F8_EX_SLOT;                // [2][129][25] (+ alignment offset)
+   float *Xs = smem;                                      // [F8_XS_DEPTH][F8_XS_FLOATS]: ring of input tiles
+   float *Ex = Xs + F8_XS_DEPTH * F8_XS_FLOATS;           // [slot][8 rows][20]
+   float *Os = Ex + F8_EX_SLOTS * F8_EX_SLOT;             // [2][129][25] (+ alignment offset)
    float *Ms = Os + 2 * F8_OS_FLOATS;                     // [2][25] per-frame mean of the log spectrum
    float *Win = Ms + 2 * 32;                              // 0.5 * Hann[256]
    float2 *Tw1 = reinterpret_cast<float2 *>( Win + 256 ); // [k1 16][i 8]: W128^(i k1)
    float2 *Twp = Tw1 + 128;                               // [j 8][i 8]: (cos, sin)(2 pi bin_a(i, j) / 256)
-   uint64_t *bars = reinterpret_cast<uint64_t *>( Twp + 64 ); // x_full[2], x_empty[2], o_full[2], o_empty[2]
-   uint64_t *x_full = bars, *x_empty = bars + 2, *o_full = bars + 4, *o_empty = bars + 6;
+   uint64_t *bars = reinterpret_cast<uint64_t *>( Twp + 64 ); // x_full[3], x_empty[3], o_full[2], o_empty[2]
+   uint64_t *x_full = bars, *x_empty = bars + F8_XS_DEPTH, *o_full = bars + 2 * F8_XS_DEPTH, *o_empty = bars + 2 * F8_XS_DEPTH + 2;
 
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    constexpr unsigned FULL = 0xffffffffu;
@@ -237,10 +239,13 @@ stft_fft8_kernel( const void *__restrict__ in, long long stream_stride, int nw, 
    }
    if ( tid == 0 )
    {
-      for ( int b = 0; b < 2; ++b )
+      for ( int b = 0; b < F8_XS_DEPTH; ++b )
       {
          tc::mbar_init( &x_full[b], 1 );
          tc::mbar_init( &x_empty[b], F8_CWARPS );
+      }
+      for ( int b = 0; b < 2; ++b )
+      {
          tc::mbar_init( &o_full[b], F8_CWARPS );
          tc::mbar_init( &o_empty[b], 1 );
       }
@@ -254,11 +259,19 @@ stft_fft8_kernel( const void *__restrict__ in, long long stream_stride, int nw, 
       F8Raw<F32> raw;
       int ci = blockIdx.x;
       if ( ci >= nchunks ) return;
+      // the ring starts with tiles 0 and 1 in place and tile 2 in registers
       f8_load_raw<F32>( raw, hyb_chunk_ptr<F32>( in, stream_stride, nw, ci ), lane );
       f8_store_x<F32>( Xs, raw, lane );
       __syncwarp();
       if ( lane == 0 ) tc::mbar_arrive( &x_full[0] );
-      if ( ci + (int)gridDim.x < nchunks ) f8_load_raw<F32>( raw, hyb_chunk_ptr<F32>( in, stream_stride, nw, ci + gridDim.x ), lane );
+      if ( ci + (int)gridDim.x < nchunks )
+      {
+         f8_load_raw<F32>( raw, hyb_chunk_ptr<F32>( in, stream_stride, nw, ci + gridDim.x ), lane );
+         f8_store_x<F32>( Xs + F8_XS_FLOATS, raw, lane );
+         __syncwarp();
+         if ( lane == 0 ) tc::mbar_arrive( &x_full[1] );
+      }
+      if ( ci + 2 * (int)gridDim.x < nchunks ) f8_load_raw<F32>( raw, hyb_chunk_ptr<F32>( in, stream_stride, nw, ci + 2 * gridDim.x ), lane );
       // Per iteration: first the next input tile (the compute warps need it the moment they finish the current chunk), then
       // the output tile of the PREVIOUS chunk: both become available at the same instant (all compute warps done with chunk
       // it-1), and the copy-out has a whole chunk of slack while a late input tile stalls 7 warps.
@@ -287,40 +300,45 @@ stft_fft8_kernel( const void *__restrict__ in, long long stream_stride, int nw, 
             for ( int off = 16; off > 0; off >>= 1 ) v += __shfl_xor_sync( FULL, v, off );
             if ( lane == 0 ) mu_out[co] = v / (float)VB_FRAMES;
          }
-         // the tile sits at offset (co & 3) so that shared and global float indices agree modulo 4: 16-byte stores
-         // everywhere except the first and last quad
+         // The tile sits at offset (co & 3) so that shared and global float indices agree modulo 4; its 16-byte-aligned body
+         // (12.9 KB) leaves as ONE bulk asynchronous copy (cp.async.bulk shared -> global, the TMA engine), the <= 3 floats in
+         // front of it and <= 3 behind it as scalar stores. With a loop of 26 x (LDS.128, STG.128) per lane this warp needed ~3 us
+         // per chunk and the compute warps waited 14 % of their time for the output tile to be free again.
          const int off = co & 3;
          float *gq = spec + ( (size_t)co * HYB_OUT_FLOATS - off );
-#pragma unroll 4
-         for ( int q = lane; q < F8_OS_FLOATS / 4; q += 32 )
+         const int s_begin = off ? 4 : 0, s_end = ( off + HYB_OUT_FLOATS ) & ~3;
+         tc::fence_async_smem(); // the tile was written with generic-proxy stores
+         if ( lane == 0 )
          {
-            const float4 v = ld4( os + 4 * q );
-            const int s0 = 4 * q;
-            if ( s0 >= off && s0 + 3 < off + HYB_OUT_FLOATS )
-               st4( gq + s0, v );
-            else
-            {
-               if ( s0 >= off && s0 < off + HYB_OUT_FLOATS ) gq[s0] = v.x;
-               if ( s0 + 1 >= off && s0 + 1 < off + HYB_OUT_FLOATS ) gq[s0 + 1] = v.y;
-               if ( s0 + 2 >= off && s0 + 2 < off + HYB_OUT_FLOATS ) gq[s0 + 2] = v.z;
-               if ( s0 + 3 >= off && s0 + 3 < off + HYB_OUT_FLOATS ) gq[s0 + 3] = v.w;
-            }
+            asm volatile( "cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"( gq + s_begin ), "r"( tc::smem_u32( os + s_begin ) ),
+                          "r"( (uint32_t)( ( s_end - s_begin ) * 4 ) )
+                          : "memory" );
+            asm volatile( "cp.async.bulk.commit_group;" ::: "memory" );
          }
+         else if ( lane < 8 )
+         {
+            const int sidx = lane < 4 ? off + ( lane - 1 ) : s_end + ( lane - 4 );
+            const bool ok = lane < 4 ? sidx < s_begin : sidx < off + HYB_OUT_FLOATS;
+            if ( ok ) gq[sidx] = os[sidx];
+         }
+         if ( lane == 0 ) asm volatile( "cp.async.bulk.wait_group.read 0;" ::: "memory" ); // the source may be overwritten from here on
          __syncwarp();
          if ( lane == 0 ) tc::mbar_arrive( &o_empty[b] );
       };
       int it = 0, cprev = -1;
       for ( ; ci < nchunks; ci += gridDim.x, ++it )
       {
-         const int b = it & 1;
-         const int cn = ci + gridDim.x;
+         const int cn = ci + 2 * gridDim.x;
          if ( cn < nchunks )
          {
-            // tile it+1 into the other buffer as soon as the compute warps are done with tile it-1
-            tc::mbar_wait( &x_empty[b ^ 1], ( ( ( it + 1 ) >> 1 ) & 1 ) ^ 1 );
-            f8_store_x<F32>( Xs + ( b ^ 1 ) * F8_XS_FLOATS, raw, lane );
+            // tile it+2 takes the place of tile it-1 as soon as the compute warps are done with that one: a warp can now be two
+            // chunks ahead of the slowest one before it has to wait (with two tiles the warps a chunk ahead paid the latency of
+            // this store on every chunk: 18 % of their time)
+            const int j = it + 2, xb = j % F8_XS_DEPTH;
+            tc::mbar_wait( &x_empty[xb], ( ( j / F8_XS_DEPTH ) & 1 ) ^ 1 );
+            f8_store_x<F32>( Xs + xb * F8_XS_FLOATS, raw, lane );
             __syncwarp();
-            if ( lane == 0 ) tc::mbar_arrive( &x_full[b ^ 1] );
+            if ( lane == 0 ) tc::mbar_arrive( &x_full[xb] );
             if ( cn + (int)gridDim.x < nchunks ) f8_load_raw<F32>( raw, hyb_chunk_ptr<F32>( in, stream_stride, nw, cn + gridDim.x ), lane );
          }
          if ( cprev >= 0 ) copy_out( cprev, it - 1 );
@@ -337,7 +355,7 @@ stft_fft8_kernel( const void *__restrict__ in, long long stream_stride, int nw, 
    const int t = live ? slot : VB_FRAMES - 1;
    unsigned nflag = 0;
 
-   float *ex = Ex + slot * F8_EX_SLOT;
+   float *ex = Ex + ( live ? slot : VB_FRAMES ) * F8_EX_SLOT;
    const int ra = i, rb = i ? 8 - i : 0; // rows owned in step 3: ra of the first pass (k1 = i), rb of the second (k1 = 16 - i; lane 0: 8)
    const float tau_scale = 2.0f * k_rel;  // the window carries the factor 1/2
    const bool l0 = ( i == 0 );
@@ -345,10 +363,10 @@ stft_fft8_kernel( const void *__restrict__ in, long long stream_stride, int nw, 
    int it = 0;
    for ( int ci = blockIdx.x; ci < nchunks; ci += gridDim.x, ++it )
    {
-      const int b = it & 1;
-      const float *xs = Xs + b * F8_XS_FLOATS;
+      const int b = it & 1, xb = it % F8_XS_DEPTH;
+      const float *xs = Xs + xb * F8_XS_FLOATS;
       float *os = Os + b * F8_OS_FLOATS + ( ci & 3 );
-      tc::mbar_wait( &x_full[b], ( it >> 1 ) & 1 );
+      tc::mbar_wait( &x_full[xb], ( it / F8_XS_DEPTH ) & 1 );
 
       // ---- step 1: windowed samples z[n1] = (y[16 n1 + 2 i], y[16 n1 + 2 i + 1]) / 2, 16-point FFT over n1 -----------
       cpx z[16];
@@ -491,7 +509,7 @@ stft_fft8_kernel( const void *__restrict__ in, long long stream_stride, int nw, 
       __syncwarp();
       if ( lane == 0 )
       {
-         tc::mbar_arrive( &x_empty[b] );
+         tc::mbar_arrive( &x_empty[xb] );
          tc::mbar_arrive( &o_full[b] );
       }
    }
