@@ -307,3 +307,31 @@ def test_cfg5_many_streams_sharded_like_ranks(oracle):
         assert np.abs(p_all[s] - ref).max() <= PTOL
         seg = vadc_b200.StreamSegmenter()
         assert "".join(seg.format(x) for x in segs[s]) == oracle.segments_text(ref)
+
+
+def test_overlapped_and_single_stream_schedules_agree():
+    """run_window overlaps the STFT of window w+1 (second CUDA stream) with the back end of window w; per-stage profiling keeps
+    everything on one stream. Same bits either way, also across calls (the hand-off events persist) and for the host path, whose
+    staging buffers are released by the STFT."""
+    S, N = 96, 23
+    pcm = np.stack([vadc_b200.synth_pcm(7000 + s, N * 1536) for s in range(S)])
+    e = vadc_b200.Engine(max_streams=S, window_chunks=4)
+    outs = []
+    for prof in (0, 1, 0):
+        e.set_profiling(prof)
+        e.reset()
+        a = e.run_streams(pcm[:, : 10 * 1536])               # two calls: state and events carried across
+        b = e.run_streams(pcm[:, 10 * 1536:])
+        outs.append(np.concatenate([a, b], axis=1))
+    e.set_profiling(0)
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    d_pcm = e.device_alloc(pcm.nbytes)
+    d_probs = e.device_alloc(S * N * 4)
+    e.h2d(d_pcm, pcm)
+    e.reset()
+    e.run_streams_device(d_pcm, pcm.shape[1], S, N, d_probs)
+    e.sync()
+    got = np.zeros((S, N), np.float32)
+    e.d2h(got, d_probs)
+    assert np.array_equal(got, outs[0])
+    e.close()
