@@ -19,8 +19,9 @@
 //
 // The compute warps never synchronise with each other: an eighth warp does all the I/O (s16/f32 chunk -> padded fp32
 // tile with its reflect images; finished log spectrogram tile -> global memory with 16-byte stores; the normalization
-// scalar) and hands tiles over through mbarriers (input tile full/empty, output tile full/empty, both double-buffered),
-// so a warp that has to re-evaluate many bins exactly delays nobody until it is a whole chunk behind.
+// scalar) and hands tiles over through mbarriers (input tile full/empty: ring of three; output tile full/empty: two; the output
+// tile leaves as one cp.async.bulk shared -> global copy), so a warp that has to re-evaluate many bins exactly delays nobody
+// until it is more than a chunk behind.
 #pragma once
 #include "common.cuh"
 #include "stft_hybrid_kernel.cuh"
