@@ -414,7 +414,8 @@ static int configure_kernels()
    CU( allow_smem( lstm_tc_kernel<1>, LTC_SMEM_BYTES ) );
    CU( allow_smem( stft_tc_kernel<false>, STC_SMEM_BYTES ) );
    CU( allow_smem( stft_tc_kernel<true>, STC_SMEM_BYTES ) );
-   CU( allow_smem( layer0_tc_kernel, L0tc::SMEM_BYTES ) );
+   CU( allow_smem( layer0_tc_kernel<false>, L0tc::SMEM_BYTES ) );
+   CU( allow_smem( layer0_tc_kernel<true>, L0tc::SMEM_BYTES ) );
    CU( allow_smem( layer_tc_kernel<1>, LtcCfg<1>::SMEM_BYTES ) );
    CU( allow_smem( layer_tc_kernel<2>, LtcCfg<2>::SMEM_BYTES ) );
    CU( allow_smem( layer_tc_kernel<3>, LtcCfg<3>::SMEM_BYTES ) );
@@ -896,7 +897,10 @@ static int launch_layer0_tc( silero_b200 *h, const float *in, float *out, int nc
 {
    const int ntiles = ( nchunks + 3 ) / 4;
    const int grid = imin( ( ntiles + L0tc::NGROUPS - 1 ) / L0tc::NGROUPS, h->sm_count );
-   layer0_tc_kernel<<<grid, L0tc::THREADS, L0tc::SMEM_BYTES, h->stream>>>( in, out, h->d_layer_tc[0], nchunks, mu, compute_mu, h->l0_dw );
+   if ( compute_mu )
+      layer0_tc_kernel<true><<<grid, L0tc::THREADS, L0tc::SMEM_BYTES, h->stream>>>( in, out, h->d_layer_tc[0], nchunks, mu, h->l0_dw );
+   else
+      layer0_tc_kernel<false><<<grid, L0tc::THREADS, L0tc::SMEM_BYTES, h->stream>>>( in, out, h->d_layer_tc[0], nchunks, mu, h->l0_dw );
    h->launches++;
    CU( cudaGetLastError() );
    return 0;

@@ -69,9 +69,12 @@ struct L0DwParams
                      // kernel's instructions and 22 % of its stall samples)
 };
 
+// COMPUTE_MU: the kernel derives the normalization scalar itself (STFT kernels that do not provide it); as a run-time flag its
+// predicated-off loads and adds still cost two issue slots per bin in the hot configuration
+template <bool COMPUTE_MU>
 __global__ void __launch_bounds__( L0tc::THREADS, 1 )
 layer0_tc_kernel( const float *__restrict__ in /*[chunk][129][25] log spectrogram*/, float *__restrict__ out /*[chunk][13][16]*/,
-                  const unsigned char *__restrict__ img, int nchunks, const float *__restrict__ mu_in, int compute_mu,
+                  const unsigned char *__restrict__ img, int nchunks, const float *__restrict__ mu_in,
                   const __grid_constant__ L0DwParams dwc )
 {
    using Cfg = L0tc;
@@ -212,7 +215,7 @@ layer0_tc_kernel( const float *__restrict__ in /*[chunk][129][25] log spectrogra
       // exposed latency); only a group's first tile pays for a stand-alone pass.
       const int next_tile = tile + gridDim.x * NGROUPS;
       const float *spn = in + (size_t)min( next_tile * 4 + wq, nchunks - 1 ) * ( VB_BINS * T ) + min( t, T - 1 );
-      if ( compute_mu )
+      if ( COMPUTE_MU )
       {
          if ( !have_next_mu )
          {
@@ -227,13 +230,15 @@ layer0_tc_kernel( const float *__restrict__ in /*[chunk][129][25] log spectrogra
       float nsum = 0.0f;
 
       // ---- 1. conv_block in 8 slices of 16 bins -----------------------------------------------------------------
-      float xq[4], xn[4], xnn[4]; // software pipeline: the next 8 bins are in flight while these 4 are converted (the spectrogram comes
-                                  // from DRAM: one group of 4 ahead left 15 % of the kernel's stall samples on the first use)
+      float xq[4], xn[4], xnn[4], xn3[4]; // software pipeline: the next 12 bins are in flight while these 4 are converted (the
+                                          // spectrogram comes from DRAM; a rotation of 4 groups also closes over the 4 groups of a
+                                          // slice, so the loop back-edge needs no register moves)
 #pragma unroll
       for ( int k = 0; k < 4; ++k )
       {
          xn[k] = __ldg( sp + k * T );
          xnn[k] = __ldg( sp + ( 4 + k ) * T );
+         xn3[k] = __ldg( sp + ( 8 + k ) * T );
       }
 #pragma unroll 1
       for ( int s = 0; s < Cfg::NSLICE; ++s )
@@ -254,9 +259,10 @@ layer0_tc_kernel( const float *__restrict__ in /*[chunk][129][25] log spectrogra
             {
                xq[k] = xn[k];
                xn[k] = xnn[k];
-               xnn[k] = __ldg( sp + min( f0 + 8 + k, VB_BINS - 1 ) * T );
+               xnn[k] = xn3[k];
+               xn3[k] = __ldg( sp + min( f0 + 12 + k, VB_BINS - 1 ) * T );
             }
-            if ( compute_mu )
+            if ( COMPUTE_MU )
             {
                float nx[4];
 #pragma unroll
@@ -299,7 +305,7 @@ layer0_tc_kernel( const float *__restrict__ in /*[chunk][129][25] log spectrogra
          }
          ++n_s[b];
       }
-      if ( compute_mu )
+      if ( COMPUTE_MU )
       {
          nsum = __fadd_rn( nsum, __ldg( spn + 128 * T ) );
          next_mu = mu_from_frame_sum( nsum );
