@@ -398,8 +398,10 @@ static int configure_kernels()
    CU( allow_smem( stft_logmag_kernel<true>, STFT_SMEM_BYTES ) );
    CU( allow_smem( stft_hybrid_kernel<false>, HYB_SMEM_BYTES ) );
    CU( allow_smem( stft_hybrid_kernel<true>, HYB_SMEM_BYTES ) );
-   CU( allow_smem( stft_fft8_kernel<false>, F8_SMEM_BYTES ) );
-   CU( allow_smem( stft_fft8_kernel<true>, F8_SMEM_BYTES ) );
+   CU( allow_smem( stft_fft8_kernel<false, false>, F8_SMEM_BYTES ) );
+   CU( allow_smem( stft_fft8_kernel<true, false>, F8_SMEM_BYTES ) );
+   CU( allow_smem( stft_fft8_kernel<false, true>, F8_SMEM_BYTES ) );
+   CU( allow_smem( stft_fft8_kernel<true, true>, F8_SMEM_BYTES ) );
    CU( allow_smem( layer_kernel<0, true>, LayerCfg<0>::SMEM_BYTES ) );
    CU( allow_smem( layer_kernel<0, false>, LayerCfg<0>::SMEM_BYTES ) );
    CU( allow_smem( layer_kernel<1, false>, LayerCfg<1>::SMEM_BYTES ) );
@@ -834,14 +836,24 @@ static int launch_stft( silero_b200 *h, const void *d_in, int in_f32, long long 
       static int per_sm8 = 0;
       if ( !per_sm8 )
       {
-         CU( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm8, stft_fft8_kernel<false>, F8_THREADS, F8_SMEM_BYTES ) );
+         CU( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm8, stft_fft8_kernel<false, false>, F8_THREADS, F8_SMEM_BYTES ) );
          if ( per_sm8 < 1 ) per_sm8 = 1;
       }
       int grid = imin( nchunks, h->sm_count * per_sm8 );
       if ( in_f32 )
-         stft_fft8_kernel<true><<<grid, F8_THREADS, F8_SMEM_BYTES, st>>>( d_in, stream_stride, nw, nchunks, h->w.basis_raw, spec, mu, h->stft_k_rel, out_mode, h->d_flagged );
+      {
+         if ( out_mode )
+            stft_fft8_kernel<true, true><<<grid, F8_THREADS, F8_SMEM_BYTES, st>>>( d_in, stream_stride, nw, nchunks, h->w.basis_raw, spec, mu, h->stft_k_rel, h->d_flagged );
+         else
+            stft_fft8_kernel<true, false><<<grid, F8_THREADS, F8_SMEM_BYTES, st>>>( d_in, stream_stride, nw, nchunks, h->w.basis_raw, spec, mu, h->stft_k_rel, h->d_flagged );
+      }
       else
-         stft_fft8_kernel<false><<<grid, F8_THREADS, F8_SMEM_BYTES, st>>>( d_in, stream_stride, nw, nchunks, h->w.basis_raw, spec, mu, h->stft_k_rel, out_mode, h->d_flagged );
+      {
+         if ( out_mode )
+            stft_fft8_kernel<false, true><<<grid, F8_THREADS, F8_SMEM_BYTES, st>>>( d_in, stream_stride, nw, nchunks, h->w.basis_raw, spec, mu, h->stft_k_rel, h->d_flagged );
+         else
+            stft_fft8_kernel<false, false><<<grid, F8_THREADS, F8_SMEM_BYTES, st>>>( d_in, stream_stride, nw, nchunks, h->w.basis_raw, spec, mu, h->stft_k_rel, h->d_flagged );
+      }
       h->bins_total += (unsigned long long)nchunks * VB_BINS * VB_FRAMES;
    }
    else

@@ -202,13 +202,21 @@ __device__ __forceinline__ void f8_fft8( cpx ( &b )[8] )
 // bin of pair slot j for lane i: lanes 1..7 pair Z[i + 16 j] with Z[128 - i - 16 j]; lane 0 owns the self-paired rows 0 and 8:
 // slots 0..3 = (8 + 16 j, 120 - 16 j), slots 4..6 = (16 (j - 3), 128 - 16 (j - 3)), slot 7 = (0, 128) i.e. DC and Nyquist
 __device__ __forceinline__ int f8_bin_a( int i, int j ) { return i ? i + 16 * j : ( j < 4 ? 8 + 16 * j : ( j < 7 ? 16 * ( j - 3 ) : 0 ) ); }
+// bin of magnitude register r of lane i: r < 8: ma[r] (bin_a), r < 16: mb[r - 8] (128 - bin_a), r = 16: m64
+__device__ __forceinline__ int f8_bin_of( int i, int r )
+{
+   const int a = f8_bin_a( i, r & 7 );
+   return r < 8 ? a : ( r < 16 ? 128 - a : 64 );
+}
 
 // basis: the reference's forward_basis_buffer [258][256] (row 0 is the periodic Hann window).
 // k_rel: fix-up threshold relative to ||windowed frame||_2. out_mode 0: log1p(m*2^20); 1: m.
-template <bool F32>
+// RAW: emit magnitudes instead of log1p(m * 2^20) (parity tap). A template parameter: as a run-time flag every one of the 17 values
+// of a pass paid a select.
+template <bool F32, bool RAW>
 __global__ void __launch_bounds__( F8_THREADS, 3 )
 stft_fft8_kernel( const void *__restrict__ in, long long stream_stride, int nw, int nchunks, const float *__restrict__ basis,
-                  float *__restrict__ spec, float *__restrict__ mu_out, float k_rel, int out_mode, unsigned long long *__restrict__ flagged )
+                  float *__restrict__ spec, float *__restrict__ mu_out, float k_rel, unsigned long long *__restrict__ flagged )
 {
    extern __shared__ __align__( 16 ) float smem[];
    float *Xs = smem;                                      // [F8_XS_DEPTH][F8_XS_FLOATS]: ring of input tiles
@@ -454,31 +462,17 @@ stft_fft8_kernel( const void *__restrict__ in, long long stream_stride, int nw, 
       }
       float m64 = 2.0f * hyb_sqrt_fast( fmaf( za[4].re, za[4].re, za[4].im * za[4].im ) ); // lane 0 only: |Y[64]| = |Z[64]|
 
-      // ---- exact re-evaluation of small bins (whole warp per bin) ---------------------------------------------------
+      // ---- which bins are small: bit r of fl <-> magnitude register r (ma[0..7], mb[0..7], m64). One vote for the whole pass
+      //      (17 vote/branch sequences, one per register, were 14 % of the pass's instructions).
+      unsigned fl = 0;
 #pragma unroll
-      for ( int r = 0; r < 17; ++r )
+      for ( int r = 0; r < 8; ++r )
       {
-         const float mv = r < 8 ? ma[r] : ( r < 16 ? mb[r - 8] : m64 );
-         unsigned m = __ballot_sync( FULL, live && mv < tau && ( r < 16 || l0 ) );
-         while ( m )
-         {
-            const int src = __ffs( m ) - 1;
-            m &= m - 1;
-            const int si = src & 7, st = warp * 4 + ( src >> 3 );
-            const int f = r < 8 ? f8_bin_a( si, r ) : ( r < 16 ? 128 - f8_bin_a( si, r - 8 ) : 64 );
-            const float exv = f8_exact_mag( xs, basis, f, st, lane );
-            if ( lane == src )
-            {
-               if ( r < 8 )
-                  ma[r] = exv;
-               else if ( r < 16 )
-                  mb[r - 8] = exv;
-               else
-                  m64 = exv;
-            }
-            ++nflag;
-         }
+         fl |= ( ma[r] < tau ? 1u : 0u ) << r;
+         fl |= ( mb[r] < tau ? 1u : 0u ) << ( 8 + r );
       }
+      fl |= ( l0 && m64 < tau ? 1u : 0u ) << 16;
+      if ( !live ) fl = 0;
 
       // ---- log1p(m * 2^20) (misc.c:40-46) into the chunk's output tile; per-frame mean (misc.c:48-62) --------------
       tc::mbar_wait( &o_empty[b], ( ( it >> 1 ) & 1 ) ^ 1 );
@@ -487,8 +481,8 @@ stft_fft8_kernel( const void *__restrict__ in, long long stream_stride, int nw, 
       for ( int j = 0; j < 8; ++j )
       {
          const int fa = f8_bin_a( i, j );
-         const float la = out_mode ? ma[j] : hyb_log1p_scaled( ma[j] );
-         const float lb = out_mode ? mb[j] : hyb_log1p_scaled( mb[j] );
+         const float la = RAW ? ma[j] : hyb_log1p_scaled( ma[j] );
+         const float lb = RAW ? mb[j] : hyb_log1p_scaled( mb[j] );
          if ( live )
          {
             os[fa * VB_FRAMES + t] = la;
@@ -498,10 +492,32 @@ stft_fft8_kernel( const void *__restrict__ in, long long stream_stride, int nw, 
       }
       if ( l0 )
       {
-         const float lv = out_mode ? m64 : hyb_log1p_scaled( m64 );
+         const float lv = RAW ? m64 : hyb_log1p_scaled( m64 );
          if ( live ) os[64 * VB_FRAMES + t] = lv;
          fsum += lv;
       }
+
+      // ---- exact re-evaluation of the small bins (whole warp per bin); the owning lane replaces the value in the tile and
+      //      corrects its frame sum (the magnitude registers cannot be indexed by a run-time r) ----------------------------------
+      for ( unsigned anym = __ballot_sync( FULL, fl != 0 ); anym; anym &= anym - 1 )
+      {
+         const int src = __ffs( anym ) - 1;
+         const int st = warp * 4 + ( src >> 3 );
+         for ( unsigned bits = __shfl_sync( FULL, fl, src ); bits; bits &= bits - 1 )
+         {
+            const int f = f8_bin_of( src & 7, __ffs( bits ) - 1 );
+            const float exv = f8_exact_mag( xs, basis, f, st, lane );
+            if ( lane == src )
+            {
+               float *po = os + f * VB_FRAMES + st;
+               const float nv = RAW ? exv : hyb_log1p_scaled( exv );
+               fsum += nv - *po;
+               *po = nv;
+            }
+            ++nflag;
+         }
+      }
+
       fsum += __shfl_xor_sync( FULL, fsum, 1 );
       fsum += __shfl_xor_sync( FULL, fsum, 2 );
       fsum += __shfl_xor_sync( FULL, fsum, 4 );
