@@ -76,6 +76,7 @@ struct silero_b200
    unsigned char *d_layer_tc[4]; // fp16 hi/lo weight images + fp32 parameters per layer (layer0_tc_kernel.cuh, layer_tc_kernel.cuh)
    size_t cap_h0_floats;
    unsigned long long *d_flagged; // bins that took the exact path (device counter)
+   size_t scratch_budget;    // bytes of window scratch pick_window may plan for (set from the device's free memory at creation)
    unsigned long long bins_total;
    cudaStream_t stream;      // compute
    cudaStream_t copy_stream; // H2D of the next window
@@ -662,6 +663,17 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    h->w.dec_b = h->d_weights + o_db;
    h->w.basis_raw = h->d_weights + o_raw;
    CU_H( cudaMalloc( &h->d_flagged, sizeof( unsigned long long ) ) );
+   {
+      size_t free_b = 0, total_b = 0;
+      h->scratch_budget = (size_t)1536 << 20;
+      if ( cudaMemGetInfo( &free_b, &total_b ) == cudaSuccess )
+      {
+         size_t b = free_b / 10;
+         if ( b < ( (size_t)1536 << 20 ) ) b = (size_t)1536 << 20;
+         if ( b > ( (size_t)12 << 30 ) ) b = (size_t)12 << 30;
+         h->scratch_budget = b;
+      }
+   }
    CU_H( cudaMemset( h->d_flagged, 0, sizeof( unsigned long long ) ) );
 
    size_t sbytes = (size_t)h->max_streams * SILERO_B200_STATE_FLOATS * sizeof( float );
@@ -759,11 +771,15 @@ static int ensure_scratch( silero_b200 *h, size_t chunks, size_t h0_floats )
 // bytes of window scratch per chunk: spec + a1..a4 + h0
 static const size_t kScratchPerChunk = ( VB_BINS * VB_FRAMES + 13 * 16 + 7 * 32 * 2 + 7 * 64 * 2 ) * sizeof( float );
 
-static int pick_window( const silero_b200 *h, int nstreams, int nchunks )
+// host_path: windows are also the granularity at which the H2D copy of the next window overlaps compute, so calls that start from
+// host memory keep the small (1.5 GB) windows; device-resident input takes the large ones
+static int pick_window( const silero_b200 *h, int nstreams, int nchunks, bool host_path = false )
 {
    if ( h->window_chunks_opt > 0 ) return h->window_chunks_opt < nchunks ? h->window_chunks_opt : nchunks;
-   // ~1.5 GB of scratch: enough chunks in flight to fill the GPU many times over
-   const size_t budget = (size_t)1536 << 20;
+   // Window scratch: a tenth of the memory that was free at creation, between 1.5 and 12 GB. Every window boundary drains the GPU
+   // seven times (persistent kernels with static tile assignment have a tail) and reloads weights into shared / tensor memory:
+   // measured on 4096 streams x 125 chunks, 18-chunk windows (1.5 GB) 19.6 ms per step, 63-chunk windows 18.9 ms, one window 18.7 ms.
+   const size_t budget = ( h->scratch_budget && !host_path ) ? h->scratch_budget : ( (size_t)1536 << 20 );
    long long per_stream = (long long)( budget / kScratchPerChunk ) / ( nstreams > 0 ? nstreams : 1 );
    if ( per_stream < 1 ) per_stream = 1;
    if ( per_stream > nchunks ) per_stream = nchunks;
@@ -1155,7 +1171,7 @@ static int run_streams_host( silero_b200 *h, const int16_t *pcm, long long strea
    timing_begin( h );
    if ( nchunks > 0 )
    {
-      const int nw_max = pick_window( h, nstreams, nchunks );
+      const int nw_max = pick_window( h, nstreams, nchunks, true );
       const size_t win_samples = (size_t)nstreams * nw_max * VB_CHUNK;
       if ( win_samples > h->pcm_stage_cap )
       {
