@@ -331,6 +331,27 @@ def main():
                      "algorithmic_tflops": 2 * STAGE_MAC[k] * chunks_per_launch / (stage_ms[k] / windows * 1e-3) / 1e12}
                  for k in stage_ms if k != "total"}
     bins_total, bins_exact = eng.stft_stats()
+    # the two rooflines of the contract, from the driver-written measured peaks (else the profiling recipe's fallbacks), for the same
+    # dominant kernel: they show why neither bounds it
+    peaks = {"hbm_gbs": 6500.0, "bf16_tflops": 1600.0, "source": "B200_PROFILING.md fallback"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            mp_ = json.load(fh)
+        peaks = {"hbm_gbs": float(mp_["hbm_gbs"]), "bf16_tflops": float(mp_.get("bf16_tflops_sustained", mp_["bf16_tflops"])), "source": "MEASURED_PEAKS.json"}
+    except Exception:
+        pass
+    alg_bytes = ALGORITHMIC_BYTES_PER_CHUNK.get(top)
+    hbm_view = None
+    if alg_bytes:
+        gbs = alg_bytes * chunks_per_launch / (top_ms_per_launch * 1e-3) / 1e9
+        hbm_view = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                    "algorithmic_bytes_per_launch": alg_bytes * chunks_per_launch,
+                    "traffic": TRAFFIC_BYTES_PER_CHUNK[top] * chunks_per_launch if TRAFFIC_BYTES_PER_CHUNK.get(top) else None,
+                    "peak_source": peaks["source"]}
+    # tensor-pipe view of the kernels that run on tcgen05: algorithmic rate, and x3 for the three partial products of the fp16/bf16 splits
+    tensor_view = {k: {"algorithmic_tflops": per_stage[k]["algorithmic_tflops"], "issued_tflops": 3 * per_stage[k]["algorithmic_tflops"],
+                       "frac_of_bf16_peak": 3 * per_stage[k]["algorithmic_tflops"] / peaks["bf16_tflops"]}
+                   for k in ("layer1", "layer2", "layer3", "layer4", "lstm0", "lstm1_decoder") if k in per_stage}
     roofline = {
         "kernel": STAGE_KERNEL[top], "bound": "fp32",
         "achieved": top_tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": top_tflops / fp32_peak,
@@ -340,6 +361,8 @@ def main():
         "share_of_step": stage_ms[top] / kernel_sum,
         "traffic": TRAFFIC_BYTES_PER_CHUNK.get(top, 0) * chunks_per_launch if TRAFFIC_BYTES_PER_CHUNK.get(top) else None,
         "stages": per_stage,
+        "hbm": hbm_view,
+        "tensor": {"bound": "tensor", "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "peak_source": peaks["source"], "kernels": tensor_view},
         "note": "achieved = ALGORITHMIC FLOPs of the reference's dense formulation (SURVEY.md 8d) / measured launch time; the STFT kernel is an FFT + "
                 "exact fix-up, so the algorithmic rate exceeds the FP32 pipe peak (frac > 1); executed_* is what the FP32 pipe really did",
         "executed_tflops": (STFT_EXECUTED_FLOP_PER_CHUNK * chunks_per_launch / (stage_ms["stft"] / windows * 1e-3) / 1e12) if top == "stft" else None,
@@ -442,6 +465,10 @@ def main():
 # dram__bytes_read.sum + dram__bytes_write.sum per chunk of each kernel, from the ncu --set full capture of one window of
 # 81 920 chunks (profiles/ncu_summary_r01h.md). For the STFT kernel the algorithmic bytes are 3 072 (s16 PCM) + 12 900 (log
 # spectrogram) + 4 (normalization scalar) = 15 976 per chunk: traffic == algorithmic, nothing is re-read.
+# algorithmic bytes per chunk of each kernel (what it must read + write once): STFT 3 072 s16 PCM + 12 900 log spectrogram + 4 scalar;
+# first layer 12 900 + 4 in, 832 out; layers 2..4 832/896/896 in, 896/896/1 792 out; LSTM layer 0 1 792 in + 1 792 packed h out
+# (state: 1 KB per stream per launch, negligible per chunk); layer 1 1 792 in, 8 out
+ALGORITHMIC_BYTES_PER_CHUNK = {"stft": 15976, "layer1": 13736, "layer2": 1728, "layer3": 1792, "layer4": 2688, "lstm0": 3584, "lstm1_decoder": 1800}
 TRAFFIC_BYTES_PER_CHUNK = {"stft": 15336, "layer1": 13714, "layer2": 1128, "layer3": 1218, "layer4": 2064, "lstm0": 3117, "lstm1_decoder": 1905}
 
 if __name__ == "__main__":
