@@ -55,8 +55,11 @@ typedef struct silero_b200 silero_b200; /* opaque engine handle */
 /* STFT evaluation. HYBRID: fp32 FFT everywhere + the reference's exact rounding
    sequence (stft.c:108-184) for every bin whose magnitude is below stft_k_rel * ||windowed frame||_2;
    EXACT: the reference's sequence for every bin (bit-identical magnitudes, ~7x slower STFT). */
-#define SILERO_B200_STFT_HYBRID 0          /* hybrid rule on the fp32 FFT kernel with 8 lanes per frame, 16 points per lane in registers
-                                              (stft_fft8_kernel.cuh) */
+#define SILERO_B200_STFT_AUTO 0            /* default: _EXACT for stream batches that run on the fp32 kernels (fewer than
+                                              SILERO_B200_LSTM_TENSOR_MIN_STREAMS streams per call: the single-stream use of the reference),
+                                              _HYBRID for the large batches of the tensor-core path */
+#define SILERO_B200_STFT_HYBRID 4          /* always the hybrid rule on the fp32 FFT kernel with 8 lanes per frame, 16 points per lane in
+                                              registers (stft_fft8_kernel.cuh) */
 #define SILERO_B200_STFT_EXACT 1
 #define SILERO_B200_STFT_HYBRID_FFT 2      /* hybrid rule on the warp-per-frame fp32 FFT kernel (stft_hybrid_kernel.cuh): the first FFT kernel,
                                               5 shuffle stages per frame, ~1.5x slower than _HYBRID */
@@ -88,7 +91,7 @@ typedef struct silero_b200_opts
    int device;          /* CUDA device ordinal (default 0) */
    int max_streams;     /* number of independent streams whose LSTM state is kept on device (default 1) */
    int window_chunks;   /* chunks per stream processed per internal pass; 0 = choose from memory budget */
-   int stft_mode;       /* SILERO_B200_STFT_HYBRID (default), _EXACT, _HYBRID_FFT or _HYBRID_TENSOR */
+   int stft_mode;       /* SILERO_B200_STFT_AUTO (default), _HYBRID, _EXACT, _HYBRID_FFT or _HYBRID_TENSOR */
    float stft_k_rel;    /* hybrid threshold; 0 = SILERO_B200_STFT_K_REL_DEFAULT */
    int lstm_mode;       /* SILERO_B200_LSTM_AUTO (default), _FP32 (CUDA-core kernel) or _TENSOR (tcgen05 kernel) */
    int layer_mode;      /* SILERO_B200_LAYERS_AUTO (default), _FP32 (CUDA-core kernels) or _TENSOR (tcgen05 kernel) */
@@ -185,6 +188,9 @@ int silero_b200_host_free_pinned( void *ptr );
 int silero_b200_last_timing( silero_b200 *h, float ms[8], long long *kernel_launches );
 /* hybrid STFT statistics since the last reset: spectrogram bins produced and bins that took the exact path */
 int silero_b200_stft_stats( silero_b200 *h, unsigned long long *bins_total, unsigned long long *bins_exact, int reset );
+/* parity tap: the engine's expf / tanhf / log1pf(|x|) (csrc/libm_exact.cuh: glibc's algorithms, used by the fp32 LSTM path, lstm.c:64-88
+   via maths.h:302-334, and by the exact STFT path, misc.c:40-46) of n host floats; must equal the C library's results bit for bit */
+int silero_b200_stage_libm( silero_b200 *h, const float *x, int n, float *out_expf, float *out_tanhf, float *out_log1pf_abs );
 /* enable (1) / disable (0) per-stage CUDA-event timing (adds events between kernels) */
 int silero_b200_set_profiling( silero_b200 *h, int enabled );
 

@@ -104,12 +104,35 @@ def test_hybrid_exact_path_alone_is_bit_exact(oracle):
     e.close()
 
 
-def test_hybrid_fix_fraction_on_speech_like_audio(engine):
+def test_hybrid_fix_fraction_on_speech_like_audio():
     pcm = np.stack([vadc_b200.synth_pcm(60 + s, 1536 * 100) for s in range(8)])
-    engine.reset(); engine.stft_stats(reset=True)
+    engine = vadc_b200.Engine(max_streams=8, stft_mode=vadc_b200.STFT_HYBRID)   # (STFT_AUTO would take the exact kernel for 8 streams)
+    engine.stft_stats(reset=True)
     engine.run_streams(pcm)
     total, exact = engine.stft_stats(reset=True)
+    engine.close()
     assert total == 8 * 100 * 3225 and 0 < exact < 0.02 * total, (total, exact)
+
+
+def test_small_batches_take_the_exact_stft(oracle):
+    """STFT_AUTO: fewer streams than the tensor-core threshold run the exact STFT kernel -- magnitudes, log1p (the C library's bits,
+    libm_exact.cuh) and the normalization scalar (the reference's summation order) are BIT-identical to the reference, so the whole
+    normalized spectrogram is; the rest of the fp32 path stays within the 1e-4 bar on a 600-chunk stream."""
+    pcm = vadc_b200.synth_pcm(50000 + 13 * 17, 1536 * 600)
+    x = f32(pcm)
+    oracle.reset()
+    st = oracle.run_stages(x)
+    e = vadc_b200.Engine(max_streams=2)
+    e.stft_stats(reset=True)
+    p, out2 = e.run_streams(pcm[None, :], want_out2=True)
+    assert e.stft_stats()[0] == 0                              # no bin went through the FFT kernels
+    e.close()
+    assert np.abs(out2[0] - st["out"]).max() <= PTOL
+    assert vadc_b200.segments_text(p[0]) == oracle.segments_text(st["out"][:, 1])
+    ex = vadc_b200.Engine(stft_mode=vadc_b200.STFT_EXACT)
+    norm, logmag = ex.stage_stft_norm(x)
+    ex.close()
+    assert np.array_equal(norm.view(np.uint32), st["norm"].view(np.uint32))
 
 
 @pytest.mark.parametrize("S,N,window", [(1, 1, 0), (3, 7, 0), (37, 70, 16), (130, 33, 5), (64, 96, 0)])
@@ -335,3 +358,27 @@ def test_overlapped_and_single_stream_schedules_agree():
     e.d2h(got, d_probs)
     assert np.array_equal(got, outs[0])
     e.close()
+
+
+def test_lstm_nonlinearities_have_the_c_librarys_bits():
+    """csrc/libm_exact.cuh: expf / tanhf of the fp32 LSTM path and log1pf of the exact STFT path equal the host C library's (the reference build's) bit for bit --
+    random arguments over the gates' range, dense samples near zero and the saturation ends, special values."""
+    libm = C.CDLL("libm.so.6")
+    libm.expf.restype = libm.tanhf.restype = libm.log1pf.restype = C.c_float
+    libm.expf.argtypes = libm.tanhf.argtypes = libm.log1pf.argtypes = [C.c_float]
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.uniform(-30, 30, 200000), rng.normal(0, 1, 100000), rng.uniform(-1e-3, 1e-3, 20000), rng.uniform(-87, 87, 50000),
+                        np.float32([0.0, -0.0, 1.0, -1.0, 0.5, 22.0, -22.0, 21.999, 1e-20, -1e-20, 0.34657359, 1.0397208, 18.7, -18.7, 43.9])]).astype(np.float32)
+    e = vadc_b200.Engine()
+    ge, gt, _ = e.stage_libm(x)
+    # log1pf over the range of magnitude * 2^20: denormal-small to 3e8, log-uniform, plus the branch points of the algorithm
+    xl = np.concatenate([np.exp(rng.uniform(np.log(1e-30), np.log(3e8), 300000)), rng.uniform(0, 1, 50000), np.float32([0.0, 0.41421, 0.41422, 0.41423, 1.0, 2.0 ** -29, 2.0 ** 25, 3.4e8])]).astype(np.float32)
+    gl = e.stage_libm(xl)[2]
+    e.close()
+    hl = np.array([libm.log1pf(float(v)) for v in xl], np.float32)
+    assert np.array_equal(gl.view(np.uint32), hl.view(np.uint32))
+    he = np.array([libm.expf(float(v)) for v in x], np.float32)
+    ht = np.array([libm.tanhf(float(v)) for v in x], np.float32)
+    assert np.array_equal(gt.view(np.uint32), ht.view(np.uint32))
+    bad = np.nonzero(ge.view(np.uint32) != he.view(np.uint32))[0]
+    assert bad.size == 0, (x[bad][:5], ge[bad][:5], he[bad][:5])

@@ -1,5 +1,5 @@
 """GPU: the two fp32 FFT kernels behind the hybrid STFT rule (stft.c:15-229 + misc.c:40-82) against the oracle.
-STFT_HYBRID is the 8-lanes-per-frame kernel (stft_fft8_kernel.cuh, default); STFT_HYBRID_FFT is the warp-per-frame
+STFT_HYBRID is the 8-lanes-per-frame kernel (stft_fft8_kernel.cuh; what STFT_AUTO, the default, runs on large stream batches); STFT_HYBRID_FFT is the warp-per-frame
 kernel (stft_hybrid_kernel.cuh). Both must flag the same kind of bins, be bit-identical to the reference on the
 flagged bins, and keep the probabilities inside the 1e-4 bar."""
 import numpy as np

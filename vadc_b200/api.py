@@ -15,7 +15,7 @@ WEIGHTS_PATH = os.path.join(_HERE, "weights", "silero_v31_16k.testtensor")
 
 CHUNK = 1536
 SAMPLE_RATE = 16000
-STFT_HYBRID, STFT_EXACT, STFT_HYBRID_FFT, STFT_HYBRID_TENSOR = 0, 1, 2, 3
+STFT_AUTO, STFT_EXACT, STFT_HYBRID_FFT, STFT_HYBRID_TENSOR, STFT_HYBRID = 0, 1, 2, 3, 4
 LSTM_AUTO, LSTM_FP32, LSTM_TENSOR = 0, 1, 2
 LAYERS_AUTO, LAYERS_FP32, LAYERS_TENSOR = 0, 1, 2
 
@@ -238,6 +238,12 @@ class Engine:
         tot, ex = C.c_ulonglong(), C.c_ulonglong()
         self._check(lib().silero_b200_stft_stats(self._h, C.byref(tot), C.byref(ex), 1 if reset else 0))
         return int(tot.value), int(ex.value)
+
+    def stage_libm(self, x):
+        x = _f32(x).reshape(-1)
+        e, t, l = np.zeros_like(x), np.zeros_like(x), np.zeros_like(x)
+        self._check(lib().silero_b200_stage_libm(self._h, _p(x), x.size, _p(e), _p(t), _p(l)))
+        return e, t, l
 
     def set_profiling(self, on):
         self._check(lib().silero_b200_set_profiling(self._h, 1 if on else 0))

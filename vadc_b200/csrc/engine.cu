@@ -63,7 +63,8 @@ struct silero_b200
    int sm_count;
    int max_streams;
    int window_chunks_opt;
-   int stft_mode;            // SILERO_B200_STFT_*
+   int stft_mode;            // kernel family: 0 = FFT hybrid (stft_fft8_kernel), SILERO_B200_STFT_EXACT, _HYBRID_FFT, _HYBRID_TENSOR
+   int stft_auto;            // SILERO_B200_STFT_AUTO: run_window picks the exact kernel for small stream batches (the fp32 path)
    unsigned char *d_stft_tc; // fp16 hi/lo basis image in K slices (stft_tc_kernel.cuh)
    unsigned long long *d_fix_list; // work list of flagged bins (stft_tc_kernel -> stft_fixup_kernel)
    size_t fix_cap;
@@ -381,7 +382,7 @@ extern "C" void silero_b200_default_opts( silero_b200_opts *o )
    o->device = 0;
    o->max_streams = 1;
    o->window_chunks = 0;
-   o->stft_mode = SILERO_B200_STFT_HYBRID;
+   o->stft_mode = SILERO_B200_STFT_AUTO;
    o->stft_k_rel = 0.0f; /* 0 = default (SILERO_B200_STFT_K_REL_DEFAULT) */
    o->lstm_mode = SILERO_B200_LSTM_AUTO;
    o->layer_mode = SILERO_B200_LAYERS_AUTO;
@@ -529,7 +530,8 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    h->window_chunks_opt = opts.window_chunks;
    h->stft_mode = ( opts.stft_mode == SILERO_B200_STFT_EXACT || opts.stft_mode == SILERO_B200_STFT_HYBRID_FFT || opts.stft_mode == SILERO_B200_STFT_HYBRID_TENSOR )
                      ? opts.stft_mode
-                     : SILERO_B200_STFT_HYBRID;
+                     : 0;
+   h->stft_auto = opts.stft_mode != SILERO_B200_STFT_HYBRID && h->stft_mode == 0;
    h->stft_k_rel = opts.stft_k_rel > 0.0f ? opts.stft_k_rel : SILERO_B200_STFT_K_REL_DEFAULT;
    h->lstm_mode = ( opts.lstm_mode == SILERO_B200_LSTM_FP32 || opts.lstm_mode == SILERO_B200_LSTM_TENSOR ) ? opts.lstm_mode : SILERO_B200_LSTM_AUTO;
    h->layer_mode = ( opts.layer_mode == SILERO_B200_LAYERS_FP32 || opts.layer_mode == SILERO_B200_LAYERS_TENSOR ) ? opts.layer_mode : SILERO_B200_LAYERS_AUTO;
@@ -847,7 +849,7 @@ static int launch_stft( silero_b200 *h, const void *d_in, int in_f32, long long 
       else
          stft_logmag_kernel<false><<<npairs * 2, STFT_THREADS, STFT_SMEM_BYTES, st>>>( d_in, stream_stride, nw, nchunks, h->w.basis_pack, spec, out_mode );
    }
-   else if ( h->stft_mode == SILERO_B200_STFT_HYBRID )
+   else if ( h->stft_mode == 0 )
    {
       static int per_sm8 = 0;
       if ( !per_sm8 )
@@ -1024,6 +1026,18 @@ static int run_window( silero_b200 *h, const void *d_in, int in_f32, long long s
    const int nchunks = nstreams * nw;
    const size_t h0_floats = (size_t)( ( nstreams + LTC_N - 1 ) / LTC_N ) * LTC_N * nw * 7 * 64;
    if ( ensure_scratch( h, (size_t)nchunks, h0_floats ) ) return SILERO_B200_ERR_CUDA;
+   // SILERO_B200_STFT_AUTO: stream batches below the tensor-core threshold take the fp32 kernels, and with them the exact STFT
+   // kernel (every magnitude and, through libm_exact.cuh, every log1p bit-identical to the reference, the normalization scalar in
+   // the reference's own order). The network amplifies ONE ulp of that scalar into up to 3e-3 of speech probability at the next
+   // speech onset of a long stream (measured on the CPU restatement), and no FFT can promise its last bit; the exact kernel costs
+   // 7x the STFT time, which only matters where thousands of streams share the GPU -- and there the FFT hybrid runs.
+   struct ModeGuard
+   {
+      silero_b200 *h;
+      int saved;
+      ~ModeGuard() { h->stft_mode = saved; }
+   } guard = { h, h->stft_mode };
+   if ( h->stft_auto && !lstm_use_tensor( h, nstreams ) ) h->stft_mode = SILERO_B200_STFT_EXACT;
    stage_mark( h, 0 );
    const bool have_mu = stft_produces_mu( h, nchunks );
    // (an input that was produced by earlier work on h->stream itself, like run_chunks' own upload, keeps the STFT on that stream)
@@ -1475,6 +1489,37 @@ extern "C" int silero_b200_host_free_pinned( void *ptr )
    return SILERO_B200_OK;
 }
 
+// parity tap for libm_exact.cuh: expf_ref / tanhf_ref of n host floats
+__global__ void libm_exact_kernel( const float *__restrict__ x, float *__restrict__ e, float *__restrict__ t, float *__restrict__ l, int n )
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if ( i >= n ) return;
+   e[i] = lme::expf_ref( x[i] );
+   t[i] = lme::tanhf_ref( x[i] );
+   l[i] = lme::log1pf_ref( fabsf( x[i] ) );
+}
+extern "C" int silero_b200_stage_libm( silero_b200 *h, const float *x, int n, float *out_expf, float *out_tanhf, float *out_log1pf_abs )
+{
+   if ( !h || !x || !out_expf || !out_tanhf || !out_log1pf_abs || n < 0 ) return set_err( SILERO_B200_ERR_ARG, "null argument" );
+   if ( n == 0 ) return SILERO_B200_OK;
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+   float *d = 0;
+   CU( cudaMalloc( &d, (size_t)n * 4 * sizeof( float ) ) );
+   cudaError_t ce = cudaMemcpyAsync( d, x, (size_t)n * sizeof( float ), cudaMemcpyHostToDevice, h->stream );
+   if ( ce == cudaSuccess )
+   {
+      libm_exact_kernel<<<( n + 255 ) / 256, 256, 0, h->stream>>>( d, d + n, d + 2 * (size_t)n, d + 3 * (size_t)n, n );
+      ce = cudaGetLastError();
+   }
+   if ( ce == cudaSuccess ) ce = cudaMemcpyAsync( out_expf, d + n, (size_t)n * sizeof( float ), cudaMemcpyDeviceToHost, h->stream );
+   if ( ce == cudaSuccess ) ce = cudaMemcpyAsync( out_tanhf, d + 2 * (size_t)n, (size_t)n * sizeof( float ), cudaMemcpyDeviceToHost, h->stream );
+   if ( ce == cudaSuccess ) ce = cudaMemcpyAsync( out_log1pf_abs, d + 3 * (size_t)n, (size_t)n * sizeof( float ), cudaMemcpyDeviceToHost, h->stream );
+   if ( ce == cudaSuccess ) ce = cudaStreamSynchronize( h->stream );
+   cudaFree( d );
+   CU( ce );
+   return SILERO_B200_OK;
+}
+
 extern "C" int silero_b200_stft_stats( silero_b200 *h, unsigned long long *bins_total, unsigned long long *bins_exact, int reset )
 {
    if ( !h ) return set_err( SILERO_B200_ERR_ARG, "null handle" );
@@ -1652,7 +1697,7 @@ extern "C" int silero_b200_stage_stft_magnitude( silero_b200 *h, const float *sa
 __global__ void log1p_scale_kernel( const float *__restrict__ mag, float *__restrict__ out, size_t n )
 {
    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-   if ( i < n ) out[i] = log1pf( __fmul_rn( mag[i], 1048576.0f ) );
+   if ( i < n ) out[i] = lme::log1pf_ref( __fmul_rn( mag[i], 1048576.0f ) ); // misc.c:40-46 with the C library's bits
 }
 
 // the mean part of adaptive_audio_normalization_inplace (misc.c:48-121), one warp per chunk; the

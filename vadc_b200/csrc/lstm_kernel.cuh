@@ -14,6 +14,7 @@
 // ping-pong [x|h] buffer in shared memory with one 64-thread named barrier per step.
 #pragma once
 #include "common.cuh"
+#include "libm_exact.cuh"
 
 #define LSTM_H 64
 #define LSTM_WS_FLOATS ( 32 * 256 * 4 )
@@ -28,7 +29,10 @@ struct LstmSmem
    static constexpr int BYTES = FLOATS * 4;
 };
 
-__device__ __forceinline__ float sigmoid_acc( float v ) { return 1.0f / ( 1.0f + expf( -v ) ); }
+// Gate nonlinearities with the bits of the reference's C library and a cell update without fused multiply-adds (lstm.c:64-88 as
+// compiled with -ffp-contract=off): this path is the one a single-stream user of the reference runs, and over a long silence a
+// nonlinearity that is off by one ulp in the same direction on every step makes the cell state drift (libm_exact.cuh).
+__device__ __forceinline__ float sigmoid_acc( float v ) { return lme::sigmoid_ref( v ); }
 
 // x:      layer input sequence [S][steps][64] (stream-major), steps = nw*7
 // hseq:   LAYER 0: output sequence [S][steps][64]; LAYER 1: optional tap of the top-layer sequence
@@ -137,10 +141,10 @@ lstm_layer_kernel( const float *__restrict__ x, float *__restrict__ hseq, float 
 #pragma unroll
          for ( int st = 0; st < ST; ++st )
          {
-            float ig = sigmoid_acc( zi[st] ), fg = sigmoid_acc( zf[st] ), gg = tanhf( zg[st] ), og = sigmoid_acc( zo[st] );
-            float cn = fg * c[st] + ig * gg;
+            float ig = sigmoid_acc( zi[st] ), fg = sigmoid_acc( zf[st] ), gg = lme::tanhf_ref( zg[st] ), og = sigmoid_acc( zo[st] );
+            float cn = __fadd_rn( __fmul_rn( fg, c[st] ), __fmul_rn( ig, gg ) );
             c[st] = cn;
-            float hn = tanhf( cn ) * og;
+            float hn = __fmul_rn( lme::tanhf_ref( cn ), og );
             nxt[st * 128 + 64 + j] = hn;
             nxt[st * 128 + j] = xn[st];
             int s = s0 + st;
@@ -181,7 +185,7 @@ lstm_layer_kernel( const float *__restrict__ x, float *__restrict__ hseq, float 
             {
                float sum = decp[( ( grp * 2 + 0 ) * 2 + head ) * ST + st] + decp[( ( grp * 2 + 1 ) * 2 + head ) * ST + st];
                float mean = sum / 7.0f + dbs[head];
-               float p = 1.0f / ( 1.0f + expf( -mean ) );
+               float p = lme::sigmoid_ref( mean );
                long long n = out_off + step / 7;
                if ( out2 ) out2[( (long long)s * out_stride + n ) * 2 + head] = p;
                if ( probs && head == 1 ) probs[(long long)s * out_stride + n] = p;

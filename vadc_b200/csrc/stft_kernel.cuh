@@ -25,6 +25,7 @@
 // cover a chunk-half, a CTA runs 2 chunks at once (20 warps per SM).
 #pragma once
 #include "common.cuh"
+#include "libm_exact.cuh"
 
 // thread = 1 bin (re + im row) x 5 frames; 64 bins x 5 frame groups = 320 threads per chunk-half;
 // a CTA runs STFT_GROUPS chunks at once
@@ -229,11 +230,11 @@ stft_logmag_kernel( const void *__restrict__ in, long long stream_stride, int nw
             im = 0.0f;
          }
          float m = sqrtf( __fadd_rn( __fmul_rn( re, re ), __fmul_rn( im, im ) ) );
-         o[f * VB_FRAMES + 5 * tg + i] = out_mode ? m : log1pf( __fmul_rn( m, 1048576.0f ) );
+         o[f * VB_FRAMES + 5 * tg + i] = out_mode ? m : lme::log1pf_ref( __fmul_rn( m, 1048576.0f ) );
          if ( special )
          {
             float m2 = sqrtf( __fadd_rn( __fmul_rn( extra, extra ), 0.0f ) );
-            o[128 * VB_FRAMES + 5 * tg + i] = out_mode ? m2 : log1pf( __fmul_rn( m2, 1048576.0f ) );
+            o[128 * VB_FRAMES + 5 * tg + i] = out_mode ? m2 : lme::log1pf_ref( __fmul_rn( m2, 1048576.0f ) );
          }
       }
    }
