@@ -75,6 +75,7 @@ typedef struct silero_b200 silero_b200; /* opaque engine handle */
 #define SILERO_B200_LSTM_FP32 1
 #define SILERO_B200_LSTM_TENSOR 2
 #define SILERO_B200_LSTM_TENSOR_MIN_STREAMS 1024
+#define SILERO_B200_LSTM_FAITHFUL 3        /* see SILERO_B200_LAYERS_FAITHFUL: either one selects the whole faithful path */
 
 /* Encoder layers 2..4. FP32: every contraction as in-thread fp32 FMA chains on the CUDA cores.
    TENSOR: the six dense contractions of a layer as tcgen05 tensor-core GEMMs over tiles of 128 tokens with the fp16x2
@@ -85,6 +86,15 @@ typedef struct silero_b200 silero_b200; /* opaque engine handle */
 #define SILERO_B200_LAYERS_FP32 1
 #define SILERO_B200_LAYERS_TENSOR 2
 #define SILERO_B200_LAYERS_TENSOR_MIN_CHUNKS 2048
+/* FAITHFUL (faithful_kernel.cuh): from the log spectrogram to the probability every rounding step of the reference's C backend
+   as built with -mavx2 -ffp-contract=off -- dotproduct_simd's lane order (maths.h:123-158), conv_tensor's variant E and generic
+   paths (conv.c:532-709), sequential means and true divisions, glibc's expf/tanhf/log1pf bit for bit, no fused multiply-add --
+   on top of the exact STFT: probabilities are bit-identical to the reference's for streams of any length (the fast kernels are
+   within 1e-5 chunk by chunk but the decoder LSTM integrates one-ulp differences over long silences).
+   About 30x slower per chunk than the tensor-core path. A fully automatic engine (stft, lstm and layer modes all AUTO) takes it
+   for calls with at most SILERO_B200_FAITHFUL_MAX_STREAMS streams -- the way the reference itself is used. */
+#define SILERO_B200_LAYERS_FAITHFUL 3
+#define SILERO_B200_FAITHFUL_MAX_STREAMS 64
 
 typedef struct silero_b200_opts
 {
@@ -93,8 +103,8 @@ typedef struct silero_b200_opts
    int window_chunks;   /* chunks per stream processed per internal pass; 0 = choose from memory budget */
    int stft_mode;       /* SILERO_B200_STFT_AUTO (default), _HYBRID, _EXACT, _HYBRID_FFT or _HYBRID_TENSOR */
    float stft_k_rel;    /* hybrid threshold; 0 = SILERO_B200_STFT_K_REL_DEFAULT */
-   int lstm_mode;       /* SILERO_B200_LSTM_AUTO (default), _FP32 (CUDA-core kernel) or _TENSOR (tcgen05 kernel) */
-   int layer_mode;      /* SILERO_B200_LAYERS_AUTO (default), _FP32 (CUDA-core kernels) or _TENSOR (tcgen05 kernel) */
+   int lstm_mode;       /* SILERO_B200_LSTM_AUTO (default), _FP32 (CUDA-core kernel), _TENSOR (tcgen05 kernel) or _FAITHFUL */
+   int layer_mode;      /* SILERO_B200_LAYERS_AUTO (default), _FP32 (CUDA-core kernels), _TENSOR (tcgen05 kernel) or _FAITHFUL */
    int reserved[1];
 } silero_b200_opts;
 

@@ -1,0 +1,75 @@
+"""The faithful path's arithmetic (vadc_b200/csrc/faithful_kernel.cuh), compiled for the host and run serially, against the
+oracle bit for bit: the normalization scalar, the four encoder layers and the decoder head. The LSTM's gate contraction is
+device code (lstm_kernel.cuh, FAITHFUL) and is covered by the GPU tests."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle_lib import ROOT, Oracle, _p
+
+import vadc_b200
+
+SRC = os.path.join(ROOT, "tests", "hostcheck", "faithful_host_check.cpp")
+SO = os.path.join(ROOT, "tests", "hostcheck", "_faithful_host.so")
+
+
+@pytest.fixture(scope="module")
+def host():
+    subprocess.run(["g++", "-O2", "-mavx2", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++", SRC, "-o", SO, "-lm"], check=True)
+    return C.CDLL(SO)
+
+
+def tensor_table(o):
+    o.lib.so_model_tensor.restype = C.c_void_p
+    return (C.c_void_p * 99)(*[o.lib.so_model_tensor(o.m, i, None, None) for i in range(99)])
+
+
+def signals():
+    rng = np.random.default_rng(5)
+    yield "speech", vadc_b200.synth_pcm(77, 1536 * 40).astype(np.float32) / np.float32(32768.0)
+    yield "noise floor", (rng.standard_normal(1536 * 6) * 0.003).astype(np.float32)
+    yield "full scale noise", rng.uniform(-1, 1, 1536 * 6).astype(np.float32)
+    yield "zeros", np.zeros(1536 * 3, np.float32)
+
+
+def test_encoder_and_decoder_bits(host):
+    o = Oracle()
+    tab = tensor_table(o)
+    for name, x in signals():
+        o.reset()
+        st = o.run_stages(x)
+        B = st["stft"].shape[0]
+        a4 = np.zeros((B, 7, 64), np.float32)
+        host.faithful_host_encoder(tab, _p(st["stft"]), B, _p(a4))
+        want = np.ascontiguousarray(st["l4"].transpose(0, 2, 1))          # [B][64][7] -> token-major
+        assert np.array_equal(a4.view(np.uint32), want.view(np.uint32)), (name, float(np.abs(a4 - want).max()))
+        out = np.zeros((B, 2), np.float32)
+        dw = np.ctypeslib.as_array(C.cast(tab[97], C.POINTER(C.c_float)), (128,))
+        db = np.ctypeslib.as_array(C.cast(tab[98], C.POINTER(C.c_float)), (2,))
+        host.faithful_host_decoder(_p(st["lstm"]), B, _p(dw), _p(db), _p(out))
+        assert np.array_equal(out.view(np.uint32), st["out"].view(np.uint32)), (name, float(np.abs(out - st["out"]).max()))
+
+
+def test_lstm_gate_order_bits(host):
+    """fq::gate_dot on the kernel's packed weight layout, layer after layer as the kernels run, against the oracle's interleaved
+    two-layer walk (lstm.c:156-218): outputs and final state bit for bit, state carried across two calls."""
+    o = Oracle()
+    tab = tensor_table(o)
+    w = np.ctypeslib.as_array(C.cast(tab[95], C.POINTER(C.c_float)), (2, 256, 128))
+    b = np.ctypeslib.as_array(C.cast(tab[96], C.POINTER(C.c_float)), (512,)).copy()
+    wpack = np.ascontiguousarray(w.reshape(2, 256, 32, 4).transpose(0, 2, 1, 3))   # [layer][k/4][row][4]
+    x = vadc_b200.synth_pcm(91, 1536 * 30).astype(np.float32) / np.float32(32768.0)
+    h = np.zeros((2, 64), np.float32)
+    c = np.zeros((2, 64), np.float32)
+    for part in (x[:1536 * 18], x[1536 * 18:]):
+        st = o.run_stages(part)                       # the oracle carries its own state across the two calls
+        B = st["l4"].shape[0]
+        seq = np.ascontiguousarray(st["l4"].transpose(0, 2, 1)).reshape(B * 7, 64)
+        out = np.zeros((B * 7, 64), np.float32)
+        host.faithful_host_lstm(_p(seq), B * 7, _p(h), _p(c), _p(wpack), _p(b), _p(out))
+        assert np.array_equal(out.view(np.uint32), st["lstm"].reshape(B * 7, 64).view(np.uint32))
+        assert np.array_equal(h.reshape(-1).view(np.uint32), o.state[:128].view(np.uint32))
+        assert np.array_equal(c.reshape(-1).view(np.uint32), o.state[128:].view(np.uint32))

@@ -1,0 +1,105 @@
+"""GPU: the faithful path (vadc_b200/csrc/faithful_kernel.cuh + lstm_layer_kernel<.., FAITHFUL>): stream batches of at most
+SILERO_B200_FAITHFUL_MAX_STREAMS streams on a fully automatic engine -- the way the reference itself is used -- and any batch on
+request. Bar: BIT-identical probabilities (both decoder outputs) and LSTM state against the oracle, which is itself pinned bit for
+bit to the unmodified reference build (tests/test_oracle_vs_ref.py); hence identical timestamps for streams of any length."""
+import numpy as np
+import pytest
+
+import vadc_b200
+from oracle_lib import Oracle, have_ref, ref_cli
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def oracle_out2(pcm):
+    return Oracle().run_pcm(pcm)
+
+
+def test_cfg1_single_stream_60s_is_bit_identical():
+    """BASELINE configs[0]: one 60 s stream (625 chunks) through run_streams, default engine."""
+    pcm = vadc_b200.synth_pcm(4242, 1536 * 625)
+    e = vadc_b200.Engine()
+    p, out2 = e.run_streams(pcm[None, :], want_out2=True)
+    h, c = e.get_state(0)
+    e.close()
+    o = Oracle()
+    ref = o.run_pcm(pcm)
+    assert np.array_equal(bits(out2[0]), bits(ref))
+    assert np.array_equal(bits(p[0]), bits(ref[:, 1]))
+    assert np.array_equal(bits(h), bits(o.state[:128])) and np.array_equal(bits(c), bits(o.state[128:]))
+
+
+@pytest.mark.parametrize("S,N,window", [(1, 1, 0), (3, 7, 0), (8, 90, 17), (64, 25, 4)])
+def test_stream_batches_windows_and_partial_tiles(S, N, window):
+    pcm = np.stack([vadc_b200.synth_pcm(600 + 7 * s, N * 1536) for s in range(S)])
+    pcm[S // 2] = 0                                                        # an all-zero stream among them
+    e = vadc_b200.Engine(max_streams=S, window_chunks=window)
+    _, out2 = e.run_streams(pcm, want_out2=True)
+    e.close()
+    for s in range(S):
+        assert np.array_equal(bits(out2[s]), bits(oracle_out2(pcm[s]))), s
+
+
+def test_long_streams_stay_bit_identical():
+    """The case the fast kernels cannot promise: thousands of chunks with long silences, where one ulp in
+    the LSTM's forget gate is integrated into the cell state. 3000 chunks (4.8 min) per stream, several windows, two calls."""
+    N = 3000
+    pcm = np.stack([vadc_b200.synth_pcm(50000 + 13 * i, N * 1536) for i in (3, 11, 17)])
+    e = vadc_b200.Engine(max_streams=3, window_chunks=700)
+    a = e.run_streams(pcm[:, : 1100 * 1536], want_out2=True)[1]
+    b = e.run_streams(pcm[:, 1100 * 1536:], want_out2=True)[1]
+    e.close()
+    out2 = np.concatenate([a, b], axis=1)
+    for s in range(3):
+        ref = oracle_out2(pcm[s])
+        assert np.array_equal(bits(out2[s]), bits(ref)), (s, float(np.abs(out2[s] - ref).max()))
+
+
+def test_run_chunks_is_bit_identical_to_backend_run():
+    """silero_b200_run_chunks == backend_run (silero.h:53-74): batches of 96 chunks and a short last one, state carried."""
+    pcm = vadc_b200.synth_pcm(99, 1536 * 230)
+    x = (pcm.astype(np.float32) / np.float32(32768.0)).reshape(-1, 1536)
+    e = vadc_b200.Engine()
+    got = np.concatenate([e.run_chunks(x[i:i + 96]) for i in range(0, len(x), 96)])
+    e.close()
+    o = Oracle()
+    want = np.concatenate([o.run_chunks(x[i:i + 96]) for i in range(0, len(x), 96)])
+    assert np.array_equal(bits(got), bits(want))
+
+
+def test_on_request_for_large_batches_and_not_taken_otherwise():
+    """LAYERS_FAITHFUL / LSTM_FAITHFUL select the path for any batch; above the automatic limit the default engine runs the fast
+    kernels (1e-4 bar), and an engine with an explicit kernel family never takes the faithful path."""
+    S, N = 80, 12
+    pcm = np.stack([vadc_b200.synth_pcm(3000 + s, N * 1536) for s in range(S)])
+    ref = np.stack([oracle_out2(pcm[s]) for s in range(S)])
+    e = vadc_b200.Engine(max_streams=S, layer_mode=vadc_b200.LAYERS_FAITHFUL)
+    out2 = e.run_streams(pcm, want_out2=True)[1]
+    windows, rem = divmod(e.last_timing()[1], 5)                 # 5 kernels per window on the faithful path
+    e.close()
+    assert rem == 0 and windows >= 1
+    assert np.array_equal(bits(out2), bits(ref))
+    e = vadc_b200.Engine(max_streams=S)
+    fast = e.run_streams(pcm, want_out2=True)[1]
+    launches = e.last_timing()[1]
+    e.close()
+    assert launches == 7 * windows and np.abs(fast - ref).max() <= 1e-4      # 7 kernels per window on the fast paths
+    e = vadc_b200.Engine(max_streams=S, lstm_mode=vadc_b200.LSTM_FP32)
+    few = e.run_streams(pcm[:4], want_out2=True)[1]
+    launches = e.last_timing()[1]
+    e.close()
+    assert launches % 7 == 0 and launches % 5 != 0 and np.abs(few - ref[:4]).max() <= 1e-4
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not present")
+def test_raw_probabilities_text_equals_the_reference_cli():
+    """The unmodified reference CLI's --raw_probabilities output ("%f" per chunk, vadc.c:992-997) from the engine's numbers."""
+    pcm = vadc_b200.synth_pcm(2024, 1536 * 400)
+    e = vadc_b200.Engine()
+    p = e.run_streams(pcm[None, :])[0]
+    e.close()
+    assert "".join("%f\n" % v for v in p) == ref_cli(pcm, "--raw_probabilities")

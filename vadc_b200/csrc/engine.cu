@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "faithful_kernel.cuh"
 #include "layer_kernel.cuh"
 #include "layer_tc_kernel.cuh"
 #include "layer0_tc_kernel.cuh"
@@ -73,6 +74,7 @@ struct silero_b200
    int lstm_mode;            // SILERO_B200_LSTM_*
    unsigned char *d_lstm_tc; // [2 layers][LTC_W_BYTES] bf16 hi/lo weight images (lstm_tc_kernel.cuh)
    int layer_mode;           // SILERO_B200_LAYERS_*
+   int faithful;             // 2: faithful_kernel.cuh path for every batch; 1: for batches of at most SILERO_B200_FAITHFUL_MAX_STREAMS streams
    L0DwParams l0_dw;         // first layer's depthwise taps, passed to layer0_tc_kernel by value
    unsigned char *d_layer_tc[4]; // fp16 hi/lo weight images + fp32 parameters per layer (layer0_tc_kernel.cuh, layer_tc_kernel.cuh)
    size_t cap_h0_floats;
@@ -85,6 +87,7 @@ struct silero_b200
    cudaEvent_t ev_spec_ready, ev_spec_free; // spectrogram buffer hand-offs between front_stream and stream
    float *d_weights;         // one allocation holding every packed weight
    DeviceWeights w;
+   fq::Weights fw;           // the container's 99 tensors as they are (faithful_kernel.cuh)
    float *state_h, *state_c; // [max_streams][2][64]
    // window scratch (grow-only)
    size_t cap_chunks;
@@ -413,6 +416,9 @@ static int configure_kernels()
    CU( allow_smem( lstm_layer_kernel<1, 4>, LstmSmem<4>::BYTES ) );
    CU( allow_smem( lstm_layer_kernel<0, 1>, LstmSmem<1>::BYTES ) );
    CU( allow_smem( lstm_layer_kernel<1, 1>, LstmSmem<1>::BYTES ) );
+   CU( allow_smem( lstm_layer_kernel<0, 1, true>, LstmSmem<1>::BYTES ) );
+   CU( allow_smem( lstm_layer_kernel<1, 1, true>, LstmSmem<1>::BYTES ) );
+   CU( allow_smem( faithful_encoder_kernel, FAITHFUL_SMEM_BYTES ) );
    CU( allow_smem( tc_probe_kernel, 200 * 1024 ) );
    CU( allow_smem( lstm_tc_kernel<0>, LTC_SMEM_BYTES ) );
    CU( allow_smem( lstm_tc_kernel<1>, LTC_SMEM_BYTES ) );
@@ -535,6 +541,10 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    h->stft_k_rel = opts.stft_k_rel > 0.0f ? opts.stft_k_rel : SILERO_B200_STFT_K_REL_DEFAULT;
    h->lstm_mode = ( opts.lstm_mode == SILERO_B200_LSTM_FP32 || opts.lstm_mode == SILERO_B200_LSTM_TENSOR ) ? opts.lstm_mode : SILERO_B200_LSTM_AUTO;
    h->layer_mode = ( opts.layer_mode == SILERO_B200_LAYERS_FP32 || opts.layer_mode == SILERO_B200_LAYERS_TENSOR ) ? opts.layer_mode : SILERO_B200_LAYERS_AUTO;
+   // the reference's own rounding sequence from the STFT to the probability (faithful_kernel.cuh): on request for any batch, and by
+   // default for the small stream batches of a fully automatic engine
+   h->faithful = ( opts.layer_mode == SILERO_B200_LAYERS_FAITHFUL || opts.lstm_mode == SILERO_B200_LSTM_FAITHFUL ) ? 2
+               : ( h->stft_auto && h->lstm_mode == SILERO_B200_LSTM_AUTO && h->layer_mode == SILERO_B200_LAYERS_AUTO ) ? 1 : 0;
 
 #define CU_H( call )                                                                                   \
    do                                                                                                  \
@@ -586,7 +596,9 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    const size_t n_l0 = LayerPack<0>::TOTAL, n_l1 = LayerPack<1>::TOTAL, n_l2 = LayerPack<2>::TOTAL, n_l3 = LayerPack<3>::TOTAL;
    const size_t n_lstm = 2 * LSTM_WS_FLOATS, n_lb = 512, n_dw = 128, n_db = 4;
    const size_t n_raw = 258 * 256;
-   const size_t total = n_basis + n_l0 + n_l1 + n_l2 + n_l3 + n_lstm + n_lb + n_dw + n_db + n_raw;
+   size_t n_all = 0; // every tensor of the container as it is, 4-float aligned (faithful_kernel.cuh)
+   for ( int i = 0; i < 99; ++i ) n_all += ( (size_t)tf.tensors[i].size + 3 ) & ~(size_t)3;
+   const size_t total = n_basis + n_l0 + n_l1 + n_l2 + n_l3 + n_lstm + n_lb + n_dw + n_db + n_raw + n_all;
    float *host = (float *)calloc( total, sizeof( float ) );
    if ( !host )
    {
@@ -605,6 +617,17 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    size_t o_dw = off; off += n_dw;
    size_t o_db = off; off += n_db;
    size_t o_raw = off; off += n_raw;
+   size_t o_all = off; off += n_all;
+   size_t all_off[99];
+   {
+      size_t o = o_all;
+      for ( int i = 0; i < 99; ++i )
+      {
+         all_off[i] = o;
+         memcpy( host + o, tf.tensors[i].data, sizeof( float ) * (size_t)tf.tensors[i].size );
+         o += ( (size_t)tf.tensors[i].size + 3 ) & ~(size_t)3;
+      }
+   }
    pack_basis( tf.tensors[0].data, host + o_basis );
    pack_layer<0>( tf.tensors + 1, host + o_l0 );
    pack_layer<1>( tf.tensors + 25, host + o_l1 );
@@ -664,6 +687,7 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    h->w.dec_w = h->d_weights + o_dw;
    h->w.dec_b = h->d_weights + o_db;
    h->w.basis_raw = h->d_weights + o_raw;
+   for ( int i = 0; i < 99; ++i ) h->fw.t[i] = h->d_weights + all_off[i];
    CU_H( cudaMalloc( &h->d_flagged, sizeof( unsigned long long ) ) );
    {
       size_t free_b = 0, total_b = 0;
@@ -998,6 +1022,38 @@ static int launch_lstm_tc( silero_b200 *h, const float *a4, int first_stream, in
    return 0;
 }
 
+// the whole path in the reference's rounding sequence (faithful_kernel.cuh)
+static bool use_faithful( const silero_b200 *h, int nstreams )
+{
+   return h->faithful == 2 || ( h->faithful == 1 && nstreams <= SILERO_B200_FAITHFUL_MAX_STREAMS );
+}
+
+static int launch_faithful_encoder( silero_b200 *h, const float *spec, float *a4, int nchunks )
+{
+   const int grid = imin( nchunks, h->sm_count * 4 );
+   faithful_encoder_kernel<<<grid, FAITHFUL_THREADS, FAITHFUL_SMEM_BYTES, h->stream>>>( spec, a4, h->fw, nchunks );
+   h->launches++;
+   CU( cudaGetLastError() );
+   return 0;
+}
+
+// one LSTM layer with the gate contractions in dotproduct_simd order; hseq receives the layer's output sequence [S][nw*7][64]
+template <int LAYER>
+static int launch_lstm_faithful( silero_b200 *h, const float *x, float *hseq, int first_stream, int nstreams, int nw )
+{
+   float *sh = h->state_h + (size_t)first_stream * SILERO_B200_STATE_FLOATS;
+   float *sc = h->state_c + (size_t)first_stream * SILERO_B200_STATE_FLOATS;
+   int ng = ( nstreams + h->sm_count - 1 ) / h->sm_count;
+   if ( ng > LSTM_MAX_GROUPS ) ng = LSTM_MAX_GROUPS;
+   if ( ng < 1 ) ng = 1;
+   const int grid = imin( ( nstreams + ng - 1 ) / ng, h->sm_count );
+   lstm_layer_kernel<LAYER, 1, true><<<grid, 64 * ng, LstmSmem<1>::BYTES, h->stream>>>( x, hseq, sh, sc, h->w.lstm_w, h->w.lstm_b, h->w.dec_w, h->w.dec_b, nstreams, nw,
+                                                                                        0, 0, 0, 0 );
+   h->launches++;
+   CU( cudaGetLastError() );
+   return 0;
+}
+
 // first encoder layer from the log spectrogram: mu = per-chunk normalization scalar if the STFT kernel produced it, else NULL
 // (the layer computes it itself, misc.c:48-121)
 static int first_layer_from_logspec( silero_b200 *h, const float *spec, float *a1, int nchunks, const float *mu )
@@ -1038,6 +1094,8 @@ static int run_window( silero_b200 *h, const void *d_in, int in_f32, long long s
       ~ModeGuard() { h->stft_mode = saved; }
    } guard = { h, h->stft_mode };
    if ( h->stft_auto && !lstm_use_tensor( h, nstreams ) ) h->stft_mode = SILERO_B200_STFT_EXACT;
+   const bool faithful = use_faithful( h, nstreams );
+   if ( faithful ) h->stft_mode = SILERO_B200_STFT_EXACT;
    stage_mark( h, 0 );
    const bool have_mu = stft_produces_mu( h, nchunks );
    // (an input that was produced by earlier work on h->stream itself, like run_chunks' own upload, keeps the STFT on that stream)
@@ -1059,6 +1117,29 @@ static int run_window( silero_b200 *h, const void *d_in, int in_f32, long long s
       CU( cudaStreamWaitEvent( h->stream, h->ev_spec_ready, 0 ) );
    }
    stage_mark( h, 1 );
+   if ( faithful )
+   {
+      // log spectrogram (bit-identical to the reference's, stft_kernel.cuh) -> encoder -> LSTM -> decoder, every step in the
+      // reference's rounding sequence: 5 launches
+      if ( launch_faithful_encoder( h, h->spec, h->a4, nchunks ) ) return SILERO_B200_ERR_CUDA;
+      CU( cudaEventRecord( h->ev_spec_free, h->stream ) );
+      stage_mark( h, 2 );
+      stage_mark( h, 3 );
+      stage_mark( h, 4 );
+      stage_mark( h, 5 );
+      if ( launch_lstm_faithful<0>( h, h->a4, h->h0, first_stream, nstreams, nw ) ) return SILERO_B200_ERR_CUDA;
+      stage_mark( h, 6 );
+      if ( launch_lstm_faithful<1>( h, h->h0, h->a4, first_stream, nstreams, nw ) ) return SILERO_B200_ERR_CUDA;
+      {
+         const long long n = (long long)nchunks * 2;
+         faithful_decoder_kernel<<<(unsigned)( ( n + 127 ) / 128 ), 128, 0, h->stream>>>( h->a4, h->w.dec_w, h->w.dec_b, nstreams, nw, d_out2, d_probs, out_stride, out_off );
+         h->launches++;
+         CU( cudaGetLastError() );
+      }
+      stage_mark( h, 7 );
+   }
+   else
+   {
    // the FFT STFT kernel also produces the normalization scalar; the others leave it to the first layer
    if ( first_layer_from_logspec( h, h->spec, h->a1, nchunks, have_mu ? h->mu : 0 ) ) return SILERO_B200_ERR_CUDA;
    CU( cudaEventRecord( h->ev_spec_free, h->stream ) );
@@ -1077,6 +1158,7 @@ static int run_window( silero_b200 *h, const void *d_in, int in_f32, long long s
                : launch_lstm<1>( h, h->h0, 0, first_stream, nstreams, nw, d_out2, d_probs, out_stride, out_off ) )
       return SILERO_B200_ERR_CUDA;
    stage_mark( h, 7 );
+   }
    if ( h->profiling && accumulate_timing )
    {
       // per-window stage times are accumulated on the host after a sync (profiling mode only)
