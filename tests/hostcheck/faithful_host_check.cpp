@@ -30,7 +30,7 @@ extern "C" void faithful_host_decoder( const float *hs /*[B][7][64]*/, int batch
       for ( int head = 0; head < 2; ++head ) out[n * 2 + head] = fq::decoder_head( hs + (size_t)n * 448, w + head * 64, b[head] );
 }
 
-// The decoder LSTM as lstm_layer_kernel<LAYER, 1, true> walks it: one layer over all steps, then the next; W packed as
+// The decoder LSTM as faithful_lstm_kernel<LAYER> walks it: one layer over all steps, then the next; W packed as
 // [layer][k/4][row][4] (pack_lstm, engine.cu), gate pre-activations through fq::gate_dot. The cell update below restates the
 // kernel's (lstm.c:64-88) with the host's libm. x: [steps][64]; state: h[2][64], c[2][64] (updated); out: [steps][64].
 extern "C" void faithful_host_lstm( const float *x, int steps, float *h, float *c, const float *wpack, const float *bias, float *out )

@@ -1,6 +1,6 @@
 """The faithful path's arithmetic (vadc_b200/csrc/faithful_kernel.cuh), compiled for the host and run serially, against the
 oracle bit for bit: the normalization scalar, the four encoder layers and the decoder head. The LSTM's gate contraction is
-device code (lstm_kernel.cuh, FAITHFUL) and is covered by the GPU tests."""
+checked below on the packed weight layout; the per-step orchestration of faithful_lstm_kernel by the GPU tests."""
 import ctypes as C
 import os
 import subprocess

@@ -1,4 +1,4 @@
-"""GPU: the faithful path (vadc_b200/csrc/faithful_kernel.cuh + lstm_layer_kernel<.., FAITHFUL>): stream batches of at most
+"""GPU: the faithful path (vadc_b200/csrc/faithful_kernel.cuh): stream batches of at most
 SILERO_B200_FAITHFUL_MAX_STREAMS streams on a fully automatic engine -- the way the reference itself is used -- and any batch on
 request. Bar: BIT-identical probabilities (both decoder outputs) and LSTM state against the oracle, which is itself pinned bit for
 bit to the unmodified reference build (tests/test_oracle_vs_ref.py); hence identical timestamps for streams of any length."""

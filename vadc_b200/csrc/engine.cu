@@ -416,8 +416,8 @@ static int configure_kernels()
    CU( allow_smem( lstm_layer_kernel<1, 4>, LstmSmem<4>::BYTES ) );
    CU( allow_smem( lstm_layer_kernel<0, 1>, LstmSmem<1>::BYTES ) );
    CU( allow_smem( lstm_layer_kernel<1, 1>, LstmSmem<1>::BYTES ) );
-   CU( allow_smem( lstm_layer_kernel<0, 1, true>, LstmSmem<1>::BYTES ) );
-   CU( allow_smem( lstm_layer_kernel<1, 1, true>, LstmSmem<1>::BYTES ) );
+   CU( allow_smem( faithful_lstm_kernel<0>, FLSTM_SMEM_BYTES ) );
+   CU( allow_smem( faithful_lstm_kernel<1>, FLSTM_SMEM_BYTES ) );
    CU( allow_smem( faithful_encoder_kernel, FAITHFUL_SMEM_BYTES ) );
    CU( allow_smem( tc_probe_kernel, 200 * 1024 ) );
    CU( allow_smem( lstm_tc_kernel<0>, LTC_SMEM_BYTES ) );
@@ -1037,18 +1037,15 @@ static int launch_faithful_encoder( silero_b200 *h, const float *spec, float *a4
    return 0;
 }
 
-// one LSTM layer with the gate contractions in dotproduct_simd order; hseq receives the layer's output sequence [S][nw*7][64]
+// one LSTM layer with the gate contractions in dotproduct_simd order (faithful_lstm_kernel: one CTA per stream); hseq receives the
+// layer's output sequence [S][nw*7][64]
 template <int LAYER>
 static int launch_lstm_faithful( silero_b200 *h, const float *x, float *hseq, int first_stream, int nstreams, int nw )
 {
    float *sh = h->state_h + (size_t)first_stream * SILERO_B200_STATE_FLOATS;
    float *sc = h->state_c + (size_t)first_stream * SILERO_B200_STATE_FLOATS;
-   int ng = ( nstreams + h->sm_count - 1 ) / h->sm_count;
-   if ( ng > LSTM_MAX_GROUPS ) ng = LSTM_MAX_GROUPS;
-   if ( ng < 1 ) ng = 1;
-   const int grid = imin( ( nstreams + ng - 1 ) / ng, h->sm_count );
-   lstm_layer_kernel<LAYER, 1, true><<<grid, 64 * ng, LstmSmem<1>::BYTES, h->stream>>>( x, hseq, sh, sc, h->w.lstm_w, h->w.lstm_b, h->w.dec_w, h->w.dec_b, nstreams, nw,
-                                                                                        0, 0, 0, 0 );
+   const int grid = imin( nstreams, h->sm_count );
+   faithful_lstm_kernel<LAYER><<<grid, FLSTM_THREADS, FLSTM_SMEM_BYTES, h->stream>>>( x, hseq, sh, sc, h->w.lstm_w, h->w.lstm_b, nstreams, nw );
    h->launches++;
    CU( cudaGetLastError() );
    return 0;

@@ -476,6 +476,75 @@ __global__ void __launch_bounds__( FAITHFUL_THREADS ) faithful_encoder_kernel( c
       fq::encoder_chunk( W, spec + (size_t)ci * ( 129 * 25 ), a4 + (size_t)ci * 448, fsm, threadIdx.x, FAITHFUL_THREADS );
 }
 
+// One layer of the decoder LSTM (lstm.c:31-218) for the faithful path: the recurrence is serial per stream, so a CTA takes one
+// stream and spreads the 256 gate rows of a step over its 256 threads. Warp w owns hidden units 8w..8w+7; lane = (gate g, unit):
+// every lane contracts ONE row over [x|h] in dotproduct_simd order (fq::gate_dot), adds its bias and applies its own gate's
+// nonlinearity (glibc's expf/tanhf bit for bit, libm_exact.cuh); the three other gates of a unit reach the g = 0 lane by shuffle,
+// which updates c (a register) and h without contraction (lstm.c:64-88). One barrier per step (ping-pong [x|h] buffers).
+// Weights: pack_lstm's [layer][k/4][row][4] image, 128 KB resident in shared memory.
+//   x: [S][steps][64] layer input; hseq: [S][steps][64] layer output; state_h/state_c: [S][2][64]
+#define FLSTM_THREADS 256
+#define FLSTM_SMEM_BYTES ( ( 32 * 256 * 4 + 2 * 128 ) * 4 )
+template <int LAYER>
+__global__ void __launch_bounds__( FLSTM_THREADS, 1 )
+faithful_lstm_kernel( const float *__restrict__ x, float *__restrict__ hseq, float *__restrict__ state_h, float *__restrict__ state_c,
+                      const float *__restrict__ wpack, const float *__restrict__ bias, int nstreams, int nw )
+{
+   extern __shared__ __align__( 16 ) float fsm[];
+   float *Ws = fsm;
+   float *xh = fsm + 32 * 256 * 4; // [2][128]
+   const int tid = threadIdx.x, lane = tid & 31, g = lane >> 3, jj = lane & 7, j = ( tid >> 5 ) * 8 + jj, row = g * 64 + j;
+   const int steps = nw * 7;
+   {
+      const float4 *src = reinterpret_cast<const float4 *>( wpack ) + (size_t)LAYER * ( 32 * 256 );
+      float4 *dst = reinterpret_cast<float4 *>( Ws );
+      for ( int i = tid; i < 32 * 256; i += FLSTM_THREADS ) dst[i] = __ldg( src + i );
+   }
+   const float b_row = bias[LAYER * 256 + row];
+   for ( int s = blockIdx.x; s < nstreams; s += gridDim.x )
+   {
+      const float *xs = x + (size_t)s * steps * 64;
+      float *hs = hseq + (size_t)s * steps * 64;
+      float c = 0.0f, h_last = 0.0f;
+      __syncthreads(); // weights staged / the previous stream's buffers are free
+      if ( g == 0 )
+      {
+         c = state_c[( (size_t)s * 2 + LAYER ) * 64 + j];
+         h_last = state_h[( (size_t)s * 2 + LAYER ) * 64 + j];
+         xh[64 + j] = h_last;
+      }
+      if ( g == 1 ) xh[j] = __ldg( xs + j );
+      __syncthreads();
+      for ( int step = 0; step < steps; ++step )
+      {
+         const float *cur = xh + ( step & 1 ) * 128;
+         float *nxt = xh + ( ( step + 1 ) & 1 ) * 128;
+         float xn = 0.0f;
+         if ( g == 1 && step + 1 < steps ) xn = __ldg( xs + (size_t)( step + 1 ) * 64 + j );
+         const float z = __fadd_rn( fq::gate_dot( cur, Ws + row * 4, 1024 ), b_row );
+         const float a = ( g == 2 ) ? lme::tanhf_ref( z ) : lme::sigmoid_ref( z );
+         const float fgv = __shfl_sync( 0xffffffffu, a, jj + 8 );
+         const float ggv = __shfl_sync( 0xffffffffu, a, jj + 16 );
+         const float ogv = __shfl_sync( 0xffffffffu, a, jj + 24 );
+         if ( g == 0 )
+         {
+            const float cn = __fadd_rn( __fmul_rn( fgv, c ), __fmul_rn( a, ggv ) );
+            c = cn;
+            h_last = __fmul_rn( lme::tanhf_ref( cn ), ogv );
+            nxt[64 + j] = h_last;
+            hs[(size_t)step * 64 + j] = h_last;
+         }
+         if ( g == 1 ) nxt[j] = xn;
+         __syncthreads();
+      }
+      if ( g == 0 )
+      {
+         state_c[( (size_t)s * 2 + LAYER ) * 64 + j] = c;
+         state_h[( (size_t)s * 2 + LAYER ) * 64 + j] = h_last;
+      }
+   }
+}
+
 // hs: top-layer LSTM outputs [S][nw*7][64] (stream-major); one thread per (stream, chunk, head)
 __global__ void faithful_decoder_kernel( const float *__restrict__ hs, const float *__restrict__ dec_w, const float *__restrict__ dec_b, int nstreams, int nw,
                                          float *__restrict__ out2, float *__restrict__ probs, long long out_stride, long long out_off )

@@ -15,7 +15,6 @@
 #pragma once
 #include "common.cuh"
 #include "libm_exact.cuh"
-#include "faithful_kernel.cuh"
 
 #define LSTM_H 64
 #define LSTM_WS_FLOATS ( 32 * 256 * 4 )
@@ -40,11 +39,7 @@ __device__ __forceinline__ float sigmoid_acc( float v ) { return lme::sigmoid_re
 // state_h, state_c: [S_total][2][64], rows first_stream.. are read and written
 // out2:   LAYER 1: [S][out_stride][2] decoder outputs written at chunk n -> out2[(s*out_stride + out_off + n)*2 + {0,1}]
 // probs:  LAYER 1: [S][out_stride] speech probability (head 1); either may be NULL
-//
-// FAITHFUL: the gate pre-activations in the reference's own rounding sequence -- dotproduct_simd (maths.h:123-158) over [x|h] with
-// separate multiplies and adds, bias added afterwards (lstm.c:31-62) -- instead of one FMA chain per gate; the decoder head is then
-// left to faithful_decoder_kernel (faithful_kernel.cuh), which reads the top layer's sequence from hseq.
-template <int LAYER, int ST, bool FAITHFUL = false>
+template <int LAYER, int ST>
 __global__ void __launch_bounds__( 64 * LSTM_MAX_GROUPS, 1 )
 lstm_layer_kernel( const float *__restrict__ x, float *__restrict__ hseq, float *__restrict__ state_h, float *__restrict__ state_c,
                    const float *__restrict__ wpack, const float *__restrict__ bias, const float *__restrict__ dec_w, const float *__restrict__ dec_b,
@@ -118,19 +113,6 @@ lstm_layer_kernel( const float *__restrict__ x, float *__restrict__ hseq, float 
          }
 
          float zi[ST], zf[ST], zg[ST], zo[ST];
-         if ( FAITHFUL )
-         {
-#pragma unroll
-            for ( int st = 0; st < ST; ++st )
-            {
-               float z[4];
-#pragma unroll 1
-               for ( int g = 0; g < 4; ++g ) z[g] = __fadd_rn( fq::gate_dot( cur + st * 128, Ws + ( g * 64 + j ) * 4, 1024 ), bs[g * 64 + j] );
-               zi[st] = z[0]; zf[st] = z[1]; zg[st] = z[2]; zo[st] = z[3];
-            }
-         }
-         else
-         {
 #pragma unroll
          for ( int st = 0; st < ST; ++st )
          {
@@ -155,7 +137,6 @@ lstm_layer_kernel( const float *__restrict__ x, float *__restrict__ hseq, float 
                zo[st] = fmaf( wo.z, v.z, zo[st] ); zo[st] = fmaf( wo.w, v.w, zo[st] );
             }
          }
-         }
          // cell update (lstm.c:64-88)
 #pragma unroll
          for ( int st = 0; st < ST; ++st )
@@ -168,14 +149,14 @@ lstm_layer_kernel( const float *__restrict__ x, float *__restrict__ hseq, float 
             nxt[st * 128 + j] = xn[st];
             int s = s0 + st;
             if ( hseq && s < nstreams ) hseq[( (size_t)s * steps + step ) * 64 + j] = hn;
-            if ( LAYER == 1 && !FAITHFUL )
+            if ( LAYER == 1 )
             {
                float r = fmaxf( hn, 0.0f );
                d0[st] = fmaf( dw0, r, d0[st] );
                d1[st] = fmaf( dw1, r, d1[st] );
             }
          }
-         if ( LAYER == 1 && !FAITHFUL && ( step % 7 ) == 6 )
+         if ( LAYER == 1 && ( step % 7 ) == 6 )
          {
             // decoder: relu -> 1x1 conv 64->2 -> mean over the chunk's 7 frames -> sigmoid
 #pragma unroll
@@ -197,7 +178,7 @@ lstm_layer_kernel( const float *__restrict__ x, float *__restrict__ hseq, float 
             }
          }
          bar_sync( 1 + grp, 64 );
-         if ( LAYER == 1 && !FAITHFUL && ( step % 7 ) == 6 && j < 2 * ST )
+         if ( LAYER == 1 && ( step % 7 ) == 6 && j < 2 * ST )
          {
             int st = j >> 1, head = j & 1, s = s0 + st;
             if ( s < nstreams )
