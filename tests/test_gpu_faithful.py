@@ -30,7 +30,7 @@ def test_cfg1_single_stream_60s_is_bit_identical():
     ref = o.run_pcm(pcm)
     assert np.array_equal(bits(out2[0]), bits(ref))
     assert np.array_equal(bits(p[0]), bits(ref[:, 1]))
-    assert np.array_equal(bits(h), bits(o.state[:128])) and np.array_equal(bits(c), bits(o.state[128:]))
+    assert np.array_equal(bits(h).reshape(-1), bits(o.state[:128])) and np.array_equal(bits(c).reshape(-1), bits(o.state[128:]))
 
 
 @pytest.mark.parametrize("S,N,window", [(1, 1, 0), (3, 7, 0), (8, 90, 17), (64, 25, 4)])
