@@ -12,6 +12,17 @@ extern "C" void faithful_host_encoder( const float *const *tensors /*[99]*/, con
 {
    fq::Weights W;
    for ( int i = 0; i < 99; ++i ) W.t[i] = tensors[i];
+   float *tt[fq::N_TRANSPOSED];
+   for ( int k = 0; k < fq::N_TRANSPOSED; ++k )
+   {
+      // the transposed copies create_impl (engine.cu) uploads next to the originals
+      int idx, n_out, n_in;
+      fq::transposed_slot( k, &idx, &n_out, &n_in );
+      tt[k] = (float *)malloc( sizeof( float ) * (size_t)n_out * n_in );
+      for ( int r = 0; r < n_out; ++r )
+         for ( int c = 0; c < n_in; ++c ) tt[k][(size_t)c * n_out + r] = tensors[idx][(size_t)r * n_in + c];
+      W.tt[k] = tt[k];
+   }
    float *sm = (float *)malloc( sizeof( float ) * fq::SM_FLOATS );
    float *logspec = (float *)malloc( sizeof( float ) * 129 * 25 );
    for ( int b = 0; b < batch; ++b )
@@ -22,6 +33,7 @@ extern "C" void faithful_host_encoder( const float *const *tensors /*[99]*/, con
    }
    free( sm );
    free( logspec );
+   for ( int k = 0; k < fq::N_TRANSPOSED; ++k ) free( tt[k] );
 }
 
 extern "C" void faithful_host_decoder( const float *hs /*[B][7][64]*/, int batch, const float *w /*[2][64]*/, const float *b /*[2]*/, float *out /*[B][2]*/ )

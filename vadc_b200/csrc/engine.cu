@@ -598,6 +598,12 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    const size_t n_raw = 258 * 256;
    size_t n_all = 0; // every tensor of the container as it is, 4-float aligned (faithful_kernel.cuh)
    for ( int i = 0; i < 99; ++i ) n_all += ( (size_t)tf.tensors[i].size + 3 ) & ~(size_t)3;
+   for ( int k = 0; k < fq::N_TRANSPOSED; ++k )
+   {
+      int idx, n_out, n_in;
+      fq::transposed_slot( k, &idx, &n_out, &n_in );
+      n_all += (size_t)n_out * n_in; // multiples of 4
+   }
    const size_t total = n_basis + n_l0 + n_l1 + n_l2 + n_l3 + n_lstm + n_lb + n_dw + n_db + n_raw + n_all;
    float *host = (float *)calloc( total, sizeof( float ) );
    if ( !host )
@@ -618,7 +624,7 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    size_t o_db = off; off += n_db;
    size_t o_raw = off; off += n_raw;
    size_t o_all = off; off += n_all;
-   size_t all_off[99];
+   size_t all_off[99], tt_off[fq::N_TRANSPOSED];
    {
       size_t o = o_all;
       for ( int i = 0; i < 99; ++i )
@@ -626,6 +632,16 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
          all_off[i] = o;
          memcpy( host + o, tf.tensors[i].data, sizeof( float ) * (size_t)tf.tensors[i].size );
          o += ( (size_t)tf.tensors[i].size + 3 ) & ~(size_t)3;
+      }
+      for ( int k = 0; k < fq::N_TRANSPOSED; ++k )
+      {
+         int idx, n_out, n_in;
+         fq::transposed_slot( k, &idx, &n_out, &n_in );
+         tt_off[k] = o;
+         const float *src = tf.tensors[idx].data; // [n_out][n_in]
+         for ( int r = 0; r < n_out; ++r )
+            for ( int c = 0; c < n_in; ++c ) host[o + (size_t)c * n_out + r] = src[(size_t)r * n_in + c];
+         o += (size_t)n_out * n_in;
       }
    }
    pack_basis( tf.tensors[0].data, host + o_basis );
@@ -688,6 +704,7 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    h->w.dec_b = h->d_weights + o_db;
    h->w.basis_raw = h->d_weights + o_raw;
    for ( int i = 0; i < 99; ++i ) h->fw.t[i] = h->d_weights + all_off[i];
+   for ( int k = 0; k < fq::N_TRANSPOSED; ++k ) h->fw.tt[k] = h->d_weights + tt_off[k];
    CU_H( cudaMalloc( &h->d_flagged, sizeof( unsigned long long ) ) );
    {
       size_t free_b = 0, total_b = 0;

@@ -96,7 +96,23 @@ FQ void barrier()
 }
 FQ float relu( float v ) { return v < 0.0f ? 0.0f : v; } // `if (v < 0) v = 0` keeps -0.0f, like the reference
 
-// maths.h:123-158 dotproduct_simd over strided operands: a[i*sa] * b[i*sb]
+struct Quad
+{
+   float x, y, z, w;
+};
+FQ Quad load4( const float *p )
+{
+#ifdef __CUDA_ARCH__
+   const float4 v = *reinterpret_cast<const float4 *>( p );
+   return Quad{ v.x, v.y, v.z, v.w };
+#else
+   return Quad{ p[0], p[1], p[2], p[3] };
+#endif
+}
+
+// maths.h:123-158 dotproduct_simd over strided operands: a[i*sa] * b[i*sb]. ROW: `a` is a contiguous, 16-byte aligned row (sa == 1)
+// and is fetched four taps per load (on the device: one LDS.128 that the whole warp shares as a broadcast).
+template <bool ROW = false>
 FQ float dot_simd( const float *a, int sa, const float *b, int sb, int n )
 {
    float r0 = 0.0f, r1 = 0.0f, r2 = 0.0f, r3 = 0.0f, r4 = 0.0f, r5 = 0.0f, r6 = 0.0f, r7 = 0.0f;
@@ -104,8 +120,23 @@ FQ float dot_simd( const float *a, int sa, const float *b, int sb, int n )
    for ( int i = 0; i < blocks; i += 16 )
    {
       float p[16];
+      if ( ROW )
+      {
 #pragma unroll
-      for ( int j = 0; j < 16; ++j ) p[j] = mul( a[( i + j ) * sa], b[( i + j ) * sb] );
+         for ( int q = 0; q < 4; ++q )
+         {
+            const Quad v = load4( a + i + 4 * q );
+            p[4 * q] = mul( v.x, b[( i + 4 * q ) * sb] );
+            p[4 * q + 1] = mul( v.y, b[( i + 4 * q + 1 ) * sb] );
+            p[4 * q + 2] = mul( v.z, b[( i + 4 * q + 2 ) * sb] );
+            p[4 * q + 3] = mul( v.w, b[( i + 4 * q + 3 ) * sb] );
+         }
+      }
+      else
+      {
+#pragma unroll
+         for ( int j = 0; j < 16; ++j ) p[j] = mul( a[( i + j ) * sa], b[( i + j ) * sb] );
+      }
       // _mm256_hadd_ps(p[0..7], p[8..15])
       r0 = add( r0, add( p[0], p[1] ) );
       r1 = add( r1, add( p[2], p[3] ) );
@@ -130,8 +161,8 @@ FQ float dot_simd( const float *a, int sa, const float *b, int sb, int n )
 }
 
 // conv.c:532-589 ("variant E", kernel size 1, hop 1): output (filter row `w`, position i) over `cin` channels of an
-// input addressed as in[c*sc + i*st]; the accumulator starts at the zero conv_tensor cleared the output with
-FQ float conv1_e( const float *in, int sc, int st, int i, const float *w, int cin, float bias )
+// input addressed as in[c*sc + i*st], filter taps w[c*sw]; the accumulator starts at the zero conv_tensor cleared the output with
+FQ float conv1_e( const float *in, int sc, int st, int i, const float *w, int sw, int cin, float bias )
 {
    float r1[8], r2[8];
 #pragma unroll
@@ -143,8 +174,8 @@ FQ float conv1_e( const float *in, int sc, int st, int i, const float *w, int ci
 #pragma unroll
       for ( int l = 0; l < 8; ++l )
       {
-         r1[l] = add( r1[l], mul( col[( j + l ) * sc], w[j + l] ) );
-         r2[l] = add( r2[l], mul( col[( j + 8 + l ) * sc], w[j + 8 + l] ) );
+         r1[l] = add( r1[l], mul( col[( j + l ) * sc], w[( j + l ) * sw] ) );
+         r2[l] = add( r2[l], mul( col[( j + 8 + l ) * sc], w[( j + 8 + l ) * sw] ) );
       }
    }
    const float h0 = add( r1[0], r1[1] ), h1 = add( r1[2], r1[3] ), h2 = add( r2[0], r2[1] ), h3 = add( r2[2], r2[3] );
@@ -152,19 +183,19 @@ FQ float conv1_e( const float *in, int sc, int st, int i, const float *w, int ci
    const float q0 = add( add( h0, h1 ), add( h2, h3 ) ), q4 = add( add( h4, h5 ), add( h6, h7 ) );
    float o = 0.0f;
    o = add( o, add( q0, q4 ) );
-   for ( ; j < cin; ++j ) o = add( o, mul( col[j * sc], w[j] ) );
+   for ( ; j < cin; ++j ) o = add( o, mul( col[j * sc], w[j * sw] ) );
    return add( o, bias );
 }
 
 // conv.c:597-709 (generic path, kernel size 1, hop `stride`): channel-outer accumulation, bias last
-FQ float conv1_generic( const float *in, int sc, int st, int i_in, const float *w, int cin, float bias )
+FQ float conv1_generic( const float *in, int sc, int st, int i_in, const float *w, int sw, int cin, float bias )
 {
    float o = 0.0f;
    const float *col = in + i_in * st;
    for ( int c = 0; c < cin; ++c )
    {
       float d = 0.0f;
-      d = add( d, mul( col[c * sc], w[c] ) );
+      d = add( d, mul( col[c * sc], w[c * sw] ) );
       o = add( o, d );
    }
    return add( o, bias );
@@ -201,10 +232,28 @@ FQ LayerShape layer_shape( int l )
    return s[l];
 }
 
-// the 99 tensors of silero_v31_16k.testtensor in container order
+// Matrices that are read with one OUTPUT per lane -- per layer: QKV, attention out-projection, FFN linear1 and linear2, the strided
+// 1x1 conv -- are kept transposed ([in][out]) as well: a warp's 32 loads of tap k then fall into one 128-byte line instead of 32
+// (ncu on the first version: 18 sectors per global load request, the L1 tag stage was the kernel's bound). The arithmetic and its
+// order do not change, only the address of each tap.
+enum
+{
+   N_TRANSPOSED = 20
+};
+FQ void transposed_slot( int slot, int *index, int *n_out, int *n_in )
+{
+   const LayerShape s = layer_shape( slot / 5 );
+   const int rel[5] = { 0, 2, 6, 8, 12 }; // qkv_w, attn_out_w, linear1_w, linear2_w, conv_w relative to qkv_w (tensor.h:131-152)
+   *index = s.first + 4 + 2 * s.proj + rel[slot % 5];
+   *n_in = s.c;
+   *n_out = ( slot % 5 == 0 ) ? 3 * s.c : s.c;
+}
+
+// the 99 tensors of silero_v31_16k.testtensor in container order + the transposed copies
 struct Weights
 {
    const float *t[99];
+   const float *tt[N_TRANSPOSED];
 };
 
 // shared-memory plan of one chunk (floats)
@@ -239,10 +288,12 @@ FQ void layer( const Weights &W, int l, float *sm, float *a4, int tid, int nt )
       proj_w = W.t[wi++];
       proj_b = W.t[wi++];
    }
-   const float *qkv_w = W.t[wi++], *qkv_b = W.t[wi++], *ao_w = W.t[wi++], *ao_b = W.t[wi++];
-   const float *n1_w = W.t[wi++], *n1_b = W.t[wi++], *l1_w = W.t[wi++], *l1_b = W.t[wi++], *l2_w = W.t[wi++], *l2_b = W.t[wi++];
-   const float *n2_w = W.t[wi++], *n2_b = W.t[wi++], *cv_w = W.t[wi++], *cv_b = W.t[wi++];
+   // (the matrices qkv_w, attn_out_w, linear1_w, linear2_w, conv_w at wi + 0, 2, 6, 8, 12 are read through their transposed copies)
+   const float *qkv_b = W.t[wi + 1], *ao_b = W.t[wi + 3], *n1_w = W.t[wi + 4], *n1_b = W.t[wi + 5], *l1_b = W.t[wi + 7], *l2_b = W.t[wi + 9];
+   const float *n2_w = W.t[wi + 10], *n2_b = W.t[wi + 11], *cv_b = W.t[wi + 13];
+   wi += 14;
    const float *bn_w = W.t[wi++], *bn_b = W.t[wi++], *bn_mean = W.t[wi++], *bn_var = W.t[wi++];
+   const float *qkv_wT = W.tt[l * 5], *ao_wT = W.tt[l * 5 + 1], *l1_wT = W.tt[l * 5 + 2], *l2_wT = W.tt[l * 5 + 3], *cv_wT = W.tt[l * 5 + 4];
 
    float *X = sm + SM_X, *DW = sm + SM_DW, *Y = sm + SM_Y, *U = sm + SM_U, *QKV = sm + SM_QKV, *A = sm + SM_A;
    float *CAT = sm + SM_CAT, *N1 = sm + SM_N1, *L1 = sm + SM_L1, *N2 = sm + SM_N2;
@@ -262,9 +313,9 @@ FQ void layer( const Weights &W, int l, float *sm, float *a4, int tid, int nt )
    for ( int e = tid; e < C * T; e += nt )
    {
       const int f = e / T, i = e - f * T;
-      float y = conv1_e( DW, T, 1, i, pw_w + f * cin, cin, pw_b[f] );
+      float y = conv1_e( DW, T, 1, i, pw_w + f * cin, 1, cin, pw_b[f] );
       if ( s.proj )
-         y = add( y, conv1_e( X, T, 1, i, proj_w + f * cin, cin, proj_b[f] ) );
+         y = add( y, conv1_e( X, T, 1, i, proj_w + f * cin, 1, cin, proj_b[f] ) );
       else
          y = add( y, X[e] );
       Y[e] = relu( y );
@@ -275,7 +326,7 @@ FQ void layer( const Weights &W, int l, float *sm, float *a4, int tid, int nt )
    for ( int e = tid; e < T * 3 * C; e += nt )
    {
       const int t = e / ( 3 * C ), o = e - t * 3 * C;
-      QKV[e] = add( dot_simd( U + t * C, 1, qkv_w + o * C, 1, C ), qkv_b[o] );
+      QKV[e] = add( dot_simd<true>( U + t * C, 1, qkv_wT + o, 3 * C, C ), qkv_b[o] );
    }
    barrier();
    // A_h[tk][tq] = (k_h[tk] . q_h[tq]) * 1/sqrt(d) (transformer.c:101-117)
@@ -284,7 +335,7 @@ FQ void layer( const Weights &W, int l, float *sm, float *a4, int tid, int nt )
       for ( int e = tid; e < 2 * T * T; e += nt )
       {
          const int h = e / ( T * T ), r = e - h * T * T, tk = r / T, tq = r - tk * T;
-         A[e] = mul( dot_simd( QKV + tk * 3 * C + C + h * d, 1, QKV + tq * 3 * C + h * d, 1, d ), scale );
+         A[e] = mul( dot_simd<true>( QKV + tk * 3 * C + C + h * d, 1, QKV + tq * 3 * C + h * d, 1, d ), scale );
       }
    }
    barrier();
@@ -317,7 +368,7 @@ FQ void layer( const Weights &W, int l, float *sm, float *a4, int tid, int nt )
    for ( int e = tid; e < T * C; e += nt )
    {
       const int t = e / C, o = e - t * C;
-      const float att = add( dot_simd( CAT + t * C, 1, ao_w + o * C, 1, C ), ao_b[o] );
+      const float att = add( dot_simd<true>( CAT + t * C, 1, ao_wT + o, C, C ), ao_b[o] );
       U[e] = add( U[e], att );
    }
    barrier();
@@ -326,13 +377,13 @@ FQ void layer( const Weights &W, int l, float *sm, float *a4, int tid, int nt )
    for ( int e = tid; e < T * C; e += nt )
    {
       const int t = e / C, o = e - t * C;
-      L1[e] = relu( add( dot_simd( N1 + t * C, 1, l1_w + o * C, 1, C ), l1_b[o] ) );
+      L1[e] = relu( add( dot_simd<true>( N1 + t * C, 1, l1_wT + o, C, C ), l1_b[o] ) );
    }
    barrier();
    for ( int e = tid; e < T * C; e += nt )
    {
       const int t = e / C, o = e - t * C;
-      const float f2 = add( dot_simd( L1 + t * C, 1, l2_w + o * C, 1, C ), l2_b[o] );
+      const float f2 = add( dot_simd<true>( L1 + t * C, 1, l2_wT + o, C, C ), l2_b[o] );
       U[e] = add( N1[e], f2 ); // (U is free again)
    }
    barrier();
@@ -342,16 +393,16 @@ FQ void layer( const Weights &W, int l, float *sm, float *a4, int tid, int nt )
    const int Tout = 1 + ( T - 1 ) / s.stride;
    for ( int e = tid; e < C * Tout; e += nt )
    {
-      const int f = e / Tout, i = e - f * Tout;
-      const float z = s.stride == 1 ? conv1_e( N2, 1, C, i, cv_w + f * C, C, cv_b[f] )
-                                    : conv1_generic( N2, 1, C, i * s.stride, cv_w + f * C, C, cv_b[f] );
+      const int i = e / C, f = e - i * C; // lanes differ in the filter: transposed taps, the input position is a broadcast
+      const float z = s.stride == 1 ? conv1_e( N2, 1, C, i, cv_wT + f, C, C, cv_b[f] )
+                                    : conv1_generic( N2, 1, C, i * s.stride, cv_wT + f, C, C, cv_b[f] );
       const float sd = root( add( bn_var[f], 1e-5f ) );
       const float nv = quot( sub( z, bn_mean[f] ), sd );
       const float v = relu( add( mul( nv, bn_w[f] ), bn_b[f] ) );
       if ( l == 3 )
          a4[i * C + f] = v;
       else
-         X[e] = v;
+         X[f * Tout + i] = v;
    }
    barrier();
 }
@@ -395,20 +446,6 @@ FQ void encoder_chunk( const Weights &W, const float *logspec, float *a4, float 
    }
    barrier();
    for ( int l = 0; l < 4; ++l ) layer( W, l, sm, a4, tid, nt );
-}
-
-struct Quad
-{
-   float x, y, z, w;
-};
-FQ Quad load4( const float *p )
-{
-#ifdef __CUDA_ARCH__
-   const float4 v = *reinterpret_cast<const float4 *>( p );
-   return Quad{ v.x, v.y, v.z, v.w };
-#else
-   return Quad{ p[0], p[1], p[2], p[3] };
-#endif
 }
 
 // One LSTM gate row over [x|h] (lstm.c:31-62: 128 taps through dotproduct_simd, maths.h:123-158; the bias is added by the caller).
@@ -469,7 +506,7 @@ FQ float decoder_head( const float *hs, const float *w /*[64]*/, float bias )
 #define FAITHFUL_SMEM_BYTES ( fq::SM_FLOATS * 4 )
 
 // spec: [nchunks][129][25] log spectrogram; a4: [nchunks][7][64]
-__global__ void __launch_bounds__( FAITHFUL_THREADS ) faithful_encoder_kernel( const float *__restrict__ spec, float *__restrict__ a4, fq::Weights W, int nchunks )
+__global__ void __launch_bounds__( FAITHFUL_THREADS, 4 ) faithful_encoder_kernel( const float *__restrict__ spec, float *__restrict__ a4, fq::Weights W, int nchunks )
 {
    extern __shared__ __align__( 16 ) float fsm[];
    for ( int ci = blockIdx.x; ci < nchunks; ci += gridDim.x )
