@@ -91,10 +91,11 @@ typedef struct silero_b200 silero_b200; /* opaque engine handle */
    paths (conv.c:532-709), sequential means and true divisions, glibc's expf/tanhf/log1pf bit for bit, no fused multiply-add --
    on top of the exact STFT: probabilities are bit-identical to the reference's for streams of any length (the fast kernels are
    within 1e-5 chunk by chunk but the decoder LSTM integrates one-ulp differences over long silences).
-   About 30x slower per chunk than the tensor-core path. A fully automatic engine (stft, lstm and layer modes all AUTO) takes it
+   Up to 128 streams it costs no more than the fp32 CUDA-core kernels (one CTA per stream runs the serial LSTM, which bounds small
+   batches either way); per chunk the encoder is ~9x slower than the tensor-core path. A fully automatic engine (stft, lstm and layer modes all AUTO) takes it
    for calls with at most SILERO_B200_FAITHFUL_MAX_STREAMS streams -- the way the reference itself is used. */
 #define SILERO_B200_LAYERS_FAITHFUL 3
-#define SILERO_B200_FAITHFUL_MAX_STREAMS 64
+#define SILERO_B200_FAITHFUL_MAX_STREAMS 128
 
 typedef struct silero_b200_opts
 {

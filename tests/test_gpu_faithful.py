@@ -33,7 +33,7 @@ def test_cfg1_single_stream_60s_is_bit_identical():
     assert np.array_equal(bits(h).reshape(-1), bits(o.state[:128])) and np.array_equal(bits(c).reshape(-1), bits(o.state[128:]))
 
 
-@pytest.mark.parametrize("S,N,window", [(1, 1, 0), (3, 7, 0), (8, 90, 17), (64, 25, 4)])
+@pytest.mark.parametrize("S,N,window", [(1, 1, 0), (3, 7, 0), (8, 90, 17), (64, 25, 4), (128, 9, 0)])
 def test_stream_batches_windows_and_partial_tiles(S, N, window):
     pcm = np.stack([vadc_b200.synth_pcm(600 + 7 * s, N * 1536) for s in range(S)])
     pcm[S // 2] = 0                                                        # an all-zero stream among them
@@ -74,7 +74,7 @@ def test_run_chunks_is_bit_identical_to_backend_run():
 def test_on_request_for_large_batches_and_not_taken_otherwise():
     """LAYERS_FAITHFUL / LSTM_FAITHFUL select the path for any batch; above the automatic limit the default engine runs the fast
     kernels (1e-4 bar), and an engine with an explicit kernel family never takes the faithful path."""
-    S, N = 80, 12
+    S, N = vadc_b200.FAITHFUL_MAX_STREAMS + 2, 12
     pcm = np.stack([vadc_b200.synth_pcm(3000 + s, N * 1536) for s in range(S)])
     ref = np.stack([oracle_out2(pcm[s]) for s in range(S)])
     e = vadc_b200.Engine(max_streams=S, layer_mode=vadc_b200.LAYERS_FAITHFUL)

@@ -18,7 +18,7 @@ SAMPLE_RATE = 16000
 STFT_AUTO, STFT_EXACT, STFT_HYBRID_FFT, STFT_HYBRID_TENSOR, STFT_HYBRID = 0, 1, 2, 3, 4
 LSTM_AUTO, LSTM_FP32, LSTM_TENSOR, LSTM_FAITHFUL = 0, 1, 2, 3
 LAYERS_AUTO, LAYERS_FP32, LAYERS_TENSOR, LAYERS_FAITHFUL = 0, 1, 2, 3
-FAITHFUL_MAX_STREAMS = 64   # SILERO_B200_FAITHFUL_MAX_STREAMS
+FAITHFUL_MAX_STREAMS = 128  # SILERO_B200_FAITHFUL_MAX_STREAMS
 
 
 class EngineError(RuntimeError):
