@@ -433,6 +433,30 @@ def main():
         v, cores, kind, sample, per_core = cpu_reference_run(2, 60.0)
         cpu = {"value": v, "unit": "audio-seconds/sec", "cores": cores, "kind": kind, "sample": sample, "per_core": per_core, "cpu": cpu_model()}
 
+    # ---- BASELINE configs[0] beside it (rank 0, N=1, not part of `value`): ONE 60 s stream through the public host call -- the way
+    # the reference itself runs. Small batches take the faithful kernels (faithful_kernel.cuh): bits compared with the oracle.
+    cfg1 = None
+    if rank == 0 and world == 1:
+        try:
+            from oracle_lib import Oracle
+            one = vadc_b200.Engine(device=local, max_streams=1)
+            pcm1 = vadc_b200.synth_pcm(4242, 625 * CHUNK)[None, :]
+            got1 = one.run_streams(pcm1, want_out2=True)[1][0]
+            best = 1e30
+            for _ in range(3):
+                one.reset()
+                t1 = time.perf_counter()
+                one.run_streams(pcm1)
+                best = min(best, time.perf_counter() - t1)
+            one.close()
+            ref1 = Oracle().run_pcm(pcm1[0])
+            cfg1 = {"workload": "cfg1: one 60 s stream (625 chunks), silero_b200_run_streams with host PCM in, probabilities out",
+                    "value": 625 * CHUNK_SECONDS / best, "unit": "audio-seconds/sec", "ms": best * 1e3,
+                    "bit_identical_to_oracle": bool(np.array_equal(got1.view(np.uint32), ref1.view(np.uint32))),
+                    "max_abs_err_vs_oracle": float(np.abs(got1 - ref1).max())}
+        except Exception as ex:                                   # informational: never costs the bench line
+            cfg1 = {"error": repr(ex)}
+
     if rank == 0:
         line = {
             "metric": "audio-seconds/sec (RTF) Silero v3.1 at 1/2/4/8 B200 vs host-CPU C backend",
@@ -442,7 +466,8 @@ def main():
             "config": {"workload": "cfg3: 4096 concurrent synthetic 16 kHz s16le streams x 10 min per GPU, per-stream LSTM state on device; "
                                    "step = 4096 streams x 125 chunks (12 s); 50 steps = the 10 minutes",
                        "streams_per_gpu": S, "chunks_per_step": C, "l2_policy": "inputs larger than L2 (1.57 GB PCM per step, rotating step buffers)",
-                       "parity_max_abs_err_vs_oracle": parity, "segments_gathered": seg_count, "sharding": "streams across ranks, no collective on the data path"},
+                       "parity_max_abs_err_vs_oracle": parity, "segments_gathered": seg_count, "sharding": "streams across ranks, no collective on the data path",
+                       "cfg1_single_stream": cfg1},
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "audio-seconds/sec", "h2d_bytes_per_step": S * C * CHUNK * 2, "d2h_bytes_per_step": S * C * 4 + S * SEG_CAP * 8 + S * 4,
                     "ms_per_step": e2e_ms / args.steps,

@@ -8,7 +8,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from oracle_lib import ROOT, Oracle, _p
+from oracle_lib import ROOT, Oracle, Reference, _p, have_ref
 
 import vadc_b200
 
@@ -73,3 +73,22 @@ def test_lstm_gate_order_bits(host):
         assert np.array_equal(out.view(np.uint32), st["lstm"].reshape(B * 7, 64).view(np.uint32))
         assert np.array_equal(h.reshape(-1).view(np.uint32), o.state[:128].view(np.uint32))
         assert np.array_equal(c.reshape(-1).view(np.uint32), o.state[128:].view(np.uint32))
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not present")
+def test_encoder_bits_against_the_unmodified_reference_build(host):
+    """Same comparison with the stage tensors of the UNMODIFIED reference backend (oracle/_ref/libvadc_ref.so) instead of the
+    restatement: magnitudes in, fourth-layer output and probabilities (through the reference's own LSTM output) bit for bit."""
+    o = Oracle()
+    tab = tensor_table(o)
+    x = vadc_b200.synth_pcm(123, 1536 * 24).astype(np.float32) / np.float32(32768.0)
+    st = Reference().run_stages(x)
+    B = st["stft"].shape[0]
+    a4 = np.zeros((B, 7, 64), np.float32)
+    host.faithful_host_encoder(tab, _p(st["stft"]), B, _p(a4))
+    assert np.array_equal(a4.view(np.uint32), np.ascontiguousarray(st["l4"].transpose(0, 2, 1)).view(np.uint32))
+    out = np.zeros((B, 2), np.float32)
+    dw = np.ctypeslib.as_array(C.cast(tab[97], C.POINTER(C.c_float)), (128,))
+    db = np.ctypeslib.as_array(C.cast(tab[98], C.POINTER(C.c_float)), (2,))
+    host.faithful_host_decoder(_p(np.ascontiguousarray(st["lstm"])), B, _p(dw), _p(db), _p(out))
+    assert np.array_equal(out.view(np.uint32), st["out"].view(np.uint32))
