@@ -2,11 +2,16 @@
 SILERO_B200_FAITHFUL_MAX_STREAMS streams on a fully automatic engine -- the way the reference itself is used -- and any batch on
 request. Bar: BIT-identical probabilities (both decoder outputs) and LSTM state against the oracle, which is itself pinned bit for
 bit to the unmodified reference build (tests/test_oracle_vs_ref.py); hence identical timestamps for streams of any length."""
+import glob
+import os
+
 import numpy as np
 import pytest
 
 import vadc_b200
-from oracle_lib import Oracle, have_ref, ref_cli
+from oracle_lib import ROOT, Oracle, have_ref, ref_cli
+
+CASES = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "e2e_*.npz")))
 
 pytestmark = pytest.mark.gpu
 
@@ -17,6 +22,18 @@ def bits(a):
 
 def oracle_out2(pcm):
     return Oracle().run_pcm(pcm)
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p) for p in CASES])
+def test_golden_vectors_of_the_unmodified_reference_bit_for_bit(path):
+    """tests/golden/e2e_*.npz hold outputs of the UNMODIFIED reference build (tests/golden/make_e2e_golden.py): both decoder outputs
+    of every chunk must come back with the same bits, and the segment text with the same bytes."""
+    g = np.load(path)
+    e = vadc_b200.Engine()
+    p, out2 = e.run_streams(g["pcm"][None, :], want_out2=True)
+    e.close()
+    assert np.array_equal(bits(out2[0]), bits(g["out2"]))
+    assert vadc_b200.segments_text(p[0]) == str(g["stdout"])
 
 
 def test_cfg1_single_stream_60s_is_bit_identical():
