@@ -25,8 +25,10 @@
 // without a GPU); the kernels at the bottom are the only device-only part.
 //
 // Mapping: one CTA per chunk walks the four layers with the chunk's activations in shared memory in the reference's
-// [C][T] layout; each stage spreads its output elements over the CTA's threads, weights come from the raw tensors of the
-// container through L1/L2 (764 KB for the whole model). This path serves tens of streams, not thousands.
+// [C][T] layout; each stage spreads its output elements over the CTA's threads, weights come from the container's tensors
+// through L1/L2 (764 KB for the whole model; matrices that are read one output per lane also exist as transposed copies so
+// that those loads coalesce). The LSTM runs one CTA per stream, the decoder head one thread per (chunk, head). This path serves
+// up to ~128 streams at the speed of the fp32 fast kernels (the serial LSTM bounds small batches either way), not thousands.
 #pragma once
 
 #if defined( __CUDACC__ )
