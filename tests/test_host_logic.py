@@ -131,3 +131,13 @@ def test_product_does_not_touch_the_oracle():
                 if f.endswith((".py", ".c", ".h", ".cu", ".cuh", "Makefile")):
                     txt = open(os.path.join(dirpath, f), errors="ignore").read()
                     assert "silero_oracle" not in txt and "oracle/" not in txt and "libvadc_ref" not in txt, os.path.join(dirpath, f)
+
+
+def test_python_constants_mirror_the_header():
+    """vadc_b200/api.py restates the numerics knobs of include/silero_b200.h for the tests and the bench."""
+    import re
+    hdr = open(os.path.join(ROOT, "include", "silero_b200.h")).read()
+    defs = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define SILERO_B200_(\w+)\s+(\d+)\b", hdr)}
+    for name in ("STFT_AUTO", "STFT_EXACT", "STFT_HYBRID", "STFT_HYBRID_FFT", "STFT_HYBRID_TENSOR", "LSTM_AUTO", "LSTM_FP32", "LSTM_TENSOR",
+                 "LSTM_FAITHFUL", "LAYERS_AUTO", "LAYERS_FP32", "LAYERS_TENSOR", "LAYERS_FAITHFUL", "FAITHFUL_MAX_STREAMS"):
+        assert getattr(vadc_b200, name) == defs[name], name
