@@ -224,7 +224,7 @@ def test_device_resident_path_equals_host_path():
     e.d2h(dev, d_probs)
     assert np.array_equal(dev, host)
     ms, launches = e.last_timing()
-    assert launches == 5 * 3 and ms["total"] > 0     # 33 streams: the faithful path, 5 kernels per window; windows of 16+16+8
+    assert launches == 4 * 3 and ms["total"] > 0     # 33 streams: the faithful path, 4 kernels per window; windows of 16+16+8
     e.device_free(d_pcm); e.device_free(d_probs); e.close()
 
 

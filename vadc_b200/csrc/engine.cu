@@ -88,6 +88,7 @@ struct silero_b200
    float *d_weights;         // one allocation holding every packed weight
    DeviceWeights w;
    fq::Weights fw;           // the container's 99 tensors as they are (faithful_kernel.cuh)
+   int *d_lstm_sync;         // [1 + max_streams]: task ticket + per-stream layer-0 progress of faithful_lstm_wave_kernel
    float *state_h, *state_c; // [max_streams][2][64]
    // window scratch (grow-only)
    size_t cap_chunks;
@@ -418,6 +419,7 @@ static int configure_kernels()
    CU( allow_smem( lstm_layer_kernel<1, 1>, LstmSmem<1>::BYTES ) );
    CU( allow_smem( faithful_lstm_kernel<0>, FLSTM_SMEM_BYTES ) );
    CU( allow_smem( faithful_lstm_kernel<1>, FLSTM_SMEM_BYTES ) );
+   CU( allow_smem( faithful_lstm_wave_kernel, FLSTM_SMEM_BYTES ) );
    CU( allow_smem( faithful_encoder_kernel, FAITHFUL_SMEM_BYTES ) );
    CU( allow_smem( tc_probe_kernel, 200 * 1024 ) );
    CU( allow_smem( lstm_tc_kernel<0>, LTC_SMEM_BYTES ) );
@@ -451,6 +453,7 @@ extern "C" void silero_b200_destroy( silero_b200 *h )
    cudaFree( h->d_out2 );
    cudaFree( h->d_f32 );
    cudaFree( h->d_flagged );
+   cudaFree( h->d_lstm_sync );
    cudaFree( h->d_lstm_tc );
    cudaFree( h->d_stft_tc );
    cudaFree( h->d_fix_list );
@@ -706,6 +709,7 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    for ( int i = 0; i < 99; ++i ) h->fw.t[i] = h->d_weights + all_off[i];
    for ( int k = 0; k < fq::N_TRANSPOSED; ++k ) h->fw.tt[k] = h->d_weights + tt_off[k];
    CU_H( cudaMalloc( &h->d_flagged, sizeof( unsigned long long ) ) );
+   CU_H( cudaMalloc( &h->d_lstm_sync, ( (size_t)h->max_streams + 1 ) * sizeof( int ) ) );
    {
       size_t free_b = 0, total_b = 0;
       h->scratch_budget = (size_t)1536 << 20;
@@ -1068,6 +1072,20 @@ static int launch_lstm_faithful( silero_b200 *h, const float *x, float *hseq, in
    return 0;
 }
 
+// both LSTM layers as one wavefront launch (faithful_lstm_wave_kernel): a4 holds the encoder's output on entry and the top layer's
+// output sequence on exit, h0 the first layer's sequence
+static int launch_lstm_faithful_wave( silero_b200 *h, float *a4, float *h0, int first_stream, int nstreams, int nw )
+{
+   float *sh = h->state_h + (size_t)first_stream * SILERO_B200_STATE_FLOATS;
+   float *sc = h->state_c + (size_t)first_stream * SILERO_B200_STATE_FLOATS;
+   CU( cudaMemsetAsync( h->d_lstm_sync, 0, ( (size_t)nstreams + 1 ) * sizeof( int ), h->stream ) );
+   const int grid = imin( 2 * nstreams, h->sm_count );
+   faithful_lstm_wave_kernel<<<grid, FLSTM_THREADS, FLSTM_SMEM_BYTES, h->stream>>>( a4, h0, a4, sh, sc, h->w.lstm_w, h->w.lstm_b, nstreams, nw, h->d_lstm_sync );
+   h->launches++;
+   CU( cudaGetLastError() );
+   return 0;
+}
+
 // first encoder layer from the log spectrogram: mu = per-chunk normalization scalar if the STFT kernel produced it, else NULL
 // (the layer computes it itself, misc.c:48-121)
 static int first_layer_from_logspec( silero_b200 *h, const float *spec, float *a1, int nchunks, const float *mu )
@@ -1134,16 +1152,15 @@ static int run_window( silero_b200 *h, const void *d_in, int in_f32, long long s
    if ( faithful )
    {
       // log spectrogram (bit-identical to the reference's, stft_kernel.cuh) -> encoder -> LSTM -> decoder, every step in the
-      // reference's rounding sequence: 5 launches
+      // reference's rounding sequence: 4 launches (both LSTM layers run as one wavefront)
       if ( launch_faithful_encoder( h, h->spec, h->a4, nchunks ) ) return SILERO_B200_ERR_CUDA;
       CU( cudaEventRecord( h->ev_spec_free, h->stream ) );
       stage_mark( h, 2 );
       stage_mark( h, 3 );
       stage_mark( h, 4 );
       stage_mark( h, 5 );
-      if ( launch_lstm_faithful<0>( h, h->a4, h->h0, first_stream, nstreams, nw ) ) return SILERO_B200_ERR_CUDA;
+      if ( launch_lstm_faithful_wave( h, h->a4, h->h0, first_stream, nstreams, nw ) ) return SILERO_B200_ERR_CUDA;
       stage_mark( h, 6 );
-      if ( launch_lstm_faithful<1>( h, h->h0, h->a4, first_stream, nstreams, nw ) ) return SILERO_B200_ERR_CUDA;
       {
          const long long n = (long long)nchunks * 2;
          faithful_decoder_kernel<<<(unsigned)( ( n + 127 ) / 128 ), 128, 0, h->stream>>>( h->a4, h->w.dec_w, h->w.dec_b, nstreams, nw, d_out2, d_probs, out_stride, out_off );
