@@ -92,3 +92,22 @@ def test_encoder_bits_against_the_unmodified_reference_build(host):
     db = np.ctypeslib.as_array(C.cast(tab[98], C.POINTER(C.c_float)), (2,))
     host.faithful_host_decoder(_p(np.ascontiguousarray(st["lstm"])), B, _p(dw), _p(db), _p(out))
     assert np.array_equal(out.view(np.uint32), st["out"].view(np.uint32))
+
+
+def test_encoder_orchestration_has_no_data_race_under_tsan():
+    """tests/hostcheck/faithful_host_race.cpp: the encoder's stage loops run by host threads with fq::barrier() as a real barrier,
+    under ThreadSanitizer: a missing or misplaced barrier is a reported data race (exit code 66; checked by deleting one), and the
+    parallel result equals the serial one. Several thread counts, so that neighbouring elements land on different threads."""
+    src = os.path.join(ROOT, "tests", "hostcheck", "faithful_host_race.cpp")
+    exe = os.path.join(ROOT, "tests", "hostcheck", "_faithful_host_race")
+    Oracle()                                                   # builds oracle/libsilero_oracle.so if it is not there yet
+    r = subprocess.run(["g++", "-O1", "-g", "-mavx2", "-ffp-contract=off", "-fsanitize=thread", "-x", "c++", src, "-o", exe,
+                        "-L" + os.path.join(ROOT, "oracle"), "-lsilero_oracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-lpthread", "-lm"],
+                       capture_output=True, text=True)
+    if r.returncode != 0 and "tsan" in r.stderr.lower():
+        pytest.skip("ThreadSanitizer runtime not available: " + r.stderr.strip().splitlines()[-1])
+    assert r.returncode == 0, r.stderr
+    for nt in (8, 5, 16):
+        r = subprocess.run([exe, vadc_b200.WEIGHTS_PATH, str(nt)], capture_output=True, text=True)
+        assert r.returncode == 0 and "ThreadSanitizer" not in r.stderr, (nt, r.stdout, r.stderr[-2000:])
+        assert "parallel == serial: yes" in r.stdout

@@ -90,10 +90,15 @@ FQ float expo( float a )
    return expf( a );
 #endif
 }
+#if !defined( __CUDACC__ ) && defined( FQ_HOST_BARRIER )
+extern "C" void fq_host_barrier( void ); // tests/hostcheck/faithful_host_race.cpp: a real barrier between host threads
+#endif
 FQ void barrier()
 {
 #ifdef __CUDA_ARCH__
    __syncthreads();
+#elif !defined( __CUDACC__ ) && defined( FQ_HOST_BARRIER )
+   fq_host_barrier();
 #endif
 }
 FQ float relu( float v ) { return v < 0.0f ? 0.0f : v; } // `if (v < 0) v = 0` keeps -0.0f, like the reference
