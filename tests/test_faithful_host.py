@@ -109,5 +109,7 @@ def test_encoder_orchestration_has_no_data_race_under_tsan():
     assert r.returncode == 0, r.stderr
     for nt in (8, 5, 16):
         r = subprocess.run([exe, vadc_b200.WEIGHTS_PATH, str(nt)], capture_output=True, text=True)
+        if "FATAL: ThreadSanitizer" in r.stderr:                # e.g. "unexpected memory mapping" under some kernels' ASLR settings
+            pytest.skip("ThreadSanitizer cannot run here: " + r.stderr.strip().splitlines()[0])
         assert r.returncode == 0 and "ThreadSanitizer" not in r.stderr, (nt, r.stdout, r.stderr[-2000:])
         assert "parallel == serial: yes" in r.stdout
