@@ -15,6 +15,7 @@
 
 #include "common.cuh"
 #include "faithful_kernel.cuh"
+#include "exact_lstm_kernel.cuh"
 #include "layer_kernel.cuh"
 #include "layer_tc_kernel.cuh"
 #include "layer0_tc_kernel.cuh"
@@ -421,6 +422,8 @@ static int configure_kernels()
    CU( allow_smem( faithful_lstm_kernel<1>, FLSTM_SMEM_BYTES ) );
    CU( allow_smem( faithful_lstm_wave_kernel, FLSTM_SMEM_BYTES ) );
    CU( allow_smem( faithful_encoder_kernel, FAITHFUL_SMEM_BYTES ) );
+   CU( allow_smem( exact_lstm_kernel<0>, XL_SMEM_BYTES ) );
+   CU( allow_smem( exact_lstm_kernel<1>, XL_SMEM_BYTES ) );
    CU( allow_smem( tc_probe_kernel, 200 * 1024 ) );
    CU( allow_smem( lstm_tc_kernel<0>, LTC_SMEM_BYTES ) );
    CU( allow_smem( lstm_tc_kernel<1>, LTC_SMEM_BYTES ) );
@@ -1086,6 +1089,20 @@ static int launch_lstm_faithful_wave( silero_b200 *h, float *a4, float *h0, int 
    return 0;
 }
 
+// one LSTM layer for any number of streams, still in the reference's rounding sequence (exact_lstm_kernel.cuh: weights in registers,
+// a CTA walks a set of streams together); hseq receives the layer's output sequence [S][nw*7][64]
+template <int LAYER>
+static int launch_lstm_exact( silero_b200 *h, const float *x, float *hseq, int first_stream, int nstreams, int nw )
+{
+   float *sh = h->state_h + (size_t)first_stream * SILERO_B200_STATE_FLOATS;
+   float *sc = h->state_c + (size_t)first_stream * SILERO_B200_STATE_FLOATS;
+   const int grid = imin( nstreams, h->sm_count );
+   exact_lstm_kernel<LAYER><<<grid, XL_THREADS, XL_SMEM_BYTES, h->stream>>>( x, hseq, sh, sc, h->w.lstm_w, h->w.lstm_b, nstreams, nw );
+   h->launches++;
+   CU( cudaGetLastError() );
+   return 0;
+}
+
 // first encoder layer from the log spectrogram: mu = per-chunk normalization scalar if the STFT kernel produced it, else NULL
 // (the layer computes it itself, misc.c:48-121)
 static int first_layer_from_logspec( silero_b200 *h, const float *spec, float *a1, int nchunks, const float *mu )
@@ -1159,7 +1176,14 @@ static int run_window( silero_b200 *h, const void *d_in, int in_f32, long long s
       stage_mark( h, 3 );
       stage_mark( h, 4 );
       stage_mark( h, 5 );
-      if ( launch_lstm_faithful_wave( h, h->a4, h->h0, first_stream, nstreams, nw ) ) return SILERO_B200_ERR_CUDA;
+      if ( nstreams > h->sm_count / 2 )
+      {
+         // more streams than the wavefront has SM pairs for: CTAs walk sets of streams together (same bits)
+         if ( launch_lstm_exact<0>( h, h->a4, h->h0, first_stream, nstreams, nw ) ) return SILERO_B200_ERR_CUDA;
+         if ( launch_lstm_exact<1>( h, h->h0, h->a4, first_stream, nstreams, nw ) ) return SILERO_B200_ERR_CUDA;
+      }
+      else if ( launch_lstm_faithful_wave( h, h->a4, h->h0, first_stream, nstreams, nw ) )
+         return SILERO_B200_ERR_CUDA;
       stage_mark( h, 6 );
       {
          const long long n = (long long)nchunks * 2;

@@ -1,0 +1,165 @@
+// vadc_b200/csrc/exact_lstm_kernel.cuh -- the decoder LSTM in the reference's rounding sequence, for ANY number of streams.
+//
+// Replaces lstm_tensor_minibatched / lstm_seq / lstm / lstm_cell (lstm.c:31-341): per step and layer z = W [x;h] + b through
+// dotproduct_simd (maths.h:123-158: 16 taps per block into eight lanes in _mm256_hadd_ps order, lanes summed left to right),
+// i,f,o = 1/(1+expf(-z)), g = tanhf(z), c = f c + i g, h = o tanhf(c) (lstm.c:64-88) -- separate multiplies and adds, glibc's
+// expf / tanhf bit for bit (libm_exact.cuh). The result is bit-identical to the reference for streams of any length.
+//
+// Why a second kernel beside faithful_lstm_wave_kernel (one CTA per stream): the recurrence is serial per stream, but thousands of
+// streams are independent. Here a CTA owns a SET of streams (stream s -> CTA s mod grid) and walks them step by step together:
+//   * the layer's weight matrix lives in REGISTERS for the whole launch: 512 threads, thread = (gate row r, half): the eight taps
+//     16b + 8 half .. + 7 of every 16-tap block b of row r, i.e. exactly the taps that feed four of dotproduct_simd's eight lanes
+//     (half 0: r0 r1 r4 r5, half 1: r2 r3 r6 r7) -- 64 weights per thread, loaded once;
+//   * [x|h] of every stream of the CTA lives in shared memory; a thread reads its 64 taps of one stream as 16 LDS.128 that the
+//     warp shares as two broadcasts, and owes 64 FMUL + 64 FADD for them: no weight traffic at all in the step loop;
+//   * streams go through in pairs: the two lanes of a row each contract their half for both streams, then swap four partial sums
+//     by one shuffle each, so that the even lane finishes the row for the first stream and the odd lane for the second (the lane
+//     sums in the reference's order, bias, the gate's own nonlinearity): no lane idles in the libm restatements;
+//   * the cell update runs on all 512 threads over (unit, stream) pairs of a sub-batch of 8 streams through a double-buffered
+//     activation tile in shared memory: one barrier per sub-batch and step.
+// Shared memory per stream: [x|h] 512 B + c 256 B, so one CTA carries up to XL_MAX_STREAMS streams per pass (more go in passes).
+//   x: [S][steps][64] layer input (stream-major), hseq: [S][steps][64] layer output, state_h/state_c: [S][2][64].
+#pragma once
+#include "common.cuh"
+#include "libm_exact.cuh"
+
+#define XL_THREADS 512
+#define XL_SUB 8                         // streams per sub-batch (one (unit, stream) pair per thread in the cell update)
+#define XL_MAX_STREAMS 256               // streams a CTA carries in one pass
+#define XL_ACT_FLOATS ( 2 * XL_SUB * 256 ) // double-buffered activation tile
+#define XL_SMEM_BYTES ( ( XL_ACT_FLOATS + XL_MAX_STREAMS * ( 128 + 64 ) ) * 4 )
+
+// four of dotproduct_simd's eight lanes over this thread's taps of one stream: acc[j] += x[2j] w[2j] + x[2j+1] w[2j+1] per block
+__device__ __forceinline__ void xl_half_row( const float *__restrict__ xh /* this thread's first tap */, const float ( &w )[64], float ( &acc )[4] )
+{
+   acc[0] = acc[1] = acc[2] = acc[3] = 0.0f;
+#pragma unroll
+   for ( int b = 0; b < 8; ++b )
+   {
+      const float4 u = ld4( xh + 16 * b ), v = ld4( xh + 16 * b + 4 );
+      acc[0] = __fadd_rn( acc[0], __fadd_rn( __fmul_rn( u.x, w[8 * b + 0] ), __fmul_rn( u.y, w[8 * b + 1] ) ) );
+      acc[1] = __fadd_rn( acc[1], __fadd_rn( __fmul_rn( u.z, w[8 * b + 2] ), __fmul_rn( u.w, w[8 * b + 3] ) ) );
+      acc[2] = __fadd_rn( acc[2], __fadd_rn( __fmul_rn( v.x, w[8 * b + 4] ), __fmul_rn( v.y, w[8 * b + 5] ) ) );
+      acc[3] = __fadd_rn( acc[3], __fadd_rn( __fmul_rn( v.z, w[8 * b + 6] ), __fmul_rn( v.w, w[8 * b + 7] ) ) );
+   }
+}
+
+template <int LAYER>
+__global__ void __launch_bounds__( XL_THREADS, 1 )
+exact_lstm_kernel( const float *__restrict__ x, float *__restrict__ hseq, float *__restrict__ state_h, float *__restrict__ state_c,
+                   const float *__restrict__ wpack /*[2][32][256][4]*/, const float *__restrict__ bias /*[2][256]*/, int nstreams, int nw )
+{
+   extern __shared__ __align__( 16 ) float xsm[];
+   float *act = xsm;                                 // [2][XL_SUB][256]
+   float *xh = xsm + XL_ACT_FLOATS;                  // [K][128]
+   float *cst = xh + XL_MAX_STREAMS * 128;           // [K][64]
+   const int tid = threadIdx.x, half = tid & 1, row = tid >> 1, gate = row >> 6;
+   const int steps = nw * 7;
+
+   // this thread's 64 weights: quads 4b + 2 half, 4b + 2 half + 1 of row `row`
+   float w[64];
+   {
+      const float4 *src = reinterpret_cast<const float4 *>( wpack ) + (size_t)LAYER * ( 32 * 256 );
+#pragma unroll
+      for ( int b = 0; b < 8; ++b )
+      {
+         const float4 q0 = __ldg( src + ( 4 * b + 2 * half ) * 256 + row ), q1 = __ldg( src + ( 4 * b + 2 * half + 1 ) * 256 + row );
+         w[8 * b + 0] = q0.x; w[8 * b + 1] = q0.y; w[8 * b + 2] = q0.z; w[8 * b + 3] = q0.w;
+         w[8 * b + 4] = q1.x; w[8 * b + 5] = q1.y; w[8 * b + 6] = q1.z; w[8 * b + 7] = q1.w;
+      }
+   }
+   const float b_row = bias[LAYER * 256 + row];
+   // cell-update role: (unit uj, stream uk of the sub-batch)
+   const int uk = tid >> 6, uj = tid & 63;
+
+   // streams of this CTA: blockIdx.x + i * gridDim.x, in passes of at most XL_MAX_STREAMS
+   const int mine = ( nstreams - (int)blockIdx.x + (int)gridDim.x - 1 ) / (int)gridDim.x;
+   for ( int pass0 = 0; pass0 < mine; pass0 += XL_MAX_STREAMS )
+   {
+      const int K = min( XL_MAX_STREAMS, mine - pass0 );
+      __syncthreads(); // the previous pass is done with the shared buffers
+      for ( int e = tid; e < K * 64; e += XL_THREADS )
+      {
+         const int k = e >> 6, j = e & 63;
+         const size_t s = (size_t)blockIdx.x + (size_t)( pass0 + k ) * gridDim.x;
+         cst[k * 64 + j] = state_c[( s * 2 + LAYER ) * 64 + j];
+         xh[k * 128 + 64 + j] = state_h[( s * 2 + LAYER ) * 64 + j];
+         xh[k * 128 + j] = __ldg( x + s * steps * 64 + j );
+      }
+      __syncthreads();
+      const int nsub = ( K + XL_SUB - 1 ) / XL_SUB;
+      int buf = 0;
+      for ( int step = 0; step < steps; ++step )
+      {
+         for ( int sb = 0; sb < nsub; ++sb, buf ^= 1 )
+         {
+            const int k0 = sb * XL_SUB, kn = min( XL_SUB, K - k0 );
+            // next step's input of my (unit, stream): in flight during the contraction
+            float xnext = 0.0f;
+            const bool upd = uk < kn;
+            const size_t us = (size_t)blockIdx.x + (size_t)( pass0 + k0 + uk ) * gridDim.x;
+            if ( upd && step + 1 < steps ) xnext = __ldg( x + ( us * steps + step + 1 ) * 64 + uj );
+            float *a = act + buf * ( XL_SUB * 256 );
+#pragma unroll 1
+            for ( int p = 0; p < kn; p += 2 )
+            {
+               const bool two = p + 1 < kn;
+               float a0[4], a1[4];
+               xl_half_row( xh + ( k0 + p ) * 128 + 8 * half, w, a0 );
+               if ( two )
+                  xl_half_row( xh + ( k0 + p + 1 ) * 128 + 8 * half, w, a1 );
+               else
+                  a1[0] = a1[1] = a1[2] = a1[3] = 0.0f;
+               // the even lane finishes stream p, the odd lane stream p + 1: swap the other stream's partial sums
+               float lo[4], hi[4];
+#pragma unroll
+               for ( int i = 0; i < 4; ++i )
+               {
+                  const float got = __shfl_xor_sync( 0xffffffffu, half ? a0[i] : a1[i], 1 );
+                  lo[i] = half ? got : a0[i];   // lanes r0 r1 r4 r5 of my stream
+                  hi[i] = half ? a1[i] : got;   // lanes r2 r3 r6 r7
+               }
+               float z = 0.0f;
+               z = __fadd_rn( z, lo[0] );
+               z = __fadd_rn( z, lo[1] );
+               z = __fadd_rn( z, hi[0] );
+               z = __fadd_rn( z, hi[1] );
+               z = __fadd_rn( z, lo[2] );
+               z = __fadd_rn( z, lo[3] );
+               z = __fadd_rn( z, hi[2] );
+               z = __fadd_rn( z, hi[3] );
+               z = __fadd_rn( z, b_row );
+               if ( !half || two )
+               {
+                  const float v = ( gate == 2 ) ? lme::tanhf_ref( z ) : lme::sigmoid_ref( z );
+                  a[( p + half ) * 256 + row] = v;
+               }
+            }
+            __syncthreads();
+            // cell update (lstm.c:64-88) of (unit uj, stream k0 + uk)
+            if ( upd )
+            {
+               const float *av = a + uk * 256;
+               const float ig = av[uj], fg = av[64 + uj], gg = av[128 + uj], og = av[192 + uj];
+               const int k = k0 + uk;
+               const float cn = __fadd_rn( __fmul_rn( fg, cst[k * 64 + uj] ), __fmul_rn( ig, gg ) );
+               const float hn = __fmul_rn( lme::tanhf_ref( cn ), og );
+               cst[k * 64 + uj] = cn;
+               xh[k * 128 + 64 + uj] = hn;
+               xh[k * 128 + uj] = xnext;
+               hseq[( us * steps + step ) * 64 + uj] = hn;
+            }
+            // with a single sub-batch the next contraction reads what this update wrote
+            if ( nsub == 1 ) __syncthreads();
+         }
+      }
+      __syncthreads();
+      for ( int e = tid; e < K * 64; e += XL_THREADS )
+      {
+         const int k = e >> 6, j = e & 63;
+         const size_t s = (size_t)blockIdx.x + (size_t)( pass0 + k ) * gridDim.x;
+         state_c[( s * 2 + LAYER ) * 64 + j] = cst[k * 64 + j];
+         state_h[( s * 2 + LAYER ) * 64 + j] = xh[k * 128 + 64 + j];
+      }
+   }
+}
