@@ -223,6 +223,9 @@ int silero_b200_stage_stft_magnitude( silero_b200 *h, const float *samples, int 
 /* the production kernels end to end from samples (STFT -> first layer with in-kernel normalization
    -> layers 2..4), every layer output tapped in the reference layout */
 int silero_b200_stage_pipeline( silero_b200 *h, const float *samples, int batch, float *l1, float *l2, float *l3, float *l4 );
+/* the same taps on the exact path's kernels (exact STFT -> exact_front_kernel -> exact_layer_kernel x 4, the reference's rounding
+   sequence): y1 [B,16,25] = conv_block output of the first layer (conv.c:761-814), l1..l4 as above */
+int silero_b200_stage_exact_pipeline( silero_b200 *h, const float *samples, int batch, float *y1, float *l1, float *l2, float *l3, float *l4 );
 /* adaptive_audio_normalization_inplace on a caller-supplied magnitude spectrogram [B,129,25] */
 int silero_b200_stage_norm( silero_b200 *h, const float *magnitude, int batch, float *norm_out );
 /* encoder (silero_v3.c:4-64) from a normalized spectrogram, every layer's output tapped */

@@ -6,6 +6,7 @@
 
 // MODE: 0 LDS.32 broadcast, 1 LDS.128 broadcast, 2 LDS.32 distinct (lane-consecutive), 3 LDS.128 distinct (lane-consecutive 16 B),
 //       4 LDS.64 broadcast, 5 LDS.128 two addresses per warp (even / odd lanes)
+//       6..9 LDS.128 with 8 (lane>>2), 8 (lane&7), 4 (lane>>3), 4 (lane&3) distinct 16-byte addresses per warp; 10,11 LDS.64 with 8 (lane>>2), 4 (lane>>3)
 // NF = independent FADDs issued per load (0, 4, 8, 16)
 template <int MODE, int NF>
 __global__ void __launch_bounds__( 1024 ) k( float *out, const float *in, int iters, long long *cycles )
@@ -18,7 +19,13 @@ __global__ void __launch_bounds__( 1024 ) k( float *out, const float *in, int it
    if ( MODE == 0 || MODE == 1 || MODE == 4 ) base = (const float *)sh;
    else if ( MODE == 2 ) base = (const float *)sh + lane;
    else if ( MODE == 3 ) base = (const float *)sh + lane * 4;
-   else base = (const float *)sh + ( lane & 1 ) * 4;
+   else if ( MODE == 5 ) base = (const float *)sh + ( lane & 1 ) * 4;
+   else if ( MODE == 6 ) base = (const float *)sh + ( lane >> 2 ) * 4;
+   else if ( MODE == 7 ) base = (const float *)sh + ( lane & 7 ) * 4;
+   else if ( MODE == 8 ) base = (const float *)sh + ( lane >> 3 ) * 4;
+   else if ( MODE == 9 ) base = (const float *)sh + ( lane & 3 ) * 4;
+   else if ( MODE == 10 ) base = (const float *)sh + ( lane >> 2 ) * 2;
+   else base = (const float *)sh + ( lane >> 3 ) * 2;
    float a[16], m = in[threadIdx.x & 255];
    for ( int i = 0; i < 16; ++i ) a[i] = in[( threadIdx.x + i ) & 255];
    float acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
@@ -35,7 +42,7 @@ __global__ void __launch_bounds__( 1024 ) k( float *out, const float *in, int it
             asm volatile( "ld.shared.f32 %0, [%1];" : "=f"( v ) : "r"( (unsigned)__cvta_generic_to_shared( p + j * 128 ) ) );
             if ( j & 1 ) acc0 = __uint_as_float( __float_as_uint( acc0 ) ^ __float_as_uint( v ) ); else acc1 = __uint_as_float( __float_as_uint( acc1 ) ^ __float_as_uint( v ) );
          }
-         else if ( MODE == 4 )
+         else if ( MODE == 4 || MODE >= 10 )
          {
             float v, w;
             asm volatile( "ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"( v ), "=f"( w ) : "r"( (unsigned)__cvta_generic_to_shared( p + j * 128 ) ) );
@@ -92,8 +99,14 @@ void run( const char *name, int threads )
 int main()
 {
    
-   for ( int threads : { 512, 1024 } )
+   for ( int threads : { 1024 } )
    {
+      ALLNF( 6, "LDS.128 8 addr (lane>>2)", threads )
+      ALLNF( 7, "LDS.128 8 addr (lane&7)", threads )
+      ALLNF( 8, "LDS.128 4 addr (lane>>3)", threads )
+      ALLNF( 9, "LDS.128 4 addr (lane&3)", threads )
+      ALLNF( 10, "LDS.64 8 addr (lane>>2)", threads )
+      ALLNF( 11, "LDS.64 4 addr (lane>>3)", threads )
       ALLNF( 0, "LDS.32 broadcast", threads )
       ALLNF( 4, "LDS.64 broadcast", threads )
       ALLNF( 1, "LDS.128 broadcast", threads )

@@ -303,6 +303,13 @@ class Engine:
         self._check(lib().silero_b200_stage_pipeline(self._h, _p(x), B, *[_p(o) for o in outs]))
         return outs
 
+    def stage_exact_pipeline(self, samples):
+        x = _f32(samples).reshape(-1, CHUNK)
+        B = x.shape[0]
+        outs = [np.zeros(s, np.float32) for s in ((B, 16, 25), (B, 16, 13), (B, 32, 7), (B, 32, 7), (B, 64, 7))]
+        self._check(lib().silero_b200_stage_exact_pipeline(self._h, _p(x), B, *[_p(o) for o in outs]))
+        return outs
+
     def stage_layer(self, layer, x):
         cin, c, t, stride = ((129, 16, 25, 2), (16, 32, 13, 2), (32, 32, 7, 1), (32, 64, 7, 1))[layer]
         x = _f32(x).reshape(-1, cin, t)

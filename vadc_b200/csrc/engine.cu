@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "faithful_kernel.cuh"
 #include "exact_lstm_kernel.cuh"
+#include "exact_encoder_kernel.cuh"
 #include "layer_kernel.cuh"
 #include "layer_tc_kernel.cuh"
 #include "layer0_tc_kernel.cuh"
@@ -25,6 +26,7 @@
 #include "stft_hybrid_kernel.cuh"
 #include "stft_fft8_kernel.cuh"
 #include "stft_kernel.cuh"
+#include "stft_sym_kernel.cuh"
 #include "stft_tc_kernel.cuh"
 #include "tc_probe.cuh"
 #include "testtensor.h"
@@ -94,6 +96,10 @@ struct silero_b200
    // window scratch (grow-only)
    size_t cap_chunks;
    float *spec, *a1, *a2, *a3, *a4, *h0, *mu;
+   int stft_sym;             // the basis has the mirror property: the exact STFT runs on stft_sym_kernel (half the arithmetic, same bits)
+   const float *basis_sym;   // [64 kquads][128 rows][4] (stft_sym_kernel.cuh)
+   float *y1;                // [chunks][16][25] conv_block output of the first layer (exact_front_kernel)
+   float *xe_scratch;        // per-CTA token scratch of exact_layer_kernel
    // host-call staging
    int16_t *pcm_stage[2];
    size_t pcm_stage_cap; // samples per buffer
@@ -152,6 +158,39 @@ static void pack_basis( const float *basis /*[258][256]*/, float *out /*[2][64][
                   out[( ( (size_t)half * 64 + kq ) * 128 + rho ) * 4 + ( v & 3 )] = basis[(size_t)row * 256 + k];
                }
       }
+}
+
+// stft_sym_kernel.cuh: does the table have the mirror property the kernel builds on? (value comparisons: +0 == -0)
+static bool basis_is_mirrored( const float *basis /*[258][256]*/ )
+{
+   for ( int k = 0; k < 256; ++k )
+   {
+      const float s = ( k & 1 ) ? -1.0f : 1.0f;
+      for ( int f = 0; f <= 128; ++f )
+         if ( basis[(size_t)( 128 - f ) * 256 + k] != s * basis[(size_t)f * 256 + k] ) return false;
+      for ( int f = 1; f < 128; ++f )
+         if ( basis[(size_t)( 129 + 128 - f ) * 256 + k] != -s * basis[(size_t)( 129 + f ) * 256 + k] ) return false;
+      if ( basis[(size_t)129 * 256 + k] != 0.0f || basis[(size_t)257 * 256 + k] != 0.0f ) return false;
+      if ( ( k & 1 ) ? basis[(size_t)64 * 256 + k] != 0.0f : basis[(size_t)( 129 + 64 ) * 256 + k] != 0.0f ) return false;
+   }
+   return true;
+}
+
+// rows of stft_sym_kernel.cuh: slot a * 64 + u; u >= 1: (re, im) of bin u; u == 0: re of bin 0 and the merged row of bin 64
+static void pack_basis_sym( const float *basis /*[258][256]*/, float *out /*[64][128][4]*/ )
+{
+   for ( int a = 0; a < 2; ++a )
+      for ( int u = 0; u < 64; ++u )
+         for ( int l = 0; l < 8; ++l )
+            for ( int g = 0; g < 4; ++g )
+               for ( int v = 0; v < 8; ++v )
+               {
+                  const int k = 64 * g + 8 * v + l;
+                  const int kq = l * 8 + g * 2 + ( v >> 2 );
+                  int row = a == 0 ? u : 129 + u;
+                  if ( u == 0 && a == 1 ) row = ( k & 1 ) ? 129 + 64 : 64;
+                  out[( (size_t)kq * 128 + a * 64 + u ) * 4 + ( v & 3 )] = basis[(size_t)row * 256 + k];
+               }
 }
 
 template <int L>
@@ -403,6 +442,8 @@ static int configure_kernels()
 {
    CU( allow_smem( stft_logmag_kernel<false>, STFT_SMEM_BYTES ) );
    CU( allow_smem( stft_logmag_kernel<true>, STFT_SMEM_BYTES ) );
+   CU( allow_smem( stft_sym_kernel<false>, SSYM_SMEM_BYTES ) );
+   CU( allow_smem( stft_sym_kernel<true>, SSYM_SMEM_BYTES ) );
    CU( allow_smem( stft_hybrid_kernel<false>, HYB_SMEM_BYTES ) );
    CU( allow_smem( stft_hybrid_kernel<true>, HYB_SMEM_BYTES ) );
    CU( allow_smem( stft_fft8_kernel<false, false>, F8_SMEM_BYTES ) );
@@ -422,6 +463,11 @@ static int configure_kernels()
    CU( allow_smem( faithful_lstm_kernel<1>, FLSTM_SMEM_BYTES ) );
    CU( allow_smem( faithful_lstm_wave_kernel, FLSTM_SMEM_BYTES ) );
    CU( allow_smem( faithful_encoder_kernel, FAITHFUL_SMEM_BYTES ) );
+   CU( allow_smem( exact_front_kernel, XF_SMEM_BYTES ) );
+   CU( allow_smem( exact_layer_kernel<0>, XeCfg<0>::SMEM_BYTES ) );
+   CU( allow_smem( exact_layer_kernel<1>, XeCfg<1>::SMEM_BYTES ) );
+   CU( allow_smem( exact_layer_kernel<2>, XeCfg<2>::SMEM_BYTES ) );
+   CU( allow_smem( exact_layer_kernel<3>, XeCfg<3>::SMEM_BYTES ) );
    CU( allow_smem( exact_lstm_kernel<0>, XL_SMEM_BYTES ) );
    CU( allow_smem( exact_lstm_kernel<1>, XL_SMEM_BYTES ) );
    CU( allow_smem( tc_probe_kernel, 200 * 1024 ) );
@@ -451,6 +497,8 @@ extern "C" void silero_b200_destroy( silero_b200 *h )
    cudaFree( h->a2 );
    cudaFree( h->a3 );
    cudaFree( h->a4 );
+   cudaFree( h->y1 );
+   cudaFree( h->xe_scratch );
    cudaFree( h->h0 );
    cudaFree( h->d_probs );
    cudaFree( h->d_out2 );
@@ -610,7 +658,8 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
       fq::transposed_slot( k, &idx, &n_out, &n_in );
       n_all += (size_t)n_out * n_in; // multiples of 4
    }
-   const size_t total = n_basis + n_l0 + n_l1 + n_l2 + n_l3 + n_lstm + n_lb + n_dw + n_db + n_raw + n_all;
+   const size_t n_bsym = SSYM_BS_FLOATS;
+   const size_t total = n_basis + n_l0 + n_l1 + n_l2 + n_l3 + n_lstm + n_lb + n_dw + n_db + n_raw + n_all + n_bsym;
    float *host = (float *)calloc( total, sizeof( float ) );
    if ( !host )
    {
@@ -630,6 +679,7 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    size_t o_db = off; off += n_db;
    size_t o_raw = off; off += n_raw;
    size_t o_all = off; off += n_all;
+   size_t o_bsym = off; off += n_bsym;
    size_t all_off[99], tt_off[fq::N_TRANSPOSED];
    {
       size_t o = o_all;
@@ -651,6 +701,8 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
       }
    }
    pack_basis( tf.tensors[0].data, host + o_basis );
+   pack_basis_sym( tf.tensors[0].data, host + o_bsym );
+   h->stft_sym = basis_is_mirrored( tf.tensors[0].data ) && !getenv( "SILERO_B200_STFT_NO_SYM" );
    pack_layer<0>( tf.tensors + 1, host + o_l0 );
    pack_layer<1>( tf.tensors + 25, host + o_l1 );
    pack_layer<2>( tf.tensors + 49, host + o_l2 );
@@ -709,6 +761,7 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    h->w.dec_w = h->d_weights + o_dw;
    h->w.dec_b = h->d_weights + o_db;
    h->w.basis_raw = h->d_weights + o_raw;
+   h->basis_sym = h->d_weights + o_bsym;
    for ( int i = 0; i < 99; ++i ) h->fw.t[i] = h->d_weights + all_off[i];
    for ( int k = 0; k < fq::N_TRANSPOSED; ++k ) h->fw.tt[k] = h->d_weights + tt_off[k];
    CU_H( cudaMalloc( &h->d_flagged, sizeof( unsigned long long ) ) );
@@ -805,8 +858,8 @@ static int ensure_scratch( silero_b200 *h, size_t chunks, size_t h0_floats )
    }
    if ( chunks <= h->cap_chunks ) return 0;
    CU( cudaStreamSynchronize( h->stream ) );
-   cudaFree( h->spec ); cudaFree( h->a1 ); cudaFree( h->a2 ); cudaFree( h->a3 ); cudaFree( h->a4 ); cudaFree( h->mu );
-   h->spec = h->a1 = h->a2 = h->a3 = h->a4 = h->mu = 0;
+   cudaFree( h->spec ); cudaFree( h->a1 ); cudaFree( h->a2 ); cudaFree( h->a3 ); cudaFree( h->a4 ); cudaFree( h->mu ); cudaFree( h->y1 );
+   h->spec = h->a1 = h->a2 = h->a3 = h->a4 = h->mu = h->y1 = 0;
    h->cap_chunks = 0;
    CU( cudaMalloc( &h->spec, chunks * VB_BINS * VB_FRAMES * sizeof( float ) ) );
    CU( cudaMalloc( &h->a1, chunks * 13 * 16 * sizeof( float ) ) );
@@ -814,12 +867,13 @@ static int ensure_scratch( silero_b200 *h, size_t chunks, size_t h0_floats )
    CU( cudaMalloc( &h->a3, chunks * 7 * 32 * sizeof( float ) ) );
    CU( cudaMalloc( &h->a4, chunks * 7 * 64 * sizeof( float ) ) );
    CU( cudaMalloc( &h->mu, chunks * sizeof( float ) ) );
+   CU( cudaMalloc( &h->y1, chunks * 16 * VB_FRAMES * sizeof( float ) ) );
    h->cap_chunks = chunks;
    return 0;
 }
 
 // bytes of window scratch per chunk: spec + a1..a4 + h0
-static const size_t kScratchPerChunk = ( VB_BINS * VB_FRAMES + 13 * 16 + 7 * 32 * 2 + 7 * 64 * 2 ) * sizeof( float );
+static const size_t kScratchPerChunk = ( VB_BINS * VB_FRAMES + 16 * VB_FRAMES + 13 * 16 + 7 * 32 * 2 + 7 * 64 * 2 ) * sizeof( float );
 
 // host_path: windows are also the granularity at which the H2D copy of the next window overlaps compute, so calls that start from
 // host memory keep the small (1.5 GB) windows; device-resident input takes the large ones
@@ -887,6 +941,14 @@ static int launch_stft( silero_b200 *h, const void *d_in, int in_f32, long long 
       }
       h->launches++;
       h->bins_total += (unsigned long long)nchunks * VB_BINS * VB_FRAMES;
+   }
+   else if ( h->stft_mode == SILERO_B200_STFT_EXACT && h->stft_sym )
+   {
+      const int grid = imin( h->sm_count, nchunks );
+      if ( in_f32 )
+         stft_sym_kernel<true><<<grid, SSYM_THREADS, SSYM_SMEM_BYTES, st>>>( d_in, stream_stride, nw, nchunks, h->basis_sym, spec, out_mode );
+      else
+         stft_sym_kernel<false><<<grid, SSYM_THREADS, SSYM_SMEM_BYTES, st>>>( d_in, stream_stride, nw, nchunks, h->basis_sym, spec, out_mode );
    }
    else if ( h->stft_mode == SILERO_B200_STFT_EXACT )
    {
@@ -1089,6 +1151,32 @@ static int launch_lstm_faithful_wave( silero_b200 *h, float *a4, float *h0, int 
    return 0;
 }
 
+// the encoder in the reference's rounding sequence, thread = token (exact_encoder_kernel.cuh): front (normalization scalar, depthwise
+// conv, the two K = 129 contractions) + one launch per layer
+template <int L>
+static int launch_exact_layer( silero_b200 *h, const float *in, float *out, int nchunks )
+{
+   using Cfg = XeCfg<L>;
+   const int grid = imin( ( nchunks + Cfg::GB - 1 ) / Cfg::GB, h->sm_count );
+   exact_layer_kernel<L><<<grid, XE_THREADS, Cfg::SMEM_BYTES, h->stream>>>( in, out, h->fw.t[L == 0 ? 1 : ( L == 1 ? 25 : ( L == 2 ? 49 : 71 ) )], h->xe_scratch, nchunks );
+   h->launches++;
+   CU( cudaGetLastError() );
+   return 0;
+}
+
+static int launch_exact_encoder( silero_b200 *h, const float *spec, float *a4, int nchunks )
+{
+   if ( !h->xe_scratch ) CU( cudaMalloc( &h->xe_scratch, XeCfg<3>::SCRATCH_FLOATS * sizeof( float ) * (size_t)h->sm_count ) );
+   const int grid = imin( ( nchunks + XF_G - 1 ) / XF_G, h->sm_count );
+   exact_front_kernel<<<grid, XF_THREADS, XF_SMEM_BYTES, h->stream>>>( spec, h->y1, h->fw.t[1], nchunks );
+   h->launches++;
+   CU( cudaGetLastError() );
+   if ( launch_exact_layer<0>( h, h->y1, h->a1, nchunks ) ) return SILERO_B200_ERR_CUDA;
+   if ( launch_exact_layer<1>( h, h->a1, h->a2, nchunks ) ) return SILERO_B200_ERR_CUDA;
+   if ( launch_exact_layer<2>( h, h->a2, h->a3, nchunks ) ) return SILERO_B200_ERR_CUDA;
+   return launch_exact_layer<3>( h, h->a3, a4, nchunks );
+}
+
 // one LSTM layer for any number of streams, still in the reference's rounding sequence (exact_lstm_kernel.cuh: weights in registers,
 // a CTA walks a set of streams together); hseq receives the layer's output sequence [S][nw*7][64]
 template <int LAYER>
@@ -1170,7 +1258,8 @@ static int run_window( silero_b200 *h, const void *d_in, int in_f32, long long s
    {
       // log spectrogram (bit-identical to the reference's, stft_kernel.cuh) -> encoder -> LSTM -> decoder, every step in the
       // reference's rounding sequence: 4 launches (both LSTM layers run as one wavefront)
-      if ( launch_faithful_encoder( h, h->spec, h->a4, nchunks ) ) return SILERO_B200_ERR_CUDA;
+      if ( getenv( "SILERO_B200_OLD_ENCODER" ) ? launch_faithful_encoder( h, h->spec, h->a4, nchunks ) : launch_exact_encoder( h, h->spec, h->a4, nchunks ) )
+         return SILERO_B200_ERR_CUDA;
       CU( cudaEventRecord( h->ev_spec_free, h->stream ) );
       stage_mark( h, 2 );
       stage_mark( h, 3 );
@@ -1914,6 +2003,39 @@ extern "C" int silero_b200_stage_pipeline( silero_b200 *h, const float *samples,
    if ( !rc && l4 && !( rc = down( h, tmp, d4.p, B * 448 ) ) ) tok_to_ref( tmp, batch, 7, 64, l4 );
    free( tmp );
    return rc ? SILERO_B200_ERR_CUDA : SILERO_B200_OK;
+}
+
+// the exact path's encoder from samples (exact STFT -> exact_front_kernel -> exact_layer_kernel x 4), every stage tapped in the
+// reference layout: y1 [B,16,25] = conv_block output of the first layer (conv.c:761), l1..l4 as in silero_b200_stage_pipeline
+extern "C" int silero_b200_stage_exact_pipeline( silero_b200 *h, const float *samples, int batch, float *y1, float *l1, float *l2, float *l3, float *l4 )
+{
+   if ( !h || !samples || batch <= 0 ) return set_err( SILERO_B200_ERR_ARG, "bad argument" );
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+   const size_t B = (size_t)batch;
+   DevBuf in;
+   if ( in.alloc( B * VB_CHUNK ) ) return SILERO_B200_ERR_CUDA;
+   if ( ensure_scratch( h, B, 0 ) ) return SILERO_B200_ERR_CUDA;
+   if ( up( h, in.p, samples, B * VB_CHUNK ) ) return SILERO_B200_ERR_CUDA;
+   const int saved = h->stft_mode;
+   h->stft_mode = SILERO_B200_STFT_EXACT;
+   int rc = launch_stft( h, in.p, 1, 0, batch, batch, h->spec, 0, 0 );
+   h->stft_mode = saved;
+   if ( rc ) return SILERO_B200_ERR_CUDA;
+   if ( launch_exact_encoder( h, h->spec, h->a4, batch ) ) return SILERO_B200_ERR_CUDA;
+   if ( y1 && down( h, y1, h->y1, B * 400 ) ) return SILERO_B200_ERR_CUDA;
+   if ( l1 && down( h, l1, h->a1, B * 208 ) ) return SILERO_B200_ERR_CUDA;
+   if ( l2 && down( h, l2, h->a2, B * 224 ) ) return SILERO_B200_ERR_CUDA;
+   if ( l3 && down( h, l3, h->a3, B * 224 ) ) return SILERO_B200_ERR_CUDA;
+   if ( l4 )
+   {
+      float *tmp = (float *)malloc( B * 448 * sizeof( float ) );
+      if ( !tmp ) return set_err( SILERO_B200_ERR_NOMEM, "out of host memory" );
+      rc = down( h, tmp, h->a4, B * 448 );
+      if ( !rc ) tok_to_ref( tmp, batch, 7, 64, l4 );
+      free( tmp );
+      if ( rc ) return SILERO_B200_ERR_CUDA;
+   }
+   return SILERO_B200_OK;
 }
 
 static int run_encoder_from( silero_b200 *h, int first_layer, const float *d_in, int batch, float *d1, float *d2, float *d3, float *d4 )
