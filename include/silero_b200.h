@@ -95,7 +95,8 @@ typedef struct silero_b200 silero_b200; /* opaque engine handle */
    batches either way); per chunk the encoder is ~9x slower than the tensor-core path. A fully automatic engine (stft, lstm and layer modes all AUTO) takes it
    for calls with at most SILERO_B200_FAITHFUL_MAX_STREAMS streams -- the way the reference itself is used. */
 #define SILERO_B200_LAYERS_FAITHFUL 3
-#define SILERO_B200_FAITHFUL_MAX_STREAMS 128
+#define SILERO_B200_FAITHFUL_MAX_STREAMS 128      /* (round 1: the largest batch the exact path served by default; it now serves any) */
+#define SILERO_B200_EXACT_TOKEN_MIN_CHUNKS 1024   /* exact path: windows of at least this many chunks run the thread-per-token encoder */
 
 typedef struct silero_b200_opts
 {
@@ -226,6 +227,15 @@ int silero_b200_stage_pipeline( silero_b200 *h, const float *samples, int batch,
 /* the same taps on the exact path's kernels (exact STFT -> exact_front_kernel -> exact_layer_kernel x 4, the reference's rounding
    sequence): y1 [B,16,25] = conv_block output of the first layer (conv.c:761-814), l1..l4 as above */
 int silero_b200_stage_exact_pipeline( silero_b200 *h, const float *samples, int batch, float *y1, float *l1, float *l2, float *l3, float *l4 );
+/* one transformer_layer on the exact path's kernels, layouts as silero_b200_stage_layer; layer 0 takes the NORMALIZED spectrogram and
+   can also return its conv_block output y1 [B,16,25] (may be NULL) */
+int silero_b200_stage_exact_layer( silero_b200 *h, int layer, const float *in, int batch, float *out, float *y1 );
+/* encoder on the exact path's kernels from a spectrogram [B,129,25]; kind 0: log1p spectrogram (normalized inside, as in production),
+   1: already normalized, 2: raw magnitude (log1p(m * 2^20) applied first, misc.c:40-46) */
+int silero_b200_stage_exact_encoder( silero_b200 *h, const float *spec, int batch, int kind, float *l1, float *l2, float *l3, float *l4 );
+/* lstm_tensor_minibatched on the exact path's kernels, arguments as silero_b200_stage_lstm; wave 0: the multi-stream kernel
+   (exact_lstm_kernel.cuh), 1: the wavefront kernel that serves few streams (faithful_lstm_wave_kernel) -- identical bits */
+int silero_b200_stage_exact_lstm( silero_b200 *h, const float *x, int batch, const float *h0, const float *c0, float *out, float *hn, float *cn, int wave );
 /* adaptive_audio_normalization_inplace on a caller-supplied magnitude spectrogram [B,129,25] */
 int silero_b200_stage_norm( silero_b200 *h, const float *magnitude, int batch, float *norm_out );
 /* encoder (silero_v3.c:4-64) from a normalized spectrogram, every layer's output tapped */

@@ -88,28 +88,29 @@ def test_run_chunks_is_bit_identical_to_backend_run():
     assert np.array_equal(bits(got), bits(want))
 
 
-def test_on_request_for_large_batches_and_not_taken_otherwise():
-    """LAYERS_FAITHFUL / LSTM_FAITHFUL select the path for any batch; above the automatic limit the default engine runs the fast
-    kernels (1e-4 bar), and an engine with an explicit kernel family never takes the faithful path."""
-    S, N = vadc_b200.FAITHFUL_MAX_STREAMS + 2, 12
+def test_default_for_any_batch_and_not_taken_by_an_explicit_fast_family():
+    """The kernel family is a property of the engine, fixed at creation: a default engine runs the exact path for ANY number of streams
+    (bit-identical whatever the batch composition); an engine created with an explicit fast mode never does (1e-4 bar)."""
+    S, N = 130, 12
     pcm = np.stack([vadc_b200.synth_pcm(3000 + s, N * 1536) for s in range(S)])
     ref = np.stack([oracle_out2(pcm[s]) for s in range(S)])
-    e = vadc_b200.Engine(max_streams=S, layer_mode=vadc_b200.LAYERS_FAITHFUL)
-    out2 = e.run_streams(pcm, want_out2=True)[1]
-    windows, rem = divmod(e.last_timing()[1], 4)                 # 4 kernels per window on the faithful path
-    e.close()
-    assert rem == 0 and windows >= 1
-    assert np.array_equal(bits(out2), bits(ref))
-    e = vadc_b200.Engine(max_streams=S)
-    fast = e.run_streams(pcm, want_out2=True)[1]
-    launches = e.last_timing()[1]
-    e.close()
-    assert launches == 7 * windows and np.abs(fast - ref).max() <= 1e-4      # 7 kernels per window on the fast paths
+    for kw in ({}, {"layer_mode": vadc_b200.LAYERS_FAITHFUL}):
+        e = vadc_b200.Engine(max_streams=S, **kw)
+        out2 = e.run_streams(pcm, want_out2=True)[1]
+        # the same streams again in other batch shapes: 4 at a time, then one by one -- same engine, same bits
+        e.reset()
+        few = np.concatenate([e.run_streams(pcm[i:i + 4], want_out2=True, first_stream=i)[1] for i in range(0, 8, 4)])
+        e.reset()
+        one = e.run_streams(pcm[5:6], want_out2=True, first_stream=5)[1]
+        e.close()
+        assert np.array_equal(bits(out2), bits(ref))
+        assert np.array_equal(bits(few), bits(ref[:8])) and np.array_equal(bits(one), bits(ref[5:6]))
     e = vadc_b200.Engine(max_streams=S, lstm_mode=vadc_b200.LSTM_FP32)
-    few = e.run_streams(pcm[:4], want_out2=True)[1]
+    fast = e.run_streams(pcm[:4], want_out2=True)[1]
     launches = e.last_timing()[1]
     e.close()
-    assert launches % 7 == 0 and np.abs(few - ref[:4]).max() <= 1e-4            # 7 kernels per window: not the faithful path
+    assert launches % 7 == 0 and np.abs(fast - ref[:4]).max() <= 1e-4            # 7 kernels per window: the fast family
+    assert not np.array_equal(bits(fast), bits(ref[:4]))
 
 
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not present")

@@ -76,9 +76,10 @@ def test_stft_bit_exact_on_edge_signals(engine_exact, oracle):
     assert np.abs(norm - st["norm"]).max() < 5e-6
 
 
-def test_hybrid_stft_on_edge_signals(engine, oracle):
-    """Hybrid mode: bins below the threshold are bit-identical to the reference (exact tree), the
+def test_hybrid_stft_on_edge_signals(oracle):
+    """Hybrid mode (opt-in fast family): bins below the threshold are bit-identical to the reference (exact tree), the
     others within HYB_REL; degenerate signals push most bins onto the exact path."""
+    engine = vadc_b200.Engine(max_streams=64, stft_mode=vadc_b200.STFT_HYBRID)
     x = _edge_signals()
     oracle.reset()
     st = oracle.run_stages(x)
@@ -91,11 +92,12 @@ def test_hybrid_stft_on_edge_signals(engine, oracle):
     assert np.abs(norm - st["norm"]).max() < 2 * HYB_REL
     engine.reset()
     assert np.abs(engine.run_chunks(x) - st["out"]).max() <= PTOL
+    engine.close()
 
 
 def test_hybrid_exact_path_alone_is_bit_exact(oracle):
     """k_rel = huge sends every bin through the warp-cooperative exact tree of the hybrid kernel."""
-    e = vadc_b200.Engine(stft_k_rel=1e30)
+    e = vadc_b200.Engine(stft_mode=vadc_b200.STFT_HYBRID, stft_k_rel=1e30)
     x = np.concatenate([_edge_signals(), f32(vadc_b200.synth_pcm(8, 1536 * 8))])
     oracle.reset()
     assert np.array_equal(e.stage_stft_magnitude(x), oracle.run_stages(x)["stft"])

@@ -310,6 +310,31 @@ class Engine:
         self._check(lib().silero_b200_stage_exact_pipeline(self._h, _p(x), B, *[_p(o) for o in outs]))
         return outs
 
+    def stage_exact_layer(self, layer, x, want_y1=False):
+        cin, c, t, stride = ((129, 16, 25, 2), (16, 32, 13, 2), (32, 32, 7, 1), (32, 64, 7, 1))[layer]
+        x = _f32(x).reshape(-1, cin, t)
+        B = x.shape[0]
+        out = np.zeros((B, c, 1 + (t - 1) // stride), np.float32)
+        y1 = np.zeros((B, 16, 25), np.float32) if (want_y1 and layer == 0) else None
+        self._check(lib().silero_b200_stage_exact_layer(self._h, layer, _p(x), B, _p(out), _p(y1)))
+        return (out, y1) if want_y1 else out
+
+    def stage_exact_encoder(self, spec, kind=0):
+        x = _f32(spec).reshape(-1, 129, 25)
+        B = x.shape[0]
+        outs = [np.zeros(s, np.float32) for s in ((B, 16, 13), (B, 32, 7), (B, 32, 7), (B, 64, 7))]
+        self._check(lib().silero_b200_stage_exact_encoder(self._h, _p(x), B, kind, *[_p(o) for o in outs]))
+        return outs
+
+    def stage_exact_lstm(self, x, h0=None, c0=None, wave=False):
+        x = _f32(x).reshape(-1, 7, 64)
+        B = x.shape[0]
+        out, hn, cn = np.zeros((B, 7, 64), np.float32), np.zeros((2, 64), np.float32), np.zeros((2, 64), np.float32)
+        h0 = _f32(h0).reshape(2, 64) if h0 is not None else None
+        c0 = _f32(c0).reshape(2, 64) if c0 is not None else None
+        self._check(lib().silero_b200_stage_exact_lstm(self._h, _p(x), B, _p(h0), _p(c0), _p(out), _p(hn), _p(cn), int(wave)))
+        return out, hn, cn
+
     def stage_layer(self, layer, x):
         cin, c, t, stride = ((129, 16, 25, 2), (16, 32, 13, 2), (32, 32, 7, 1), (32, 64, 7, 1))[layer]
         x = _f32(x).reshape(-1, cin, t)

@@ -463,7 +463,8 @@ static int configure_kernels()
    CU( allow_smem( faithful_lstm_kernel<1>, FLSTM_SMEM_BYTES ) );
    CU( allow_smem( faithful_lstm_wave_kernel, FLSTM_SMEM_BYTES ) );
    CU( allow_smem( faithful_encoder_kernel, FAITHFUL_SMEM_BYTES ) );
-   CU( allow_smem( exact_front_kernel, XF_SMEM_BYTES ) );
+   CU( allow_smem( exact_front_kernel<true>, XF_SMEM_BYTES ) );
+   CU( allow_smem( exact_front_kernel<false>, XF_SMEM_BYTES ) );
    CU( allow_smem( exact_layer_kernel<0>, XeCfg<0>::SMEM_BYTES ) );
    CU( allow_smem( exact_layer_kernel<1>, XeCfg<1>::SMEM_BYTES ) );
    CU( allow_smem( exact_layer_kernel<2>, XeCfg<2>::SMEM_BYTES ) );
@@ -595,10 +596,28 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    h->stft_k_rel = opts.stft_k_rel > 0.0f ? opts.stft_k_rel : SILERO_B200_STFT_K_REL_DEFAULT;
    h->lstm_mode = ( opts.lstm_mode == SILERO_B200_LSTM_FP32 || opts.lstm_mode == SILERO_B200_LSTM_TENSOR ) ? opts.lstm_mode : SILERO_B200_LSTM_AUTO;
    h->layer_mode = ( opts.layer_mode == SILERO_B200_LAYERS_FP32 || opts.layer_mode == SILERO_B200_LAYERS_TENSOR ) ? opts.layer_mode : SILERO_B200_LAYERS_AUTO;
-   // the reference's own rounding sequence from the STFT to the probability (faithful_kernel.cuh): on request for any batch, and by
-   // default for the small stream batches of a fully automatic engine
-   h->faithful = ( opts.layer_mode == SILERO_B200_LAYERS_FAITHFUL || opts.lstm_mode == SILERO_B200_LSTM_FAITHFUL ) ? 2
-               : ( h->stft_auto && h->lstm_mode == SILERO_B200_LSTM_AUTO && h->layer_mode == SILERO_B200_LAYERS_AUTO ) ? 1 : 0;
+   // The kernel family is decided HERE, once per engine, never per call: a persistent stream must not change arithmetic when the
+   // caller's batch shape changes (a stream's LSTM state integrates one-ulp differences over minutes).
+   //   * every mode AUTO (the default), or FAITHFUL requested: the exact path -- the reference's own rounding sequence from the STFT to
+   //     the probability (stft_sym_kernel / exact_encoder_kernel / exact_lstm_kernel, faithful_lstm_wave_kernel for few streams), for
+   //     ANY number of streams; results are bit-identical to the reference whatever the batch composition;
+   //   * any explicit fast mode (STFT_HYBRID*, LSTM_FP32/TENSOR, LAYERS_FP32/TENSOR): the fast family (1e-4 per chunk, drifts on long
+   //     streams: DESIGN.md section 2); its remaining AUTO members are resolved from max_streams, also once.
+   const bool all_auto = h->stft_auto && h->lstm_mode == SILERO_B200_LSTM_AUTO && h->layer_mode == SILERO_B200_LAYERS_AUTO;
+   h->faithful = ( opts.layer_mode == SILERO_B200_LAYERS_FAITHFUL || opts.lstm_mode == SILERO_B200_LSTM_FAITHFUL || all_auto ) ? 2 : 0;
+   if ( h->faithful )
+   {
+      h->stft_mode = SILERO_B200_STFT_EXACT;
+      h->stft_auto = 0;
+   }
+   else
+   {
+      const bool big = h->max_streams >= SILERO_B200_LSTM_TENSOR_MIN_STREAMS;
+      if ( h->lstm_mode == SILERO_B200_LSTM_AUTO ) h->lstm_mode = big ? SILERO_B200_LSTM_TENSOR : SILERO_B200_LSTM_FP32;
+      if ( h->layer_mode == SILERO_B200_LAYERS_AUTO ) h->layer_mode = big ? SILERO_B200_LAYERS_TENSOR : SILERO_B200_LAYERS_FP32;
+      if ( h->stft_auto && h->lstm_mode != SILERO_B200_LSTM_TENSOR ) h->stft_mode = SILERO_B200_STFT_EXACT;
+      h->stft_auto = 0;
+   }
 
 #define CU_H( call )                                                                                   \
    do                                                                                                  \
@@ -1048,9 +1067,8 @@ static int launch_layer0_tc( silero_b200 *h, const float *in, float *out, int nc
 
 static bool layers_use_tensor( const silero_b200 *h, int nchunks )
 {
-   if ( h->layer_mode == SILERO_B200_LAYERS_TENSOR ) return true;
-   if ( h->layer_mode == SILERO_B200_LAYERS_FP32 ) return false;
-   return nchunks >= SILERO_B200_LAYERS_TENSOR_MIN_CHUNKS;
+   (void)nchunks; // decided once per engine (create_impl), not per call
+   return h->layer_mode == SILERO_B200_LAYERS_TENSOR;
 }
 
 // layers 2..4 of the encoder on whichever kernel family the engine is configured for
@@ -1086,9 +1104,8 @@ static int launch_lstm( silero_b200 *h, const float *x, float *hseq, int first_s
 
 static bool lstm_use_tensor( const silero_b200 *h, int nstreams )
 {
-   if ( h->lstm_mode == SILERO_B200_LSTM_TENSOR ) return true;
-   if ( h->lstm_mode == SILERO_B200_LSTM_FP32 ) return false;
-   return nstreams >= SILERO_B200_LSTM_TENSOR_MIN_STREAMS;
+   (void)nstreams; // decided once per engine (create_impl), not per call
+   return h->lstm_mode == SILERO_B200_LSTM_TENSOR;
 }
 
 // tensor-core LSTM (lstm_tc_kernel.cuh): layer 0 consumes a4 and leaves its packed h sequence in h->h0
@@ -1111,7 +1128,8 @@ static int launch_lstm_tc( silero_b200 *h, const float *a4, int first_stream, in
 // the whole path in the reference's rounding sequence (faithful_kernel.cuh)
 static bool use_faithful( const silero_b200 *h, int nstreams )
 {
-   return h->faithful == 2 || ( h->faithful == 1 && nstreams <= SILERO_B200_FAITHFUL_MAX_STREAMS );
+   (void)nstreams; // decided once per engine (create_impl), not per call
+   return h->faithful != 0;
 }
 
 static int launch_faithful_encoder( silero_b200 *h, const float *spec, float *a4, int nchunks )
@@ -1164,13 +1182,22 @@ static int launch_exact_layer( silero_b200 *h, const float *in, float *out, int 
    return 0;
 }
 
-static int launch_exact_encoder( silero_b200 *h, const float *spec, float *a4, int nchunks )
+static int launch_exact_front( silero_b200 *h, const float *spec, float *y1, int nchunks, bool normalize = true )
 {
    if ( !h->xe_scratch ) CU( cudaMalloc( &h->xe_scratch, XeCfg<3>::SCRATCH_FLOATS * sizeof( float ) * (size_t)h->sm_count ) );
    const int grid = imin( ( nchunks + XF_G - 1 ) / XF_G, h->sm_count );
-   exact_front_kernel<<<grid, XF_THREADS, XF_SMEM_BYTES, h->stream>>>( spec, h->y1, h->fw.t[1], nchunks );
+   if ( normalize )
+      exact_front_kernel<true><<<grid, XF_THREADS, XF_SMEM_BYTES, h->stream>>>( spec, y1, h->fw.t[1], nchunks );
+   else
+      exact_front_kernel<false><<<grid, XF_THREADS, XF_SMEM_BYTES, h->stream>>>( spec, y1, h->fw.t[1], nchunks );
    h->launches++;
    CU( cudaGetLastError() );
+   return 0;
+}
+
+static int launch_exact_encoder( silero_b200 *h, const float *spec, float *a4, int nchunks, bool normalize = true )
+{
+   if ( launch_exact_front( h, spec, h->y1, nchunks, normalize ) ) return SILERO_B200_ERR_CUDA;
    if ( launch_exact_layer<0>( h, h->y1, h->a1, nchunks ) ) return SILERO_B200_ERR_CUDA;
    if ( launch_exact_layer<1>( h, h->a1, h->a2, nchunks ) ) return SILERO_B200_ERR_CUDA;
    if ( launch_exact_layer<2>( h, h->a2, h->a3, nchunks ) ) return SILERO_B200_ERR_CUDA;
@@ -1219,20 +1246,8 @@ static int run_window( silero_b200 *h, const void *d_in, int in_f32, long long s
    const int nchunks = nstreams * nw;
    const size_t h0_floats = (size_t)( ( nstreams + LTC_N - 1 ) / LTC_N ) * LTC_N * nw * 7 * 64;
    if ( ensure_scratch( h, (size_t)nchunks, h0_floats ) ) return SILERO_B200_ERR_CUDA;
-   // SILERO_B200_STFT_AUTO: stream batches below the tensor-core threshold take the fp32 kernels, and with them the exact STFT
-   // kernel (every magnitude and, through libm_exact.cuh, every log1p bit-identical to the reference, the normalization scalar in
-   // the reference's own order). The network amplifies ONE ulp of that scalar into up to 3e-3 of speech probability at the next
-   // speech onset of a long stream (measured on the CPU restatement), and no FFT can promise its last bit; the exact kernel costs
-   // 7x the STFT time, which only matters where thousands of streams share the GPU -- and there the FFT hybrid runs.
-   struct ModeGuard
-   {
-      silero_b200 *h;
-      int saved;
-      ~ModeGuard() { h->stft_mode = saved; }
-   } guard = { h, h->stft_mode };
-   if ( h->stft_auto && !lstm_use_tensor( h, nstreams ) ) h->stft_mode = SILERO_B200_STFT_EXACT;
+   // (which kernels run is a property of the engine, fixed at creation: create_impl)
    const bool faithful = use_faithful( h, nstreams );
-   if ( faithful ) h->stft_mode = SILERO_B200_STFT_EXACT;
    stage_mark( h, 0 );
    const bool have_mu = stft_produces_mu( h, nchunks );
    // (an input that was produced by earlier work on h->stream itself, like run_chunks' own upload, keeps the STFT on that stream)
@@ -1258,7 +1273,9 @@ static int run_window( silero_b200 *h, const void *d_in, int in_f32, long long s
    {
       // log spectrogram (bit-identical to the reference's, stft_kernel.cuh) -> encoder -> LSTM -> decoder, every step in the
       // reference's rounding sequence: 4 launches (both LSTM layers run as one wavefront)
-      if ( getenv( "SILERO_B200_OLD_ENCODER" ) ? launch_faithful_encoder( h, h->spec, h->a4, nchunks ) : launch_exact_encoder( h, h->spec, h->a4, nchunks ) )
+      // two mappings of the same arithmetic (identical bits): a CTA per chunk for small windows (more parallelism: latency), a thread
+      // per token from SILERO_B200_EXACT_TOKEN_MIN_CHUNKS chunks up (no partial warps, one barrier per layer: throughput)
+      if ( nchunks < SILERO_B200_EXACT_TOKEN_MIN_CHUNKS ? launch_faithful_encoder( h, h->spec, h->a4, nchunks ) : launch_exact_encoder( h, h->spec, h->a4, nchunks ) )
          return SILERO_B200_ERR_CUDA;
       CU( cudaEventRecord( h->ev_spec_free, h->stream ) );
       stage_mark( h, 2 );
@@ -1887,6 +1904,7 @@ static void ref_to_tok( const float *ref, int B, int C, int T, float *tok )
 }
 
 __global__ void subtract_chunk_mean_kernel( const float *__restrict__ logmag, float *__restrict__ out, int nchunks );
+__global__ void log1p_scale_kernel( const float *__restrict__ mag, float *__restrict__ out, size_t n );
 
 extern "C" int silero_b200_stage_stft_norm( silero_b200 *h, const float *samples, int batch, float *norm_out, float *logmag_out )
 {
@@ -2038,6 +2056,76 @@ extern "C" int silero_b200_stage_exact_pipeline( silero_b200 *h, const float *sa
    return SILERO_B200_OK;
 }
 
+// one transformer_layer on the exact path's kernels; layer 0 takes the NORMALIZED spectrogram [B,129,25] (exact_front_kernel without
+// its normalization + exact_layer_kernel<0>), y1 (optional) its conv_block output [B,16,25]; layouts as silero_b200_stage_layer
+extern "C" int silero_b200_stage_exact_layer( silero_b200 *h, int layer, const float *in, int batch, float *out, float *y1 )
+{
+   if ( !h || !in || batch <= 0 || layer < 0 || layer > 3 ) return set_err( SILERO_B200_ERR_ARG, "bad argument" );
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+   const size_t B = (size_t)batch;
+   const LayerDims d = layer_dims( layer );
+   const size_t n_in = B * d.cin * d.t, n_out = B * d.c * ( 1 + ( d.t - 1 ) / d.stride );
+   DevBuf din, dy, dout;
+   if ( din.alloc( n_in ) || dy.alloc( B * 400 ) || dout.alloc( n_out ) ) return SILERO_B200_ERR_CUDA;
+   if ( up( h, din.p, in, n_in ) ) return SILERO_B200_ERR_CUDA;
+   if ( !h->xe_scratch ) CU( cudaMalloc( &h->xe_scratch, XeCfg<3>::SCRATCH_FLOATS * sizeof( float ) * (size_t)h->sm_count ) );
+   int rc = 0;
+   if ( layer == 0 )
+   {
+      rc = launch_exact_front( h, din.p, dy.p, batch, false );
+      if ( !rc ) rc = launch_exact_layer<0>( h, dy.p, dout.p, batch );
+   }
+   else if ( layer == 1 ) rc = launch_exact_layer<1>( h, din.p, dout.p, batch );
+   else if ( layer == 2 ) rc = launch_exact_layer<2>( h, din.p, dout.p, batch );
+   else rc = launch_exact_layer<3>( h, din.p, dout.p, batch );
+   if ( rc ) return SILERO_B200_ERR_CUDA;
+   if ( y1 && layer == 0 && down( h, y1, dy.p, B * 400 ) ) return SILERO_B200_ERR_CUDA;
+   if ( out )
+   {
+      if ( layer < 3 ) { if ( down( h, out, dout.p, n_out ) ) return SILERO_B200_ERR_CUDA; }
+      else
+      {
+         float *tmp = (float *)malloc( n_out * sizeof( float ) );
+         if ( !tmp ) return set_err( SILERO_B200_ERR_NOMEM, "out of host memory" );
+         rc = down( h, tmp, dout.p, n_out );
+         if ( !rc ) tok_to_ref( tmp, batch, 7, 64, out );
+         free( tmp );
+         if ( rc ) return SILERO_B200_ERR_CUDA;
+      }
+   }
+   return SILERO_B200_OK;
+}
+
+// the exact path's encoder from a spectrogram [B,129,25]; kind 0: log1p spectrogram (the front kernel normalizes, as in production),
+// 1: already normalized, 2: raw magnitude (log1p(m * 2^20) is applied first, misc.c:40-46)
+extern "C" int silero_b200_stage_exact_encoder( silero_b200 *h, const float *spec, int batch, int kind, float *l1, float *l2, float *l3, float *l4 )
+{
+   if ( !h || !spec || batch <= 0 || kind < 0 || kind > 2 ) return set_err( SILERO_B200_ERR_ARG, "bad argument" );
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+   const size_t B = (size_t)batch;
+   if ( ensure_scratch( h, B, 0 ) ) return SILERO_B200_ERR_CUDA;
+   if ( up( h, h->spec, spec, B * 3225 ) ) return SILERO_B200_ERR_CUDA;
+   if ( kind == 2 )
+   {
+      log1p_scale_kernel<<<(unsigned)( ( B * 3225 + 255 ) / 256 ), 256, 0, h->stream>>>( h->spec, h->spec, B * 3225 );
+      CU( cudaGetLastError() );
+   }
+   if ( launch_exact_encoder( h, h->spec, h->a4, batch, kind != 1 ) ) return SILERO_B200_ERR_CUDA;
+   if ( l1 && down( h, l1, h->a1, B * 208 ) ) return SILERO_B200_ERR_CUDA;
+   if ( l2 && down( h, l2, h->a2, B * 224 ) ) return SILERO_B200_ERR_CUDA;
+   if ( l3 && down( h, l3, h->a3, B * 224 ) ) return SILERO_B200_ERR_CUDA;
+   if ( l4 )
+   {
+      float *tmp = (float *)malloc( B * 448 * sizeof( float ) );
+      if ( !tmp ) return set_err( SILERO_B200_ERR_NOMEM, "out of host memory" );
+      const int rc = down( h, tmp, h->a4, B * 448 );
+      if ( !rc ) tok_to_ref( tmp, batch, 7, 64, l4 );
+      free( tmp );
+      if ( rc ) return SILERO_B200_ERR_CUDA;
+   }
+   return SILERO_B200_OK;
+}
+
 static int run_encoder_from( silero_b200 *h, int first_layer, const float *d_in, int batch, float *d1, float *d2, float *d3, float *d4 )
 {
    if ( first_layer <= 0 && ( layers_use_tensor( h, batch ) ? launch_layer0_tc( h, d_in, d1, batch, 0 ) : launch_layer<0, false>( h, d_in, d1, batch ) ) )
@@ -2165,6 +2253,42 @@ extern "C" int silero_b200_stage_lstm( silero_b200 *h, const float *x, int batch
    h->state_c = sc.p;
    int rc = launch_lstm<0>( h, dx.p, dh0.p, 0, 1, batch, 0, 0, 0, 0 );
    if ( !rc ) rc = launch_lstm<1>( h, dh0.p, dtop.p, 0, 1, batch, 0, 0, 0, 0 );
+   h->state_h = save_h;
+   h->state_c = save_c;
+   if ( rc ) return rc;
+   if ( out && down( h, out, dtop.p, n ) ) return SILERO_B200_ERR_CUDA;
+   if ( hn && down( h, hn, sh.p, 128 ) ) return SILERO_B200_ERR_CUDA;
+   if ( cn && down( h, cn, sc.p, 128 ) ) return SILERO_B200_ERR_CUDA;
+   CU( cudaStreamSynchronize( h->stream ) );
+   return SILERO_B200_OK;
+}
+
+// the same on the exact path's kernel (exact_lstm_kernel: weights in registers; here one stream)
+extern "C" int silero_b200_stage_exact_lstm( silero_b200 *h, const float *x, int batch, const float *h0, const float *c0, float *out, float *hn, float *cn, int wave )
+{
+   if ( !h || !x || batch <= 0 ) return set_err( SILERO_B200_ERR_ARG, "bad argument" );
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+   const size_t n = (size_t)batch * 7 * 64;
+   DevBuf dx, dh0, dtop, sh, sc;
+   if ( dx.alloc( n ) || dh0.alloc( n ) || dtop.alloc( n ) || sh.alloc( 128 ) || sc.alloc( 128 ) ) return SILERO_B200_ERR_CUDA;
+   if ( up( h, dx.p, x, n ) ) return SILERO_B200_ERR_CUDA;
+   if ( h0 ) { if ( up( h, sh.p, h0, 128 ) ) return SILERO_B200_ERR_CUDA; } else CU( cudaMemsetAsync( sh.p, 0, 512, h->stream ) );
+   if ( c0 ) { if ( up( h, sc.p, c0, 128 ) ) return SILERO_B200_ERR_CUDA; } else CU( cudaMemsetAsync( sc.p, 0, 512, h->stream ) );
+   float *save_h = h->state_h, *save_c = h->state_c;
+   h->state_h = sh.p;
+   h->state_c = sc.p;
+   int rc;
+   if ( wave )
+   {
+      // the wavefront kernel works in place: the input buffer receives the top layer's sequence
+      rc = launch_lstm_faithful_wave( h, dx.p, dh0.p, 0, 1, batch );
+      if ( !rc ) rc = cudaMemcpyAsync( dtop.p, dx.p, n * sizeof( float ), cudaMemcpyDeviceToDevice, h->stream ) == cudaSuccess ? 0 : SILERO_B200_ERR_CUDA;
+   }
+   else
+   {
+      rc = launch_lstm_exact<0>( h, dx.p, dh0.p, 0, 1, batch );
+      if ( !rc ) rc = launch_lstm_exact<1>( h, dh0.p, dtop.p, 0, 1, batch );
+   }
    h->state_h = save_h;
    h->state_c = save_c;
    if ( rc ) return rc;

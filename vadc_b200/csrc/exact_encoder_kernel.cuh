@@ -206,7 +206,9 @@ __device__ __forceinline__ void layer_norm_r( float ( &x )[C], const float *__re
 __host__ __device__ constexpr int al4c( int x ) { return ( x + 3 ) & ~3; }
 #define XF_SMEM_BYTES ( XF_SMEM_FLOATS * 4 )
 
-// spec: [nchunks][129][25] log1p spectrogram; y1: [nchunks][16][25] conv_block output of the first layer; wl: the first layer's tensors
+// spec: [nchunks][129][25] log1p spectrogram (NORM: the normalization scalar is computed and subtracted here; !NORM: the input is
+// already normalized -- parity taps); y1: [nchunks][16][25] conv_block output of the first layer; wl: the first layer's tensors
+template <bool NORM>
 __global__ void __launch_bounds__( XF_THREADS, 1 ) exact_front_kernel( const float *__restrict__ spec, float *__restrict__ y1, const float *__restrict__ wl, int nchunks )
 {
    constexpr xe::LayerOff O = xe::layer_off( 0 );
@@ -247,6 +249,8 @@ __global__ void __launch_bounds__( XF_THREADS, 1 ) exact_front_kernel( const flo
          for ( int i = tid; i < n; i += XF_THREADS ) Xs[i] = __ldg( src + i );
       }
       __syncthreads();
+      if ( NORM )
+      {
       // misc.c:48-62: per-frame mean over the bins, sequential sum, division
       if ( fq == 0 && tok && g < ng )
       {
@@ -285,6 +289,7 @@ __global__ void __launch_bounds__( XF_THREADS, 1 ) exact_front_kernel( const flo
          for ( int i = tid; i < n; i += XF_THREADS ) Xs[i] = xe::sub( Xs[i], MU[i / ( VB_BINS * VB_FRAMES )] );
       }
       __syncthreads();
+      }
       // depthwise k = 5, zero pad 2 (conv.c:17-53, 60-113): the taps that exist, left to right from 0, then bias + sum; ReLU
       {
          const int n = ng * VB_BINS * VB_FRAMES;
