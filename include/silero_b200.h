@@ -212,6 +212,9 @@ int silero_b200_timer_stop( silero_b200 *h, float *ms );
 /* FP32 FMA-pipe throughput this device sustains (TFLOP/s, independent FFMA chains): the roofline
    denominator for the CUDA-core kernels of this engine */
 int silero_b200_measure_fp32_peak( silero_b200 *h, float *tflops );
+/* the same with separately rounded multiplies and adds (independent FMUL -> FADD chains, one FLOP per instruction): the roofline
+   denominator of the exact path, whose arithmetic may not be contracted into FMAs */
+int silero_b200_measure_fp32_unfused_peak( silero_b200 *h, float *tflops );
 
 /* ---- parity taps (the reference's per-stage functions; host pointers; stateless unless noted) -
    Layouts are the reference's: spectrogram [B,129,25]; layer outputs [B,16,13] [B,32,7] [B,32,7]

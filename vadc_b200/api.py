@@ -270,6 +270,11 @@ class Engine:
         return float(tf.value)
 
     # ---- parity taps ----------------------------------------------------------------------------
+    def measure_fp32_unfused_peak(self):
+        v = C.c_float()
+        self._check(lib().silero_b200_measure_fp32_unfused_peak(self._h, C.byref(v)))
+        return float(v.value)
+
     def stage_stft_magnitude(self, samples):
         x = _f32(samples).reshape(-1, CHUNK)
         out = np.zeros((x.shape[0], 129, 25), np.float32)
@@ -441,7 +446,18 @@ class StreamSegmenter:
         return buf.raw[:n].decode()
 
 
+_synth = None
+
+
 def synth_pcm(seed, nsamples, kind=0):
+    """Deterministic synthetic s16le test audio (csrc/synth.c). Host C in its own small library: generating input never loads the
+    CUDA engine (bench.py's CPU reference arm depends on that)."""
+    global _synth
+    if _synth is None:
+        path = os.path.join(_HERE, "libvadc_synth.so")
+        if not os.path.exists(path):
+            raise EngineError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`" % path)
+        _synth = C.CDLL(path)
     out = np.zeros(nsamples, np.int16)
-    lib().vadc_synth_pcm(C.c_ulonglong(seed), kind, C.c_longlong(nsamples), _p(out))
+    _synth.vadc_synth_pcm(C.c_ulonglong(seed), kind, C.c_longlong(nsamples), _p(out))
     return out

@@ -1271,26 +1271,46 @@ static int run_window( silero_b200 *h, const void *d_in, int in_f32, long long s
    stage_mark( h, 1 );
    if ( faithful )
    {
-      // log spectrogram (bit-identical to the reference's, stft_kernel.cuh) -> encoder -> LSTM -> decoder, every step in the
-      // reference's rounding sequence: 4 launches (both LSTM layers run as one wavefront)
-      // two mappings of the same arithmetic (identical bits): a CTA per chunk for small windows (more parallelism: latency), a thread
-      // per token from SILERO_B200_EXACT_TOKEN_MIN_CHUNKS chunks up (no partial warps, one barrier per layer: throughput)
-      if ( nchunks < SILERO_B200_EXACT_TOKEN_MIN_CHUNKS ? launch_faithful_encoder( h, h->spec, h->a4, nchunks ) : launch_exact_encoder( h, h->spec, h->a4, nchunks ) )
-         return SILERO_B200_ERR_CUDA;
-      CU( cudaEventRecord( h->ev_spec_free, h->stream ) );
-      stage_mark( h, 2 );
-      stage_mark( h, 3 );
-      stage_mark( h, 4 );
-      stage_mark( h, 5 );
+      // log spectrogram (bit-identical to the reference's) -> encoder -> LSTM -> decoder, every step in the reference's rounding
+      // sequence. Two mappings of the same arithmetic per stage, chosen per window by its shape (identical bits, so the choice is
+      // free): the encoder as a CTA per chunk for small windows (more parallelism: latency) or a thread per token from
+      // SILERO_B200_EXACT_TOKEN_MIN_CHUNKS chunks up (no partial warps, one barrier per layer: throughput); the LSTM as a wavefront
+      // of (stream, layer) CTAs while there are SM pairs for every stream, else CTAs that walk sets of streams together.
+      // Stage times (profiling): [2] front + rest of layer 1, [3..5] layers 2..4, [6] LSTM layer 0, [7] LSTM layer 1 + decoder head
+      // (small windows: [2] the whole encoder, [6] both LSTM layers).
+      if ( nchunks < SILERO_B200_EXACT_TOKEN_MIN_CHUNKS )
+      {
+         if ( launch_faithful_encoder( h, h->spec, h->a4, nchunks ) ) return SILERO_B200_ERR_CUDA;
+         CU( cudaEventRecord( h->ev_spec_free, h->stream ) );
+         stage_mark( h, 2 );
+         stage_mark( h, 3 );
+         stage_mark( h, 4 );
+         stage_mark( h, 5 );
+      }
+      else
+      {
+         if ( launch_exact_front( h, h->spec, h->y1, nchunks ) ) return SILERO_B200_ERR_CUDA;
+         CU( cudaEventRecord( h->ev_spec_free, h->stream ) );
+         if ( launch_exact_layer<0>( h, h->y1, h->a1, nchunks ) ) return SILERO_B200_ERR_CUDA;
+         stage_mark( h, 2 );
+         if ( launch_exact_layer<1>( h, h->a1, h->a2, nchunks ) ) return SILERO_B200_ERR_CUDA;
+         stage_mark( h, 3 );
+         if ( launch_exact_layer<2>( h, h->a2, h->a3, nchunks ) ) return SILERO_B200_ERR_CUDA;
+         stage_mark( h, 4 );
+         if ( launch_exact_layer<3>( h, h->a3, h->a4, nchunks ) ) return SILERO_B200_ERR_CUDA;
+         stage_mark( h, 5 );
+      }
       if ( nstreams > h->sm_count / 2 )
       {
-         // more streams than the wavefront has SM pairs for: CTAs walk sets of streams together (same bits)
          if ( launch_lstm_exact<0>( h, h->a4, h->h0, first_stream, nstreams, nw ) ) return SILERO_B200_ERR_CUDA;
+         stage_mark( h, 6 );
          if ( launch_lstm_exact<1>( h, h->h0, h->a4, first_stream, nstreams, nw ) ) return SILERO_B200_ERR_CUDA;
       }
-      else if ( launch_lstm_faithful_wave( h, h->a4, h->h0, first_stream, nstreams, nw ) )
-         return SILERO_B200_ERR_CUDA;
-      stage_mark( h, 6 );
+      else
+      {
+         if ( launch_lstm_faithful_wave( h, h->a4, h->h0, first_stream, nstreams, nw ) ) return SILERO_B200_ERR_CUDA;
+         stage_mark( h, 6 );
+      }
       {
          const long long n = (long long)nchunks * 2;
          faithful_decoder_kernel<<<(unsigned)( ( n + 127 ) / 128 ), 128, 0, h->stream>>>( h->a4, h->w.dec_w, h->w.dec_b, nstreams, nw, d_out2, d_probs, out_stride, out_off );
@@ -1848,6 +1868,47 @@ __global__ void __launch_bounds__( 256 ) fp32_peak_kernel( float *out, int iters
 #pragma unroll
    for ( int i = 0; i < 16; ++i ) s += acc[i];
    if ( s == 123.456f ) out[0] = s; // never true; keeps the chains alive
+}
+
+// the same with the multiply and the add as separately rounded instructions (FMUL, FADD): what the exact path's kernels may use.
+// One FLOP per instruction: half the FMA figure is the roofline of arithmetic that must not be contracted.
+__global__ void __launch_bounds__( 256 ) fp32_unfused_peak_kernel( float *out, int iters, float a, float b )
+{
+   float acc[16];
+#pragma unroll
+   for ( int i = 0; i < 16; ++i ) acc[i] = (float)( threadIdx.x + i );
+   for ( int it = 0; it < iters; ++it )
+   {
+#pragma unroll
+      for ( int i = 0; i < 16; ++i ) acc[i] = __fadd_rn( __fmul_rn( acc[i], a ), b );
+   }
+   float s = 0.0f;
+#pragma unroll
+   for ( int i = 0; i < 16; ++i ) s += acc[i];
+   if ( s == 123.456f ) out[0] = s;
+}
+
+extern "C" int silero_b200_measure_fp32_unfused_peak( silero_b200 *h, float *tflops )
+{
+   if ( !h || !tflops ) return set_err( SILERO_B200_ERR_ARG, "null argument" );
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+   DevBuf o;
+   if ( o.alloc( 4 ) ) return SILERO_B200_ERR_CUDA;
+   const int iters = 1 << 14, blocks = h->sm_count * 8, threads = 256;
+   float best = 0.0f;
+   for ( int rep = 0; rep < 5; ++rep )
+   {
+      CU( cudaEventRecord( h->ev_stage[0], h->stream ) );
+      fp32_unfused_peak_kernel<<<blocks, threads, 0, h->stream>>>( o.p, iters, 0.999f, 0.001f );
+      CU( cudaEventRecord( h->ev_stage[1], h->stream ) );
+      CU( cudaEventSynchronize( h->ev_stage[1] ) );
+      float ms = 0.0f;
+      CU( cudaEventElapsedTime( &ms, h->ev_stage[0], h->ev_stage[1] ) );
+      float tf = 2.0f * 16.0f * (float)iters * (float)blocks * (float)threads / ( ms * 1e-3f ) / 1e12f;
+      if ( rep > 0 && tf > best ) best = tf;
+   }
+   *tflops = best;
+   return SILERO_B200_OK;
 }
 
 extern "C" int silero_b200_measure_fp32_peak( silero_b200 *h, float *tflops )
