@@ -182,6 +182,25 @@ int silero_b200_run_streams_segments_device( silero_b200 *h, const int16_t *d_pc
 int silero_b200_segment_probs_device( silero_b200 *h, const float *d_probs, long long stride, int first_stream, int nstreams, int nchunks,
                                       int end_of_stream, vadc_segment *d_segs, int cap, int *d_counts );
 
+/* ---- several GPUs, one host process: the stream scheduler across the devices of a box (vadc_b200/csrc/group.c) ----------------
+   A group owns one engine per device and one host thread per engine. Global stream s lives on device s / streams_per_device
+   (= ceil(max_streams / ndevices)) for its whole life, LSTM and segmenter state included. A call fans the caller's stream range out
+   to the devices that own a part of it; every device reads and writes ITS slice of the caller's host buffers in place (same
+   layouts as silero_b200_run_streams_segments), so the per-stream results arrive gathered in the caller's arrays. No collective,
+   no device-to-device traffic. opts->max_streams is the TOTAL over all devices; opts->device is ignored.
+   Calls on one group must not overlap. Errors: silero_b200_group_last_error (thread-local). */
+#define SILERO_B200_GROUP_MAX_DEVICES 16
+typedef struct silero_b200_group silero_b200_group;
+int silero_b200_group_create( const void *testtensor_bytes, size_t nbytes, const int *devices, int ndevices, const silero_b200_opts *opts, silero_b200_group **out );
+int silero_b200_group_create_from_file( const char *path, const int *devices, int ndevices, const silero_b200_opts *opts, silero_b200_group **out );
+void silero_b200_group_destroy( silero_b200_group *g );
+int silero_b200_group_get_info( const silero_b200_group *g, int *ndevices, int *streams_per_device, int *max_streams );
+int silero_b200_group_run_streams_segments( silero_b200_group *g, const int16_t *pcm, long long stream_stride, int first_stream, int nstreams, int nchunks,
+                                            int end_of_stream, vadc_segment *segs, int cap, int *counts, float *probs );
+int silero_b200_group_reset( silero_b200_group *g, int first_stream, int nstreams );            /* LSTM and segmenter state */
+int silero_b200_group_segments_configure( silero_b200_group *g, const vadc_seg_params *params ); /* NULL: the reference's defaults */
+const char *silero_b200_group_last_error( void );
+
 /* per-stream LSTM state (zero after create / reset); h_out,c_out: host f32 [128] = [2][64] */
 int silero_b200_reset( silero_b200 *h, int first_stream, int nstreams );
 int silero_b200_get_state( silero_b200 *h, int stream, float *h_out, float *c_out );
@@ -203,6 +222,11 @@ int silero_b200_stft_stats( silero_b200 *h, unsigned long long *bins_total, unsi
 /* parity tap: the engine's expf / tanhf / log1pf(|x|) (csrc/libm_exact.cuh: glibc's algorithms, used by the fp32 LSTM path, lstm.c:64-88
    via maths.h:302-334, and by the exact STFT path, misc.c:40-46) of n host floats; must equal the C library's results bit for bit */
 int silero_b200_stage_libm( silero_b200 *h, const float *x, int n, float *out_expf, float *out_tanhf, float *out_log1pf_abs );
+/* test hook for the failure path of the few-streams LSTM wavefront (faithful_lstm_wave_kernel): stall_producer != 0 makes the layer-0
+   tasks never publish their progress, spin_limit (> 0) bounds the consumers' polls. A consumer that gives up raises the engine's
+   error word; the next synchronizing call (run_streams, sync, wait) returns SILERO_B200_ERR_CUDA and the streams' state is untouched.
+   (0, 0) restores normal operation. */
+int silero_b200_debug_wavefront( silero_b200 *h, int stall_producer, int spin_limit );
 /* enable (1) / disable (0) per-stage CUDA-event timing (adds events between kernels) */
 int silero_b200_set_profiling( silero_b200 *h, int enabled );
 

@@ -121,3 +121,23 @@ def test_raw_probabilities_text_equals_the_reference_cli():
     p = e.run_streams(pcm[None, :])[0]
     e.close()
     assert "".join("%f\n" % v for v in p) == ref_cli(pcm, "--raw_probabilities")
+
+
+def test_a_lost_wavefront_producer_is_an_error_not_a_wrong_answer():
+    """faithful_lstm_wave_kernel: the layer-1 task of a stream polls its layer-0 partner's progress. With the test hook the producer
+    never publishes: the consumer gives up after the poll limit, the CALL FAILS (SILERO_B200_ERR_CUDA, no silent garbage) and the
+    stream's persistent state is left as it was; the engine is usable again afterwards."""
+    pcm = vadc_b200.synth_pcm(99, 30 * 1536)[None, :]
+    e = vadc_b200.Engine(max_streams=1)
+    good = e.run_streams(pcm, want_out2=True)[1]
+    h0, c0 = e.get_state(0)
+    e.debug_wavefront(stall_producer=True, spin_limit=2000)
+    with pytest.raises(vadc_b200.EngineError, match="lost its layer-0 producer"):
+        e.run_streams(pcm)
+    h1, c1 = e.get_state(0)
+    assert np.array_equal(bits(h1[1]), bits(h0[1])) and np.array_equal(bits(c1[1]), bits(c0[1]))   # layer 1 (the consumer) kept its state
+    e.debug_wavefront()
+    e.reset()
+    again = e.run_streams(pcm, want_out2=True)[1]
+    e.close()
+    assert np.array_equal(bits(again), bits(good))

@@ -110,6 +110,10 @@ def test_bad_weights_are_rejected_before_any_device_use():
     assert L.silero_b200_create(blob, C.c_size_t(len(blob)), None, C.byref(h)) == -2
     assert b"99" in L.silero_b200_last_error()
     assert L.silero_b200_create(None, C.c_size_t(0), None, C.byref(h)) == -1
+    # a header whose size arithmetic wraps in 32 bits (dims 32768 x 32768 -> size 2^30, size * 4 == 0 == nbytes): must be rejected, not read
+    import struct
+    evil = struct.pack("<ii", 1, 1) + struct.pack("<i", 1) + b"x" + struct.pack("<iiiii", 2, 32768, 32768, 1 << 30, 0)
+    assert L.silero_b200_create(evil, C.c_size_t(len(evil)), None, C.byref(h)) == -2 and not h.value
 
 
 def test_no_cpu_fallback_without_device():

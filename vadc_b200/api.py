@@ -246,6 +246,9 @@ class Engine:
         self._check(lib().silero_b200_stage_libm(self._h, _p(x), x.size, _p(e), _p(t), _p(l)))
         return e, t, l
 
+    def debug_wavefront(self, stall_producer=False, spin_limit=0):
+        self._check(lib().silero_b200_debug_wavefront(self._h, int(stall_producer), int(spin_limit)))
+
     def set_profiling(self, on):
         self._check(lib().silero_b200_set_profiling(self._h, 1 if on else 0))
 
@@ -378,6 +381,76 @@ class Engine:
         cyc = C.c_longlong(0)
         self._check(lib().silero_b200_stage_tc_gemm(self._h, _p(a), _p(b), b.shape[0], a.shape[1], nsplit, reps, _p(d), C.byref(cyc)))
         return d, cyc.value
+
+
+class Group:
+    """Several GPUs in one host process (silero_b200_group_*, csrc/group.c): streams sharded in contiguous blocks, one host thread
+    per device, results gathered in the caller's arrays."""
+
+    def __init__(self, devices, max_streams, weights=None, **kw):
+        L = lib()
+        L.silero_b200_group_last_error.restype = C.c_char_p
+        opts = Opts()
+        L.silero_b200_default_opts(C.byref(opts))
+        opts.max_streams = max_streams
+        for k, v in kw.items():
+            setattr(opts, k, v)
+        devs = (C.c_int * len(devices))(*devices)
+        self._g = C.c_void_p()
+        if weights is None:
+            weights = WEIGHTS_PATH
+        if isinstance(weights, (bytes, bytearray)):
+            rc = L.silero_b200_group_create(bytes(weights), C.c_size_t(len(weights)), devs, len(devices), C.byref(opts), C.byref(self._g))
+        else:
+            rc = L.silero_b200_group_create_from_file(os.fsencode(weights), devs, len(devices), C.byref(opts), C.byref(self._g))
+        self._check(rc)
+        self.max_streams = max_streams
+
+    def _check(self, rc):
+        if rc != 0:
+            raise EngineError("silero_b200_group error %d: %s" % (rc, lib().silero_b200_group_last_error().decode()))
+
+    def close(self):
+        if self._g:
+            lib().silero_b200_group_destroy(self._g)
+            self._g = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self):
+        n, per, mx = C.c_int(), C.c_int(), C.c_int()
+        self._check(lib().silero_b200_group_get_info(self._g, C.byref(n), C.byref(per), C.byref(mx)))
+        return {"ndevices": n.value, "streams_per_device": per.value, "max_streams": mx.value}
+
+    def segments_configure(self, params=None):
+        self._check(lib().silero_b200_group_segments_configure(self._g, C.byref(params) if params is not None else None))
+
+    def reset(self, first_stream=0, nstreams=None):
+        self._check(lib().silero_b200_group_reset(self._g, first_stream, self.max_streams - first_stream if nstreams is None else nstreams))
+
+    def run_streams_segments(self, pcm, nchunks=None, end_of_stream=False, cap=None, first_stream=0):
+        """pcm: int16 [S, nsamples]. Returns (probs [S, nchunks], list of per-stream [(start_chunk, end_chunk), ...])."""
+        assert pcm.dtype == np.int16 and pcm.ndim == 2 and pcm.strides[1] == 2
+        S = pcm.shape[0]
+        if nchunks is None:
+            nchunks = pcm.shape[1] // CHUNK
+        if cap is None:
+            cap = nchunks // 2 + 2
+        probs = np.zeros((S, nchunks), np.float32)
+        segs = np.zeros((S, cap, 2), np.int32)
+        counts = np.zeros(S, np.int32)
+        self._check(lib().silero_b200_group_run_streams_segments(self._g, _p(pcm), C.c_longlong(pcm.strides[0] // 2), first_stream, S, nchunks,
+                                                                 int(end_of_stream), _p(segs), cap, _p(counts), _p(probs)))
+        return probs, [[tuple(p) for p in segs[s, :min(counts[s], cap)].tolist()] for s in range(S)]
+
+    def run_streams_segments_ptr(self, pcm_ptr, stream_stride, nstreams, nchunks, end_of_stream, segs_ptr, cap, counts_ptr, probs_ptr=None, first_stream=0):
+        self._check(lib().silero_b200_group_run_streams_segments(self._g, C.c_void_p(pcm_ptr), C.c_longlong(stream_stride), first_stream, nstreams, nchunks,
+                                                                 int(end_of_stream), C.c_void_p(segs_ptr), cap, C.c_void_p(counts_ptr),
+                                                                 C.c_void_p(probs_ptr) if probs_ptr else None))
 
 
 def pinned_empty(shape, dtype):

@@ -92,6 +92,10 @@ struct silero_b200
    DeviceWeights w;
    fq::Weights fw;           // the container's 99 tensors as they are (faithful_kernel.cuh)
    int *d_lstm_sync;         // [1 + max_streams]: task ticket + per-stream layer-0 progress of faithful_lstm_wave_kernel
+   int *err_word;            // mapped pinned host word a kernel raises when it gives up (wavefront consumer whose producer is lost)
+   int *d_err_word;          // its device address
+   int wave_spin_limit;      // polls before a wavefront consumer gives up (debug taps lower it)
+   int debug_stall_producer; // test hook: layer-0 tasks never publish progress
    float *state_h, *state_c; // [max_streams][2][64]
    // window scratch (grow-only)
    size_t cap_chunks;
@@ -506,6 +510,7 @@ extern "C" void silero_b200_destroy( silero_b200 *h )
    cudaFree( h->d_f32 );
    cudaFree( h->d_flagged );
    cudaFree( h->d_lstm_sync );
+   if ( h->err_word ) cudaFreeHost( h->err_word );
    cudaFree( h->d_lstm_tc );
    cudaFree( h->d_stft_tc );
    cudaFree( h->d_fix_list );
@@ -785,6 +790,10 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    for ( int k = 0; k < fq::N_TRANSPOSED; ++k ) h->fw.tt[k] = h->d_weights + tt_off[k];
    CU_H( cudaMalloc( &h->d_flagged, sizeof( unsigned long long ) ) );
    CU_H( cudaMalloc( &h->d_lstm_sync, ( (size_t)h->max_streams + 1 ) * sizeof( int ) ) );
+   CU_H( cudaHostAlloc( (void **)&h->err_word, sizeof( int ), cudaHostAllocMapped ) );
+   *h->err_word = 0;
+   CU_H( cudaHostGetDevicePointer( (void **)&h->d_err_word, h->err_word, 0 ) );
+   h->wave_spin_limit = 1 << 24;
    {
       size_t free_b = 0, total_b = 0;
       h->scratch_budget = (size_t)1536 << 20;
@@ -1163,7 +1172,8 @@ static int launch_lstm_faithful_wave( silero_b200 *h, float *a4, float *h0, int 
    float *sc = h->state_c + (size_t)first_stream * SILERO_B200_STATE_FLOATS;
    CU( cudaMemsetAsync( h->d_lstm_sync, 0, ( (size_t)nstreams + 1 ) * sizeof( int ), h->stream ) );
    const int grid = imin( 2 * nstreams, h->sm_count );
-   faithful_lstm_wave_kernel<<<grid, FLSTM_THREADS, FLSTM_SMEM_BYTES, h->stream>>>( a4, h0, a4, sh, sc, h->w.lstm_w, h->w.lstm_b, nstreams, nw, h->d_lstm_sync );
+   faithful_lstm_wave_kernel<<<grid, FLSTM_THREADS, FLSTM_SMEM_BYTES, h->stream>>>( a4, h0, a4, sh, sc, h->w.lstm_w, h->w.lstm_b, nstreams, nw, h->d_lstm_sync,
+                                                                                    h->d_err_word, h->wave_spin_limit, h->debug_stall_producer );
    h->launches++;
    CU( cudaGetLastError() );
    return 0;
@@ -1398,11 +1408,29 @@ extern "C" int silero_b200_run_streams_device( silero_b200 *h, const int16_t *d_
    return SILERO_B200_OK;
 }
 
+// after a synchronization point: did a kernel give up? (faithful_lstm_wave_kernel's consumers raise the word instead of hanging)
+static int check_err_word( silero_b200 *h )
+{
+   const int e = *(volatile int *)h->err_word;
+   if ( !e ) return 0;
+   *(volatile int *)h->err_word = 0;
+   return set_err( SILERO_B200_ERR_CUDA, "LSTM wavefront: the layer-1 task of stream %d lost its layer-0 producer (no progress within the poll limit); "
+                                         "the stream's state was left untouched, the call's results are invalid", e - 1 );
+}
+
 extern "C" int silero_b200_sync( silero_b200 *h )
 {
    if ( !h ) return set_err( SILERO_B200_ERR_ARG, "null handle" );
    if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
    CU( cudaStreamSynchronize( h->stream ) );
+   return check_err_word( h );
+}
+
+extern "C" int silero_b200_debug_wavefront( silero_b200 *h, int stall_producer, int spin_limit )
+{
+   if ( !h ) return set_err( SILERO_B200_ERR_ARG, "null handle" );
+   h->debug_stall_producer = stall_producer;
+   h->wave_spin_limit = spin_limit > 0 ? spin_limit : ( 1 << 24 );
    return SILERO_B200_OK;
 }
 
@@ -1540,7 +1568,7 @@ static int run_streams_host( silero_b200 *h, const int16_t *pcm, long long strea
       return SILERO_B200_OK;
    }
    CU( cudaStreamSynchronize( h->stream ) );
-   return SILERO_B200_OK;
+   return check_err_word( h );
 }
 
 extern "C" int silero_b200_submit_streams_segments( silero_b200 *h, const int16_t *pcm, long long stream_stride, int first_stream, int nstreams, int nchunks,
@@ -1570,7 +1598,7 @@ extern "C" int silero_b200_wait( silero_b200 *h, unsigned long long ticket )
    if ( h->ticket_seq > ticket + 4 ) return SILERO_B200_OK; // its event slot has been reused, and submit waited on it before reusing it
    if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
    CU( cudaEventSynchronize( h->done_ev[ticket % 4] ) );
-   return SILERO_B200_OK;
+   return check_err_word( h );
 }
 
 extern "C" int silero_b200_run_streams( silero_b200 *h, const int16_t *pcm, long long stream_stride, int first_stream, int nstreams, int nchunks,

@@ -617,7 +617,8 @@ __device__ __forceinline__ void st_release_gpu( int *p, int v )
 
 __global__ void __launch_bounds__( FLSTM_THREADS, 1 )
 faithful_lstm_wave_kernel( const float *x0, float *h0seq, float *out1, float *__restrict__ state_h, float *__restrict__ state_c,
-                           const float *__restrict__ wpack, const float *__restrict__ bias, int nstreams, int nw, int *sync )
+                           const float *__restrict__ wpack, const float *__restrict__ bias, int nstreams, int nw, int *sync, int *err_word, int spin_limit,
+                           int debug_stall_producer )
 {
    extern __shared__ __align__( 16 ) float fsm[];
    __shared__ int s_ticket;
@@ -647,15 +648,23 @@ faithful_lstm_wave_kernel( const float *x0, float *h0seq, float *out1, float *__
       float *hs = ( layer == 0 ? h0seq : out1 ) + (size_t)s * steps * 64;
       int *progress = sync + 1 + s;
       int seen = layer == 0 ? steps : 0; // layer 0 reads the encoder's output, complete before this launch
-      // x_t for the consumer: wait until the producer has completed step t (bounded: a lost producer costs the result, not a hang)
+      bool lost = false;
+      // x_t for the consumer: wait until the producer has completed step t. The wait is bounded (a lost producer must not hang the
+      // GPU), and a consumer that gives up SAYS so: it raises the engine's error word (mapped host memory, checked by the host at its
+      // next synchronization point: the call fails with SILERO_B200_ERR_CUDA) and the task leaves the persistent state untouched.
       auto fetch = [&]( int t ) -> float {
-         if ( seen <= t )
+         if ( seen <= t && !lost )
          {
             int spins = 0;
             do
             {
                seen = ld_acquire_gpu( progress );
-            } while ( seen <= t && ++spins < ( 1 << 24 ) );
+            } while ( seen <= t && ++spins < spin_limit );
+            if ( seen <= t )
+            {
+               lost = true;
+               atomicExch( err_word, 1 + s );
+            }
          }
          return __ldcg( xs + (size_t)t * 64 + j );
       };
@@ -689,9 +698,10 @@ faithful_lstm_wave_kernel( const float *x0, float *h0seq, float *out1, float *__
          }
          if ( g == 1 ) nxt[j] = xn;
          __syncthreads();
-         if ( layer == 0 && tid == 0 ) st_release_gpu( progress, step + 1 ); // every thread's h of this step is ordered before by the barrier
+         if ( layer == 0 && tid == 0 && !debug_stall_producer ) st_release_gpu( progress, step + 1 ); // every thread's h of this step is ordered before by the barrier
       }
-      if ( g == 0 )
+      const int any_lost = __syncthreads_or( lost ? 1 : 0 );
+      if ( g == 0 && !any_lost )
       {
          state_c[( (size_t)s * 2 + layer ) * 64 + j] = c;
          state_h[( (size_t)s * 2 + layer ) * 64 + j] = h_last;

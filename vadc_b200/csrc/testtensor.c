@@ -62,9 +62,15 @@ int vb_testtensor_parse( const void *bytes, size_t nbytes, vb_tensor_file *out, 
       for ( int d = 0; d < t[i].ndim; ++d )
          if ( take_i32( &c, &t[i].dims[d] ) || t[i].dims[d] < 0 ) goto bad;
       if ( take_i32( &c, &t[i].size ) || take_i32( &c, &nb ) || t[i].size < 0 ) goto bad;
+      /* all in 64 bits with a cap per step: a crafted header (dims 32768 x 32768, nbytes 0) must not wrap `size * 4` or the product */
+      if ( t[i].size > 0x7fffffff / 4 || nb < 0 ) goto bad;
       long long prod = 1;
-      for ( int d = 0; d < t[i].ndim; ++d ) prod *= t[i].dims[d];
-      if ( prod != t[i].size || nb != t[i].size * 4 || c.off + (size_t)nb > c.n ) goto bad;
+      for ( int d = 0; d < t[i].ndim; ++d )
+      {
+         prod *= t[i].dims[d];
+         if ( prod > 0x7fffffffll ) goto bad;
+      }
+      if ( prod != (long long)t[i].size || (long long)nb != (long long)t[i].size * 4 || c.off + (size_t)nb > c.n ) goto bad;
       c.off += (size_t)nb;
       total += ( (size_t)t[i].size + 3 ) & ~(size_t)3;
    }

@@ -14,7 +14,9 @@
  * New: any number of raw s16le FILES may be given; each file is an independent stream, all of them
  * are pushed through the multi-stream scheduler at once (per-stream LSTM and segmenter state on the
  * GPU, segments produced by the on-device segmenter) and the per-file results are printed in
- * argument order ("# path" header lines when there is more than one file).
+ * argument order ("# path" header lines when there is more than one file). --devices 0,1,2,... spreads
+ * the files over several GPUs of the box (silero_b200_group_*: one host thread per device, streams
+ * sharded in contiguous blocks, results gathered in argument order); --device N picks one.
  */
 #define _POSIX_C_SOURCE 200809L
 #include <errno.h>
@@ -34,6 +36,7 @@ typedef struct cli_opts
    int batch;
    float start_seconds;
    int raw_probabilities, stats, device, audio_source;
+   int devices[SILERO_B200_GROUP_MAX_DEVICES], ndevices;
    const char *model;
    const char **files;
    int nfiles;
@@ -60,6 +63,19 @@ static int parse_args( int argc, char **argv, cli_opts *o )
       else if ( !strcmp( a, "--stats" ) ) o->stats = 1;
       else if ( !strcmp( a, "--output_centi_seconds" ) ) o->seg.centiseconds = 1;
       else if ( !strcmp( a, "--model" ) ) { if ( i + 1 < argc ) o->model = argv[++i]; }
+      else if ( !strcmp( a, "--devices" ) )
+      {
+         /* comma-separated CUDA ordinals: the multi-file mode shards its streams over them */
+         if ( i + 1 < argc )
+            for ( const char *p = argv[++i]; *p && o->ndevices < SILERO_B200_GROUP_MAX_DEVICES; )
+            {
+               char *end;
+               long v = strtol( p, &end, 10 );
+               if ( end == p ) break;
+               if ( v >= 0 ) o->devices[o->ndevices++] = (int)v;
+               p = *end == ',' ? end + 1 : end;
+            }
+      }
       else if ( !strcmp( a, "--min_silence" ) ) fdst = &o->seg.min_silence_ms;
       else if ( !strcmp( a, "--min_speech" ) ) fdst = &o->seg.min_speech_ms;
       else if ( !strcmp( a, "--threshold" ) ) fdst = &o->seg.threshold;
@@ -220,7 +236,8 @@ static int run_fd( silero_b200 *h, const cli_opts *o, int in_fd, int skip_on_rea
    vadc_segmenter_init( &seg, &o->seg );
    double total_speech = 0.0, t0 = now_s();
    long long total_samples = 0;
-   /* --start_seconds: the reference seeks with ffmpeg -ss (vadc.c:537); on a pipe the samples are read and dropped */
+   /* --start_seconds: the reference hands it to ffmpeg only (-ss, vadc.c:537) and ignores it for stdin (init_buffered_stream_stdin,
+      vadc.c:610-627, 818): so does this program. skip_on_read is for callers that decode without a seeking child. */
    long long skip = skip_on_read ? (long long)( (double)o->start_seconds * SILERO_B200_SAMPLE_RATE ) * 2 : 0;
    while ( skip > 0 )
    {
@@ -293,9 +310,15 @@ static int by_length_desc( const void *a, const void *b )
    return x->order - y->order;
 }
 
-static int run_files( silero_b200 *h, const cli_opts *o )
+static int run_files( silero_b200_group *h, const cli_opts *o )
 {
    const int S = o->nfiles;
+   int rc = 1; /* every exit goes through `done`: buffers are released on errors too */
+   int16_t *pcm = 0;
+   vadc_segment *segs = 0, *tmp = 0;
+   int *nseg = 0, *cnt = 0;
+   float *probs = 0, *ptmp = 0;
+   FILE *f = 0;
    file_stream *fs = (file_stream *)calloc( (size_t)S, sizeof( file_stream ) );
    if ( !fs ) return 1;
    const long long skip_samples = (long long)( (double)o->start_seconds * SILERO_B200_SAMPLE_RATE );
@@ -305,26 +328,27 @@ static int run_files( silero_b200 *h, const cli_opts *o )
       long long samples = 0;
       if ( is_raw_pcm_name( o->files[i] ) )
       {
-         FILE *f = fopen( o->files[i], "rb" );
+         f = fopen( o->files[i], "rb" );
          if ( !f )
          {
             fprintf( stderr, "Error: cannot open %s\n", o->files[i] );
-            return 1;
+            goto done;
          }
          fseek( f, 0, SEEK_END );
          samples = ftell( f ) / 2 - skip_samples;
          fclose( f );
+         f = 0;
       }
       else
       {
          /* decoded by an ffmpeg child, which also does the --start_seconds seek (-ss) */
          pid_t pid = 0;
          int fd = spawn_ffmpeg( o->files[i], o->start_seconds, o->audio_source, &pid );
-         if ( fd < 0 ) return 1;
+         if ( fd < 0 ) goto done;
          fs[i].decoded = slurp_fd( fd, &samples );
          close( fd );
          waitpid( pid, 0, 0 );
-         if ( !fs[i].decoded ) return 1;
+         if ( !fs[i].decoded ) goto done;
       }
       fs[i].path = o->files[i];
       fs[i].order = i;
@@ -334,11 +358,11 @@ static int run_files( silero_b200 *h, const cli_opts *o )
    /* longest first: at any time the streams that still have audio are a prefix of the stream numbering */
    qsort( fs, (size_t)S, sizeof( file_stream ), by_length_desc );
    const long long stride = ( maxchunks > 0 ? maxchunks : 1 ) * SILERO_B200_CHUNK_SAMPLES;
-   int16_t *pcm = 0;
    if ( silero_b200_host_alloc_pinned( (size_t)S * (size_t)stride * sizeof( int16_t ), (void **)&pcm ) )
    {
       fprintf( stderr, "Error: %s\n", silero_b200_last_error() );
-      return 1;
+      pcm = 0;
+      goto done;
    }
    for ( int s = 0; s < S; ++s )
    {
@@ -350,30 +374,37 @@ static int run_files( silero_b200 *h, const cli_opts *o )
          fs[s].decoded = 0;
          continue;
       }
-      FILE *f = fopen( fs[s].path, "rb" );
-      if ( !f ) return 1;
+      f = fopen( fs[s].path, "rb" );
+      if ( !f ) goto done;
       fseek( f, skip_samples * 2, SEEK_SET );
       if ( fread( pcm + (size_t)s * stride, 2, want, f ) != want )
       {
          fprintf( stderr, "Error: short read on %s\n", fs[s].path );
-         return 1;
+         goto done;
       }
       fclose( f );
+      f = 0;
    }
    /* results per stream */
    const int cap = (int)( maxchunks / 2 + 2 );
-   vadc_segment *segs = (vadc_segment *)malloc( (size_t)S * cap * sizeof( vadc_segment ) );
-   int *nseg = (int *)calloc( (size_t)S, sizeof( int ) );
-   float *probs = o->raw_probabilities ? (float *)malloc( (size_t)S * ( maxchunks > 0 ? maxchunks : 1 ) * sizeof( float ) ) : 0;
+   segs = (vadc_segment *)malloc( (size_t)S * cap * sizeof( vadc_segment ) );
+   nseg = (int *)calloc( (size_t)S, sizeof( int ) );
+   probs = o->raw_probabilities ? (float *)malloc( (size_t)S * ( maxchunks > 0 ? maxchunks : 1 ) * sizeof( float ) ) : 0;
    const int B = o->batch * 16; /* chunks per stream and call: large calls keep the GPU busy */
-   vadc_segment *tmp = (vadc_segment *)malloc( (size_t)S * ( B / 2 + 2 ) * sizeof( vadc_segment ) );
-   int *cnt = (int *)malloc( (size_t)S * sizeof( int ) );
-   float *ptmp = o->raw_probabilities ? (float *)malloc( (size_t)S * B * sizeof( float ) ) : 0;
-   if ( !segs || !nseg || !tmp || !cnt || ( o->raw_probabilities && ( !probs || !ptmp ) ) ) return 1;
-   if ( silero_b200_segments_configure( h, &o->seg ) ) return 1;
-   double t0 = now_s();
-   long long total_samples = 0;
    const int tcap = B / 2 + 2;
+   tmp = (vadc_segment *)malloc( (size_t)S * tcap * sizeof( vadc_segment ) );
+   cnt = (int *)malloc( (size_t)S * sizeof( int ) );
+   ptmp = o->raw_probabilities ? (float *)malloc( (size_t)S * B * sizeof( float ) ) : 0;
+   if ( !segs || !nseg || !tmp || !cnt || ( o->raw_probabilities && ( !probs || !ptmp ) ) ) goto done;
+   if ( silero_b200_group_segments_configure( h, &o->seg ) )
+   {
+      fprintf( stderr, "Error: %s\n", silero_b200_group_last_error() );
+      goto done;
+   }
+   vadc_segmenter fmt;
+   vadc_segmenter_init( &fmt, &o->seg );
+   double t0 = now_s(), total_speech = 0.0;
+   long long total_samples = 0;
    for ( long long n0 = 0; n0 < maxchunks; n0 += B )
    {
       /* streams [0, full) have a full slice left, [full, active) end inside this slice */
@@ -395,23 +426,29 @@ static int run_files( silero_b200 *h, const cli_opts *o )
                while ( s_stop < s_end && fs[s_stop].nchunks == fs[s_begin].nchunks ) ++s_stop;
             }
             const int ns = s_stop - s_begin;
-            if ( silero_b200_run_streams_segments( h, pcm + (size_t)s_begin * stride + (size_t)n0 * SILERO_B200_CHUNK_SAMPLES, stride, s_begin, ns, n,
-                                                   pass == 1 ? 1 : 0, tmp, tcap, cnt, ptmp ) )
+            if ( silero_b200_group_run_streams_segments( h, pcm + (size_t)s_begin * stride + (size_t)n0 * SILERO_B200_CHUNK_SAMPLES, stride, s_begin, ns, n,
+                                                         pass == 1 ? 1 : 0, tmp, tcap, cnt, ptmp ) )
             {
-               fprintf( stderr, "Error: %s\n", silero_b200_last_error() );
-               return 1;
+               fprintf( stderr, "Error: %s\n", silero_b200_group_last_error() );
+               goto done;
             }
             for ( int i = 0; i < ns; ++i )
             {
                const int s = s_begin + i;
-               for ( int j = 0; j < cnt[i] && j < tcap && nseg[s] < cap; ++j ) segs[(size_t)s * cap + nseg[s]++] = tmp[(size_t)i * tcap + j];
+               for ( int j = 0; j < cnt[i] && j < tcap && nseg[s] < cap; ++j )
+               {
+                  float tb, te;
+                  vadc_segment_times( &fmt, tmp[(size_t)i * tcap + j], &tb, &te );
+                  total_speech += (double)te - (double)tb; /* the --stats line counts the speech of all files */
+                  segs[(size_t)s * cap + nseg[s]++] = tmp[(size_t)i * tcap + j];
+               }
                if ( probs ) memcpy( probs + (size_t)s * maxchunks + n0, ptmp + (size_t)i * n, (size_t)n * sizeof( float ) );
             }
             total_samples += (long long)ns * n * SILERO_B200_CHUNK_SAMPLES;
             s_begin = s_stop;
          }
       }
-      if ( o->stats ) print_stats( 0.0, total_samples, t0 );
+      if ( o->stats ) print_stats( total_speech, total_samples, t0 );
    }
    /* streams whose length is an exact multiple of the slice were never closed: flush them (no audio, end of stream) */
    for ( int s = 0; s < S; )
@@ -423,14 +460,22 @@ static int run_files( silero_b200 *h, const cli_opts *o )
       }
       int e = s + 1;
       while ( e < S && fs[e].nchunks == fs[s].nchunks ) ++e;
-      if ( silero_b200_run_streams_segments( h, 0, 0, s, e - s, 0, 1, tmp, tcap, cnt, 0 ) ) return 1;
+      if ( silero_b200_group_run_streams_segments( h, 0, 0, s, e - s, 0, 1, tmp, tcap, cnt, 0 ) )
+      {
+         fprintf( stderr, "Error: %s\n", silero_b200_group_last_error() );
+         goto done;
+      }
       for ( int i = 0; i < e - s; ++i )
-         for ( int j = 0; j < cnt[i] && j < tcap && nseg[s + i] < cap; ++j ) segs[(size_t)( s + i ) * cap + nseg[s + i]++] = tmp[(size_t)i * tcap + j];
+         for ( int j = 0; j < cnt[i] && j < tcap && nseg[s + i] < cap; ++j )
+         {
+            float tb, te;
+            vadc_segment_times( &fmt, tmp[(size_t)i * tcap + j], &tb, &te );
+            total_speech += (double)te - (double)tb;
+            segs[(size_t)( s + i ) * cap + nseg[s + i]++] = tmp[(size_t)i * tcap + j];
+         }
       s = e;
    }
    /* print in argument order */
-   vadc_segmenter fmt;
-   vadc_segmenter_init( &fmt, &o->seg );
    for ( int order = 0; order < S; ++order )
    {
       int s = 0;
@@ -447,10 +492,18 @@ static int run_files( silero_b200 *h, const cli_opts *o )
          }
    }
    fflush( stdout );
-   if ( o->stats ) fputc( '\n', stderr );
-   silero_b200_host_free_pinned( pcm );
+   if ( o->stats )
+   {
+      print_stats( total_speech, total_samples, t0 );
+      fputc( '\n', stderr );
+   }
+   rc = 0;
+done:
+   if ( f ) fclose( f );
+   if ( pcm ) silero_b200_host_free_pinned( pcm );
+   for ( int i = 0; i < S; ++i ) free( fs[i].decoded );
    free( segs ); free( nseg ); free( probs ); free( tmp ); free( cnt ); free( ptmp ); free( fs );
-   return 0;
+   return rc;
 }
 
 int main( int argc, char **argv )
@@ -477,8 +530,27 @@ int main( int argc, char **argv )
    }
    silero_b200_opts eo;
    silero_b200_default_opts( &eo );
-   eo.device = o.device;
+   eo.device = o.ndevices > 0 ? o.devices[0] : o.device;
    eo.max_streams = o.nfiles > 1 ? o.nfiles : 1;
+   const int files_mode = !( o.nfiles == 0 || ( o.nfiles == 1 && !is_raw_pcm_name( o.files[0] ) ) );
+   if ( files_mode )
+   {
+      /* many files = many streams, over one or several GPUs (--devices): the group scheduler */
+      if ( o.ndevices == 0 ) o.devices[o.ndevices++] = o.device;
+      if ( o.ndevices > o.nfiles ) o.ndevices = o.nfiles;
+      silero_b200_group *g = 0;
+      if ( silero_b200_group_create_from_file( weights, o.devices, o.ndevices, &eo, &g ) != SILERO_B200_OK )
+      {
+         fprintf( stderr, "Error: %s\n", silero_b200_group_last_error() );
+         free( o.files );
+         return 1;
+      }
+      fprintf( stderr, "batch size: %d\n", o.batch ); /* vadc.c:716 */
+      const int rcf = run_files( g, &o );
+      silero_b200_group_destroy( g );
+      free( o.files );
+      return rcf;
+   }
    silero_b200 *h = 0;
    if ( silero_b200_create_from_file( weights, &eo, &h ) != SILERO_B200_OK )
    {
@@ -488,7 +560,7 @@ int main( int argc, char **argv )
    fprintf( stderr, "batch size: %d\n", o.batch ); /* vadc.c:716 */
    int rc;
    if ( o.nfiles == 0 )
-      rc = run_fd( h, &o, 0, 1 );
+      rc = run_fd( h, &o, 0, 0 );
    else if ( o.nfiles == 1 && !is_raw_pcm_name( o.files[0] ) )
    {
       /* the reference's named-input mode: stream the ffmpeg child's output through the same loop as stdin */
@@ -504,7 +576,7 @@ int main( int argc, char **argv )
       }
    }
    else
-      rc = run_files( h, &o );
+      rc = 1; /* (files mode returned above) */
    silero_b200_destroy( h );
    free( o.files );
    return rc;
