@@ -284,23 +284,35 @@ __global__ void __launch_bounds__( XF_THREADS, 1 ) exact_front_kernel( const flo
          MU[tid] = xe::quot( total, 25.0f );
       }
       __syncthreads();
+      for ( int gg = 0; gg < ng; ++gg )
       {
-         const int n = ng * VB_BINS * VB_FRAMES;
-         for ( int i = tid; i < n; i += XF_THREADS ) Xs[i] = xe::sub( Xs[i], MU[i / ( VB_BINS * VB_FRAMES )] );
+         const float mu = MU[gg];
+         float *xg = Xs + gg * ( VB_BINS * VB_FRAMES );
+         for ( int i = tid; i < VB_BINS * VB_FRAMES; i += XF_THREADS ) xg[i] = xe::sub( xg[i], mu );
       }
       __syncthreads();
       }
       // depthwise k = 5, zero pad 2 (conv.c:17-53, 60-113): the taps that exist, left to right from 0, then bias + sum; ReLU
       {
+         // element i = (row gc = g * 129 + c, frame ti); the indices advance incrementally (512 = 20 rows + 12 frames) instead of by division
          const int n = ng * VB_BINS * VB_FRAMES;
+         int gc = tid / VB_FRAMES, ti = tid - gc * VB_FRAMES, c = gc; // tid < 512 < 129 * 25: the first element is in chunk 0
          for ( int i = tid; i < n; i += XF_THREADS )
          {
-            const int gc = i / VB_FRAMES, ti = i - gc * VB_FRAMES, c = gc % VB_BINS;
             const float *a = Xs + gc * VB_FRAMES, *k = dww + c * 5;
-            const int k0 = ti < 2 ? 2 - ti : 0, k1 = ti + 2 >= VB_FRAMES ? VB_FRAMES + 1 - ti : 4;
             float r = 0.0f;
-            for ( int kk = k0; kk <= k1; ++kk ) r = xe::add( r, xe::mul( a[ti + kk - 2], k[kk] ) );
+#pragma unroll
+            for ( int kk = 0; kk < 5; ++kk )
+            {
+               const int tt = ti + kk - 2;
+               if ( tt >= 0 && tt < VB_FRAMES ) r = xe::add( r, xe::mul( a[tt], k[kk] ) );
+            }
             Ds[i] = xe::relu( xe::add( dwb[c], r ) );
+            ti += XF_THREADS % VB_FRAMES;
+            gc += XF_THREADS / VB_FRAMES;
+            c += XF_THREADS / VB_FRAMES;
+            if ( ti >= VB_FRAMES ) { ti -= VB_FRAMES; ++gc; ++c; }
+            if ( c >= VB_BINS ) c -= VB_BINS;
          }
       }
       __syncthreads();

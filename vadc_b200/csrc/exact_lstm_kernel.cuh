@@ -15,8 +15,10 @@
 //   * streams go through in pairs: the two lanes of a row each contract their half for both streams, then swap four partial sums
 //     by one shuffle each, so that the even lane finishes the row for the first stream and the odd lane for the second (the lane
 //     sums in the reference's order, bias, the gate's own nonlinearity): no lane idles in the libm restatements;
-//   * the cell update runs on all 512 threads over (unit, stream) pairs of a sub-batch of 8 streams through a double-buffered
-//     activation tile in shared memory: one barrier per sub-batch and step.
+//   * the gate nonlinearities and the cell update run on all 512 threads over (unit, stream) pairs of a sub-batch of 8 streams
+//     through a double-buffered tile of pre-activations in shared memory: every thread evaluates the same three sigmoids and two
+//     tanh (no warp is the slow one at the barrier, as the tanh rows were when each row's owner applied its own nonlinearity);
+//     one barrier per sub-batch and step.
 // Shared memory per stream: [x|h] 512 B + c 256 B, so one CTA carries up to XL_MAX_STREAMS streams per pass (more go in passes).
 //   x: [S][steps][64] layer input (stream-major), hseq: [S][steps][64] layer output, state_h/state_c: [S][2][64].
 #pragma once
@@ -50,10 +52,12 @@ exact_lstm_kernel( const float *__restrict__ x, float *__restrict__ hseq, float 
                    const float *__restrict__ wpack /*[2][32][256][4]*/, const float *__restrict__ bias /*[2][256]*/, int nstreams, int nw )
 {
    extern __shared__ __align__( 16 ) float xsm[];
-   float *act = xsm;                                 // [2][XL_SUB][256]
+   __shared__ unsigned long long exp_tab[32];
+   lme::stage_exp2f_tab( exp_tab, threadIdx.x );
+   float *act = xsm;                                 // [2][XL_SUB][256] pre-activations z = W [x;h] + b
    float *xh = xsm + XL_ACT_FLOATS;                  // [K][128]
    float *cst = xh + XL_MAX_STREAMS * 128;           // [K][64]
-   const int tid = threadIdx.x, half = tid & 1, row = tid >> 1, gate = row >> 6;
+   const int tid = threadIdx.x, half = tid & 1, row = tid >> 1;
    const int steps = nw * 7;
 
    // this thread's 64 weights: quads 4b + 2 half, 4b + 2 half + 1 of row `row`
@@ -129,18 +133,15 @@ exact_lstm_kernel( const float *__restrict__ x, float *__restrict__ hseq, float 
                z = __fadd_rn( z, hi[2] );
                z = __fadd_rn( z, hi[3] );
                z = __fadd_rn( z, b_row );
-               if ( !half || two )
-               {
-                  const float v = ( gate == 2 ) ? lme::tanhf_ref( z ) : lme::sigmoid_ref( z );
-                  a[( p + half ) * 256 + row] = v;
-               }
+               if ( !half || two ) a[( p + half ) * 256 + row] = z;
             }
             __syncthreads();
             // cell update (lstm.c:64-88) of (unit uj, stream k0 + uk)
             if ( upd )
             {
                const float *av = a + uk * 256;
-               const float ig = av[uj], fg = av[64 + uj], gg = av[128 + uj], og = av[192 + uj];
+               const float ig = lme::sigmoid_ref( av[uj], exp_tab ), fg = lme::sigmoid_ref( av[64 + uj], exp_tab );
+               const float gg = lme::tanhf_ref( av[128 + uj] ), og = lme::sigmoid_ref( av[192 + uj], exp_tab );
                const int k = k0 + uk;
                const float cn = __fadd_rn( __fmul_rn( fg, cst[k * 64 + uj] ), __fmul_rn( ig, gg ) );
                const float hn = __fmul_rn( lme::tanhf_ref( cn ), og );

@@ -27,7 +27,10 @@ __device__ __constant__ const unsigned long long EXP2F_TAB[32] = {
    0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull, 0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full,
    0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull };
 
-__device__ __forceinline__ float expf_ref( float x )
+// tab: EXP2F_TAB, or a copy of it in shared memory (32 x 8 bytes): lanes index the table with different k, which the constant cache
+// serves one address at a time (measured: 5 % of the LSTM kernel's stall samples sat on this load) while shared memory serves the
+// whole warp in one or two wavefronts
+__device__ __forceinline__ float expf_ref( float x, const unsigned long long *tab = EXP2F_TAB )
 {
    const double InvLn2N = 0x1.71547652b82fep+0 * 32.0, SHIFT = 0x1.8p+52;
    const double C0 = 0x1.c6af84b912394p-5 / 32.0 / 32.0 / 32.0, C1 = 0x1.ebfce50fac4f3p-3 / 32.0 / 32.0, C2 = 0x1.62e42ff0c52d6p-1 / 32.0;
@@ -38,7 +41,7 @@ __device__ __forceinline__ float expf_ref( float x )
    const unsigned long long ki = (unsigned long long)__double_as_longlong( kd );
    kd = __dadd_rn( kd, -SHIFT );
    const double r = __dadd_rn( z, -kd );
-   const double s = __longlong_as_double( (long long)( EXP2F_TAB[ki & 31] + ( ki << 47 ) ) );
+   const double s = __longlong_as_double( (long long)( tab[ki & 31] + ( ki << 47 ) ) );
    z = __dadd_rn( __dmul_rn( C0, r ), C1 );
    const double r2 = __dmul_rn( r, r );
    double y = __dadd_rn( __dmul_rn( C2, r ), 1.0 );
@@ -241,5 +244,10 @@ __device__ __forceinline__ float log1pf_ref( float x )
 }
 
 // maths.h:327-334: 1 / (1 + expf(-x))
-__device__ __forceinline__ float sigmoid_ref( float v ) { return fdiv( 1.0f, fadd( 1.0f, expf_ref( -v ) ) ); }
+__device__ __forceinline__ float sigmoid_ref( float v, const unsigned long long *tab = EXP2F_TAB ) { return fdiv( 1.0f, fadd( 1.0f, expf_ref( -v, tab ) ) ); }
+// copy of the table for expf_ref( x, tab ); call with all threads of the CTA, then synchronize
+__device__ __forceinline__ void stage_exp2f_tab( unsigned long long *dst, int tid )
+{
+   if ( tid < 32 ) dst[tid] = EXP2F_TAB[tid];
+}
 } // namespace lme
