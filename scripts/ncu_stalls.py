@@ -3,9 +3,10 @@ usage: python scripts/ncu_stalls.py <rep> <kernel-regex> [top-n]"""
 import collections, csv, io, subprocess, sys
 rep, kre = sys.argv[1], sys.argv[2]
 topn = int(sys.argv[3]) if len(sys.argv) > 3 else 25
+inst = int(sys.argv[4]) if len(sys.argv) > 4 else 0   # which matching launch (0 = first)
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kre, "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
-hi = next(i for i, r in enumerate(rows) if "Instructions Executed" in r)
+hi = [i for i, r in enumerate(rows) if "Instructions Executed" in r][inst]
 hdr = rows[hi]
 iS, iE, iSamp = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("# Samples")
 stall_cols = [(i, h) for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
