@@ -19,8 +19,7 @@
 //   it for odd k -- a difference between +0 and -0 that vanishes at the first non-zero addend, and at the squares otherwise.)
 //
 // Mapping: the 128 rows (128 KB) are resident in shared memory for the whole launch, one CTA per SM, one chunk at a time per CTA.
-// compute thread = (unit u = bin pair (u, 128-u), half of the eight lanes, group of five frames): 64 x 2 x 5 = 640 threads (+ 32 that
-// stage the input, see the kernel). A thread walks
+// thread = (unit u = bin pair (u, 128-u), half of the eight lanes, group of five frames): 64 x 2 x 5 = 640 threads. A thread walks
 // its four lanes exactly like stft_kernel.cuh walks all eight (tree state for 2 rows x 5 frames in registers), keeps the plain and
 // the alternating pair sums, and meets its partner (lane ^ 16: same unit, other half) in one shuffle per value: the half-0 thread
 // finishes bin u, the half-1 thread bin 128-u -- magnitude and log1p are spread over all 640 threads.
@@ -29,125 +28,63 @@
 #include "libm_exact.cuh"
 #include "stft_kernel.cuh"
 
-#define SSYM_COMPUTE 640
-#define SSYM_THREADS ( SSYM_COMPUTE + 32 )     // + one producer warp
-#define SSYM_NBUF 3                             // ring of chunk tiles
+#define SSYM_THREADS 640
 #define SSYM_BS_FLOATS ( 64 * 128 * 4 )
-#define SSYM_SMEM_BYTES ( ( SSYM_BS_FLOATS + SSYM_NBUF * STFT_XS_FLOATS ) * 4 )
-
-__device__ __forceinline__ uint32_t ssym_smem_u32( const void *p ) { return (uint32_t)__cvta_generic_to_shared( p ); }
-__device__ __forceinline__ void ssym_mbar_init( uint64_t *bar, uint32_t count )
-{
-   asm volatile( "mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"( ssym_smem_u32( bar ) ), "r"( count ) : "memory" );
-}
-__device__ __forceinline__ void ssym_mbar_arrive( uint64_t *bar )
-{
-   asm volatile( "{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"( ssym_smem_u32( bar ) ) : "memory" );
-}
-__device__ __forceinline__ void ssym_mbar_wait( uint64_t *bar, uint32_t parity )
-{
-   uint32_t ok;
-   do
-   {
-      asm volatile( "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                    : "=r"( ok )
-                    : "r"( ssym_smem_u32( bar ) ), "r"( parity )
-                    : "memory" );
-   } while ( !ok );
-}
+#define SSYM_SMEM_BYTES ( ( SSYM_BS_FLOATS + 2 * STFT_XS_FLOATS ) * 4 )
 
 // out_mode 0: log1p(mag * 2^20) (production); 1: raw magnitude (parity tap for stft.c alone)
 //
-// Warps 0..19 compute, warp 20 produces: it converts the PCM of chunk n+1, n+2 into padded, permuted tiles (a ring of SSYM_NBUF) while the
-// compute warps work on chunk n. Tiles change hands through mbarriers (full[b]: the 32 producer lanes arrive; empty[b]: the 640 compute
-// threads arrive after their last read), so no warp ever waits for the slowest of the other nineteen: with one __syncthreads per chunk
-// 16 % of all stall samples sat on that barrier (profiles/ncu_summary_exact_r02a.md).
-// (672 threads x 96 registers = 64 512 of the SM's 65 536: __launch_bounds__ would round the block up to 768 threads and cap at 80)
+// One __syncthreads per chunk hands the double-buffered input tile over. Tried and measured slower (r02): a ring of four tiles with
+// mbarrier hand-over (full / empty) so that warps may run a chunk ahead of each other -- 15.8 ms instead of 13.0 ms per 131 072 chunks:
+// the main loop is issue-bound (36 % of the stall samples are "not selected", 9 % "dispatch"), and the polling warps take issue slots
+// from the working ones; a dedicated 21st producer warp does not fit (six warps on one scheduler x 96 registers > its 16 384).
 template <bool F32>
-__global__ void __maxnreg__( 96 )
+__global__ void __launch_bounds__( SSYM_THREADS, 1 )
 stft_sym_kernel( const void *__restrict__ in, long long stream_stride, int nw, int nchunks, const float *__restrict__ basis_sym /*[64][128][4]*/,
                  float *__restrict__ spec, int out_mode )
 {
    extern __shared__ __align__( 16 ) float smem[];
-   __shared__ __align__( 8 ) uint64_t bar_full[SSYM_NBUF], bar_empty[SSYM_NBUF];
    float *Bs = smem;
-   float *Xs_all = smem + SSYM_BS_FLOATS; // [SSYM_NBUF][1792]
+   float *Xs_all = smem + SSYM_BS_FLOATS; // [2 buffers][1792]
    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+   const int tg = w >> 2;                              // frames 5 tg .. 5 tg + 4
+   const int u = ( ( w & 3 ) << 4 ) | ( lane & 15 );   // unit: bins u and 128 - u
+   const int half = lane >> 4;                         // lanes 4 half .. 4 half + 3 of the tree
+   const bool special = u == 0;                        // rows: re of bin 0, merged row of bin 64
    {
       const float4 *src = reinterpret_cast<const float4 *>( basis_sym );
       float4 *dst = reinterpret_cast<float4 *>( Bs );
       for ( int i = tid; i < SSYM_BS_FLOATS / 4; i += SSYM_THREADS ) dst[i] = __ldg( src + i );
    }
-   if ( tid == 0 )
-   {
-      for ( int b = 0; b < SSYM_NBUF; ++b )
-      {
-         ssym_mbar_init( &bar_full[b], 32 );
-         ssym_mbar_init( &bar_empty[b], SSYM_COMPUTE );
-      }
-      asm volatile( "fence.mbarrier_init.release.cluster;" ::: "memory" );
-   }
+   constexpr int NV = F32 ? 384 : 192; // 16-byte vectors per chunk
+   int4 raw = make_int4( 0, 0, 0, 0 );
+   int ci = blockIdx.x;
+   if ( ci < nchunks && tid < NV ) raw = __ldg( (const int4 *)stft_chunk_ptr<F32>( in, stream_stride, nw, ci ) + tid );
    __syncthreads();
 
-   if ( w == SSYM_COMPUTE / 32 )
+   int buf = 0;
+   for ( ; ci < nchunks; ci += gridDim.x, buf ^= 1 )
    {
-      // ---- producer warp: PCM -> tile ring ------------------------------------------------------------------------------
-      constexpr int NV = F32 ? 384 : 192; // 16-byte vectors per chunk
-      constexpr int PER = NV / 32;
-      int4 raw[PER];
-      int ci = blockIdx.x;
-      if ( ci < nchunks )
+      float *xs = Xs_all + buf * STFT_XS_FLOATS;
+      if ( tid < NV )
       {
-         const int4 *src = (const int4 *)stft_chunk_ptr<F32>( in, stream_stride, nw, ci );
-#pragma unroll
-         for ( int i = 0; i < PER; ++i ) raw[i] = __ldg( src + lane + 32 * i );
-      }
-      for ( int n = 0; ci < nchunks; ci += gridDim.x, ++n )
-      {
-         const int b = n % SSYM_NBUF;
-         if ( n >= SSYM_NBUF ) ssym_mbar_wait( &bar_empty[b], ( ( n / SSYM_NBUF ) - 1 ) & 1 );
-         float *xs = Xs_all + b * STFT_XS_FLOATS;
-#pragma unroll
-         for ( int i = 0; i < PER; ++i )
+         if ( F32 )
          {
-            const int q = lane + 32 * i;
-            if ( F32 )
-            {
-               const float *f = reinterpret_cast<const float *>( &raw[i] );
+            const float *f = reinterpret_cast<const float *>( &raw );
 #pragma unroll
-               for ( int e = 0; e < 4; ++e ) stft_put( xs, 4 * q + e, f[e] );
-            }
-            else
-            {
-               const short *hh = reinterpret_cast<const short *>( &raw[i] );
-               // (float)s16 / 32768.0f (vadc.c:884,898); the division by a power of two is exact
-#pragma unroll
-               for ( int e = 0; e < 8; ++e ) stft_put( xs, 8 * q + e, (float)hh[e] * ( 1.0f / 32768.0f ) );
-            }
+            for ( int e = 0; e < 4; ++e ) stft_put( xs, 4 * tid + e, f[e] );
          }
-         ssym_mbar_arrive( &bar_full[b] );
-         const int cn = ci + gridDim.x;
-         if ( cn < nchunks )
+         else
          {
-            const int4 *src = (const int4 *)stft_chunk_ptr<F32>( in, stream_stride, nw, cn );
+            const short *hh = reinterpret_cast<const short *>( &raw );
+            // (float)s16 / 32768.0f (vadc.c:884,898); the division by a power of two is exact
 #pragma unroll
-            for ( int i = 0; i < PER; ++i ) raw[i] = __ldg( src + lane + 32 * i );
+            for ( int e = 0; e < 8; ++e ) stft_put( xs, 8 * tid + e, (float)hh[e] * ( 1.0f / 32768.0f ) );
          }
       }
-      return;
-   }
-
-   // ---- compute warps ---------------------------------------------------------------------------------------------------
-   const int tg = w >> 2;                              // frames 5 tg .. 5 tg + 4
-   const int u = ( ( w & 3 ) << 4 ) | ( lane & 15 );   // unit: bins u and 128 - u
-   const int half = lane >> 4;                         // lanes 4 half .. 4 half + 3 of the tree
-   const bool special = u == 0;                        // rows: re of bin 0, merged row of bin 64
-   int n = 0;
-   for ( int ci = blockIdx.x; ci < nchunks; ci += gridDim.x, ++n )
-   {
-      const int b = n % SSYM_NBUF;
-      const float *xs = Xs_all + b * STFT_XS_FLOATS;
-      ssym_mbar_wait( &bar_full[b], ( n / SSYM_NBUF ) & 1 );
+      __syncthreads(); // tile complete; the other buffer (previous chunk) is no longer read by anyone
+      const int cn = ci + gridDim.x;
+      if ( cn < nchunks && tid < NV ) raw = __ldg( (const int4 *)stft_chunk_ptr<F32>( in, stream_stride, nw, cn ) + tid );
 
       float Sp[2][5], Sm[2][5];
 #pragma unroll 1
@@ -198,7 +135,6 @@ stft_sym_kernel( const void *__restrict__ in, long long stream_stride, int nw, i
                }
          }
       }
-      ssym_mbar_arrive( &bar_empty[b] ); // (every load of the tile has been consumed by the arithmetic above)
 
       // lanes 0..3 (half 0) + lanes 4..7 (half 1): the half-0 thread takes the plain sums (bin u), the half-1 thread the alternating ones (bin 128-u)
       float *o = spec + (size_t)ci * ( VB_BINS * VB_FRAMES ) + 5 * tg;
