@@ -52,58 +52,48 @@ enum
 
 typedef struct silero_b200 silero_b200; /* opaque engine handle */
 
-/* STFT evaluation. HYBRID: fp32 FFT everywhere + the reference's exact rounding
-   sequence (stft.c:108-184) for every bin whose magnitude is below stft_k_rel * ||windowed frame||_2;
-   EXACT: the reference's sequence for every bin (bit-identical magnitudes, ~7x slower STFT). */
-#define SILERO_B200_STFT_AUTO 0            /* default: _EXACT for stream batches that run on the fp32 kernels (fewer than
-                                              SILERO_B200_LSTM_TENSOR_MIN_STREAMS streams per call: the single-stream use of the reference),
-                                              _HYBRID for the large batches of the tensor-core path */
-#define SILERO_B200_STFT_HYBRID 4          /* always the hybrid rule on the fp32 FFT kernel with 8 lanes per frame, 16 points per lane in
-                                              registers (stft_fft8_kernel.cuh) */
+/* Kernel families. The family is a property of the ENGINE, decided when it is created (never per call: a persistent stream must not
+   change arithmetic when the caller's batch shape changes):
+     exact  every mode AUTO (the default), or LAYERS_FAITHFUL / LSTM_FAITHFUL: the reference's own rounding sequence from the STFT to the
+            probability (stft_sym_kernel, exact_front/layer kernels, exact_lstm_kernel; few streams: CTA-per-chunk encoder and LSTM
+            wavefront -- same bits). Results are bit-identical to the reference build for ANY number of streams and any stream length.
+     fast   any explicit STFT_HYBRID / LSTM_FP32 / LSTM_TENSOR / LAYERS_FP32 / LAYERS_TENSOR: FFT-hybrid STFT, FMA chains or tcgen05
+            tensor-core contractions with split operands, SFU nonlinearities. ~7x the throughput, within 1e-4 of the reference chunk by
+            chunk on short streams; on long streams the decoder LSTM integrates the one-ulp differences. Opt-in. */
+/* STFT evaluation. HYBRID: fp32 FFT everywhere + the reference's exact rounding sequence (stft.c:108-184) for every bin whose magnitude is
+   below stft_k_rel * ||windowed frame||_2 (stft_fft8_kernel.cuh); EXACT: the reference's sequence for every bin (bit-identical
+   magnitudes; stft_sym_kernel.cuh, or stft_kernel.cuh for a basis without the mirror property). */
+#define SILERO_B200_STFT_AUTO 0            /* default: _EXACT, except in a fast-family engine whose LSTM runs on the tensor cores (_HYBRID) */
+#define SILERO_B200_STFT_HYBRID 4
 #define SILERO_B200_STFT_EXACT 1
-#define SILERO_B200_STFT_HYBRID_FFT 2      /* hybrid rule on the warp-per-frame fp32 FFT kernel (stft_hybrid_kernel.cuh): the first FFT kernel,
-                                              5 shuffle stages per frame, ~1.5x slower than _HYBRID */
-#define SILERO_B200_STFT_HYBRID_TENSOR 3   /* hybrid rule on the tcgen05 DFT-as-GEMM kernel (stft_tc_kernel.cuh): 25 % faster STFT, but the
-                                              tensor-core accumulator costs 10x in |dY| and probabilities reach 1.1e-4 on long streams:
-                                              opt-in, not a drop-in under the 1e-4 bar */
 #define SILERO_B200_STFT_K_REL_DEFAULT 0.004f
 
-/* Decoder LSTM evaluation. FP32: gate contractions as fp32 FMA chains on the CUDA cores
-   (any stream count). TENSOR: tcgen05 tensor-core GEMM over tiles of 32 streams with the bf16x2 split
-   (3 partial products, fp32 accumulation). AUTO picks TENSOR from SILERO_B200_LSTM_TENSOR_MIN_STREAMS streams up. */
+/* Decoder LSTM of a fast-family engine. FP32: gate contractions as fp32 FMA chains on the CUDA cores. TENSOR: tcgen05 tensor-core GEMM
+   over tiles of 32 streams with the bf16x2 split (3 partial products, fp32 accumulation). In a fast-family engine AUTO resolves, at
+   creation, to TENSOR when max_streams >= SILERO_B200_LSTM_TENSOR_MIN_STREAMS, else FP32. FAITHFUL selects the exact path. */
 #define SILERO_B200_LSTM_AUTO 0
 #define SILERO_B200_LSTM_FP32 1
 #define SILERO_B200_LSTM_TENSOR 2
 #define SILERO_B200_LSTM_TENSOR_MIN_STREAMS 1024
-#define SILERO_B200_LSTM_FAITHFUL 3        /* see SILERO_B200_LAYERS_FAITHFUL: either one selects the whole faithful path */
+#define SILERO_B200_LSTM_FAITHFUL 3
 
-/* Encoder layers 2..4. FP32: every contraction as in-thread fp32 FMA chains on the CUDA cores.
-   TENSOR: the six dense contractions of a layer as tcgen05 tensor-core GEMMs over tiles of 128 tokens with the fp16x2
-   split (hi/lo, 3 partial products, 22 significant bits per operand, fp32 accumulation); depthwise conv, attention core,
-   layer/batch norm stay fp32 on the CUDA cores. AUTO picks TENSOR from SILERO_B200_LAYERS_TENSOR_MIN_CHUNKS chunks per
-   pass up. The first layer (129 -> 16 channels) always runs on the CUDA cores. */
+/* Encoder layers of a fast-family engine. FP32: every contraction as in-thread fp32 FMA chains on the CUDA cores. TENSOR: the dense
+   contractions as tcgen05 tensor-core GEMMs over tiles of 128 tokens with the fp16x2 split (hi/lo, 3 partial products, 22 significant
+   bits per operand, fp32 accumulation). AUTO resolves like the LSTM's, from max_streams, at creation. FAITHFUL selects the exact path
+   (either FAITHFUL flag selects all of it: exact STFT, encoder, LSTM, decoder). */
 #define SILERO_B200_LAYERS_AUTO 0
 #define SILERO_B200_LAYERS_FP32 1
 #define SILERO_B200_LAYERS_TENSOR 2
-#define SILERO_B200_LAYERS_TENSOR_MIN_CHUNKS 2048
-/* FAITHFUL (faithful_kernel.cuh): from the log spectrogram to the probability every rounding step of the reference's C backend
-   as built with -mavx2 -ffp-contract=off -- dotproduct_simd's lane order (maths.h:123-158), conv_tensor's variant E and generic
-   paths (conv.c:532-709), sequential means and true divisions, glibc's expf/tanhf/log1pf bit for bit, no fused multiply-add --
-   on top of the exact STFT: probabilities are bit-identical to the reference's for streams of any length (the fast kernels are
-   within 1e-5 chunk by chunk but the decoder LSTM integrates one-ulp differences over long silences).
-   Up to 128 streams it costs no more than the fp32 CUDA-core kernels (one CTA per stream runs the serial LSTM, which bounds small
-   batches either way); per chunk the encoder is ~9x slower than the tensor-core path. A fully automatic engine (stft, lstm and layer modes all AUTO) takes it
-   for calls with at most SILERO_B200_FAITHFUL_MAX_STREAMS streams -- the way the reference itself is used. */
 #define SILERO_B200_LAYERS_FAITHFUL 3
-#define SILERO_B200_FAITHFUL_MAX_STREAMS 128      /* (round 1: the largest batch the exact path served by default; it now serves any) */
-#define SILERO_B200_EXACT_TOKEN_MIN_CHUNKS 1024   /* exact path: windows of at least this many chunks run the thread-per-token encoder */
+#define SILERO_B200_EXACT_TOKEN_MIN_CHUNKS 1024   /* exact path: windows of at least this many chunks run the thread-per-token encoder
+                                                     (below: a CTA per chunk -- more parallelism for small windows; identical bits) */
 
 typedef struct silero_b200_opts
 {
    int device;          /* CUDA device ordinal (default 0) */
    int max_streams;     /* number of independent streams whose LSTM state is kept on device (default 1) */
    int window_chunks;   /* chunks per stream processed per internal pass; 0 = choose from memory budget */
-   int stft_mode;       /* SILERO_B200_STFT_AUTO (default), _HYBRID, _EXACT, _HYBRID_FFT or _HYBRID_TENSOR */
+   int stft_mode;       /* SILERO_B200_STFT_AUTO (default), _HYBRID or _EXACT */
    float stft_k_rel;    /* hybrid threshold; 0 = SILERO_B200_STFT_K_REL_DEFAULT */
    int lstm_mode;       /* SILERO_B200_LSTM_AUTO (default), _FP32 (CUDA-core kernel), _TENSOR (tcgen05 kernel) or _FAITHFUL */
    int layer_mode;      /* SILERO_B200_LAYERS_AUTO (default), _FP32 (CUDA-core kernels), _TENSOR (tcgen05 kernel) or _FAITHFUL */
@@ -222,7 +212,7 @@ int silero_b200_stft_stats( silero_b200 *h, unsigned long long *bins_total, unsi
 /* parity tap: the engine's expf / tanhf / log1pf(|x|) (csrc/libm_exact.cuh: glibc's algorithms, used by the fp32 LSTM path, lstm.c:64-88
    via maths.h:302-334, and by the exact STFT path, misc.c:40-46) of n host floats; must equal the C library's results bit for bit */
 int silero_b200_stage_libm( silero_b200 *h, const float *x, int n, float *out_expf, float *out_tanhf, float *out_log1pf_abs );
-/* test hook for the failure path of the few-streams LSTM wavefront (faithful_lstm_wave_kernel): stall_producer != 0 makes the layer-0
+/* test hook for the failure path of the few-streams LSTM wavefront (exact_lstm_kernel<true>): stall_producer != 0 makes the layer-0
    tasks never publish their progress, spin_limit (> 0) bounds the consumers' polls. A consumer that gives up raises the engine's
    error word; the next synchronizing call (run_streams, sync, wait) returns SILERO_B200_ERR_CUDA and the streams' state is untouched.
    (0, 0) restores normal operation. */
@@ -261,7 +251,7 @@ int silero_b200_stage_exact_layer( silero_b200 *h, int layer, const float *in, i
    1: already normalized, 2: raw magnitude (log1p(m * 2^20) applied first, misc.c:40-46) */
 int silero_b200_stage_exact_encoder( silero_b200 *h, const float *spec, int batch, int kind, float *l1, float *l2, float *l3, float *l4 );
 /* lstm_tensor_minibatched on the exact path's kernels, arguments as silero_b200_stage_lstm; wave 0: the multi-stream kernel
-   (exact_lstm_kernel.cuh), 1: the wavefront kernel that serves few streams (faithful_lstm_wave_kernel) -- identical bits */
+   (exact_lstm_kernel.cuh), 1: its two-layer wavefront launch, which serves few streams -- identical bits */
 int silero_b200_stage_exact_lstm( silero_b200 *h, const float *x, int batch, const float *h0, const float *c0, float *out, float *hn, float *cn, int wave );
 /* adaptive_audio_normalization_inplace on a caller-supplied magnitude spectrogram [B,129,25] */
 int silero_b200_stage_norm( silero_b200 *h, const float *magnitude, int batch, float *norm_out );
@@ -283,11 +273,6 @@ int silero_b200_stage_lstm( silero_b200 *h, const float *x, int batch, const flo
                             float *out, float *hn, float *cn );
 /* decoder_tensor (silero_v3.c:305): in [B,64,7] -> out [B,2] */
 int silero_b200_stage_decoder( silero_b200 *h, const float *in, int batch, float *out );
-/* tensor-core plumbing tap (vadc_b200/csrc/tc_probe.cuh): D[128][N] = A[128][K] * B[N][K]^T evaluated by
- * tcgen05.mma with the bf16 x nsplit scheme (1: plain bf16, 2: 3 partial products, 3: 6 partial products).
- * reps > 1 repeats the MMA phase; *cycles (optional) receives the SM cycles spent in it. */
-int silero_b200_stage_tc_gemm( silero_b200 *h, const float *A, const float *B, int N, int K, int nsplit, int reps, float *D, long long *cycles );
-
 #ifdef __cplusplus
 }
 #endif

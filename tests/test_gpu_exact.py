@@ -142,7 +142,7 @@ def test_fixture_lstm():
 
 
 def test_lstm_kernels_agree_bit_for_bit():
-    """One stream: the multi-stream kernel (weights in registers) and the wavefront kernel (a CTA per stream and layer) on a long
+    """One stream: the multi-stream kernel (weights in registers) and the two-layer wavefront launch of the same kernel on a long
     sequence from a non-zero state: same outputs, same final state."""
     rng = np.random.default_rng(3)
     x = np.maximum(rng.standard_normal((60, 7, 64)).astype(np.float32), 0)
@@ -158,7 +158,7 @@ def test_lstm_kernels_agree_bit_for_bit():
 # ---- the whole path ----------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("S,N,window", [(75, 20, 7), (149, 12, 0), (300, 30, 11), (1185, 9, 4)])
 def test_batch_shapes_around_the_kernel_switches(S, N, window):
-    """Stream counts around the points where the engine changes mapping (wavefront LSTM <-> multi-stream LSTM at SMs / 2 streams,
+    """Stream counts around the points where the engine changes mapping (LSTM wavefront launch <-> one launch per layer at 10 x SMs / 2 streams,
     CTA-per-chunk <-> thread-per-token encoder at 1024 chunks per window; one and two streams per LSTM CTA): identical bits."""
     base = [vadc_b200.synth_pcm(900 + 17 * i, CHUNK * N) for i in range(16)]
     pcm = np.stack([np.roll(base[s % 16], CHUNK * ((s // 16) % N)) for s in range(S)])
@@ -192,3 +192,31 @@ def test_long_streams_at_scale_gate():
         assert np.array_equal(bits(probs[s]), bits(ref[:, 1])), (s, worst)
         assert vadc_b200.segments_text(probs[s]) == Oracle().segments_text(ref[:, 1])
     assert worst == 0.0
+
+
+def test_throughput_does_not_fall_when_streams_are_added():
+    """No regime cliff: with the kernel family fixed per engine, the device-resident rate (chunks per second) of a call must not drop when
+    the caller adds streams -- across the points where the engine changes kernel mapping (740/741 streams: LSTM wavefront launch -> one launch per layer;
+    1024 chunks per window: encoder CTA-per-chunk -> thread-per-token). 10 % tolerance for timer noise on these short runs."""
+    N = 32
+    base = [vadc_b200.synth_pcm(100 + i, CHUNK * N) for i in range(8)]
+    rates = []
+    sizes = (16, 64, 74, 75, 128, 129, 296, 297, 512, 740, 741, 1023, 1024, 4096)
+    e = vadc_b200.Engine(max_streams=max(sizes))
+    for S in sizes:
+        pcm = np.stack([base[s % 8] for s in range(S)])
+        d_pcm, d_probs = e.device_alloc(pcm.nbytes), e.device_alloc(S * N * 4)
+        e.h2d(d_pcm, pcm)
+        best = 0.0
+        for _ in range(3):
+            e.reset()
+            e.timer_start()
+            e.run_streams_device(d_pcm, pcm.shape[1], S, N, d_probs)
+            ms = e.timer_stop()
+            best = max(best, S * N / ms)
+        e.device_free(d_pcm)
+        e.device_free(d_probs)
+        rates.append(best)
+    e.close()
+    for (s0, r0), (s1, r1) in zip(zip(sizes, rates), list(zip(sizes, rates))[1:]):
+        assert r1 >= 0.9 * r0, "rate drops from %d streams (%.0f chunks/ms) to %d streams (%.0f chunks/ms): %r" % (s0, r0, s1, r1, list(zip(sizes, rates)))

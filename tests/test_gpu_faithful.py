@@ -124,7 +124,7 @@ def test_raw_probabilities_text_equals_the_reference_cli():
 
 
 def test_a_lost_wavefront_producer_is_an_error_not_a_wrong_answer():
-    """faithful_lstm_wave_kernel: the layer-1 task of a stream polls its layer-0 partner's progress. With the test hook the producer
+    """exact_lstm_kernel's two-layer wavefront (few streams): the layer-1 CTA of a stream group polls its layer-0 partner's progress. With the test hook the producer
     never publishes: the consumer gives up after the poll limit, the CALL FAILS (SILERO_B200_ERR_CUDA, no silent garbage) and the
     stream's persistent state is left as it was; the engine is usable again afterwards."""
     pcm = vadc_b200.synth_pcm(99, 30 * 1536)[None, :]

@@ -1,41 +1,11 @@
-"""tcgen05 plumbing (vadc_b200/csrc/tc_common.cuh): descriptors, TMEM round trip and the bf16 split
-scheme against an fp64 host product. Needs a B200."""
+"""The opt-in fast family's tcgen05 kernels (layer0_tc / layer_tc / lstm_tc over vadc_b200/csrc/tc_common.cuh) against the oracle and the
+reference's fixtures: within 1e-4 on short streams (their documented bar). Needs a B200."""
 import numpy as np
 import pytest
 
 import vadc_b200
 
 pytestmark = pytest.mark.gpu
-
-
-@pytest.fixture(scope="module")
-def eng():
-    e = vadc_b200.Engine(max_streams=4)
-    yield e
-    e.close()
-
-
-@pytest.mark.parametrize("n,k", [(16, 16), (16, 128), (32, 128), (64, 64), (48, 128)])
-@pytest.mark.parametrize("nsplit,tol", [(1, 2e-2), (2, 1e-4), (3, 2e-5)])  # the TMEM accumulator itself limits S=3 to ~7e-6 (measured; truncating adds)
-def test_tc_gemm_matches_fp64(eng, n, k, nsplit, tol):
-    rng = np.random.default_rng(n * 1000 + k + nsplit)
-    a = rng.standard_normal((128, k)).astype(np.float32)
-    b = rng.standard_normal((n, k)).astype(np.float32)
-    d, _ = eng.stage_tc_gemm(a, b, nsplit=nsplit)
-    ref = a.astype(np.float64) @ b.astype(np.float64).T
-    scale = np.sqrt(k)
-    assert np.abs(d - ref).max() / scale <= tol
-
-
-def test_tc_gemm_row_and_column_identity(eng):
-    """A = one-hot rows, B = distinct integers: checks the row->lane and column mapping exactly."""
-    k, n = 128, 32
-    a = np.zeros((128, k), np.float32)
-    a[np.arange(128), np.arange(128) % k] = 1.0
-    b = (np.arange(n)[:, None] * 128 + np.arange(k)[None, :]).astype(np.float32) / 8.0   # exact in bf16? no: use nsplit 3
-    d, _ = eng.stage_tc_gemm(a, b, nsplit=3)
-    ref = a.astype(np.float64) @ b.astype(np.float64).T
-    assert np.array_equal(d.astype(np.float64), ref)
 
 
 @pytest.mark.parametrize("S,N,window", [(70, 40, 16), (33, 21, 0), (1, 9, 4)])
@@ -133,77 +103,3 @@ def test_tc_layers_end_to_end_vs_oracle(S, N, window):
         assert vadc_b200.segments_text(pt[s]) == oracle.segments_text(ref[:, 1]), s
     assert worst <= 1e-4, worst
     et.close()
-
-
-# ---- tensor-core STFT (vadc_b200/csrc/stft_tc_kernel.cuh) -------------------------------------------------------
-@pytest.fixture(scope="module")
-def eng_stc():
-    e = vadc_b200.Engine(max_streams=64, stft_mode=vadc_b200.STFT_HYBRID_TENSOR)
-    yield e
-    e.close()
-
-
-@pytest.mark.parametrize("batch", [1, 3, 4, 5, 41])
-def test_tc_stft_magnitudes_vs_oracle(eng_stc, batch):
-    """DFT-as-GEMM on tcgen05 (fp16x2 split) + exact fix-up of small bins, f32 input path, partial tiles.
-    Bins above the hybrid threshold: relative error <= 1e-3 (measured 2e-4); flagged bins are bit-identical."""
-    from oracle_lib import Oracle
-    o = Oracle()
-    pcm = vadc_b200.synth_pcm(4242 + batch, 1536 * batch)
-    x = (pcm.astype(np.float32) / np.float32(32768)).reshape(-1, 1536)
-    ref = o.run_stages(x)["stft"]
-    eng_stc.stft_stats(reset=True)
-    mag = eng_stc.stage_stft_magnitude(x)
-    tot, ex = eng_stc.stft_stats(reset=True)
-    assert tot == batch * 129 * 25 and ex < 0.02 * tot
-    assert (np.abs(mag - ref) <= 1e-3 * ref).all()
-    r = ref.astype(np.float64)
-    wf_norm = np.sqrt((r[:, 0] ** 2 + r[:, 128] ** 2 + 2 * (r[:, 1:128] ** 2).sum(axis=1)) / 256.0)[:, None, :]   # Parseval
-    small = ref < 2e-3 * wf_norm                        # safely below the 4e-3 * ||windowed frame|| rule
-    assert np.array_equal(mag[small], ref[small])
-    if batch == 41:
-        assert ex > 100 and small.sum() > 50
-
-
-def test_tc_stft_degenerate_inputs(eng_stc):
-    """All-zero chunks (nothing flagged, log1p(0) = 0), full-scale DC and a pure tone (nearly every bin flagged: the work
-    list overflows and the in-kernel exact path takes over), LSB noise: magnitudes bit-identical wherever flagged."""
-    from oracle_lib import Oracle
-    o = Oracle()
-    n = np.arange(1536 * 3)
-    sig = np.zeros((4, 1536 * 3), np.float32)
-    sig[1] = 1.0 - 2.0 ** -15
-    sig[2] = np.round(12000 * np.sin(2 * np.pi * 1000.0 * n / 16000.0)) / 32768.0
-    sig[3] = (np.random.default_rng(1).integers(-1, 2, n.size)) / 32768.0
-    for i in range(4):
-        x = sig[i].reshape(-1, 1536)
-        ref = o.run_stages(x)["stft"]
-        mag = eng_stc.stage_stft_magnitude(x)
-        assert (np.abs(mag - ref) <= 1e-3 * ref + 1e-30).all(), i
-        norm_t, _ = eng_stc.stage_stft_norm(x)
-        o.reset()
-        assert np.abs(norm_t - o.run_stages(x)["norm"]).max() < 2e-3, i
-    assert np.array_equal(eng_stc.stage_stft_magnitude(sig[0].reshape(-1, 1536)), np.zeros((3, 129, 25), np.float32))
-
-
-@pytest.mark.parametrize("S,N,window", [(37, 23, 0), (2, 130, 50), (1, 9, 4)])
-def test_tc_stft_end_to_end_vs_oracle(S, N, window):
-    """Whole pipeline with every tensor-core kernel forced on (STFT, layers, LSTM): s16 input, several windows."""
-    from oracle_lib import Oracle
-    oracle = Oracle()
-    pcm = np.stack([vadc_b200.synth_pcm(9000 + s, N * 1536, kind=(0 if s % 5 else 2)) for s in range(S)])
-    e = vadc_b200.Engine(max_streams=S, window_chunks=window, stft_mode=vadc_b200.STFT_HYBRID_TENSOR,
-                         layer_mode=vadc_b200.LAYERS_TENSOR, lstm_mode=vadc_b200.LSTM_TENSOR)
-    p, out2 = e.run_streams(pcm, want_out2=True)
-    worst = 0.0
-    for s in sorted(set([0, S // 2, S - 1]) | set(range(0, S, 9))):
-        oracle.reset()
-        ref = oracle.run_pcm(pcm[s])
-        worst = max(worst, float(np.abs(out2[s] - ref).max()))
-        assert vadc_b200.segments_text(p[s]) == oracle.segments_text(ref[:, 1]), s
-    assert worst <= 1e-4, worst
-    x = (pcm[0].astype(np.float32) / np.float32(32768)).reshape(-1, 1536)
-    e.reset()
-    oracle.reset()
-    assert np.abs(e.run_chunks(x) - oracle.run_chunks(x)).max() <= 1e-4      # f32 entry point (backend_run)
-    e.close()

@@ -142,6 +142,6 @@ def test_python_constants_mirror_the_header():
     import re
     hdr = open(os.path.join(ROOT, "include", "silero_b200.h")).read()
     defs = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define SILERO_B200_(\w+)\s+(\d+)\b", hdr)}
-    for name in ("STFT_AUTO", "STFT_EXACT", "STFT_HYBRID", "STFT_HYBRID_FFT", "STFT_HYBRID_TENSOR", "LSTM_AUTO", "LSTM_FP32", "LSTM_TENSOR",
-                 "LSTM_FAITHFUL", "LAYERS_AUTO", "LAYERS_FP32", "LAYERS_TENSOR", "LAYERS_FAITHFUL", "FAITHFUL_MAX_STREAMS"):
+    for name in ("STFT_AUTO", "STFT_EXACT", "STFT_HYBRID", "LSTM_AUTO", "LSTM_FP32", "LSTM_TENSOR",
+                 "LSTM_FAITHFUL", "LAYERS_AUTO", "LAYERS_FP32", "LAYERS_TENSOR", "LAYERS_FAITHFUL"):
         assert getattr(vadc_b200, name) == defs[name], name

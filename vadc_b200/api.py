@@ -15,10 +15,9 @@ WEIGHTS_PATH = os.path.join(_HERE, "weights", "silero_v31_16k.testtensor")
 
 CHUNK = 1536
 SAMPLE_RATE = 16000
-STFT_AUTO, STFT_EXACT, STFT_HYBRID_FFT, STFT_HYBRID_TENSOR, STFT_HYBRID = 0, 1, 2, 3, 4
+STFT_AUTO, STFT_EXACT, STFT_HYBRID = 0, 1, 4
 LSTM_AUTO, LSTM_FP32, LSTM_TENSOR, LSTM_FAITHFUL = 0, 1, 2, 3
 LAYERS_AUTO, LAYERS_FP32, LAYERS_TENSOR, LAYERS_FAITHFUL = 0, 1, 2, 3
-FAITHFUL_MAX_STREAMS = 128  # SILERO_B200_FAITHFUL_MAX_STREAMS
 
 
 class EngineError(RuntimeError):
@@ -372,15 +371,6 @@ class Engine:
         out = np.zeros((x.shape[0], 2), np.float32)
         self._check(lib().silero_b200_stage_decoder(self._h, _p(x), x.shape[0], _p(out)))
         return out
-
-    def stage_tc_gemm(self, a, b, nsplit=2, reps=1):
-        """D[128,N] = A[128,K] @ B[N,K]^T on tcgen05 (bf16 x nsplit). Returns (D, cycles of the MMA phase)."""
-        a, b = _f32(a), _f32(b)
-        assert a.shape[0] == 128 and a.shape[1] == b.shape[1]
-        d = np.zeros((128, b.shape[0]), np.float32)
-        cyc = C.c_longlong(0)
-        self._check(lib().silero_b200_stage_tc_gemm(self._h, _p(a), _p(b), b.shape[0], a.shape[1], nsplit, reps, _p(d), C.byref(cyc)))
-        return d, cyc.value
 
 
 class Group:

@@ -7,6 +7,7 @@
 #include "silero_b200.h"
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -23,12 +24,9 @@
 #include "lstm_kernel.cuh"
 #include "lstm_tc_kernel.cuh"
 #include "segment_kernel.cuh"
-#include "stft_hybrid_kernel.cuh"
 #include "stft_fft8_kernel.cuh"
 #include "stft_kernel.cuh"
 #include "stft_sym_kernel.cuh"
-#include "stft_tc_kernel.cuh"
-#include "tc_probe.cuh"
 #include "testtensor.h"
 #include "vadc_segmenter.h"
 
@@ -69,15 +67,11 @@ struct silero_b200
    int window_chunks_opt;
    int stft_mode;            // kernel family: 0 = FFT hybrid (stft_fft8_kernel), SILERO_B200_STFT_EXACT, _HYBRID_FFT, _HYBRID_TENSOR
    int stft_auto;            // SILERO_B200_STFT_AUTO: run_window picks the exact kernel for small stream batches (the fp32 path)
-   unsigned char *d_stft_tc; // fp16 hi/lo basis image in K slices (stft_tc_kernel.cuh)
-   unsigned long long *d_fix_list; // work list of flagged bins (stft_tc_kernel -> stft_fixup_kernel)
-   size_t fix_cap;
-   unsigned int *d_fix_count;
    float stft_k_rel;         // hybrid: exact re-evaluation below k_rel * ||frame||
    int lstm_mode;            // SILERO_B200_LSTM_*
    unsigned char *d_lstm_tc; // [2 layers][LTC_W_BYTES] bf16 hi/lo weight images (lstm_tc_kernel.cuh)
    int layer_mode;           // SILERO_B200_LAYERS_*
-   int faithful;             // 2: faithful_kernel.cuh path for every batch; 1: for batches of at most SILERO_B200_FAITHFUL_MAX_STREAMS streams
+   int faithful;             // != 0: the exact path (reference's rounding sequence) for every call; fixed at creation
    L0DwParams l0_dw;         // first layer's depthwise taps, passed to layer0_tc_kernel by value
    unsigned char *d_layer_tc[4]; // fp16 hi/lo weight images + fp32 parameters per layer (layer0_tc_kernel.cuh, layer_tc_kernel.cuh)
    size_t cap_h0_floats;
@@ -91,7 +85,7 @@ struct silero_b200
    float *d_weights;         // one allocation holding every packed weight
    DeviceWeights w;
    fq::Weights fw;           // the container's 99 tensors as they are (faithful_kernel.cuh)
-   int *d_lstm_sync;         // [1 + max_streams]: task ticket + per-stream layer-0 progress of faithful_lstm_wave_kernel
+   int *d_lstm_sync;         // [1 + groups]: role ticket + per-group layer-0 progress of the exact_lstm_kernel wavefront
    int *err_word;            // mapped pinned host word a kernel raises when it gives up (wavefront consumer whose producer is lost)
    int *d_err_word;          // its device address
    int wave_spin_limit;      // polls before a wavefront consumer gives up (debug taps lower it)
@@ -356,26 +350,6 @@ static void pack_layer_tc( const float *blob, unsigned char *img )
    memcpy( f + Cfg::F_BNB, blob + P::BNB, sizeof( float ) * C );
 }
 
-// basis image for stft_tc_kernel: [K slice (8)][split][k-chunk (4)][n (256)][8] fp16; column n = 2f -> row f (Re), 2f+1 -> row 129+f (Im),
-// n = 0 -> row 0, n = 1 -> row 128 (rows 129 and 257 are identically zero)
-static void pack_stft_tc( const float *basis /*[258][256]*/, unsigned char *img )
-{
-   for ( int n = 0; n < 256; ++n )
-   {
-      const int f = n >> 1;
-      const int row = n == 0 ? 0 : ( n == 1 ? 128 : ( ( n & 1 ) ? 129 + f : f ) );
-      for ( int k = 0; k < 256; ++k )
-      {
-         const float v = basis[(size_t)row * 256 + k];
-         const __half hi = __float2half_rn( v );
-         const __half lo = __float2half_rn( v - __half2float( hi ) );
-         const size_t off = (size_t)( k >> 5 ) * STC_B_SLICE + (size_t)( ( k >> 3 ) & 3 ) * STC_B_LBO + (size_t)n * 16 + (size_t)( k & 7 ) * 2;
-         memcpy( img + off, &hi, 2 );
-         memcpy( img + off + STC_B_SPLIT, &lo, 2 );
-      }
-   }
-}
-
 // image of the first layer for layer0_tc_kernel, from the LayerPack<0> blob
 static void pack_layer0_tc( const float *blob, unsigned char *img )
 {
@@ -448,8 +422,6 @@ static int configure_kernels()
    CU( allow_smem( stft_logmag_kernel<true>, STFT_SMEM_BYTES ) );
    CU( allow_smem( stft_sym_kernel<false>, SSYM_SMEM_BYTES ) );
    CU( allow_smem( stft_sym_kernel<true>, SSYM_SMEM_BYTES ) );
-   CU( allow_smem( stft_hybrid_kernel<false>, HYB_SMEM_BYTES ) );
-   CU( allow_smem( stft_hybrid_kernel<true>, HYB_SMEM_BYTES ) );
    CU( allow_smem( stft_fft8_kernel<false, false>, F8_SMEM_BYTES ) );
    CU( allow_smem( stft_fft8_kernel<true, false>, F8_SMEM_BYTES ) );
    CU( allow_smem( stft_fft8_kernel<false, true>, F8_SMEM_BYTES ) );
@@ -463,9 +435,6 @@ static int configure_kernels()
    CU( allow_smem( lstm_layer_kernel<1, 4>, LstmSmem<4>::BYTES ) );
    CU( allow_smem( lstm_layer_kernel<0, 1>, LstmSmem<1>::BYTES ) );
    CU( allow_smem( lstm_layer_kernel<1, 1>, LstmSmem<1>::BYTES ) );
-   CU( allow_smem( faithful_lstm_kernel<0>, FLSTM_SMEM_BYTES ) );
-   CU( allow_smem( faithful_lstm_kernel<1>, FLSTM_SMEM_BYTES ) );
-   CU( allow_smem( faithful_lstm_wave_kernel, FLSTM_SMEM_BYTES ) );
    CU( allow_smem( faithful_encoder_kernel, FAITHFUL_SMEM_BYTES ) );
    CU( allow_smem( exact_front_kernel<true>, XF_SMEM_BYTES ) );
    CU( allow_smem( exact_front_kernel<false>, XF_SMEM_BYTES ) );
@@ -473,13 +442,10 @@ static int configure_kernels()
    CU( allow_smem( exact_layer_kernel<1>, XeCfg<1>::SMEM_BYTES ) );
    CU( allow_smem( exact_layer_kernel<2>, XeCfg<2>::SMEM_BYTES ) );
    CU( allow_smem( exact_layer_kernel<3>, XeCfg<3>::SMEM_BYTES ) );
-   CU( allow_smem( exact_lstm_kernel<0>, XL_SMEM_BYTES ) );
-   CU( allow_smem( exact_lstm_kernel<1>, XL_SMEM_BYTES ) );
-   CU( allow_smem( tc_probe_kernel, 200 * 1024 ) );
+   CU( allow_smem( exact_lstm_kernel<false>, XL_SMEM_BYTES ) );
+   CU( allow_smem( exact_lstm_kernel<true>, XL_SMEM_BYTES ) );
    CU( allow_smem( lstm_tc_kernel<0>, LTC_SMEM_BYTES ) );
    CU( allow_smem( lstm_tc_kernel<1>, LTC_SMEM_BYTES ) );
-   CU( allow_smem( stft_tc_kernel<false>, STC_SMEM_BYTES ) );
-   CU( allow_smem( stft_tc_kernel<true>, STC_SMEM_BYTES ) );
    CU( allow_smem( layer0_tc_kernel<false>, L0tc::SMEM_BYTES ) );
    CU( allow_smem( layer0_tc_kernel<true>, L0tc::SMEM_BYTES ) );
    CU( allow_smem( layer_tc_kernel<1>, LtcCfg<1>::SMEM_BYTES ) );
@@ -512,9 +478,6 @@ extern "C" void silero_b200_destroy( silero_b200 *h )
    cudaFree( h->d_lstm_sync );
    if ( h->err_word ) cudaFreeHost( h->err_word );
    cudaFree( h->d_lstm_tc );
-   cudaFree( h->d_stft_tc );
-   cudaFree( h->d_fix_list );
-   cudaFree( h->d_fix_count );
    for ( int i = 0; i < 4; ++i ) cudaFree( h->d_layer_tc[i] );
    cudaFree( h->d_seg_state );
    cudaFree( h->d_segs );
@@ -594,9 +557,7 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    h->device = opts.device;
    h->max_streams = opts.max_streams;
    h->window_chunks_opt = opts.window_chunks;
-   h->stft_mode = ( opts.stft_mode == SILERO_B200_STFT_EXACT || opts.stft_mode == SILERO_B200_STFT_HYBRID_FFT || opts.stft_mode == SILERO_B200_STFT_HYBRID_TENSOR )
-                     ? opts.stft_mode
-                     : 0;
+   h->stft_mode = opts.stft_mode == SILERO_B200_STFT_EXACT ? SILERO_B200_STFT_EXACT : 0;
    h->stft_auto = opts.stft_mode != SILERO_B200_STFT_HYBRID && h->stft_mode == 0;
    h->stft_k_rel = opts.stft_k_rel > 0.0f ? opts.stft_k_rel : SILERO_B200_STFT_K_REL_DEFAULT;
    h->lstm_mode = ( opts.lstm_mode == SILERO_B200_LSTM_FP32 || opts.lstm_mode == SILERO_B200_LSTM_TENSOR ) ? opts.lstm_mode : SILERO_B200_LSTM_AUTO;
@@ -604,7 +565,7 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    // The kernel family is decided HERE, once per engine, never per call: a persistent stream must not change arithmetic when the
    // caller's batch shape changes (a stream's LSTM state integrates one-ulp differences over minutes).
    //   * every mode AUTO (the default), or FAITHFUL requested: the exact path -- the reference's own rounding sequence from the STFT to
-   //     the probability (stft_sym_kernel / exact_encoder_kernel / exact_lstm_kernel, faithful_lstm_wave_kernel for few streams), for
+   //     the probability (stft_sym_kernel / exact_encoder_kernel / exact_lstm_kernel), for
    //     ANY number of streams; results are bit-identical to the reference whatever the batch composition;
    //   * any explicit fast mode (STFT_HYBRID*, LSTM_FP32/TENSOR, LAYERS_FP32/TENSOR): the fast family (1e-4 per chunk, drifts on long
    //     streams: DESIGN.md section 2); its remaining AUTO members are resolved from max_streams, also once.
@@ -734,8 +695,6 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    pack_lstm( tf.tensors[95].data, host + o_lstm );
    unsigned char *tc_img = (unsigned char *)calloc( 2, LTC_W_BYTES );
    if ( tc_img ) pack_lstm_tc( tf.tensors[95].data, tc_img );
-   unsigned char *stc_img = (unsigned char *)malloc( STC_B_IMAGE );
-   if ( stc_img ) pack_stft_tc( tf.tensors[0].data, stc_img );
    unsigned char *ltc_img[4] = { (unsigned char *)malloc( L0tc::IMG_BYTES ), (unsigned char *)malloc( LtcCfg<1>::IMG_BYTES ), (unsigned char *)malloc( LtcCfg<2>::IMG_BYTES ),
                                  (unsigned char *)malloc( LtcCfg<3>::IMG_BYTES ) };
    const size_t ltc_bytes[4] = { L0tc::IMG_BYTES, LtcCfg<1>::IMG_BYTES, LtcCfg<2>::IMG_BYTES, LtcCfg<3>::IMG_BYTES };
@@ -763,10 +722,6 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    if ( ce == cudaSuccess ) ce = cudaMalloc( &h->d_lstm_tc, 2 * LTC_W_BYTES );
    if ( ce == cudaSuccess ) ce = cudaMemcpy( h->d_lstm_tc, tc_img, 2 * LTC_W_BYTES, cudaMemcpyHostToDevice );
    free( tc_img );
-   if ( ce == cudaSuccess && !stc_img ) ce = cudaErrorMemoryAllocation;
-   if ( ce == cudaSuccess ) ce = cudaMalloc( &h->d_stft_tc, STC_B_IMAGE );
-   if ( ce == cudaSuccess ) ce = cudaMemcpy( h->d_stft_tc, stc_img, STC_B_IMAGE, cudaMemcpyHostToDevice );
-   free( stc_img );
    for ( int l = 0; l < 4; ++l )
    {
       if ( ce == cudaSuccess && !ltc_img[l] ) ce = cudaErrorMemoryAllocation;
@@ -927,50 +882,19 @@ static int pick_window( const silero_b200 *h, int nstreams, int nchunks, bool ho
 // ---------------------------------------------------------------------------------------------
 static inline int imin( int a, int b ) { return a < b ? a : b; }
 
-static bool stft_use_tensor( const silero_b200 *h, int nchunks )
-{
-   // opt-in only: the tensor-core accumulator truncates (measured |dY| ~ 1.3e-6 ||frame|| vs 1.3e-7 for the fp32 FFT), which
-   // leaves too little of the 1e-4 probability budget on long streams (measured 1.08e-4 on 7 minutes)
-   (void)nchunks;
-   return h->stft_mode == SILERO_B200_STFT_HYBRID_TENSOR;
-}
-
 // mu (optional): receives the adaptive-normalization scalar per chunk when the selected kernel produces it (the FFT
 // kernel); the tensor-core and exact kernels leave it to the first layer (the caller checks stft_produces_mu)
-static bool stft_produces_mu( const silero_b200 *h, int nchunks ) { return h->stft_mode != SILERO_B200_STFT_EXACT && !stft_use_tensor( h, nchunks ); }
+static bool stft_produces_mu( const silero_b200 *h, int nchunks )
+{
+   (void)nchunks;
+   return h->stft_mode != SILERO_B200_STFT_EXACT;
+}
 
 static int launch_stft( silero_b200 *h, const void *d_in, int in_f32, long long stream_stride, int nw, int nchunks, float *spec, int out_mode, float *mu = 0,
                         cudaStream_t st = 0 )
 {
-   if ( !st ) st = h->stream; // (the tensor-core mode always runs on h->stream: it has a work list and a second kernel)
-   if ( stft_use_tensor( h, nchunks ) )
-   {
-      const int ntiles = ( nchunks + 3 ) / 4;
-      const int grid = imin( ntiles, h->sm_count );
-      // work list for the flagged bins: 1/64 of all bins (4x the rate of speech-like audio); overflow is handled in-kernel
-      size_t want = (size_t)nchunks * VB_BINS * VB_FRAMES / 64 + 4096;
-      if ( want > 0xfffffff0ull ) want = 0xfffffff0ull;
-      if ( grow( &h->d_fix_list, &h->fix_cap, want ) ) return SILERO_B200_ERR_CUDA;
-      if ( !h->d_fix_count ) CU( cudaMalloc( &h->d_fix_count, sizeof( unsigned int ) ) );
-      CU( cudaMemsetAsync( h->d_fix_count, 0, sizeof( unsigned int ), h->stream ) );
-      const unsigned int cap = (unsigned int)h->fix_cap;
-      const int fgrid = h->sm_count * 8;
-      if ( in_f32 )
-      {
-         stft_tc_kernel<true><<<grid, STC_THREADS, STC_SMEM_BYTES, h->stream>>>( d_in, stream_stride, nw, nchunks, h->d_stft_tc, h->w.basis_raw, spec, h->stft_k_rel, out_mode,
-                                                                                 h->d_flagged, h->d_fix_list, h->d_fix_count, cap );
-         stft_fixup_kernel<true><<<fgrid, 256, 0, h->stream>>>( d_in, stream_stride, nw, h->w.basis_raw, spec, h->d_fix_list, h->d_fix_count, cap, out_mode, h->d_flagged, nchunks );
-      }
-      else
-      {
-         stft_tc_kernel<false><<<grid, STC_THREADS, STC_SMEM_BYTES, h->stream>>>( d_in, stream_stride, nw, nchunks, h->d_stft_tc, h->w.basis_raw, spec, h->stft_k_rel, out_mode,
-                                                                                  h->d_flagged, h->d_fix_list, h->d_fix_count, cap );
-         stft_fixup_kernel<false><<<fgrid, 256, 0, h->stream>>>( d_in, stream_stride, nw, h->w.basis_raw, spec, h->d_fix_list, h->d_fix_count, cap, out_mode, h->d_flagged, nchunks );
-      }
-      h->launches++;
-      h->bins_total += (unsigned long long)nchunks * VB_BINS * VB_FRAMES;
-   }
-   else if ( h->stft_mode == SILERO_B200_STFT_EXACT && h->stft_sym )
+   if ( !st ) st = h->stream;
+   if ( h->stft_mode == SILERO_B200_STFT_EXACT && h->stft_sym )
    {
       const int grid = imin( h->sm_count, nchunks );
       if ( in_f32 )
@@ -1010,21 +934,6 @@ static int launch_stft( silero_b200 *h, const void *d_in, int in_f32, long long 
          else
             stft_fft8_kernel<false, false><<<grid, F8_THREADS, F8_SMEM_BYTES, st>>>( d_in, stream_stride, nw, nchunks, h->w.basis_raw, spec, mu, h->stft_k_rel, h->d_flagged );
       }
-      h->bins_total += (unsigned long long)nchunks * VB_BINS * VB_FRAMES;
-   }
-   else
-   {
-      static int per_sm = 0;
-      if ( !per_sm )
-      {
-         CU( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm, stft_hybrid_kernel<false>, HYB_THREADS, HYB_SMEM_BYTES ) );
-         if ( per_sm < 1 ) per_sm = 1;
-      }
-      int grid = imin( nchunks, h->sm_count * per_sm );
-      if ( in_f32 )
-         stft_hybrid_kernel<true><<<grid, HYB_THREADS, HYB_SMEM_BYTES, st>>>( d_in, stream_stride, nw, nchunks, h->w.basis_raw, spec, mu, h->stft_k_rel, out_mode, h->d_flagged );
-      else
-         stft_hybrid_kernel<false><<<grid, HYB_THREADS, HYB_SMEM_BYTES, st>>>( d_in, stream_stride, nw, nchunks, h->w.basis_raw, spec, mu, h->stft_k_rel, out_mode, h->d_flagged );
       h->bins_total += (unsigned long long)nchunks * VB_BINS * VB_FRAMES;
    }
    h->launches++;
@@ -1150,35 +1059,6 @@ static int launch_faithful_encoder( silero_b200 *h, const float *spec, float *a4
    return 0;
 }
 
-// one LSTM layer with the gate contractions in dotproduct_simd order (faithful_lstm_kernel: one CTA per stream); hseq receives the
-// layer's output sequence [S][nw*7][64]
-template <int LAYER>
-static int launch_lstm_faithful( silero_b200 *h, const float *x, float *hseq, int first_stream, int nstreams, int nw )
-{
-   float *sh = h->state_h + (size_t)first_stream * SILERO_B200_STATE_FLOATS;
-   float *sc = h->state_c + (size_t)first_stream * SILERO_B200_STATE_FLOATS;
-   const int grid = imin( nstreams, h->sm_count );
-   faithful_lstm_kernel<LAYER><<<grid, FLSTM_THREADS, FLSTM_SMEM_BYTES, h->stream>>>( x, hseq, sh, sc, h->w.lstm_w, h->w.lstm_b, nstreams, nw );
-   h->launches++;
-   CU( cudaGetLastError() );
-   return 0;
-}
-
-// both LSTM layers as one wavefront launch (faithful_lstm_wave_kernel): a4 holds the encoder's output on entry and the top layer's
-// output sequence on exit, h0 the first layer's sequence
-static int launch_lstm_faithful_wave( silero_b200 *h, float *a4, float *h0, int first_stream, int nstreams, int nw )
-{
-   float *sh = h->state_h + (size_t)first_stream * SILERO_B200_STATE_FLOATS;
-   float *sc = h->state_c + (size_t)first_stream * SILERO_B200_STATE_FLOATS;
-   CU( cudaMemsetAsync( h->d_lstm_sync, 0, ( (size_t)nstreams + 1 ) * sizeof( int ), h->stream ) );
-   const int grid = imin( 2 * nstreams, h->sm_count );
-   faithful_lstm_wave_kernel<<<grid, FLSTM_THREADS, FLSTM_SMEM_BYTES, h->stream>>>( a4, h0, a4, sh, sc, h->w.lstm_w, h->w.lstm_b, nstreams, nw, h->d_lstm_sync,
-                                                                                    h->d_err_word, h->wave_spin_limit, h->debug_stall_producer );
-   h->launches++;
-   CU( cudaGetLastError() );
-   return 0;
-}
-
 // the encoder in the reference's rounding sequence, thread = token (exact_encoder_kernel.cuh): front (normalization scalar, depthwise
 // conv, the two K = 129 contractions) + one launch per layer
 template <int L>
@@ -1214,16 +1094,34 @@ static int launch_exact_encoder( silero_b200 *h, const float *spec, float *a4, i
    return launch_exact_layer<3>( h, h->a3, a4, nchunks );
 }
 
-// one LSTM layer for any number of streams, still in the reference's rounding sequence (exact_lstm_kernel.cuh: weights in registers,
-// a CTA walks a set of streams together); hseq receives the layer's output sequence [S][nw*7][64]
-template <int LAYER>
-static int launch_lstm_exact( silero_b200 *h, const float *x, float *hseq, int first_stream, int nstreams, int nw )
+// the decoder LSTM in the reference's rounding sequence (exact_lstm_kernel.cuh: weights in registers, a CTA walks a set of streams
+// together). x0: encoder output [S][nw*7][64] on entry, top layer's output sequence on exit; h0: the first layer's sequence.
+// Few streams (2 x groups <= SMs): both layers in one wavefront launch; else one launch per layer.
+#define XL_WAVE_MAX_PER_CTA 10 // measured: the wavefront wins up to ~10 streams per CTA (297 streams: 1.09 vs 1.59 ms), two launches win from ~1000 streams on (4096: 9.4 vs 9.9 ms)
+static int launch_lstm_exact( silero_b200 *h, float *x0, float *h0, int first_stream, int nstreams, int nw, int force_mode = 0 )
 {
    float *sh = h->state_h + (size_t)first_stream * SILERO_B200_STATE_FLOATS;
    float *sc = h->state_c + (size_t)first_stream * SILERO_B200_STATE_FLOATS;
-   const int grid = imin( nstreams, h->sm_count );
-   exact_lstm_kernel<LAYER><<<grid, XL_THREADS, XL_SMEM_BYTES, h->stream>>>( x, hseq, sh, sc, h->w.lstm_w, h->w.lstm_b, nstreams, nw );
-   h->launches++;
+   const int half_sms = h->sm_count / 2;
+   const bool wave = force_mode ? force_mode == 1 : nstreams <= half_sms * XL_WAVE_MAX_PER_CTA;
+   if ( wave )
+   {
+      const int groups = imin( nstreams, half_sms );
+      CU( cudaMemsetAsync( h->d_lstm_sync, 0, ( (size_t)groups + 1 ) * sizeof( int ), h->stream ) );
+      exact_lstm_kernel<true><<<2 * groups, XL_THREADS, XL_SMEM_BYTES, h->stream>>>( x0, h0, x0, sh, sc, h->w.lstm_w, h->w.lstm_b, nstreams, nw, 0, h->d_lstm_sync,
+                                                                                     h->d_err_word, h->wave_spin_limit, h->debug_stall_producer );
+      h->launches++;
+   }
+   else
+   {
+      const int grid = imin( nstreams, h->sm_count );
+      for ( int layer = 0; layer < 2; ++layer )
+      {
+         exact_lstm_kernel<false><<<grid, XL_THREADS, XL_SMEM_BYTES, h->stream>>>( x0, h0, x0, sh, sc, h->w.lstm_w, h->w.lstm_b, nstreams, nw, layer, 0, h->d_err_word,
+                                                                                   0, 0 );
+         h->launches++;
+      }
+   }
    CU( cudaGetLastError() );
    return 0;
 }
@@ -1236,9 +1134,16 @@ static int first_layer_from_logspec( silero_b200 *h, const float *spec, float *a
    return mu ? launch_layer<0, false>( h, spec, a1, nchunks, ENTRY_LAYER, TAP_LAYER, mu ) : launch_layer<0, true>( h, spec, a1, nchunks );
 }
 
+// Stage boundaries of a window: a CUDA event when per-stage profiling is on, and always an NVTX range (header-only nvtx3: a no-op
+// unless a profiler is attached) named after the reference function(s) the stage replaces -- the counterpart of the reference's Tracy
+// zones (TracyCZone in stft.c, conv.c, transformer.c, lstm.c, silero_v3.c).
+static const char *const kStageNames[8] = { "window", "my_stft+log1p (stft.c:15, misc.c:40)", "transformer_layer 1 (transformer.c:237)", "transformer_layer 2",
+                                            "transformer_layer 3", "transformer_layer 4", "lstm layer 0 (lstm.c:228)", "lstm layer 1 + decoder (silero_v3.c:231)" };
 static void stage_mark( silero_b200 *h, int i )
 {
    if ( h->profiling ) cudaEventRecord( h->ev_stage[i], h->stream );
+   if ( i > 0 ) nvtxRangePop();
+   if ( i < 7 ) nvtxRangePushA( kStageNames[i + 1] );
 }
 
 // one window: nstreams x nw chunks; input chunk (s, n) at d_in + s*stream_stride + n*1536
@@ -1261,7 +1166,7 @@ static int run_window( silero_b200 *h, const void *d_in, int in_f32, long long s
    stage_mark( h, 0 );
    const bool have_mu = stft_produces_mu( h, nchunks );
    // (an input that was produced by earlier work on h->stream itself, like run_chunks' own upload, keeps the STFT on that stream)
-   const bool overlap = !h->profiling && !stft_use_tensor( h, nchunks ) && !input_is_ordered_on_stream;
+   const bool overlap = !h->profiling && !input_is_ordered_on_stream;
    cudaStream_t fs = overlap ? h->front_stream : h->stream;
    if ( overlap )
    {
@@ -1310,17 +1215,8 @@ static int run_window( silero_b200 *h, const void *d_in, int in_f32, long long s
          if ( launch_exact_layer<3>( h, h->a3, h->a4, nchunks ) ) return SILERO_B200_ERR_CUDA;
          stage_mark( h, 5 );
       }
-      if ( nstreams > h->sm_count / 2 )
-      {
-         if ( launch_lstm_exact<0>( h, h->a4, h->h0, first_stream, nstreams, nw ) ) return SILERO_B200_ERR_CUDA;
-         stage_mark( h, 6 );
-         if ( launch_lstm_exact<1>( h, h->h0, h->a4, first_stream, nstreams, nw ) ) return SILERO_B200_ERR_CUDA;
-      }
-      else
-      {
-         if ( launch_lstm_faithful_wave( h, h->a4, h->h0, first_stream, nstreams, nw ) ) return SILERO_B200_ERR_CUDA;
-         stage_mark( h, 6 );
-      }
+      if ( launch_lstm_exact( h, h->a4, h->h0, first_stream, nstreams, nw ) ) return SILERO_B200_ERR_CUDA;
+      stage_mark( h, 6 );
       {
          const long long n = (long long)nchunks * 2;
          faithful_decoder_kernel<<<(unsigned)( ( n + 127 ) / 128 ), 128, 0, h->stream>>>( h->a4, h->w.dec_w, h->w.dec_b, nstreams, nw, d_out2, d_probs, out_stride, out_off );
@@ -1408,7 +1304,7 @@ extern "C" int silero_b200_run_streams_device( silero_b200 *h, const int16_t *d_
    return SILERO_B200_OK;
 }
 
-// after a synchronization point: did a kernel give up? (faithful_lstm_wave_kernel's consumers raise the word instead of hanging)
+// after a synchronization point: did a kernel give up? (the consumers of exact_lstm_kernel's wavefront raise the word instead of hanging)
 static int check_err_word( silero_b200 *h )
 {
    const int e = *(volatile int *)h->err_word;
@@ -2367,17 +2263,9 @@ extern "C" int silero_b200_stage_exact_lstm( silero_b200 *h, const float *x, int
    h->state_h = sh.p;
    h->state_c = sc.p;
    int rc;
-   if ( wave )
-   {
-      // the wavefront kernel works in place: the input buffer receives the top layer's sequence
-      rc = launch_lstm_faithful_wave( h, dx.p, dh0.p, 0, 1, batch );
-      if ( !rc ) rc = cudaMemcpyAsync( dtop.p, dx.p, n * sizeof( float ), cudaMemcpyDeviceToDevice, h->stream ) == cudaSuccess ? 0 : SILERO_B200_ERR_CUDA;
-   }
-   else
-   {
-      rc = launch_lstm_exact<0>( h, dx.p, dh0.p, 0, 1, batch );
-      if ( !rc ) rc = launch_lstm_exact<1>( h, dh0.p, dtop.p, 0, 1, batch );
-   }
+   // (in place: the input buffer receives the top layer's sequence)
+   rc = launch_lstm_exact( h, dx.p, dh0.p, 0, 1, batch, wave ? 1 : 2 );
+   if ( !rc ) rc = cudaMemcpyAsync( dtop.p, dx.p, n * sizeof( float ), cudaMemcpyDeviceToDevice, h->stream ) == cudaSuccess ? 0 : SILERO_B200_ERR_CUDA;
    h->state_h = save_h;
    h->state_c = save_c;
    if ( rc ) return rc;
@@ -2418,23 +2306,3 @@ extern "C" int silero_b200_stage_decoder( silero_b200 *h, const float *in, int b
    return down( h, out, dout.p, (size_t)batch * 2 ) ? SILERO_B200_ERR_CUDA : SILERO_B200_OK;
 }
 
-// ---------------------------------------------------------------------------------------------
-// tensor-core plumbing tap: D[128][N] = A[128][K] * B[N][K]^T on tcgen05 with the bf16xS split
-// ---------------------------------------------------------------------------------------------
-extern "C" int silero_b200_stage_tc_gemm( silero_b200 *h, const float *A, const float *B, int N, int K, int nsplit, int reps, float *D, long long *cycles )
-{
-   if ( !h || !A || !B || !D ) return set_err( SILERO_B200_ERR_ARG, "null argument" );
-   if ( N < 16 || N > 256 || ( N % 16 ) || K < 16 || K > 128 || ( K % 16 ) || nsplit < 1 || nsplit > 3 || reps < 1 )
-      return set_err( SILERO_B200_ERR_ARG, "tc_gemm: need N in 16..256 step 16, K in 16..128 step 16, nsplit 1..3" );
-   const size_t smem = (size_t)nsplit * ( K / 8 ) * ( 128 + N ) * 16;
-   if ( smem > 200 * 1024 ) return set_err( SILERO_B200_ERR_ARG, "tc_gemm: tile does not fit in shared memory" );
-   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
-   DevBuf a, b, d, c;
-   if ( a.alloc( (size_t)128 * K ) || b.alloc( (size_t)N * K ) || d.alloc( (size_t)128 * N ) || c.alloc( 2 ) ) return SILERO_B200_ERR_CUDA;
-   if ( up( h, a.p, A, (size_t)128 * K ) || up( h, b.p, B, (size_t)N * K ) ) return SILERO_B200_ERR_CUDA;
-   tc_probe_kernel<<<1, TCP_THREADS, smem, h->stream>>>( a.p, b.p, d.p, N, K, nsplit, reps, reinterpret_cast<long long *>( c.p ) );
-   CU( cudaGetLastError() );
-   if ( down( h, D, d.p, (size_t)128 * N ) ) return SILERO_B200_ERR_CUDA;
-   if ( cycles ) CU( cudaMemcpy( cycles, c.p, sizeof( long long ), cudaMemcpyDeviceToHost ) );
-   return SILERO_B200_OK;
-}

@@ -5,8 +5,8 @@
 // i,f,o = 1/(1+expf(-z)), g = tanhf(z), c = f c + i g, h = o tanhf(c) (lstm.c:64-88) -- separate multiplies and adds, glibc's
 // expf / tanhf bit for bit (libm_exact.cuh). The result is bit-identical to the reference for streams of any length.
 //
-// Why a second kernel beside faithful_lstm_wave_kernel (one CTA per stream): the recurrence is serial per stream, but thousands of
-// streams are independent. Here a CTA owns a SET of streams (stream s -> CTA s mod grid) and walks them step by step together:
+// The recurrence is serial per stream, but streams are independent: a CTA owns a SET of streams (stream s -> CTA s mod grid) and walks
+// them step by step together:
 //   * the layer's weight matrix lives in REGISTERS for the whole launch: 512 threads, thread = (gate row r, half): the eight taps
 //     16b + 8 half .. + 7 of every 16-tap block b of row r, i.e. exactly the taps that feed four of dotproduct_simd's eight lanes
 //     (half 0: r0 r1 r4 r5, half 1: r2 r3 r6 r7) -- 64 weights per thread, loaded once;
@@ -46,24 +46,61 @@ __device__ __forceinline__ void xl_half_row( const float *__restrict__ xh /* thi
    }
 }
 
-template <int LAYER>
+__device__ __forceinline__ int xl_ld_acquire( const int *p )
+{
+   int v;
+   asm volatile( "ld.acquire.gpu.global.s32 %0, [%1];" : "=r"( v ) : "l"( p ) : "memory" );
+   return v;
+}
+__device__ __forceinline__ void xl_st_release( int *p, int v )
+{
+   asm volatile( "st.release.gpu.global.s32 [%0], %1;" ::"l"( p ), "r"( v ) : "memory" );
+}
+
+// WAVE = false: one layer per launch (layer_arg), CTA b owns streams b, b + grid, ...  -- any number of streams.
+// WAVE = true:  BOTH layers in one launch as a wavefront, for stream counts that leave SMs free (2 x groups <= SMs): the grid is
+//   2 G CTAs; a CTA draws a ticket (2 g = layer 0 of stream group g, 2 g + 1 = layer 1 of the same group: whoever holds a layer-1
+//   ticket knows its layer-0 partner has already been STARTED -- no co-residency assumption, no deadlock whatever else shares the
+//   GPU); the layer-1 CTA consumes the layer-0 CTA's output sequence while it is being produced, a step or two behind, so a step of
+//   both layers costs what a step of one does. Hand-off per group through progress[g] = steps the layer-0 CTA has completed
+//   (st.release.gpu after a CTA barrier / ld.acquire.gpu + ld.global.cg). The consumer's wait is bounded: if the producer is lost the
+//   consumer raises err_word (mapped host memory; the host fails the call at its next synchronization) and leaves the state untouched.
+//   Layer 1 may write its output over the encoder output (x0 == out1): it writes row t after layer 0 has completed step t, and by
+//   then layer 0 has read rows 0..t+1 for good (rows are 256 bytes, 256-byte aligned).
+//   sync: [0] ticket counter, [1 + g] progress of group g; zeroed by the host before the launch.
+template <bool WAVE>
 __global__ void __launch_bounds__( XL_THREADS, 1 )
-exact_lstm_kernel( const float *__restrict__ x, float *__restrict__ hseq, float *__restrict__ state_h, float *__restrict__ state_c,
-                   const float *__restrict__ wpack /*[2][32][256][4]*/, const float *__restrict__ bias /*[2][256]*/, int nstreams, int nw )
+exact_lstm_kernel( const float *x0, float *h0seq, float *out1, float *__restrict__ state_h, float *__restrict__ state_c,
+                   const float *__restrict__ wpack /*[2][32][256][4]*/, const float *__restrict__ bias /*[2][256]*/, int nstreams, int nw, int layer_arg,
+                   int *sync, int *err_word, int spin_limit, int debug_stall_producer )
 {
    extern __shared__ __align__( 16 ) float xsm[];
    __shared__ unsigned long long exp_tab[32];
+   __shared__ int s_ticket;
    lme::stage_exp2f_tab( exp_tab, threadIdx.x );
    float *act = xsm;                                 // [2][XL_SUB][256] pre-activations z = W [x;h] + b
    float *xh = xsm + XL_ACT_FLOATS;                  // [K][128]
    float *cst = xh + XL_MAX_STREAMS * 128;           // [K][64]
    const int tid = threadIdx.x, half = tid & 1, row = tid >> 1;
    const int steps = nw * 7;
+   int grp = blockIdx.x, ngrp = gridDim.x, layer = layer_arg;
+   if ( WAVE )
+   {
+      if ( tid == 0 ) s_ticket = atomicAdd( sync, 1 );
+      __syncthreads();
+      grp = s_ticket >> 1;
+      layer = s_ticket & 1;
+      ngrp = gridDim.x >> 1;
+   }
+   const bool consumer = WAVE && layer == 1;
+   const float *x = layer == 0 ? x0 : h0seq;
+   float *hseq = layer == 0 ? h0seq : out1;
+   int *progress = WAVE ? sync + 1 + grp : 0;
 
    // this thread's 64 weights: quads 4b + 2 half, 4b + 2 half + 1 of row `row`
    float w[64];
    {
-      const float4 *src = reinterpret_cast<const float4 *>( wpack ) + (size_t)LAYER * ( 32 * 256 );
+      const float4 *src = reinterpret_cast<const float4 *>( wpack ) + (size_t)layer * ( 32 * 256 );
 #pragma unroll
       for ( int b = 0; b < 8; ++b )
       {
@@ -72,23 +109,44 @@ exact_lstm_kernel( const float *__restrict__ x, float *__restrict__ hseq, float 
          w[8 * b + 4] = q1.x; w[8 * b + 5] = q1.y; w[8 * b + 6] = q1.z; w[8 * b + 7] = q1.w;
       }
    }
-   const float b_row = bias[LAYER * 256 + row];
+   const float b_row = bias[layer * 256 + row];
    // cell-update role: (unit uj, stream uk of the sub-batch)
    const int uk = tid >> 6, uj = tid & 63;
+   int seen = 0;
+   bool lost = false;
+   // input row t of a stream; the consumer of a wavefront first waits until its producer has completed step t
+   auto fetch = [&]( size_t s, int t ) -> float {
+      const float *p = x + ( s * steps + t ) * 64 + uj;
+      if ( !consumer ) return __ldg( p );
+      if ( seen <= t && !lost )
+      {
+         int spins = 0;
+         do
+         {
+            seen = xl_ld_acquire( progress );
+         } while ( seen <= t && ++spins < spin_limit );
+         if ( seen <= t )
+         {
+            lost = true;
+            atomicExch( err_word, 1 + (int)s );
+         }
+      }
+      return __ldcg( p );
+   };
 
-   // streams of this CTA: blockIdx.x + i * gridDim.x, in passes of at most XL_MAX_STREAMS
-   const int mine = ( nstreams - (int)blockIdx.x + (int)gridDim.x - 1 ) / (int)gridDim.x;
+   // streams of this CTA: grp + i * ngrp, in passes of at most XL_MAX_STREAMS (a wavefront launch always fits one pass)
+   const int mine = ( nstreams - grp + ngrp - 1 ) / ngrp;
    for ( int pass0 = 0; pass0 < mine; pass0 += XL_MAX_STREAMS )
    {
       const int K = min( XL_MAX_STREAMS, mine - pass0 );
       __syncthreads(); // the previous pass is done with the shared buffers
       for ( int e = tid; e < K * 64; e += XL_THREADS )
       {
-         const int k = e >> 6, j = e & 63;
-         const size_t s = (size_t)blockIdx.x + (size_t)( pass0 + k ) * gridDim.x;
-         cst[k * 64 + j] = state_c[( s * 2 + LAYER ) * 64 + j];
-         xh[k * 128 + 64 + j] = state_h[( s * 2 + LAYER ) * 64 + j];
-         xh[k * 128 + j] = __ldg( x + s * steps * 64 + j );
+         const int k = e >> 6, j = e & 63; // (j == uj: XL_THREADS is a multiple of 64)
+         const size_t s = (size_t)grp + (size_t)( pass0 + k ) * ngrp;
+         cst[k * 64 + j] = state_c[( s * 2 + layer ) * 64 + j];
+         xh[k * 128 + 64 + j] = state_h[( s * 2 + layer ) * 64 + j];
+         xh[k * 128 + j] = fetch( s, 0 );
       }
       __syncthreads();
       const int nsub = ( K + XL_SUB - 1 ) / XL_SUB;
@@ -101,8 +159,8 @@ exact_lstm_kernel( const float *__restrict__ x, float *__restrict__ hseq, float 
             // next step's input of my (unit, stream): in flight during the contraction
             float xnext = 0.0f;
             const bool upd = uk < kn;
-            const size_t us = (size_t)blockIdx.x + (size_t)( pass0 + k0 + uk ) * gridDim.x;
-            if ( upd && step + 1 < steps ) xnext = __ldg( x + ( us * steps + step + 1 ) * 64 + uj );
+            const size_t us = (size_t)grp + (size_t)( pass0 + k0 + uk ) * ngrp;
+            if ( upd && step + 1 < steps ) xnext = fetch( us, step + 1 );
             float *a = act + buf * ( XL_SUB * 256 );
 #pragma unroll 1
             for ( int p = 0; p < kn; p += 2 )
@@ -136,7 +194,7 @@ exact_lstm_kernel( const float *__restrict__ x, float *__restrict__ hseq, float 
                if ( !half || two ) a[( p + half ) * 256 + row] = z;
             }
             __syncthreads();
-            // cell update (lstm.c:64-88) of (unit uj, stream k0 + uk)
+            // gate nonlinearities and cell update (lstm.c:64-88) of (unit uj, stream k0 + uk)
             if ( upd )
             {
                const float *av = a + uk * 256;
@@ -150,17 +208,21 @@ exact_lstm_kernel( const float *__restrict__ x, float *__restrict__ hseq, float 
                xh[k * 128 + uj] = xnext;
                hseq[( us * steps + step ) * 64 + uj] = hn;
             }
-            // with a single sub-batch the next contraction reads what this update wrote
-            if ( nsub == 1 ) __syncthreads();
+            // with a single sub-batch the next contraction reads what this update wrote; a wavefront producer publishes the step
+            // after every thread's h of it has been stored (the barrier orders the stores before thread 0's release)
+            const bool publish = WAVE && layer == 0 && sb == nsub - 1;
+            if ( nsub == 1 || publish ) __syncthreads();
+            if ( publish && tid == 0 && !debug_stall_producer ) xl_st_release( progress, step + 1 );
          }
       }
-      __syncthreads();
-      for ( int e = tid; e < K * 64; e += XL_THREADS )
-      {
-         const int k = e >> 6, j = e & 63;
-         const size_t s = (size_t)blockIdx.x + (size_t)( pass0 + k ) * gridDim.x;
-         state_c[( s * 2 + LAYER ) * 64 + j] = cst[k * 64 + j];
-         state_h[( s * 2 + LAYER ) * 64 + j] = xh[k * 128 + 64 + j];
-      }
+      const int any_lost = __syncthreads_or( lost ? 1 : 0 );
+      if ( !any_lost )
+         for ( int e = tid; e < K * 64; e += XL_THREADS )
+         {
+            const int k = e >> 6, j = e & 63;
+            const size_t s = (size_t)grp + (size_t)( pass0 + k ) * ngrp;
+            state_c[( s * 2 + layer ) * 64 + j] = cst[k * 64 + j];
+            state_h[( s * 2 + layer ) * 64 + j] = xh[k * 128 + 64 + j];
+         }
    }
 }

@@ -520,195 +520,6 @@ __global__ void __launch_bounds__( FAITHFUL_THREADS, 4 ) faithful_encoder_kernel
       fq::encoder_chunk( W, spec + (size_t)ci * ( 129 * 25 ), a4 + (size_t)ci * 448, fsm, threadIdx.x, FAITHFUL_THREADS );
 }
 
-// One layer of the decoder LSTM (lstm.c:31-218) for the faithful path: the recurrence is serial per stream, so a CTA takes one
-// stream and spreads the 256 gate rows of a step over its 256 threads. Warp w owns hidden units 8w..8w+7; lane = (gate g, unit):
-// every lane contracts ONE row over [x|h] in dotproduct_simd order (fq::gate_dot), adds its bias and applies its own gate's
-// nonlinearity (glibc's expf/tanhf bit for bit, libm_exact.cuh); the three other gates of a unit reach the g = 0 lane by shuffle,
-// which updates c (a register) and h without contraction (lstm.c:64-88). One barrier per step (ping-pong [x|h] buffers).
-// Weights: pack_lstm's [layer][k/4][row][4] image, 128 KB resident in shared memory.
-//   x: [S][steps][64] layer input; hseq: [S][steps][64] layer output; state_h/state_c: [S][2][64]
-#define FLSTM_THREADS 256
-#define FLSTM_SMEM_BYTES ( ( 32 * 256 * 4 + 2 * 128 ) * 4 )
-template <int LAYER>
-__global__ void __launch_bounds__( FLSTM_THREADS, 1 )
-faithful_lstm_kernel( const float *__restrict__ x, float *__restrict__ hseq, float *__restrict__ state_h, float *__restrict__ state_c,
-                      const float *__restrict__ wpack, const float *__restrict__ bias, int nstreams, int nw )
-{
-   extern __shared__ __align__( 16 ) float fsm[];
-   float *Ws = fsm;
-   float *xh = fsm + 32 * 256 * 4; // [2][128]
-   const int tid = threadIdx.x, lane = tid & 31, g = lane >> 3, jj = lane & 7, j = ( tid >> 5 ) * 8 + jj, row = g * 64 + j;
-   const int steps = nw * 7;
-   {
-      const float4 *src = reinterpret_cast<const float4 *>( wpack ) + (size_t)LAYER * ( 32 * 256 );
-      float4 *dst = reinterpret_cast<float4 *>( Ws );
-      for ( int i = tid; i < 32 * 256; i += FLSTM_THREADS ) dst[i] = __ldg( src + i );
-   }
-   const float b_row = bias[LAYER * 256 + row];
-   for ( int s = blockIdx.x; s < nstreams; s += gridDim.x )
-   {
-      const float *xs = x + (size_t)s * steps * 64;
-      float *hs = hseq + (size_t)s * steps * 64;
-      float c = 0.0f, h_last = 0.0f;
-      __syncthreads(); // weights staged / the previous stream's buffers are free
-      if ( g == 0 )
-      {
-         c = state_c[( (size_t)s * 2 + LAYER ) * 64 + j];
-         h_last = state_h[( (size_t)s * 2 + LAYER ) * 64 + j];
-         xh[64 + j] = h_last;
-      }
-      if ( g == 1 ) xh[j] = __ldg( xs + j );
-      __syncthreads();
-      for ( int step = 0; step < steps; ++step )
-      {
-         const float *cur = xh + ( step & 1 ) * 128;
-         float *nxt = xh + ( ( step + 1 ) & 1 ) * 128;
-         float xn = 0.0f;
-         if ( g == 1 && step + 1 < steps ) xn = __ldg( xs + (size_t)( step + 1 ) * 64 + j );
-         const float z = __fadd_rn( fq::gate_dot( cur, Ws + row * 4, 1024 ), b_row );
-         const float a = ( g == 2 ) ? lme::tanhf_ref( z ) : lme::sigmoid_ref( z );
-         const float fgv = __shfl_sync( 0xffffffffu, a, jj + 8 );
-         const float ggv = __shfl_sync( 0xffffffffu, a, jj + 16 );
-         const float ogv = __shfl_sync( 0xffffffffu, a, jj + 24 );
-         if ( g == 0 )
-         {
-            const float cn = __fadd_rn( __fmul_rn( fgv, c ), __fmul_rn( a, ggv ) );
-            c = cn;
-            h_last = __fmul_rn( lme::tanhf_ref( cn ), ogv );
-            nxt[64 + j] = h_last;
-            hs[(size_t)step * 64 + j] = h_last;
-         }
-         if ( g == 1 ) nxt[j] = xn;
-         __syncthreads();
-      }
-      if ( g == 0 )
-      {
-         state_c[( (size_t)s * 2 + LAYER ) * 64 + j] = c;
-         state_h[( (size_t)s * 2 + LAYER ) * 64 + j] = h_last;
-      }
-   }
-}
-
-// Both LSTM layers of a window in ONE launch, as a wavefront: task (stream s, layer l) is one CTA walking that layer's steps exactly
-// like faithful_lstm_kernel; the layer-1 task of a stream consumes the layer-0 task's output sequence while it is being produced,
-// a few steps behind, so that ONE stream keeps two SMs busy and its serial scan takes steps x 2.6 us instead of 2 x steps x 2.6 us
-// (the scan is what bounds single streams: BASELINE cfg1 / cfg4).
-//   * tasks are handed out by an atomic ticket (2s = layer 0, 2s + 1 = layer 1): whoever holds a layer-1 ticket knows its layer-0
-//     partner has already been STARTED by some CTA, and a layer-0 task never waits for anything -- no co-residency assumption, no
-//     deadlock, whatever else shares the GPU (the next window's STFT does);
-//   * hand-off per stream through progress[s] = layer-0 steps completed: the producer's threads store h, meet at the step's
-//     barrier, then thread 0 publishes the count with st.release.gpu; a consumer lane that is about to fetch x_t = h0[t] spins on
-//     ld.acquire.gpu until the count exceeds t (only when the value it saw last is not enough: a consumer that has fallen a few
-//     steps behind polls rarely) and reads the row with ld.global.cg;
-//   * layer 1 may write its output sequence over the window's encoder output (x0 == out1 in the engine): it writes row t after
-//     layer 0 has completed step t, and by then layer 0 has read rows 0..t+1 for good and only reads rows above t + 1 from there on
-//     (rows are 256 bytes, 256-byte aligned: no cache line is shared between a row being written and a row still to be read).
-// sync: [0] ticket counter, [1 + s] progress of stream s; zeroed by the host before the launch.
-__device__ __forceinline__ int ld_acquire_gpu( const int *p )
-{
-   int v;
-   asm volatile( "ld.acquire.gpu.global.s32 %0, [%1];" : "=r"( v ) : "l"( p ) : "memory" );
-   return v;
-}
-__device__ __forceinline__ void st_release_gpu( int *p, int v )
-{
-   asm volatile( "st.release.gpu.global.s32 [%0], %1;" ::"l"( p ), "r"( v ) : "memory" );
-}
-
-__global__ void __launch_bounds__( FLSTM_THREADS, 1 )
-faithful_lstm_wave_kernel( const float *x0, float *h0seq, float *out1, float *__restrict__ state_h, float *__restrict__ state_c,
-                           const float *__restrict__ wpack, const float *__restrict__ bias, int nstreams, int nw, int *sync, int *err_word, int spin_limit,
-                           int debug_stall_producer )
-{
-   extern __shared__ __align__( 16 ) float fsm[];
-   __shared__ int s_ticket;
-   float *Ws = fsm;
-   float *xh = fsm + 32 * 256 * 4; // [2][128]
-   const int tid = threadIdx.x, lane = tid & 31, g = lane >> 3, jj = lane & 7, j = ( tid >> 5 ) * 8 + jj, row = g * 64 + j;
-   const int steps = nw * 7;
-   int loaded = -1;
-   float b_row = 0.0f;
-   for ( ;; )
-   {
-      __syncthreads(); // the previous task is done with the shared buffers and with s_ticket
-      if ( tid == 0 ) s_ticket = atomicAdd( sync, 1 );
-      __syncthreads();
-      const int ticket = s_ticket;
-      if ( ticket >= 2 * nstreams ) break;
-      const int s = ticket >> 1, layer = ticket & 1;
-      if ( layer != loaded )
-      {
-         const float4 *src = reinterpret_cast<const float4 *>( wpack ) + (size_t)layer * ( 32 * 256 );
-         float4 *dst = reinterpret_cast<float4 *>( Ws );
-         for ( int i = tid; i < 32 * 256; i += FLSTM_THREADS ) dst[i] = __ldg( src + i );
-         b_row = bias[layer * 256 + row];
-         loaded = layer;
-      }
-      const float *xs = ( layer == 0 ? x0 : h0seq ) + (size_t)s * steps * 64;
-      float *hs = ( layer == 0 ? h0seq : out1 ) + (size_t)s * steps * 64;
-      int *progress = sync + 1 + s;
-      int seen = layer == 0 ? steps : 0; // layer 0 reads the encoder's output, complete before this launch
-      bool lost = false;
-      // x_t for the consumer: wait until the producer has completed step t. The wait is bounded (a lost producer must not hang the
-      // GPU), and a consumer that gives up SAYS so: it raises the engine's error word (mapped host memory, checked by the host at its
-      // next synchronization point: the call fails with SILERO_B200_ERR_CUDA) and the task leaves the persistent state untouched.
-      auto fetch = [&]( int t ) -> float {
-         if ( seen <= t && !lost )
-         {
-            int spins = 0;
-            do
-            {
-               seen = ld_acquire_gpu( progress );
-            } while ( seen <= t && ++spins < spin_limit );
-            if ( seen <= t )
-            {
-               lost = true;
-               atomicExch( err_word, 1 + s );
-            }
-         }
-         return __ldcg( xs + (size_t)t * 64 + j );
-      };
-      float c = 0.0f, h_last = 0.0f;
-      if ( g == 0 )
-      {
-         c = state_c[( (size_t)s * 2 + layer ) * 64 + j];
-         h_last = state_h[( (size_t)s * 2 + layer ) * 64 + j];
-         xh[64 + j] = h_last;
-      }
-      if ( g == 1 ) xh[j] = fetch( 0 );
-      __syncthreads();
-      for ( int step = 0; step < steps; ++step )
-      {
-         const float *cur = xh + ( step & 1 ) * 128;
-         float *nxt = xh + ( ( step + 1 ) & 1 ) * 128;
-         float xn = 0.0f;
-         if ( g == 1 && step + 1 < steps ) xn = fetch( step + 1 );
-         const float z = __fadd_rn( fq::gate_dot( cur, Ws + row * 4, 1024 ), b_row );
-         const float a = ( g == 2 ) ? lme::tanhf_ref( z ) : lme::sigmoid_ref( z );
-         const float fgv = __shfl_sync( 0xffffffffu, a, jj + 8 );
-         const float ggv = __shfl_sync( 0xffffffffu, a, jj + 16 );
-         const float ogv = __shfl_sync( 0xffffffffu, a, jj + 24 );
-         if ( g == 0 )
-         {
-            const float cn = __fadd_rn( __fmul_rn( fgv, c ), __fmul_rn( a, ggv ) );
-            c = cn;
-            h_last = __fmul_rn( lme::tanhf_ref( cn ), ogv );
-            nxt[64 + j] = h_last;
-            hs[(size_t)step * 64 + j] = h_last;
-         }
-         if ( g == 1 ) nxt[j] = xn;
-         __syncthreads();
-         if ( layer == 0 && tid == 0 && !debug_stall_producer ) st_release_gpu( progress, step + 1 ); // every thread's h of this step is ordered before by the barrier
-      }
-      const int any_lost = __syncthreads_or( lost ? 1 : 0 );
-      if ( g == 0 && !any_lost )
-      {
-         state_c[( (size_t)s * 2 + layer ) * 64 + j] = c;
-         state_h[( (size_t)s * 2 + layer ) * 64 + j] = h_last;
-      }
-   }
-}
-
 // hs: top-layer LSTM outputs [S][nw*7][64] (stream-major); one thread per (stream, chunk, head)
 __global__ void faithful_decoder_kernel( const float *__restrict__ hs, const float *__restrict__ dec_w, const float *__restrict__ dec_b, int nstreams, int nw,
                                          float *__restrict__ out2, float *__restrict__ probs, long long out_stride, long long out_off )

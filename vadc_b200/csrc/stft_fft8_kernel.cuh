@@ -24,7 +24,7 @@
 // until it is more than a chunk behind.
 #pragma once
 #include "common.cuh"
-#include "stft_hybrid_kernel.cuh"
+#include "stft_fft_common.cuh"
 #include "tc_common.cuh"
 
 #define F8_CWARPS 7                      // compute warps
