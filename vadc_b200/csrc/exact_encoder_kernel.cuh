@@ -597,3 +597,8 @@ exact_layer_kernel( const float *__restrict__ in, float *__restrict__ out, const
       }
    }
 }
+
+// Tried and measured (r02): the same layer with TWO tokens per thread (256 threads x 255 registers, every weight quad feeding both
+// tokens: half the LDS traffic per multiply-add). Bit-identical, not faster (12.1 ms against 11.5 ms for the four layers of 131 072
+// chunks): two warps per scheduler with two tokens each hide the weight-load latency no better than four warps with one, and the
+// shared-memory pipe was never the bound (34 % busy). The one-token kernel stays.
