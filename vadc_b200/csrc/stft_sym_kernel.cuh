@@ -32,6 +32,37 @@
 #define SSYM_BS_FLOATS ( 64 * 128 * 4 )
 #define SSYM_SMEM_BYTES ( ( SSYM_BS_FLOATS + 2 * STFT_XS_FLOATS ) * 4 )
 
+// two fp32 values in a 64-bit register pair, for the packed add of sm_100 (add.rn.f32x2 -> FADD2): each half is an IEEE addition
+typedef unsigned long long ssym2;
+__device__ __forceinline__ ssym2 ssym_pack( float lo, float hi )
+{
+   ssym2 r;
+   asm( "mov.b64 %0, {%1,%2};" : "=l"( r ) : "f"( lo ), "f"( hi ) );
+   return r;
+}
+__device__ __forceinline__ void ssym_unpack( ssym2 v, float &lo, float &hi ) { asm( "mov.b64 {%0,%1}, %2;" : "=f"( lo ), "=f"( hi ) : "l"( v ) ); }
+__device__ __forceinline__ ssym2 ssym_add2( ssym2 a, ssym2 b )
+{
+   ssym2 c;
+   asm( "add.rn.f32x2 %0, %1, %2;" : "=l"( c ) : "l"( a ), "l"( b ) );
+   return c;
+}
+__device__ __forceinline__ ssym2 ssym_sub2( ssym2 a, ssym2 b )
+{
+   ssym2 c;
+   asm( "sub.rn.f32x2 %0, %1, %2;" : "=l"( c ) : "l"( a ), "l"( b ) );
+   return c;
+}
+// stft_tree8 for two frames (x*, y*) that share the basis quads: scalar products, packed adds
+__device__ __forceinline__ ssym2 ssym_tree8x2( const float4 xa, const float4 xb, const float4 ya, const float4 yb, const float4 b0, const float4 b1 )
+{
+   const ssym2 p0 = ssym_pack( __fmul_rn( xa.x, b0.x ), __fmul_rn( ya.x, b0.x ) ), p1 = ssym_pack( __fmul_rn( xa.y, b0.y ), __fmul_rn( ya.y, b0.y ) );
+   const ssym2 p2 = ssym_pack( __fmul_rn( xa.z, b0.z ), __fmul_rn( ya.z, b0.z ) ), p3 = ssym_pack( __fmul_rn( xa.w, b0.w ), __fmul_rn( ya.w, b0.w ) );
+   const ssym2 p4 = ssym_pack( __fmul_rn( xb.x, b1.x ), __fmul_rn( yb.x, b1.x ) ), p5 = ssym_pack( __fmul_rn( xb.y, b1.y ), __fmul_rn( yb.y, b1.y ) );
+   const ssym2 p6 = ssym_pack( __fmul_rn( xb.z, b1.z ), __fmul_rn( yb.z, b1.z ) ), p7 = ssym_pack( __fmul_rn( xb.w, b1.w ), __fmul_rn( yb.w, b1.w ) );
+   return ssym_add2( ssym_add2( ssym_add2( p0, p1 ), ssym_add2( p2, p3 ) ), ssym_add2( ssym_add2( p4, p5 ), ssym_add2( p6, p7 ) ) );
+}
+
 // out_mode 0: log1p(mag * 2^20) (production); 1: raw magnitude (parity tap for stft.c alone)
 //
 // One __syncthreads per chunk hands the double-buffered input tile over. Tried and measured slower (r02): a ring of four tiles with
@@ -86,16 +117,24 @@ stft_sym_kernel( const void *__restrict__ in, long long stream_stride, int nw, i
       const int cn = ci + gridDim.x;
       if ( cn < nchunks && tid < NV ) raw = __ldg( (const int4 *)stft_chunk_ptr<F32>( in, stream_stride, nw, cn ) + tid );
 
-      float Sp[2][5], Sm[2][5];
+      // Frames go through in pairs (0,1), (2,3) + frame 4: the two frames of a pair share every basis value, their products are
+      // separate FMULs into adjacent registers, and every ADD of the tree is one packed FADD2 (add.rn.f32x2, sm_100: two independently
+      // rounded IEEE additions in one issue slot). 128 instead of 160 issue slots per (lane, group) for the same 160 operations: the
+      // main loop is issue-bound. Multiplies stay scalar on purpose: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (even
+      // with --fmad=false), which would change the rounding; tests/test_host_logic.py checks the kernel's SASS for FFMA2.
+      ssym2 Sp[2][2], Sm[2][2]; // [row][pair]
+      float Sp4[2], Sm4[2];     // frame 4
 #pragma unroll 1
       for ( int lp2 = 0; lp2 < 2; ++lp2 )
       {
-         float TL[2][5];
+         ssym2 TL[2][2];
+         float TL4[2];
 #pragma unroll
          for ( int lo = 0; lo < 2; ++lo )
          {
             const int l = 4 * half + 2 * lp2 + lo;
-            float A[2][5], Bv[2][5];
+            ssym2 A[2][2], Bv[2][2];
+            float A4[2], B4[2];
 #pragma unroll
             for ( int g = 0; g < 4; ++g )
             {
@@ -103,37 +142,71 @@ stft_sym_kernel( const void *__restrict__ in, long long stream_stride, int nw, i
                const float4 re0 = ld4( bq ), re1 = ld4( bq + 128 * 4 );
                const float4 im0 = ld4( bq + 64 * 4 ), im1 = ld4( bq + 64 * 4 + 128 * 4 );
 #pragma unroll
-               for ( int i = 0; i < 5; ++i )
+               for ( int pr = 0; pr < 2; ++pr )
                {
-                  const float *xp = xs + ( 5 * tg + i + g ) * 64 + l * 8;
+                  const float *xp = xs + ( 5 * tg + 2 * pr + g ) * 64 + l * 8;
+                  const float4 xa = ld4( xp ), xb = ld4( xp + 4 ), ya = ld4( xp + 64 ), yb = ld4( xp + 68 );
+                  const ssym2 rr = ssym_tree8x2( xa, xb, ya, yb, re0, re1 );
+                  const ssym2 ri = ssym_tree8x2( xa, xb, ya, yb, im0, im1 );
+                  if ( g == 0 ) { A[0][pr] = rr; A[1][pr] = ri; }
+                  else if ( g == 1 ) { A[0][pr] = ssym_add2( A[0][pr], rr ); A[1][pr] = ssym_add2( A[1][pr], ri ); }
+                  else if ( g == 2 ) { Bv[0][pr] = rr; Bv[1][pr] = ri; }
+                  else { Bv[0][pr] = ssym_add2( Bv[0][pr], rr ); Bv[1][pr] = ssym_add2( Bv[1][pr], ri ); }
+               }
+               {
+                  const float *xp = xs + ( 5 * tg + 4 + g ) * 64 + l * 8;
                   const float4 xa = ld4( xp ), xb = ld4( xp + 4 );
                   const float rr = stft_tree8( xa, xb, re0, re1 );
                   const float ri = stft_tree8( xa, xb, im0, im1 );
-                  if ( g == 0 ) { A[0][i] = rr; A[1][i] = ri; }
-                  else if ( g == 1 ) { A[0][i] = __fadd_rn( A[0][i], rr ); A[1][i] = __fadd_rn( A[1][i], ri ); }
-                  else if ( g == 2 ) { Bv[0][i] = rr; Bv[1][i] = ri; }
-                  else { Bv[0][i] = __fadd_rn( Bv[0][i], rr ); Bv[1][i] = __fadd_rn( Bv[1][i], ri ); }
+                  if ( g == 0 ) { A4[0] = rr; A4[1] = ri; }
+                  else if ( g == 1 ) { A4[0] = __fadd_rn( A4[0], rr ); A4[1] = __fadd_rn( A4[1], ri ); }
+                  else if ( g == 2 ) { B4[0] = rr; B4[1] = ri; }
+                  else { B4[0] = __fadd_rn( B4[0], rr ); B4[1] = __fadd_rn( B4[1], ri ); }
                }
             }
 #pragma unroll
             for ( int a = 0; a < 2; ++a )
+            {
+               // plain and alternating sum of the lane pair; the merged row of bin 64 keeps its even and odd lanes apart
+               const bool split = special && a == 1;
 #pragma unroll
-               for ( int i = 0; i < 5; ++i )
+               for ( int pr = 0; pr < 2; ++pr )
                {
-                  const float R = __fadd_rn( A[a][i], Bv[a][i] );
+                  const ssym2 R = ssym_add2( A[a][pr], Bv[a][pr] );
                   if ( lo == 0 )
-                     TL[a][i] = R;
+                     TL[a][pr] = R;
                   else
                   {
-                     // plain and alternating sum of the lane pair; the merged row of bin 64 keeps its even and odd lanes apart
-                     const bool split = special && a == 1;
-                     const float pr = split ? TL[a][i] : __fadd_rn( TL[a][i], R );
-                     const float pm = split ? R : __fsub_rn( TL[a][i], R );
-                     if ( lp2 == 0 ) { Sp[a][i] = pr; Sm[a][i] = pm; }
-                     else { Sp[a][i] = __fadd_rn( Sp[a][i], pr ); Sm[a][i] = __fadd_rn( Sm[a][i], pm ); }
+                     const ssym2 sum = ssym_add2( TL[a][pr], R ), dif = ssym_sub2( TL[a][pr], R );
+                     const ssym2 vp = split ? TL[a][pr] : sum, vm = split ? R : dif;
+                     if ( lp2 == 0 ) { Sp[a][pr] = vp; Sm[a][pr] = vm; }
+                     else { Sp[a][pr] = ssym_add2( Sp[a][pr], vp ); Sm[a][pr] = ssym_add2( Sm[a][pr], vm ); }
                   }
                }
+               const float R4 = __fadd_rn( A4[a], B4[a] );
+               if ( lo == 0 )
+                  TL4[a] = R4;
+               else
+               {
+                  const float vp = split ? TL4[a] : __fadd_rn( TL4[a], R4 ), vm = split ? R4 : __fsub_rn( TL4[a], R4 );
+                  if ( lp2 == 0 ) { Sp4[a] = vp; Sm4[a] = vm; }
+                  else { Sp4[a] = __fadd_rn( Sp4[a], vp ); Sm4[a] = __fadd_rn( Sm4[a], vm ); }
+               }
+            }
          }
+      }
+      float Sps[2][5], Sms[2][5]; // back to one value per frame
+#pragma unroll
+      for ( int a = 0; a < 2; ++a )
+      {
+#pragma unroll
+         for ( int pr = 0; pr < 2; ++pr )
+         {
+            ssym_unpack( Sp[a][pr], Sps[a][2 * pr], Sps[a][2 * pr + 1] );
+            ssym_unpack( Sm[a][pr], Sms[a][2 * pr], Sms[a][2 * pr + 1] );
+         }
+         Sps[a][4] = Sp4[a];
+         Sms[a][4] = Sm4[a];
       }
 
       // lanes 0..3 (half 0) + lanes 4..7 (half 1): the half-0 thread takes the plain sums (bin u), the half-1 thread the alternating ones (bin 128-u)
@@ -146,8 +219,8 @@ stft_sym_kernel( const void *__restrict__ in, long long stream_stride, int nw, i
 #pragma unroll
          for ( int a = 0; a < 2; ++a )
          {
-            const float got = __shfl_xor_sync( 0xffffffffu, half ? Sp[a][i] : Sm[a][i], 16 );
-            y[a] = half ? __fadd_rn( got, Sm[a][i] ) : __fadd_rn( Sp[a][i], got );
+            const float got = __shfl_xor_sync( 0xffffffffu, half ? Sps[a][i] : Sms[a][i], 16 );
+            y[a] = half ? __fadd_rn( got, Sms[a][i] ) : __fadd_rn( Sps[a][i], got );
          }
          // unit 0: half 0 holds re(bin 0), re(bin 64); half 1 holds re(bin 128), im(bin 64)
          const float im64 = __shfl_xor_sync( 0xffffffffu, y[1], 16 );
