@@ -67,8 +67,9 @@ __device__ __forceinline__ ssym2 ssym_tree8x2( const float4 xa, const float4 xb,
 //
 // One __syncthreads per chunk hands the double-buffered input tile over. Tried and measured slower (r02): a ring of four tiles with
 // mbarrier hand-over (full / empty) so that warps may run a chunk ahead of each other -- 15.8 ms instead of 13.0 ms per 131 072 chunks:
-// the main loop is issue-bound (36 % of the stall samples are "not selected", 9 % "dispatch"), and the polling warps take issue slots
-// from the working ones; a dedicated 21st producer warp does not fit (six warps on one scheduler x 96 registers > its 16 384).
+// (every thread arriving) and 14.2 ms (one arrival per warp). The unrolled main loop is ~60 KB of code: warps that the barrier keeps in
+// step share their instruction fetches, warps that drift apart do not. A dedicated 21st producer warp does not fit (six warps on one
+// scheduler x 96 registers > its 16 384).
 template <bool F32>
 __global__ void __launch_bounds__( SSYM_THREADS, 1 )
 stft_sym_kernel( const void *__restrict__ in, long long stream_stride, int nw, int nchunks, const float *__restrict__ basis_sym /*[64][128][4]*/,
