@@ -145,3 +145,27 @@ def test_python_constants_mirror_the_header():
     for name in ("STFT_AUTO", "STFT_EXACT", "STFT_HYBRID", "LSTM_AUTO", "LSTM_FP32", "LSTM_TENSOR",
                  "LSTM_FAITHFUL", "LAYERS_AUTO", "LAYERS_FP32", "LAYERS_TENSOR", "LAYERS_FAITHFUL"):
         assert getattr(vadc_b200, name) == defs[name], name
+
+
+def test_exact_kernels_contain_no_contracted_packed_arithmetic():
+    """The exact path may not fuse a multiply with an add. Scalar mul.rn / add.rn are never contracted, but ptxas 12.9 turns
+    mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (even with --fmad=false), so the kernels use packed ADDS only, fed by scalar multiplies.
+    This reads the SASS of the built library: no FFMA2 and no FMUL2 in any exact-path kernel, FADD2 present in the STFT."""
+    import re
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", vadc_b200.LIB_PATH], capture_output=True, text=True).stdout
+    seen = {}
+    for part in re.split(r"\n\s*Function : ", sass)[1:]:
+        name = part.split("\n", 1)[0]
+        if not any(k in name for k in ("stft_sym_kernel", "stft_logmag_kernel", "exact_front_kernel", "exact_layer_kernel", "exact_lstm_kernel",
+                                        "faithful_encoder_kernel", "faithful_decoder_kernel")):
+            continue
+        ops = re.findall(r"^\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_]+)", part, re.M)
+        seen[name] = (ops.count("FFMA2"), ops.count("FMUL2"), ops.count("FADD2"))
+    assert len(seen) >= 10, sorted(seen)
+    for name, (ffma2, fmul2, fadd2) in seen.items():
+        assert ffma2 == 0 and fmul2 == 0, (name, ffma2, fmul2)
+    assert any(v[2] > 0 for k, v in seen.items() if "stft_sym_kernel" in k)
