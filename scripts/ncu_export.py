@@ -19,7 +19,7 @@ def val(r, name):
     return v * {"ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1.0}.get(u, 1.0)
 
 
-# packed FP32 instructions (FADD2 / FMUL2 / FFMA2, sm_100) are not in the op_fadd / op_fmul / op_ffma thread-instruction metrics: take
+# Packed FP32 instructions (FADD2 / FMUL2 / FFMA2, sm_100) are not in the op_fadd / op_fmul / op_ffma thread-instruction metrics: take
 # their warp-level execution counts from the source page (x 32 lanes; the kernels that use them run full warps there)
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 srows = list(csv.reader(io.StringIO(src)))
@@ -48,7 +48,8 @@ for li, r in enumerate(body):
     fmul = val(r, "smsp__sass_thread_inst_executed_op_fmul_pred_on.sum.per_cycle_elapsed") * cyc
     ffma = val(r, "smsp__sass_thread_inst_executed_op_ffma_pred_on.sum.per_cycle_elapsed") * cyc
     dram = val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum")
-    pk = packed[li] if li < len(packed) else {"FADD2": 0, "FMUL2": 0, "FFMA2": 0}
+    pk = packed[2 * li] if 2 * li < len(packed) else   # (the source page lists every launch twice)\
+         {"FADD2": 0, "FMUL2": 0, "FFMA2": 0}
     packed_flop = 32.0 * (2 * pk["FADD2"] + 2 * pk["FMUL2"] + 4 * pk["FFMA2"])
     k = {"seconds_under_ncu": val(r, "gpu__time_duration.sum"), "fadd": fadd, "fmul": fmul, "ffma": ffma,
          "fadd2_warp_instructions": pk["FADD2"], "fmul2_warp_instructions": pk["FMUL2"], "ffma2_warp_instructions": pk["FFMA2"],
