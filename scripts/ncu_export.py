@@ -48,8 +48,8 @@ for li, r in enumerate(body):
     fmul = val(r, "smsp__sass_thread_inst_executed_op_fmul_pred_on.sum.per_cycle_elapsed") * cyc
     ffma = val(r, "smsp__sass_thread_inst_executed_op_ffma_pred_on.sum.per_cycle_elapsed") * cyc
     dram = val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum")
-    pk = packed[2 * li] if 2 * li < len(packed) else   # (the source page lists every launch twice)\
-         {"FADD2": 0, "FMUL2": 0, "FFMA2": 0}
+    # (the source page lists every launch twice)
+    pk = packed[2 * li] if 2 * li < len(packed) else {"FADD2": 0, "FMUL2": 0, "FFMA2": 0}
     packed_flop = 32.0 * (2 * pk["FADD2"] + 2 * pk["FMUL2"] + 4 * pk["FFMA2"])
     k = {"seconds_under_ncu": val(r, "gpu__time_duration.sum"), "fadd": fadd, "fmul": fmul, "ffma": ffma,
          "fadd2_warp_instructions": pk["FADD2"], "fmul2_warp_instructions": pk["FMUL2"], "ffma2_warp_instructions": pk["FFMA2"],
