@@ -39,7 +39,7 @@ STAGE_MAC = {"stft": 1651200, "layer1": 181053, "layer2": 112208, "layer3": 6160
 # the exact path's kernels behind each stage time (engine.cu run_window) and their names in the committed ncu export
 STAGE_KERNELS = {"stft": ["stft_sym_kernel<0>"], "layer1": ["exact_front_kernel<1>", "exact_layer_kernel<0>"], "layer2": ["exact_layer_kernel<1>"],
                  "layer3": ["exact_layer_kernel<2>"], "layer4": ["exact_layer_kernel<3>"], "lstm0": ["exact_lstm_kernel<0>"],
-                 "lstm1_decoder": ["exact_lstm_kernel<1>", "faithful_decoder_kernel"]}
+                 "lstm1_decoder": ["exact_lstm_kernel<0>", "faithful_decoder_kernel"]}   # (<0> = one launch per layer, the same kernel for both)
 # algorithmic bytes per chunk of each stage (what it must read + write once): STFT 3 072 s16 PCM + 12 900 log spectrogram; first layer
 # 12 900 in, 832 out; layers 2..4 832/896/896 in, 896/896/1 792 out; LSTM layers 1 792 in + 1 792 out each (state: 1 KB per stream per
 # launch, negligible per chunk), + 8 out for the decoder head

@@ -1098,7 +1098,8 @@ static int launch_exact_encoder( silero_b200 *h, const float *spec, float *a4, i
 // together). x0: encoder output [S][nw*7][64] on entry, top layer's output sequence on exit; h0: the first layer's sequence.
 // Few streams (2 x groups <= SMs): both layers in one wavefront launch; else one launch per layer.
 #define XL_WAVE_MAX_PER_CTA 10 // measured: the wavefront wins up to ~10 streams per CTA (297 streams: 1.09 vs 1.59 ms), two launches win from ~1000 streams on (4096: 9.4 vs 9.9 ms)
-static int launch_lstm_exact( silero_b200 *h, float *x0, float *h0, int first_stream, int nstreams, int nw, int force_mode = 0 )
+static void stage_mark( silero_b200 *h, int i );
+static int launch_lstm_exact( silero_b200 *h, float *x0, float *h0, int first_stream, int nstreams, int nw, int force_mode = 0, bool mark_layers = false )
 {
    float *sh = h->state_h + (size_t)first_stream * SILERO_B200_STATE_FLOATS;
    float *sc = h->state_c + (size_t)first_stream * SILERO_B200_STATE_FLOATS;
@@ -1120,8 +1121,10 @@ static int launch_lstm_exact( silero_b200 *h, float *x0, float *h0, int first_st
          exact_lstm_kernel<false><<<grid, XL_THREADS, XL_SMEM_BYTES, h->stream>>>( x0, h0, x0, sh, sc, h->w.lstm_w, h->w.lstm_b, nstreams, nw, layer, 0, h->d_err_word,
                                                                                    0, 0 );
          h->launches++;
+         if ( mark_layers && layer == 0 ) stage_mark( h, 6 ); // stage [6] = layer 0, [7] = layer 1 + decoder head
       }
    }
+   if ( mark_layers && wave ) stage_mark( h, 6 );             // one launch: stage [6] = both layers, [7] = decoder head
    CU( cudaGetLastError() );
    return 0;
 }
@@ -1215,8 +1218,7 @@ static int run_window( silero_b200 *h, const void *d_in, int in_f32, long long s
          if ( launch_exact_layer<3>( h, h->a3, h->a4, nchunks ) ) return SILERO_B200_ERR_CUDA;
          stage_mark( h, 5 );
       }
-      if ( launch_lstm_exact( h, h->a4, h->h0, first_stream, nstreams, nw ) ) return SILERO_B200_ERR_CUDA;
-      stage_mark( h, 6 );
+      if ( launch_lstm_exact( h, h->a4, h->h0, first_stream, nstreams, nw, 0, true ) ) return SILERO_B200_ERR_CUDA;
       {
          const long long n = (long long)nchunks * 2;
          faithful_decoder_kernel<<<(unsigned)( ( n + 127 ) / 128 ), 128, 0, h->stream>>>( h->a4, h->w.dec_w, h->w.dec_b, nstreams, nw, d_out2, d_probs, out_stride, out_off );
