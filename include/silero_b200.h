@@ -250,6 +250,8 @@ int silero_b200_stage_exact_layer( silero_b200 *h, int layer, const float *in, i
 /* encoder on the exact path's kernels from a spectrogram [B,129,25]; kind 0: log1p spectrogram (normalized inside, as in production),
    1: already normalized, 2: raw magnitude (log1p(m * 2^20) applied first, misc.c:40-46) */
 int silero_b200_stage_exact_encoder( silero_b200 *h, const float *spec, int batch, int kind, float *l1, float *l2, float *l3, float *l4 );
+/* softmax_inplace_stable (tensor.h:751-784) over the rows of x [rows][cols] in the exact path's arithmetic (the reference's softmax fixture) */
+int silero_b200_stage_exact_softmax( silero_b200 *h, const float *x, int rows, int cols, float *out );
 /* lstm_tensor_minibatched on the exact path's kernels, arguments as silero_b200_stage_lstm; wave 0: the multi-stream kernel
    (exact_lstm_kernel.cuh), 1: its two-layer wavefront launch, which serves few streams -- identical bits */
 int silero_b200_stage_exact_lstm( silero_b200 *h, const float *x, int batch, const float *h0, const float *c0, float *out, float *hn, float *cn, int wave );

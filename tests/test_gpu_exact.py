@@ -134,6 +134,21 @@ def test_fixture_first_layer_conv_block():
     assert np.abs(out - exp).max() < ATOL
 
 
+def test_fixture_softmax():
+    """The reference's 100 x 100 softmax fixture (test.c:900) on the GPU: the attention's softmax arithmetic (tensor.h:751-784) as a
+    row tap; also bit-identical to the oracle's restatement."""
+    import ctypes as C
+    x, exp = fx("softmax_test")
+    e = vadc_b200.Engine()
+    got = e.stage_exact_softmax(np.asarray(x, np.float32).reshape(100, 100))
+    e.close()
+    assert np.abs(got - np.asarray(exp).reshape(100, 100)).max() < ATOL
+    o = Oracle()
+    y = np.ascontiguousarray(np.asarray(x, np.float32).reshape(100, 100)).copy()
+    o.lib.so_softmax_rows(y.ctypes.data_as(C.c_void_p), 100, 100)
+    assert np.array_equal(bits(got), bits(y))
+
+
 def test_fixture_lstm():
     x, h0, c0, w, b, exp = fx("lstm_nito_reference_randn")
     e = engine({95: w, 96: b})

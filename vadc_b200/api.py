@@ -333,6 +333,12 @@ class Engine:
         self._check(lib().silero_b200_stage_exact_encoder(self._h, _p(x), B, kind, *[_p(o) for o in outs]))
         return outs
 
+    def stage_exact_softmax(self, x):
+        x = _f32(x)
+        out = np.zeros_like(x)
+        self._check(lib().silero_b200_stage_exact_softmax(self._h, _p(x), x.shape[0], x.shape[1], _p(out)))
+        return out
+
     def stage_exact_lstm(self, x, h0=None, c0=None, wave=False):
         x = _f32(x).reshape(-1, 7, 64)
         B = x.shape[0]

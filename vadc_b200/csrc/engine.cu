@@ -2250,6 +2250,19 @@ extern "C" int silero_b200_stage_lstm( silero_b200 *h, const float *x, int batch
    return SILERO_B200_OK;
 }
 
+// softmax_inplace_stable (tensor.h:751-784) over the rows of a host matrix, in the exact path's arithmetic
+extern "C" int silero_b200_stage_exact_softmax( silero_b200 *h, const float *x, int rows, int cols, float *out )
+{
+   if ( !h || !x || !out || rows <= 0 || cols <= 0 ) return set_err( SILERO_B200_ERR_ARG, "bad argument" );
+   if ( use_device( h ) ) return SILERO_B200_ERR_CUDA;
+   DevBuf d;
+   if ( d.alloc( (size_t)rows * cols ) ) return SILERO_B200_ERR_CUDA;
+   if ( up( h, d.p, x, (size_t)rows * cols ) ) return SILERO_B200_ERR_CUDA;
+   exact_softmax_rows_kernel<<<( rows + 63 ) / 64, 64, 0, h->stream>>>( d.p, rows, cols );
+   CU( cudaGetLastError() );
+   return down( h, out, d.p, (size_t)rows * cols );
+}
+
 // the same on the exact path's kernel (exact_lstm_kernel: weights in registers; here one stream)
 extern "C" int silero_b200_stage_exact_lstm( silero_b200 *h, const float *x, int batch, const float *h0, const float *c0, float *out, float *hn, float *cn, int wave )
 {

@@ -193,7 +193,30 @@ __device__ __forceinline__ void layer_norm_r( float ( &x )[C], const float *__re
 #pragma unroll
    for ( int i = 0; i < C; ++i ) x[i] = add( mul( sub( mul( x[i], rstd ), mr ), w[i] ), b[i] );
 }
+// tensor.h:751-784 softmax_inplace_stable on one row in memory: running max, expf of the differences, sequential sum, one reciprocal,
+// one multiply per element -- the arithmetic exact_layer_kernel applies to its attention rows (there the row lives in registers)
+__device__ __forceinline__ void softmax_row( float *row, int n )
+{
+   float mx = row[0];
+   for ( int i = 0; i < n; ++i )
+      if ( row[i] > mx ) mx = row[i];
+   float sum = 0.0f;
+   for ( int i = 0; i < n; ++i )
+   {
+      row[i] = lme::expf_ref( sub( row[i], mx ) );
+      sum = add( sum, row[i] );
+   }
+   const float inv = quot( 1.0f, sum );
+   for ( int i = 0; i < n; ++i ) row[i] = mul( row[i], inv );
+}
 } // namespace xe
+
+// parity tap for the reference's softmax fixture (test.c:900, 100 x 100): thread = row
+__global__ void exact_softmax_rows_kernel( float *x, int rows, int cols )
+{
+   const int r = blockIdx.x * blockDim.x + threadIdx.x;
+   if ( r < rows ) xe::softmax_row( x + (size_t)r * cols, cols );
+}
 
 // ------------------------------------------------------------------------------------------------------------------------------
 // front: normalization scalar + depthwise conv + the first layer's pointwise / projection contractions (K = 129)
