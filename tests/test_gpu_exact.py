@@ -149,6 +149,21 @@ def test_fixture_softmax():
     assert np.array_equal(bits(got), bits(y))
 
 
+def test_expf_underflow_range():
+    """expf between the last normal result and the underflow to zero (-87.3 .. -103.97): glibc rounds the double result to a denormal,
+    takes __math_may_uflowf below log(2^-149) and returns 0 below log(2^-150). Round 1's restatement returned 0 from -103 on (found by
+    the softmax fixture, whose rows span +-450)."""
+    import ctypes as C
+    lib = C.CDLL("libm.so.6")
+    lib.expf.restype, lib.expf.argtypes = C.c_float, [C.c_float]
+    x = np.concatenate([np.linspace(-104.5, -86.0, 20001).astype(np.float32), np.float32([-103.97208, -103.972076, -103.2789, -103.27893, 88.7, 88.73])])
+    want = np.array([lib.expf(float(v)) for v in x], np.float32)
+    e = vadc_b200.Engine()
+    got = e.stage_libm(x)[0]
+    e.close()
+    assert np.array_equal(bits(got), bits(want))
+
+
 def test_fixture_lstm():
     x, h0, c0, w, b, exp = fx("lstm_nito_reference_randn")
     e = engine({95: w, 96: b})

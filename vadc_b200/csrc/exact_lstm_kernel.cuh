@@ -194,12 +194,33 @@ exact_lstm_kernel( const float *x0, float *h0seq, float *out1, float *__restrict
                if ( !half || two ) a[( p + half ) * 256 + row] = z;
             }
             __syncthreads();
+            // One or two streams in the sub-batch (few streams per CTA: the latency-bound shapes, down to ONE stream): 64 or 128 threads
+            // would each evaluate five libm restatements in a row on otherwise idle schedulers (measured on one stream: 73 % of the step).
+            // Instead all 512 threads take one gate value each first -- thread = (stream, gate, unit), two warps per gate, no divergence --
+            // so that the serial chain of a step is one nonlinearity + the cell's tanh instead of five evaluations.
+            const bool spread = kn <= 2;
+            if ( spread )
+            {
+               const int sk = tid >> 8, sg = ( tid >> 6 ) & 3;
+               if ( sk < kn )
+               {
+                  float *pz = a + sk * 256 + sg * 64 + uj;
+                  *pz = sg == 2 ? lme::tanhf_ref( *pz ) : lme::sigmoid_ref( *pz, exp_tab );
+               }
+               __syncthreads();
+            }
             // gate nonlinearities and cell update (lstm.c:64-88) of (unit uj, stream k0 + uk)
             if ( upd )
             {
                const float *av = a + uk * 256;
-               const float ig = lme::sigmoid_ref( av[uj], exp_tab ), fg = lme::sigmoid_ref( av[64 + uj], exp_tab );
-               const float gg = lme::tanhf_ref( av[128 + uj] ), og = lme::sigmoid_ref( av[192 + uj], exp_tab );
+               float ig = av[uj], fg = av[64 + uj], gg = av[128 + uj], og = av[192 + uj];
+               if ( !spread )
+               {
+                  ig = lme::sigmoid_ref( ig, exp_tab );
+                  fg = lme::sigmoid_ref( fg, exp_tab );
+                  gg = lme::tanhf_ref( gg );
+                  og = lme::sigmoid_ref( og, exp_tab );
+               }
                const int k = k0 + uk;
                const float cn = __fadd_rn( __fmul_rn( fg, cst[k * 64 + uj] ), __fmul_rn( ig, gg ) );
                const float hn = __fmul_rn( lme::tanhf_ref( cn ), og );
