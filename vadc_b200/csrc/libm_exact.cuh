@@ -14,13 +14,37 @@
 // everywhere, expf identical except at two arguments (|x| = 32.56.. and 63.1.., where the library's FMA build rounds the double
 // polynomial the other way). No fused multiply-add may be formed here: everything goes through the _rn intrinsics.
 #pragma once
-#include <cuda_runtime.h>
 #include <stdint.h>
+#if defined( __CUDACC__ )
+#include <cuda_runtime.h>
+#define LME_FN __device__ __forceinline__
+#define LME_TAB __device__ __constant__ const
+#else
+// Host build (tests/hostcheck/libm_exhaustive.cpp: every function below swept over ALL floats of its domain against the C library):
+// the intrinsics become plain IEEE operations; compile with -ffp-contract=off so that nothing is fused.
+#include <math.h>
+#include <string.h>
+#define LME_FN static inline
+#define LME_TAB static const
+static inline float __fmul_rn( float a, float b ) { return a * b; }
+static inline float __fadd_rn( float a, float b ) { return a + b; }
+static inline float __fsub_rn( float a, float b ) { return a - b; }
+static inline float __fdiv_rn( float a, float b ) { return a / b; }
+static inline double __dmul_rn( double a, double b ) { return a * b; }
+static inline double __dadd_rn( double a, double b ) { return a + b; }
+static inline float __double2float_rn( double a ) { return (float)a; }
+static inline uint32_t __float_as_uint( float a ) { uint32_t u; memcpy( &u, &a, 4 ); return u; }
+static inline int __float_as_int( float a ) { int u; memcpy( &u, &a, 4 ); return u; }
+static inline float __uint_as_float( uint32_t u ) { float a; memcpy( &a, &u, 4 ); return a; }
+static inline float __int_as_float( int u ) { float a; memcpy( &a, &u, 4 ); return a; }
+static inline long long __double_as_longlong( double a ) { long long u; memcpy( &u, &a, 8 ); return u; }
+static inline double __longlong_as_double( long long u ) { double a; memcpy( &a, &u, 8 ); return a; }
+#endif
 
 namespace lme
 {
 // asuint64( 2^(i/32) ) - ( i << 47 ), i < 32
-__device__ __constant__ const unsigned long long EXP2F_TAB[32] = {
+LME_TAB unsigned long long EXP2F_TAB[32] = {
    0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull, 0x3fef72b83c7d517bull, 0x3fef54873168b9aaull,
    0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull, 0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull, 0x3feedea64c123422ull, 0x3feece086061892dull,
    0x3feebfdad5362a27ull, 0x3feeb42b569d4f82ull, 0x3feeab07dd485429ull, 0x3feea47eb03a5585ull, 0x3feea09e667f3bcdull, 0x3fee9f75e8ec5f74ull,
@@ -31,7 +55,7 @@ __device__ __constant__ const unsigned long long EXP2F_TAB[32] = {
 // tab: EXP2F_TAB, or a copy of it in shared memory (32 x 8 bytes): lanes index the table with different k, which the constant cache
 // serves one address at a time (measured: 5 % of the LSTM kernel's stall samples sat on this load) while shared memory serves the
 // whole warp in one or two wavefronts
-__device__ __forceinline__ float expf_ref( float x, const unsigned long long *tab = EXP2F_TAB )
+LME_FN float expf_ref( float x, const unsigned long long *tab = EXP2F_TAB )
 {
    const double InvLn2N = 0x1.71547652b82fep+0 * 32.0, SHIFT = 0x1.8p+52;
    const double C0 = 0x1.c6af84b912394p-5 / 32.0 / 32.0 / 32.0, C1 = 0x1.ebfce50fac4f3p-3 / 32.0 / 32.0, C2 = 0x1.62e42ff0c52d6p-1 / 32.0;
@@ -54,14 +78,14 @@ __device__ __forceinline__ float expf_ref( float x, const unsigned long long *ta
    return __double2float_rn( y );
 }
 
-__device__ __forceinline__ float fmul( float a, float b ) { return __fmul_rn( a, b ); }
-__device__ __forceinline__ float fadd( float a, float b ) { return __fadd_rn( a, b ); }
-__device__ __forceinline__ float fsub( float a, float b ) { return __fsub_rn( a, b ); }
-__device__ __forceinline__ float fdiv( float a, float b ) { return __fdiv_rn( a, b ); }
-__device__ __forceinline__ float word( uint32_t u ) { return __uint_as_float( u ); }
+LME_FN float fmul( float a, float b ) { return __fmul_rn( a, b ); }
+LME_FN float fadd( float a, float b ) { return __fadd_rn( a, b ); }
+LME_FN float fsub( float a, float b ) { return __fsub_rn( a, b ); }
+LME_FN float fdiv( float a, float b ) { return __fdiv_rn( a, b ); }
+LME_FN float word( uint32_t u ) { return __uint_as_float( u ); }
 
 // fdlibm expm1f (finite arguments; callers pass |x| <= 44)
-__device__ __forceinline__ float expm1f_ref( float x )
+LME_FN float expm1f_ref( float x )
 {
    const float one = 1.0f, huge = 1.0e+30f, tiny = 1.0e-30f, ln2_hi = 6.9313812256e-01f, ln2_lo = 9.0580006145e-06f, invln2 = 1.4426950216e+00f;
    const float Q1 = -3.3333335072e-02f, Q2 = 1.5873016091e-03f, Q3 = -7.9365076090e-05f, Q4 = 4.0082177293e-06f, Q5 = -2.0109921195e-07f;
@@ -77,40 +101,27 @@ __device__ __forceinline__ float expm1f_ref( float x )
          if ( fadd( x, tiny ) < 0.0f ) return fsub( tiny, one );
       }
    }
-   if ( hx > 0x3eb17218u ) // |x| > 0.5 ln 2
-   {
-      if ( hx < 0x3F851592u ) // |x| < 1.5 ln 2
-      {
-         if ( xsb == 0 )
-         {
-            hi = fsub( x, ln2_hi );
-            lo = ln2_lo;
-            k = 1;
-         }
-         else
-         {
-            hi = fadd( x, ln2_hi );
-            lo = -ln2_lo;
-            k = -1;
-         }
-      }
-      else
-      {
-         k = (int)fadd( fmul( invln2, x ), xsb == 0 ? 0.5f : -0.5f );
-         t = (float)k;
-         hi = fsub( x, fmul( t, ln2_hi ) );
-         lo = fmul( t, ln2_lo );
-      }
-      x = fsub( hi, lo );
-      c = fsub( fsub( hi, x ), lo );
-   }
-   else if ( hx < 0x33000000u ) // |x| < 2^-25
+   if ( hx < 0x33000000u ) // |x| < 2^-25
    {
       t = fadd( huge, x );
       return fsub( x, fsub( t, fadd( huge, x ) ) );
    }
-   else
-      k = 0;
+   // Argument reduction without divergence (the lanes of a warp hold pre-activations of all sizes, and every divergent path is
+   // executed by the whole warp). fdlibm's three cases collapse into one formula: for 0.5 ln2 < |x| < 1.5 ln2 it sets k = +-1,
+   // hi = x -+ ln2_hi, lo = +-ln2_lo -- exactly what the general case computes from t = (float)k = +-1 (1 * ln2_hi and 1 * ln2_lo are
+   // exact), so only k itself needs the select; |x| <= 0.5 ln2 keeps x and c = 0 (k = 0).
+   {
+      const bool reduce = hx > 0x3eb17218u, near = hx < 0x3F851592u; // |x| > 0.5 ln 2, |x| < 1.5 ln 2
+      const int kg = (int)fadd( fmul( invln2, x ), xsb == 0 ? 0.5f : -0.5f );
+      k = reduce ? ( near ? ( xsb == 0 ? 1 : -1 ) : kg ) : 0;
+      t = (float)k;
+      hi = fsub( x, fmul( t, ln2_hi ) );
+      lo = fmul( t, ln2_lo );
+      const float xr = fsub( hi, lo );
+      const float cr = fsub( fsub( hi, xr ), lo );
+      x = reduce ? xr : x;
+      c = reduce ? cr : 0.0f;
+   }
    hfx = fmul( 0.5f, x );
    hxs = fmul( x, hfx );
    r1 = fadd( one, fmul( hxs, fadd( Q1, fmul( hxs, fadd( Q2, fmul( hxs, fadd( Q3, fmul( hxs, fadd( Q4, fmul( hxs, Q5 ) ) ) ) ) ) ) ) ) );
@@ -147,7 +158,7 @@ __device__ __forceinline__ float expm1f_ref( float x )
    return y;
 }
 
-__device__ __forceinline__ float tanhf_ref( float x )
+LME_FN float tanhf_ref( float x )
 {
    const float one = 1.0f, two = 2.0f, tiny = 1.0e-30f;
    float t, z;
@@ -157,16 +168,12 @@ __device__ __forceinline__ float tanhf_ref( float x )
    {
       if ( ix == 0 ) return x;
       if ( ix < 0x24000000u ) return fmul( x, fadd( one, x ) );
-      if ( ix >= 0x3f800000u )
-      {
-         t = expm1f_ref( fmul( two, fabsf( x ) ) );
-         z = fsub( one, fdiv( two, fadd( t, two ) ) );
-      }
-      else
-      {
-         t = expm1f_ref( fmul( -two, fabsf( x ) ) );
-         z = fdiv( -t, fadd( t, two ) );
-      }
+      // one expm1f for both ranges (inlined twice, a warp with arguments on both sides of 1 ran both copies in turn):
+      // |x| >= 1: t = expm1f(2|x|), z = 1 - 2/(t+2);  |x| < 1: t = expm1f(-2|x|), z = -t/(t+2)
+      const bool big = ix >= 0x3f800000u;
+      t = expm1f_ref( fmul( big ? two : -two, fabsf( x ) ) );
+      const float q = fdiv( big ? two : -t, fadd( t, two ) );
+      z = big ? fsub( one, q ) : q;
    }
    else
       z = fsub( one, tiny );
@@ -175,7 +182,7 @@ __device__ __forceinline__ float tanhf_ref( float x )
 
 // fdlibm log1pf (s_log1pf.c) for x >= 0 (misc.c:40-46 applies it to magnitude * 2^20); checked on the host against the C library over
 // ALL 2 139 095 040 non-negative floats: identical
-__device__ __forceinline__ float log1pf_ref( float x )
+LME_FN float log1pf_ref( float x )
 {
    const float ln2_hi = 6.9313812256e-01f, ln2_lo = 9.0580006145e-06f;
    const float Lp1 = 6.6666668653e-01f, Lp2 = 4.0000000596e-01f, Lp3 = 2.8571429849e-01f, Lp4 = 2.2222198546e-01f, Lp5 = 1.8183572590e-01f,
@@ -248,10 +255,12 @@ __device__ __forceinline__ float log1pf_ref( float x )
 }
 
 // maths.h:327-334: 1 / (1 + expf(-x))
-__device__ __forceinline__ float sigmoid_ref( float v, const unsigned long long *tab = EXP2F_TAB ) { return fdiv( 1.0f, fadd( 1.0f, expf_ref( -v, tab ) ) ); }
+LME_FN float sigmoid_ref( float v, const unsigned long long *tab = EXP2F_TAB ) { return fdiv( 1.0f, fadd( 1.0f, expf_ref( -v, tab ) ) ); }
+#if defined( __CUDACC__ )
 // copy of the table for expf_ref( x, tab ); call with all threads of the CTA, then synchronize
-__device__ __forceinline__ void stage_exp2f_tab( unsigned long long *dst, int tid )
+LME_FN void stage_exp2f_tab( unsigned long long *dst, int tid )
 {
    if ( tid < 32 ) dst[tid] = EXP2F_TAB[tid];
 }
+#endif
 } // namespace lme
