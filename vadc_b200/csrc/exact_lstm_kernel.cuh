@@ -177,6 +177,7 @@ exact_lstm_kernel( const float *x0, float *h0seq, float *out1, float *__restrict
                copy_row( xh + ( k0 + uk ) * XL_ROW + xn + uj, us, step + 1 );
             }
             float *a = act + buf * ( XL_SUB * 256 );
+            const bool spread = kn <= 4; // (measured: up to four streams the row owners' 1-2 evaluations + the cell's tanh beat five evaluations in the cell-update phase)
 #pragma unroll 1
             for ( int p = 0; p < kn; p += 2 )
             {
@@ -206,24 +207,13 @@ exact_lstm_kernel( const float *x0, float *h0seq, float *out1, float *__restrict
                z = __fadd_rn( z, hi[2] );
                z = __fadd_rn( z, hi[3] );
                z = __fadd_rn( z, b_row );
-               if ( !half || two ) a[( p + half ) * 256 + row] = z;
+               // Up to four streams in the sub-batch (few streams per CTA: the latency-bound shapes, down to ONE stream): the lane that
+               // finished a row applies the row's own gate nonlinearity right here (a warp's 16 rows belong to one gate: no divergence),
+               // so that the serial chain of a step is one nonlinearity + the cell's tanh. With more streams the cell-update phase takes
+               // all five evaluations: there every thread does the same work and no warp is the slow one at the barrier.
+               if ( !half || two ) a[( p + half ) * 256 + row] = !spread ? z : ( ( row >> 6 ) == 2 ? lme::tanhf_ref( z ) : lme::sigmoid_ref( z, exp_tab ) );
             }
             __syncthreads();
-            // One or two streams in the sub-batch (few streams per CTA: the latency-bound shapes, down to ONE stream): 64 or 128 threads
-            // would each evaluate five libm restatements in a row on otherwise idle schedulers (measured on one stream: 73 % of the step).
-            // Instead all 512 threads take one gate value each first -- thread = (stream, gate, unit), two warps per gate, no divergence --
-            // so that the serial chain of a step is one nonlinearity + the cell's tanh instead of five evaluations.
-            const bool spread = kn <= 2;
-            if ( spread )
-            {
-               const int sk = tid >> 8, sg = ( tid >> 6 ) & 3;
-               if ( sk < kn )
-               {
-                  float *pz = a + sk * 256 + sg * 64 + uj;
-                  *pz = sg == 2 ? lme::tanhf_ref( *pz ) : lme::sigmoid_ref( *pz, exp_tab );
-               }
-               __syncthreads();
-            }
             // gate nonlinearities and cell update (lstm.c:64-88) of (unit uj, stream k0 + uk)
             if ( upd )
             {
