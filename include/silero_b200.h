@@ -85,7 +85,7 @@ typedef struct silero_b200 silero_b200; /* opaque engine handle */
 #define SILERO_B200_LAYERS_FP32 1
 #define SILERO_B200_LAYERS_TENSOR 2
 #define SILERO_B200_LAYERS_FAITHFUL 3
-#define SILERO_B200_EXACT_TOKEN_MIN_CHUNKS 1024   /* exact path: windows of at least this many chunks run the thread-per-token encoder
+#define SILERO_B200_EXACT_TOKEN_MIN_CHUNKS 1536   /* exact path: windows of at least this many chunks run the thread-per-token encoder
                                                      (below: a CTA per chunk -- more parallelism for small windows; identical bits) */
 
 typedef struct silero_b200_opts

@@ -12,7 +12,7 @@ from oracle_lib import Oracle
 fast = len(sys.argv) > 1 and sys.argv[1] == "fast"
 bits = lambda a: np.ascontiguousarray(a, np.float32).view(np.uint32)
 ok = True
-for S, N in ((2, 12), (160, 7), (800, 2)):
+for S, N in ((2, 12), (160, 10), (800, 2)):
     pcm = np.stack([vadc_b200.synth_pcm(10 + (s % 6), N * 1536) for s in range(S)])
     e = vadc_b200.Engine(max_streams=S)
     e.segments_configure()
