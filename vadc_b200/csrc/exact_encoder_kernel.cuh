@@ -225,7 +225,7 @@ __global__ void exact_softmax_rows_kernel( float *x, int rows, int cols )
 #define XF_G 5                                   // chunks per batch: 125 tokens x 4 feature quarters = 500 threads
 #define XF_TILE 16128                            // XF_G * 129 * 25 = 16125 floats, padded to keep what follows 16-byte aligned
 #define XF_W_FLOATS ( VB_BINS * 32 )              // [c][16 pw | 16 proj]
-#define XF_SMEM_FLOATS ( 2 * XF_TILE + XF_W_FLOATS + al4c( VB_BINS * 5 ) + al4c( VB_BINS ) + 32 + XF_G * 32 * 2 + 32 )
+#define XF_SMEM_FLOATS ( 3 * XF_TILE + XF_W_FLOATS + al4c( VB_BINS * 5 ) + al4c( VB_BINS ) + 32 + XF_G * 32 * 2 + 32 )
 __host__ __device__ constexpr int al4c( int x ) { return ( x + 3 ) & ~3; }
 #define XF_SMEM_BYTES ( XF_SMEM_FLOATS * 4 )
 
@@ -236,8 +236,8 @@ __global__ void __launch_bounds__( XF_THREADS, 1 ) exact_front_kernel( const flo
 {
    constexpr xe::LayerOff O = xe::layer_off( 0 );
    extern __shared__ __align__( 16 ) float fsm[];
-   float *Xs = fsm;                      // [g][129][25] log spectrogram, then minus the normalization scalar
-   float *Ds = Xs + XF_TILE;             // [g][129][25] relu(depthwise conv)
+   float *Xa = fsm;                      // [2 buffers][g][129][25] log spectrogram as the STFT wrote it (+ up to 3 floats of alignment shift)
+   float *Ds = Xa + 2 * XF_TILE;         // [g][129][25] relu(depthwise conv)
    float *Wf = Ds + XF_TILE;             // [129][32]
    float *dww = Wf + XF_W_FLOATS;        // [129][5]
    float *dwb = dww + al4c( VB_BINS * 5 ); // [129]
@@ -262,16 +262,35 @@ __global__ void __launch_bounds__( XF_THREADS, 1 ) exact_front_kernel( const flo
    const int fq = tid >> 7, m = tid & 127;       // feature quarter, token of the batch (m < 125)
    const int g = m / VB_FRAMES, t = m - g * VB_FRAMES;
    const bool tok = m < XF_G * VB_FRAMES;
-   for ( int c0 = blockIdx.x * XF_G; c0 < nchunks; c0 += gridDim.x * XF_G )
+
+   // The batch after the current one is on its way (cp.async) while this one is computed. A batch starts at float c0 * 3225 of the
+   // spectrogram -- 4-byte aligned only -- so the tile lands shifted by (address / 4) % 4 floats: 16-byte copies for the aligned body,
+   // 4-byte copies for the ragged ends, nothing outside the batch is read. Returns the shift.
+   auto fetch = [&]( int c0, float *buf ) -> int {
+      const float *src = spec + (size_t)c0 * ( VB_BINS * VB_FRAMES );
+      const int n = min( XF_G, nchunks - c0 ) * ( VB_BINS * VB_FRAMES );
+      const int shift = (int)( ( reinterpret_cast<size_t>( src ) >> 2 ) & 3 ), head = ( 4 - shift ) & 3;
+      float *dst = buf + shift;
+      const unsigned d0 = (unsigned)__cvta_generic_to_shared( dst );
+      const int nv = ( n - head ) >> 2, tail0 = head + 4 * nv;
+      if ( tid < head ) asm volatile( "cp.async.ca.shared.global [%0], [%1], 4;" ::"r"( d0 + 4u * tid ), "l"( src + tid ) : "memory" );
+      for ( int i = tid; i < nv; i += XF_THREADS )
+         asm volatile( "cp.async.cg.shared.global [%0], [%1], 16;" ::"r"( d0 + 4u * ( head + 4 * i ) ), "l"( src + head + 4 * i ) : "memory" );
+      if ( tail0 + tid < n ) asm volatile( "cp.async.ca.shared.global [%0], [%1], 4;" ::"r"( d0 + 4u * ( tail0 + tid ) ), "l"( src + tail0 + tid ) : "memory" );
+      return shift;
+   };
+   int c0 = blockIdx.x * XF_G, buf = 0, shift = 0;
+   if ( c0 < nchunks ) shift = fetch( c0, Xa );
+   for ( ; c0 < nchunks; c0 += gridDim.x * XF_G, buf ^= 1 )
    {
       const int ng = min( XF_G, nchunks - c0 );
-      __syncthreads(); // the previous batch is done with the tiles (and the weights are staged)
+      const float *Xs = Xa + buf * XF_TILE + shift;
+      asm volatile( "cp.async.wait_all;" ::: "memory" );
+      __syncthreads(); // this batch has landed; the previous one is done with the other tile and with Ds (and the weights are staged)
       {
-         const float *src = spec + (size_t)c0 * ( VB_BINS * VB_FRAMES );
-         const int n = ng * VB_BINS * VB_FRAMES;
-         for ( int i = tid; i < n; i += XF_THREADS ) Xs[i] = __ldg( src + i );
+         const int cn = c0 + gridDim.x * XF_G;
+         if ( cn < nchunks ) shift = fetch( cn, Xa + ( buf ^ 1 ) * XF_TILE );
       }
-      __syncthreads();
       if ( NORM )
       {
       // misc.c:48-62: per-frame mean over the bins, sequential sum, division
@@ -307,35 +326,49 @@ __global__ void __launch_bounds__( XF_THREADS, 1 ) exact_front_kernel( const flo
          MU[tid] = xe::quot( total, 25.0f );
       }
       __syncthreads();
-      for ( int gg = 0; gg < ng; ++gg )
-      {
-         const float mu = MU[gg];
-         float *xg = Xs + gg * ( VB_BINS * VB_FRAMES );
-         for ( int i = tid; i < VB_BINS * VB_FRAMES; i += XF_THREADS ) xg[i] = xe::sub( xg[i], mu );
       }
-      __syncthreads();
-      }
-      // depthwise k = 5, zero pad 2 (conv.c:17-53, 60-113): the taps that exist, left to right from 0, then bias + sum; ReLU
+      // The normalization scalar is subtracted where a value is used (misc.c:84-124 does it in place; the difference is the same
+      // number wherever it is formed), which saves the pass over the tile.
+      // depthwise k = 5, zero pad 2 (conv.c:17-53, 60-113): the taps that exist, left to right from 0, then bias + sum; ReLU.
+      // task = (row g * 129 + c, five frames): nine inputs, five weights in registers; only the outer two taps of the first and the last
+      // segment of a row can fall into the padding.
       {
-         // element i = (row gc = g * 129 + c, frame ti); the indices advance incrementally (512 = 20 rows + 12 frames) instead of by division
-         const int n = ng * VB_BINS * VB_FRAMES;
-         int gc = tid / VB_FRAMES, ti = tid - gc * VB_FRAMES, c = gc; // tid < 512 < 129 * 25: the first element is in chunk 0
-         for ( int i = tid; i < n; i += XF_THREADS )
+         const int ntask = ng * VB_BINS * 5;
+         for ( int task = tid; task < ntask; task += XF_THREADS )
          {
-            const float *a = Xs + gc * VB_FRAMES, *k = dww + c * 5;
-            float r = 0.0f;
+            const int r = task / 5, seg = task - 5 * r;
+            const int gg = r / VB_BINS, c = r - gg * VB_BINS;
+            const float mu = NORM ? MU[gg] : 0.0f;
+            const float *a = Xs + 5 * task; // row r, frame 5 seg
+            float x[9];
 #pragma unroll
-            for ( int kk = 0; kk < 5; ++kk )
+            for ( int q = 0; q < 9; ++q )
             {
-               const int tt = ti + kk - 2;
-               if ( tt >= 0 && tt < VB_FRAMES ) r = xe::add( r, xe::mul( a[tt], k[kk] ) );
+               const bool valid = q < 2 ? seg != 0 : ( q > 6 ? seg != 4 : true );
+               const float v = valid ? a[q - 2] : 0.0f;
+               x[q] = NORM ? xe::sub( v, mu ) : v;
             }
-            Ds[i] = xe::relu( xe::add( dwb[c], r ) );
-            ti += XF_THREADS % VB_FRAMES;
-            gc += XF_THREADS / VB_FRAMES;
-            c += XF_THREADS / VB_FRAMES;
-            if ( ti >= VB_FRAMES ) { ti -= VB_FRAMES; ++gc; ++c; }
-            if ( c >= VB_BINS ) c -= VB_BINS;
+            const float *k = dww + c * 5;
+            const float k0 = k[0], k1 = k[1], k2 = k[2], k3 = k[3], k4 = k[4], bias = dwb[c];
+            const float kw[5] = { k0, k1, k2, k3, k4 };
+#pragma unroll
+            for ( int j = 0; j < 5; ++j )
+            {
+               float rr = 0.0f;
+#pragma unroll
+               for ( int kk = 0; kk < 5; ++kk )
+               {
+                  const int q = j + kk;
+                  const float nr = xe::add( rr, xe::mul( x[q], kw[kk] ) );
+                  if ( q < 2 )
+                     rr = seg != 0 ? nr : rr;
+                  else if ( q > 6 )
+                     rr = seg != 4 ? nr : rr;
+                  else
+                     rr = nr;
+               }
+               Ds[5 * task + j] = xe::relu( xe::add( bias, rr ) );
+            }
          }
       }
       __syncthreads();
@@ -347,6 +380,7 @@ __global__ void __launch_bounds__( XF_THREADS, 1 ) exact_front_kernel( const flo
       {
          const float *xc = Xs + g * ( VB_BINS * VB_FRAMES ) + t, *dc = Ds + g * ( VB_BINS * VB_FRAMES ) + t;
          const float *wq = Wf + 4 * fq;
+         const float mu = NORM ? MU[g] : 0.0f;
          float st[8][5]; // [output: 0..3 pointwise, 4..7 projection][tree stack: four folded entries + the leaf just pushed]
          constexpr int leaf[16] = { 0, 1, 2, 3, 8, 9, 10, 11, 4, 5, 6, 7, 12, 13, 14, 15 };
 #pragma unroll
@@ -358,7 +392,7 @@ __global__ void __launch_bounds__( XF_THREADS, 1 ) exact_front_kernel( const flo
             for ( int b = 0; b < 8; ++b )
             {
                const int c = 16 * b + mm;
-               const float dv = dc[c * VB_FRAMES], xv = xc[c * VB_FRAMES];
+               const float dv = dc[c * VB_FRAMES], xv = NORM ? xe::sub( xc[c * VB_FRAMES], mu ) : xc[c * VB_FRAMES];
                const float4 wp = ld4( wq + c * 32 ), wj = ld4( wq + c * 32 + 16 );
                const float p[8] = { xe::mul( dv, wp.x ), xe::mul( dv, wp.y ), xe::mul( dv, wp.z ), xe::mul( dv, wp.w ),
                                     xe::mul( xv, wj.x ), xe::mul( xv, wj.y ), xe::mul( xv, wj.z ), xe::mul( xv, wj.w ) };
@@ -378,7 +412,7 @@ __global__ void __launch_bounds__( XF_THREADS, 1 ) exact_front_kernel( const flo
                n >>= 1;
             }
          }
-         const float dv = dc[128 * VB_FRAMES], xv = xc[128 * VB_FRAMES];
+         const float dv = dc[128 * VB_FRAMES], xv = NORM ? xe::sub( xc[128 * VB_FRAMES], mu ) : xc[128 * VB_FRAMES];
          const float4 wp = ld4( wq + 128 * 32 ), wj = ld4( wq + 128 * 32 + 16 );
          const float tp[8] = { xe::mul( dv, wp.x ), xe::mul( dv, wp.y ), xe::mul( dv, wp.z ), xe::mul( dv, wp.w ),
                                xe::mul( xv, wj.x ), xe::mul( xv, wj.y ), xe::mul( xv, wj.z ), xe::mul( xv, wj.w ) };

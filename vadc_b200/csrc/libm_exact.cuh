@@ -213,7 +213,9 @@ LME_FN float log1pf_ref( float x )
          hu = __float_as_int( u );
          k = ( hu >> 23 ) - 127;
          c = ( k > 0 ) ? fsub( 1.0f, fsub( u, x ) ) : fsub( x, fsub( u, 1.0f ) );
-         c = fdiv( c, u );
+         // 1 + x is exact for most x in [1, 2^24): c is then +0, and (+0) / u == +0 for the u > 0 of this domain. Skipping the division
+         // there is not only cheaper on the host: on the device a zero numerator sends the division down its slow path.
+         if ( c != 0.0f ) c = fdiv( c, u );
       }
       else
       {

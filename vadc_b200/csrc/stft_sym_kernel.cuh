@@ -23,6 +23,10 @@
 // its four lanes exactly like stft_kernel.cuh walks all eight (tree state for 2 rows x 5 frames in registers), keeps the plain and
 // the alternating pair sums, and meets its partner (lane ^ 16: same unit, other half) in one shuffle per value: the half-0 thread
 // finishes bin u, the half-1 thread bin 128-u -- magnitude and log1p are spread over all 640 threads.
+// Bin 64 (the second row of unit 0) would give the five warps that hold unit 0 ten magnitudes + log1p per thread instead of five,
+// and warp w runs on scheduler w % 4: all five sit on scheduler 0, which made every other warp wait ~17 % of the kernel at the
+// chunk barrier (r02c profile). Its 25 (re, im) pairs go through shared memory instead and ONE warp finishes them after the next
+// barrier, 25 lanes wide.
 #pragma once
 #include "common.cuh"
 #include "libm_exact.cuh"
@@ -30,7 +34,9 @@
 
 #define SSYM_THREADS 640
 #define SSYM_BS_FLOATS ( 64 * 128 * 4 )
-#define SSYM_SMEM_BYTES ( ( SSYM_BS_FLOATS + 2 * STFT_XS_FLOATS ) * 4 )
+#define SSYM_B64_FLOATS ( 2 * VB_FRAMES * 2 ) // bin 64: [2 buffers][25 frames](re, im)
+#define SSYM_SMEM_BYTES ( ( SSYM_BS_FLOATS + 2 * STFT_XS_FLOATS + SSYM_B64_FLOATS ) * 4 )
+#define SSYM_B64_WARP 19 // the warp that finishes bin 64 (no staging work, a scheduler without the two-staging-warp load)
 
 // two fp32 values in a 64-bit register pair, for the packed add of sm_100 (add.rn.f32x2 -> FADD2): each half is an IEEE addition
 typedef unsigned long long ssym2;
@@ -78,6 +84,7 @@ stft_sym_kernel( const void *__restrict__ in, long long stream_stride, int nw, i
    extern __shared__ __align__( 16 ) float smem[];
    float *Bs = smem;
    float *Xs_all = smem + SSYM_BS_FLOATS; // [2 buffers][1792]
+   float *B64 = Xs_all + 2 * STFT_XS_FLOATS; // [2 buffers][25][2]
    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
    const int tg = w >> 2;                              // frames 5 tg .. 5 tg + 4
    const int u = ( ( w & 3 ) << 4 ) | ( lane & 15 );   // unit: bins u and 128 - u
@@ -94,8 +101,18 @@ stft_sym_kernel( const void *__restrict__ in, long long stream_stride, int nw, i
    if ( ci < nchunks && tid < NV ) raw = __ldg( (const int4 *)stft_chunk_ptr<F32>( in, stream_stride, nw, ci ) + tid );
    __syncthreads();
 
-   int buf = 0;
-   for ( ; ci < nchunks; ci += gridDim.x, buf ^= 1 )
+   // bin 64 of chunk `cprev` from the pairs the unit-0 lanes left in B64[pbuf] (the caller has passed a barrier since)
+   auto finish_bin64 = [&]( int cprev, int pbuf ) {
+      if ( w == SSYM_B64_WARP && lane < VB_FRAMES )
+      {
+         const float2 v = *reinterpret_cast<const float2 *>( B64 + ( pbuf * VB_FRAMES + lane ) * 2 );
+         const float m2 = sqrtf( __fadd_rn( __fmul_rn( v.x, v.x ), __fmul_rn( v.y, v.y ) ) );
+         spec[(size_t)cprev * ( VB_BINS * VB_FRAMES ) + 64 * VB_FRAMES + lane] = out_mode ? m2 : lme::log1pf_ref( __fmul_rn( m2, 1048576.0f ) );
+      }
+   };
+
+   int buf = 0, cprev = -1;
+   for ( ; ci < nchunks; cprev = ci, ci += gridDim.x, buf ^= 1 )
    {
       float *xs = Xs_all + buf * STFT_XS_FLOATS;
       if ( tid < NV )
@@ -117,6 +134,7 @@ stft_sym_kernel( const void *__restrict__ in, long long stream_stride, int nw, i
       __syncthreads(); // tile complete; the other buffer (previous chunk) is no longer read by anyone
       const int cn = ci + gridDim.x;
       if ( cn < nchunks && tid < NV ) raw = __ldg( (const int4 *)stft_chunk_ptr<F32>( in, stream_stride, nw, cn ) + tid );
+      if ( cprev >= 0 ) finish_bin64( cprev, buf ^ 1 );
 
       // Frames go through in pairs (0,1), (2,3) + frame 4: the two frames of a pair share every basis value, their products are
       // separate FMULs into adjacent registers, and every ADD of the tree is one packed FADD2 (add.rn.f32x2, sm_100: two independently
@@ -224,15 +242,15 @@ stft_sym_kernel( const void *__restrict__ in, long long stream_stride, int nw, i
             y[a] = half ? __fadd_rn( got, Sms[a][i] ) : __fadd_rn( Sps[a][i], got );
          }
          // unit 0: half 0 holds re(bin 0), re(bin 64); half 1 holds re(bin 128), im(bin 64)
-         const float im64 = __shfl_xor_sync( 0xffffffffu, y[1], 16 );
+         if ( special ) B64[( buf * VB_FRAMES + 5 * tg + i ) * 2 + half] = y[1];
          const float re = y[0], im = special ? 0.0f : y[1];
          const float m = sqrtf( __fadd_rn( __fmul_rn( re, re ), __fmul_rn( im, im ) ) );
          o[bin * VB_FRAMES + i] = out_mode ? m : lme::log1pf_ref( __fmul_rn( m, 1048576.0f ) );
-         if ( special && half == 0 )
-         {
-            const float m2 = sqrtf( __fadd_rn( __fmul_rn( y[1], y[1] ), __fmul_rn( im64, im64 ) ) );
-            o[64 * VB_FRAMES + i] = out_mode ? m2 : lme::log1pf_ref( __fmul_rn( m2, 1048576.0f ) );
-         }
       }
+   }
+   if ( cprev >= 0 )
+   {
+      __syncthreads();
+      finish_bin64( cprev, buf ^ 1 );
    }
 }
