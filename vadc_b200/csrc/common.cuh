@@ -80,6 +80,30 @@ struct DeviceWeights
 __device__ __forceinline__ float4 ld4( const float *p ) { return *reinterpret_cast<const float4 *>( p ); }
 __device__ __forceinline__ void st4( float *p, float4 v ) { *reinterpret_cast<float4 *>( p ) = v; }
 
+// Two fp32 values in a 64-bit register pair for the packed add of sm_100 (add.rn.f32x2 -> FADD2): each half is an independently
+// rounded IEEE addition, one issue slot for both. Multiplies stay scalar on purpose: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2
+// into FFMA2 (even with --fmad=false), which would change the rounding; tests/test_host_logic.py checks the SASS for FFMA2 / FMUL2.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2( float lo, float hi )
+{
+   f32x2 r;
+   asm( "mov.b64 %0, {%1,%2};" : "=l"( r ) : "f"( lo ), "f"( hi ) );
+   return r;
+}
+__device__ __forceinline__ void unpk2( f32x2 v, float &lo, float &hi ) { asm( "mov.b64 {%0,%1}, %2;" : "=f"( lo ), "=f"( hi ) : "l"( v ) ); }
+__device__ __forceinline__ f32x2 add2( f32x2 a, f32x2 b )
+{
+   f32x2 c;
+   asm( "add.rn.f32x2 %0, %1, %2;" : "=l"( c ) : "l"( a ), "l"( b ) );
+   return c;
+}
+__device__ __forceinline__ f32x2 sub2( f32x2 a, f32x2 b )
+{
+   f32x2 c;
+   asm( "sub.rn.f32x2 %0, %1, %2;" : "=l"( c ) : "l"( a ), "l"( b ) );
+   return c;
+}
+
 // named barrier over `nthreads` threads (multiple of 32); id 1..15 (0 is __syncthreads)
 __device__ __forceinline__ void bar_sync( int id, int nthreads )
 {

@@ -38,27 +38,12 @@
 #define SSYM_SMEM_BYTES ( ( SSYM_BS_FLOATS + 2 * STFT_XS_FLOATS + SSYM_B64_FLOATS ) * 4 )
 #define SSYM_B64_WARP 19 // the warp that finishes bin 64 (no staging work, a scheduler without the two-staging-warp load)
 
-// two fp32 values in a 64-bit register pair, for the packed add of sm_100 (add.rn.f32x2 -> FADD2): each half is an IEEE addition
-typedef unsigned long long ssym2;
-__device__ __forceinline__ ssym2 ssym_pack( float lo, float hi )
-{
-   ssym2 r;
-   asm( "mov.b64 %0, {%1,%2};" : "=l"( r ) : "f"( lo ), "f"( hi ) );
-   return r;
-}
-__device__ __forceinline__ void ssym_unpack( ssym2 v, float &lo, float &hi ) { asm( "mov.b64 {%0,%1}, %2;" : "=f"( lo ), "=f"( hi ) : "l"( v ) ); }
-__device__ __forceinline__ ssym2 ssym_add2( ssym2 a, ssym2 b )
-{
-   ssym2 c;
-   asm( "add.rn.f32x2 %0, %1, %2;" : "=l"( c ) : "l"( a ), "l"( b ) );
-   return c;
-}
-__device__ __forceinline__ ssym2 ssym_sub2( ssym2 a, ssym2 b )
-{
-   ssym2 c;
-   asm( "sub.rn.f32x2 %0, %1, %2;" : "=l"( c ) : "l"( a ), "l"( b ) );
-   return c;
-}
+// packed adds (common.cuh)
+typedef f32x2 ssym2;
+__device__ __forceinline__ ssym2 ssym_pack( float lo, float hi ) { return pk2( lo, hi ); }
+__device__ __forceinline__ void ssym_unpack( ssym2 v, float &lo, float &hi ) { unpk2( v, lo, hi ); }
+__device__ __forceinline__ ssym2 ssym_add2( ssym2 a, ssym2 b ) { return add2( a, b ); }
+__device__ __forceinline__ ssym2 ssym_sub2( ssym2 a, ssym2 b ) { return sub2( a, b ); }
 // stft_tree8 for two frames (x*, y*) that share the basis quads: scalar products, packed adds
 __device__ __forceinline__ ssym2 ssym_tree8x2( const float4 xa, const float4 xb, const float4 ya, const float4 yb, const float4 b0, const float4 b1 )
 {
