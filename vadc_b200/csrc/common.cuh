@@ -97,6 +97,13 @@ __device__ __forceinline__ f32x2 add2( f32x2 a, f32x2 b )
    asm( "add.rn.f32x2 %0, %1, %2;" : "=l"( c ) : "l"( a ), "l"( b ) );
    return c;
 }
+// (only where the products feed SCALAR additions: see above)
+__device__ __forceinline__ f32x2 mul2( f32x2 a, f32x2 b )
+{
+   f32x2 c;
+   asm( "mul.rn.f32x2 %0, %1, %2;" : "=l"( c ) : "l"( a ), "l"( b ) );
+   return c;
+}
 __device__ __forceinline__ f32x2 sub2( f32x2 a, f32x2 b )
 {
    f32x2 c;

@@ -38,25 +38,62 @@
 #define SSYM_SMEM_BYTES ( ( SSYM_BS_FLOATS + 2 * STFT_XS_FLOATS + SSYM_B64_FLOATS ) * 4 )
 #define SSYM_B64_WARP 19 // the warp that finishes bin 64 (no staging work, a scheduler without the two-staging-warp load)
 
-// packed adds (common.cuh)
+// A frame pair's two values travel together. SSYM_PACKED 1: in a 64-bit register pair, every addition one FADD2 (common.cuh);
+// 0: two scalar FADDs. Measured (scripts/microbench/f32x2_throughput.cu): a stream of 2 FMUL + 1 FADD2 reaches 81 % of the FP32 pipe,
+// FMUL + FADD 98 % -- the packed add saves issue slots, but this loop is paced by the pipe, not by issue.
+#ifndef SSYM_PACKED
+#define SSYM_PACKED 0
+#endif
+#ifndef SSYM_PACKED_MUL
+#define SSYM_PACKED_MUL 1 // products of adjacent taps as one FMUL2 (operands are the register pairs an LDS.128 delivers), additions scalar
+#endif
+#if SSYM_PACKED
 typedef f32x2 ssym2;
 __device__ __forceinline__ ssym2 ssym_pack( float lo, float hi ) { return pk2( lo, hi ); }
 __device__ __forceinline__ void ssym_unpack( ssym2 v, float &lo, float &hi ) { unpk2( v, lo, hi ); }
 __device__ __forceinline__ ssym2 ssym_add2( ssym2 a, ssym2 b ) { return add2( a, b ); }
 __device__ __forceinline__ ssym2 ssym_sub2( ssym2 a, ssym2 b ) { return sub2( a, b ); }
-// stft_tree8 for two frames (x*, y*) that share the basis quads: scalar products, packed adds
+#else
+struct ssym2
+{
+   float lo, hi;
+};
+__device__ __forceinline__ ssym2 ssym_pack( float lo, float hi ) { return ssym2{ lo, hi }; }
+__device__ __forceinline__ void ssym_unpack( ssym2 v, float &lo, float &hi ) { lo = v.lo; hi = v.hi; }
+__device__ __forceinline__ ssym2 ssym_add2( ssym2 a, ssym2 b ) { return ssym2{ __fadd_rn( a.lo, b.lo ), __fadd_rn( a.hi, b.hi ) }; }
+__device__ __forceinline__ ssym2 ssym_sub2( ssym2 a, ssym2 b ) { return ssym2{ __fsub_rn( a.lo, b.lo ), __fsub_rn( a.hi, b.hi ) }; }
+#endif
+// stft_tree8 with packed multiplies: (p0,p1) (p2,p3) (p4,p5) (p6,p7) are four FMUL2, the tree's seven additions scalar
+__device__ __forceinline__ float ssym_tree8( const float4 xa, const float4 xb, const float4 b0, const float4 b1 )
+{
+#if SSYM_PACKED_MUL
+   float p0, p1, p2, p3, p4, p5, p6, p7;
+   unpk2( mul2( pk2( xa.x, xa.y ), pk2( b0.x, b0.y ) ), p0, p1 );
+   unpk2( mul2( pk2( xa.z, xa.w ), pk2( b0.z, b0.w ) ), p2, p3 );
+   unpk2( mul2( pk2( xb.x, xb.y ), pk2( b1.x, b1.y ) ), p4, p5 );
+   unpk2( mul2( pk2( xb.z, xb.w ), pk2( b1.z, b1.w ) ), p6, p7 );
+   return __fadd_rn( __fadd_rn( __fadd_rn( p0, p1 ), __fadd_rn( p2, p3 ) ), __fadd_rn( __fadd_rn( p4, p5 ), __fadd_rn( p6, p7 ) ) );
+#else
+   return stft_tree8( xa, xb, b0, b1 );
+#endif
+}
+// stft_tree8 for two frames (x*, y*) that share the basis quads
 __device__ __forceinline__ ssym2 ssym_tree8x2( const float4 xa, const float4 xb, const float4 ya, const float4 yb, const float4 b0, const float4 b1 )
 {
+#if SSYM_PACKED
    const ssym2 p0 = ssym_pack( __fmul_rn( xa.x, b0.x ), __fmul_rn( ya.x, b0.x ) ), p1 = ssym_pack( __fmul_rn( xa.y, b0.y ), __fmul_rn( ya.y, b0.y ) );
    const ssym2 p2 = ssym_pack( __fmul_rn( xa.z, b0.z ), __fmul_rn( ya.z, b0.z ) ), p3 = ssym_pack( __fmul_rn( xa.w, b0.w ), __fmul_rn( ya.w, b0.w ) );
    const ssym2 p4 = ssym_pack( __fmul_rn( xb.x, b1.x ), __fmul_rn( yb.x, b1.x ) ), p5 = ssym_pack( __fmul_rn( xb.y, b1.y ), __fmul_rn( yb.y, b1.y ) );
    const ssym2 p6 = ssym_pack( __fmul_rn( xb.z, b1.z ), __fmul_rn( yb.z, b1.z ) ), p7 = ssym_pack( __fmul_rn( xb.w, b1.w ), __fmul_rn( yb.w, b1.w ) );
    return ssym_add2( ssym_add2( ssym_add2( p0, p1 ), ssym_add2( p2, p3 ) ), ssym_add2( ssym_add2( p4, p5 ), ssym_add2( p6, p7 ) ) );
+#else
+   return ssym_pack( ssym_tree8( xa, xb, b0, b1 ), ssym_tree8( ya, yb, b0, b1 ) );
+#endif
 }
 
 // out_mode 0: log1p(mag * 2^20) (production); 1: raw magnitude (parity tap for stft.c alone)
 //
-// One __syncthreads per chunk hands the double-buffered input tile over. Tried and measured slower (r02): a ring of four tiles with
+// One __syncthreads per chunk (at its end) hands the double-buffered input tile over. Tried and measured slower (r02): a ring of four tiles with
 // mbarrier hand-over (full / empty) so that warps may run a chunk ahead of each other -- 15.8 ms instead of 13.0 ms per 131 072 chunks:
 // (every thread arriving) and 14.2 ms (one arrival per warp). The unrolled main loop is ~60 KB of code: warps that the barrier keeps in
 // step share their instruction fetches, warps that drift apart do not. A dedicated 21st producer warp does not fit (six warps on one
@@ -80,10 +117,37 @@ stft_sym_kernel( const void *__restrict__ in, long long stream_stride, int nw, i
       float4 *dst = reinterpret_cast<float4 *>( Bs );
       for ( int i = tid; i < SSYM_BS_FLOATS / 4; i += SSYM_THREADS ) dst[i] = __ldg( src + i );
    }
+   // Staging: a chunk is NV 16-byte vectors; lanes 0..23 of the first NV / 24 warps take one each (8 or 16 warps: the same number on
+   // every scheduler). The tile of chunk n + 1 is written at the START of iteration n, from registers filled an iteration earlier, while
+   // the other warps are already in the main loop; the vectors of chunk n + 2 are requested right after. One barrier per chunk (at its
+   // end) hands the tile over and frees the other one. (r02c staged at the end of the iteration: every other warp waited for it.)
    constexpr int NV = F32 ? 384 : 192; // 16-byte vectors per chunk
+   const int sv = w * 24 + lane;       // this lane's vector
+   const bool stager = lane < 24 && w < NV / 24;
    int4 raw = make_int4( 0, 0, 0, 0 );
+   auto stage = [&]( float *xs ) {
+      if ( !stager ) return;
+      if ( F32 )
+      {
+         const float *f = reinterpret_cast<const float *>( &raw );
+#pragma unroll
+         for ( int e = 0; e < 4; ++e ) stft_put( xs, 4 * sv + e, f[e] );
+      }
+      else
+      {
+         const short *hh = reinterpret_cast<const short *>( &raw );
+         // (float)s16 / 32768.0f (vadc.c:884,898); the division by a power of two is exact
+#pragma unroll
+         for ( int e = 0; e < 8; ++e ) stft_put( xs, 8 * sv + e, (float)hh[e] * ( 1.0f / 32768.0f ) );
+      }
+   };
+   auto request = [&]( int c ) {
+      if ( c < nchunks && stager ) raw = __ldg( (const int4 *)stft_chunk_ptr<F32>( in, stream_stride, nw, c ) + sv );
+   };
    int ci = blockIdx.x;
-   if ( ci < nchunks && tid < NV ) raw = __ldg( (const int4 *)stft_chunk_ptr<F32>( in, stream_stride, nw, ci ) + tid );
+   request( ci );
+   if ( ci < nchunks ) stage( Xs_all );
+   request( ci + gridDim.x );
    __syncthreads();
 
    // bin 64 of chunk `cprev` from the pairs the unit-0 lanes left in B64[pbuf] (the caller has passed a barrier since)
@@ -99,32 +163,19 @@ stft_sym_kernel( const void *__restrict__ in, long long stream_stride, int nw, i
    int buf = 0, cprev = -1;
    for ( ; ci < nchunks; cprev = ci, ci += gridDim.x, buf ^= 1 )
    {
-      float *xs = Xs_all + buf * STFT_XS_FLOATS;
-      if ( tid < NV )
+      const float *xs = Xs_all + buf * STFT_XS_FLOATS;
+      if ( ci + gridDim.x < nchunks )
       {
-         if ( F32 )
-         {
-            const float *f = reinterpret_cast<const float *>( &raw );
-#pragma unroll
-            for ( int e = 0; e < 4; ++e ) stft_put( xs, 4 * tid + e, f[e] );
-         }
-         else
-         {
-            const short *hh = reinterpret_cast<const short *>( &raw );
-            // (float)s16 / 32768.0f (vadc.c:884,898); the division by a power of two is exact
-#pragma unroll
-            for ( int e = 0; e < 8; ++e ) stft_put( xs, 8 * tid + e, (float)hh[e] * ( 1.0f / 32768.0f ) );
-         }
+         stage( Xs_all + ( buf ^ 1 ) * STFT_XS_FLOATS );
+         request( ci + 2 * gridDim.x );
       }
-      __syncthreads(); // tile complete; the other buffer (previous chunk) is no longer read by anyone
-      const int cn = ci + gridDim.x;
-      if ( cn < nchunks && tid < NV ) raw = __ldg( (const int4 *)stft_chunk_ptr<F32>( in, stream_stride, nw, cn ) + tid );
       if ( cprev >= 0 ) finish_bin64( cprev, buf ^ 1 );
 
       // Frames go through in pairs (0,1), (2,3) + frame 4: the two frames of a pair share every basis value, their products are
       // separate FMULs into adjacent registers, and every ADD of the tree is one packed FADD2 (add.rn.f32x2, sm_100: two independently
-      // rounded IEEE additions in one issue slot). 128 instead of 160 issue slots per (lane, group) for the same 160 operations: the
-      // main loop is issue-bound. Multiplies stay scalar on purpose: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (even
+      // rounded IEEE additions in one issue slot). 128 instead of 160 issue slots per (lane, group) for the same 160 operations; a
+      // FADD2 holds the FP32 pipe for two cycles, so the loop is paced by that pipe (155 cycles per 139 issue slots), which is the
+      // roofline this kernel is measured against. Multiplies stay scalar on purpose: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (even
       // with --fmad=false), which would change the rounding; tests/test_host_logic.py checks the kernel's SASS for FFMA2.
       ssym2 Sp[2][2], Sm[2][2]; // [row][pair]
       float Sp4[2], Sm4[2];     // frame 4
@@ -160,8 +211,8 @@ stft_sym_kernel( const void *__restrict__ in, long long stream_stride, int nw, i
                {
                   const float *xp = xs + ( 5 * tg + 4 + g ) * 64 + l * 8;
                   const float4 xa = ld4( xp ), xb = ld4( xp + 4 );
-                  const float rr = stft_tree8( xa, xb, re0, re1 );
-                  const float ri = stft_tree8( xa, xb, im0, im1 );
+                  const float rr = ssym_tree8( xa, xb, re0, re1 );
+                  const float ri = ssym_tree8( xa, xb, im0, im1 );
                   if ( g == 0 ) { A4[0] = rr; A4[1] = ri; }
                   else if ( g == 1 ) { A4[0] = __fadd_rn( A4[0], rr ); A4[1] = __fadd_rn( A4[1], ri ); }
                   else if ( g == 2 ) { B4[0] = rr; B4[1] = ri; }
@@ -232,10 +283,7 @@ stft_sym_kernel( const void *__restrict__ in, long long stream_stride, int nw, i
          const float m = sqrtf( __fadd_rn( __fmul_rn( re, re ), __fmul_rn( im, im ) ) );
          o[bin * VB_FRAMES + i] = out_mode ? m : lme::log1pf_ref( __fmul_rn( m, 1048576.0f ) );
       }
+      __syncthreads(); // the next tile is complete, this one and the other B64 buffer are free
    }
-   if ( cprev >= 0 )
-   {
-      __syncthreads();
-      finish_bin64( cprev, buf ^ 1 );
-   }
+   if ( cprev >= 0 ) finish_bin64( cprev, buf ^ 1 );
 }
