@@ -149,8 +149,10 @@ def test_python_constants_mirror_the_header():
 
 def test_exact_kernels_contain_no_contracted_packed_arithmetic():
     """The exact path may not fuse a multiply with an add. Scalar mul.rn / add.rn are never contracted, but ptxas 12.9 turns
-    mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (even with --fmad=false), so the kernels use packed ADDS only, fed by scalar multiplies.
-    This reads the SASS of the built library: no FFMA2 and no FMUL2 in any exact-path kernel, FADD2 present in the STFT."""
+    mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (even with --fmad=false). The kernels therefore pack EITHER the multiplies (FMUL2 on the
+    register pairs an LDS.128 delivers, feeding scalar adds -- the default) OR the adds (FADD2 fed by scalar multiplies), never both
+    in one kernel. This reads the SASS of the built library: no FFMA2 in any exact-path kernel, no kernel with FMUL2 and FADD2,
+    FMUL2 present in the STFT."""
     import re
     import shutil
     import subprocess
@@ -167,5 +169,5 @@ def test_exact_kernels_contain_no_contracted_packed_arithmetic():
         seen[name] = (ops.count("FFMA2"), ops.count("FMUL2"), ops.count("FADD2"))
     assert len(seen) >= 10, sorted(seen)
     for name, (ffma2, fmul2, fadd2) in seen.items():
-        assert ffma2 == 0 and fmul2 == 0, (name, ffma2, fmul2)
-    assert any(v[2] > 0 for k, v in seen.items() if "stft_sym_kernel" in k)
+        assert ffma2 == 0 and not (fmul2 > 0 and fadd2 > 0), (name, ffma2, fmul2, fadd2)
+    assert any(v[1] > 0 for k, v in seen.items() if "stft_sym_kernel" in k)

@@ -36,6 +36,29 @@ __device__ __forceinline__ float relu( float v ) { return v < 0.0f ? 0.0f : v; }
 
 __host__ __device__ constexpr int al4( int x ) { return ( x + 3 ) & ~3; }
 
+// four products a[0..3] * v.{x,y,z,w}: two FMUL2 (mul.rn.f32x2: each half an IEEE product) on register pairs; the additions that
+// consume them stay scalar (common.cuh: a packed product feeding a packed add would be contracted by ptxas)
+#ifndef XE_PACKED_MUL
+#define XE_PACKED_MUL 1
+#endif
+__device__ __forceinline__ void mul2f( float a0, float a1, float b0, float b1, float &p0, float &p1 )
+{
+#if XE_PACKED_MUL
+   unpk2( mul2( pk2( a0, a1 ), pk2( b0, b1 ) ), p0, p1 );
+#else
+   p0 = mul( a0, b0 ); p1 = mul( a1, b1 );
+#endif
+}
+__device__ __forceinline__ void mul4( const float *a, const float4 v, float &p0, float &p1, float &p2, float &p3 )
+{
+#if XE_PACKED_MUL
+   unpk2( mul2( pk2( a[0], a[1] ), pk2( v.x, v.y ) ), p0, p1 );
+   unpk2( mul2( pk2( a[2], a[3] ), pk2( v.z, v.w ) ), p2, p3 );
+#else
+   p0 = mul( a[0], v.x ); p1 = mul( a[1], v.y ); p2 = mul( a[2], v.z ); p3 = mul( a[3], v.w );
+#endif
+}
+
 // offsets (floats) of a layer's tensors inside the engine's copy of the container: consecutive tensors, each padded to 4 floats
 // (tensor.h:114-152 order)
 struct LayerOff
@@ -93,10 +116,7 @@ __device__ __forceinline__ float dot_simd_r( const float ( &a )[K], const float 
       for ( int q = 0; q < 4; ++q )
       {
          const float4 v = ld4( w + 16 * b + 4 * q );
-         p[4 * q + 0] = mul( a[16 * b + 4 * q + 0], v.x );
-         p[4 * q + 1] = mul( a[16 * b + 4 * q + 1], v.y );
-         p[4 * q + 2] = mul( a[16 * b + 4 * q + 2], v.z );
-         p[4 * q + 3] = mul( a[16 * b + 4 * q + 3], v.w );
+         mul4( &a[16 * b + 4 * q], v, p[4 * q + 0], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3] );
       }
       // _mm256_hadd_ps( p[0..7], p[8..15] ): lanes 0 1 | 2 3 <- second vector | 4 5 | 6 7 <- second vector
       const float s0 = add( p[0], p[1] ), s1 = add( p[2], p[3] ), s2 = add( p[8], p[9] ), s3 = add( p[10], p[11] );
@@ -134,8 +154,8 @@ __device__ __forceinline__ float conv1_e_r( const float ( &x )[K], const float *
       for ( int q = 0; q < 4; ++q )
       {
          const float4 v = ld4( w + 16 * b + 4 * q );
-         const float p0 = mul( x[16 * b + 4 * q + 0], v.x ), p1 = mul( x[16 * b + 4 * q + 1], v.y );
-         const float p2 = mul( x[16 * b + 4 * q + 2], v.z ), p3 = mul( x[16 * b + 4 * q + 3], v.w );
+         float p0, p1, p2, p3;
+         mul4( &x[16 * b + 4 * q], v, p0, p1, p2, p3 );
          if ( b == 0 )
          {
             a[4 * q + 0] = p0; a[4 * q + 1] = p1; a[4 * q + 2] = p2; a[4 * q + 3] = p3;
@@ -163,10 +183,12 @@ __device__ __forceinline__ float conv1_generic_r( const float ( &x )[K], const f
    for ( int q = 0; q < K / 4; ++q )
    {
       const float4 v = ld4( w + 4 * q );
-      o = add( o, mul( x[4 * q + 0], v.x ) );
-      o = add( o, mul( x[4 * q + 1], v.y ) );
-      o = add( o, mul( x[4 * q + 2], v.z ) );
-      o = add( o, mul( x[4 * q + 3], v.w ) );
+      float p0, p1, p2, p3;
+      mul4( &x[4 * q], v, p0, p1, p2, p3 );
+      o = add( o, p0 );
+      o = add( o, p1 );
+      o = add( o, p2 );
+      o = add( o, p3 );
    }
    return add( o, bias );
 }
@@ -551,7 +573,7 @@ exact_layer_kernel( const float *__restrict__ in, float *__restrict__ out, const
                   {
                      float p[16];
 #pragma unroll
-                     for ( int j = 0; j < 16; ++j ) p[j] = xe::mul( kh[16 * b + j], q[16 * b + j] );
+                     for ( int j = 0; j < 16; j += 2 ) xe::mul2f( kh[16 * b + j], kh[16 * b + j + 1], q[16 * b + j], q[16 * b + j + 1], p[j], p[j + 1] );
                      const float s[8] = { xe::add( p[0], p[1] ), xe::add( p[2], p[3] ), xe::add( p[8], p[9] ), xe::add( p[10], p[11] ),
                                           xe::add( p[4], p[5] ), xe::add( p[6], p[7] ), xe::add( p[12], p[13] ), xe::add( p[14], p[15] ) };
 #pragma unroll
@@ -589,7 +611,7 @@ exact_layer_kernel( const float *__restrict__ in, float *__restrict__ out, const
                {
                   float p[16];
 #pragma unroll
-                  for ( int i = 0; i < 16; ++i ) p[i] = xe::mul( A[i], vcol[i] );
+                  for ( int i = 0; i < 16; i += 2 ) xe::mul2f( A[i], A[i + 1], vcol[i], vcol[i + 1], p[i], p[i + 1] );
                   const float s[8] = { xe::add( p[0], p[1] ), xe::add( p[2], p[3] ), xe::add( p[8], p[9] ), xe::add( p[10], p[11] ),
                                        xe::add( p[4], p[5] ), xe::add( p[6], p[7] ), xe::add( p[12], p[13] ), xe::add( p[14], p[15] ) };
 #pragma unroll

@@ -32,6 +32,9 @@
 #define XL_ROW 192                       // per stream: x of this step | x of the next step (cp.async target) | h -- the two x slots alternate
 #define XL_SMEM_BYTES ( ( XL_ACT_FLOATS + XL_MAX_STREAMS * ( XL_ROW + 64 ) ) * 4 )
 
+#ifndef XL_PACKED_MUL
+#define XL_PACKED_MUL 1 // 1: FMUL2 products + scalar adds per stream; 0: scalar products + FADD2 across the stream pair
+#endif
 // four of dotproduct_simd's eight lanes over this thread's taps of one stream: acc[j] += x[2j] w[2j] + x[2j+1] w[2j+1] per block
 __device__ __forceinline__ void xl_half_row( const float *__restrict__ xp /* x: this thread's first tap */, const float *__restrict__ hp /* h: likewise */,
                                              const float ( &w )[64], float ( &acc )[4] )
@@ -42,10 +45,23 @@ __device__ __forceinline__ void xl_half_row( const float *__restrict__ xp /* x: 
    {
       const float *src = b < 4 ? xp + 16 * b : hp + 16 * ( b - 4 );
       const float4 u = ld4( src ), v = ld4( src + 4 );
+#if XL_PACKED_MUL
+      // the two products of a lane as one FMUL2 (mul.rn.f32x2 on the register pairs of the LDS.128 and of the weights), scalar adds
+      float p[8];
+      unpk2( mul2( pk2( u.x, u.y ), pk2( w[8 * b + 0], w[8 * b + 1] ) ), p[0], p[1] );
+      unpk2( mul2( pk2( u.z, u.w ), pk2( w[8 * b + 2], w[8 * b + 3] ) ), p[2], p[3] );
+      unpk2( mul2( pk2( v.x, v.y ), pk2( w[8 * b + 4], w[8 * b + 5] ) ), p[4], p[5] );
+      unpk2( mul2( pk2( v.z, v.w ), pk2( w[8 * b + 6], w[8 * b + 7] ) ), p[6], p[7] );
+      acc[0] = __fadd_rn( acc[0], __fadd_rn( p[0], p[1] ) );
+      acc[1] = __fadd_rn( acc[1], __fadd_rn( p[2], p[3] ) );
+      acc[2] = __fadd_rn( acc[2], __fadd_rn( p[4], p[5] ) );
+      acc[3] = __fadd_rn( acc[3], __fadd_rn( p[6], p[7] ) );
+#else
       acc[0] = __fadd_rn( acc[0], __fadd_rn( __fmul_rn( u.x, w[8 * b + 0] ), __fmul_rn( u.y, w[8 * b + 1] ) ) );
       acc[1] = __fadd_rn( acc[1], __fadd_rn( __fmul_rn( u.z, w[8 * b + 2] ), __fmul_rn( u.w, w[8 * b + 3] ) ) );
       acc[2] = __fadd_rn( acc[2], __fadd_rn( __fmul_rn( v.x, w[8 * b + 4] ), __fmul_rn( v.y, w[8 * b + 5] ) ) );
       acc[3] = __fadd_rn( acc[3], __fadd_rn( __fmul_rn( v.z, w[8 * b + 6] ), __fmul_rn( v.w, w[8 * b + 7] ) ) );
+#endif
    }
 }
 
@@ -204,13 +220,16 @@ exact_lstm_kernel( const float *x0, float *h0seq, float *out1, float *__restrict
             {
                const bool two = p + 1 < kn;
                float a0[4], a1[4];
-               if ( two )
+               if ( two && !XL_PACKED_MUL )
                   xl_half_row_pair( xh + ( k0 + p ) * XL_ROW + xs + 8 * half, xh + ( k0 + p ) * XL_ROW + 128 + 8 * half,
                                     xh + ( k0 + p + 1 ) * XL_ROW + xs + 8 * half, xh + ( k0 + p + 1 ) * XL_ROW + 128 + 8 * half, w, a0, a1 );
                else
                {
                   xl_half_row( xh + ( k0 + p ) * XL_ROW + xs + 8 * half, xh + ( k0 + p ) * XL_ROW + 128 + 8 * half, w, a0 );
-                  a1[0] = a1[1] = a1[2] = a1[3] = 0.0f;
+                  if ( two )
+                     xl_half_row( xh + ( k0 + p + 1 ) * XL_ROW + xs + 8 * half, xh + ( k0 + p + 1 ) * XL_ROW + 128 + 8 * half, w, a1 );
+                  else
+                     a1[0] = a1[1] = a1[2] = a1[3] = 0.0f;
                }
                // the even lane finishes stream p, the odd lane stream p + 1: swap the other stream's partial sums
                float lo[4], hi[4];
