@@ -260,7 +260,7 @@ __global__ void __launch_bounds__( XF_THREADS, 1 ) exact_front_kernel( const flo
    extern __shared__ __align__( 16 ) float fsm[];
    float *Xa = fsm;                      // [2 buffers][g][129][25] log spectrogram as the STFT wrote it (+ up to 3 floats of alignment shift)
    float *Ds = Xa + 2 * XF_TILE;         // [g][129][25] relu(depthwise conv)
-   float *Wf = Ds + XF_TILE;             // [129][32]
+   float *Wf = Ds + XF_TILE;             // [129][16 features]{pw, proj}
    float *dww = Wf + XF_W_FLOATS;        // [129][5]
    float *dwb = dww + al4c( VB_BINS * 5 ); // [129]
    float *pb = dwb + al4c( VB_BINS );    // [16 pw_b | 16 proj_b]
@@ -271,8 +271,9 @@ __global__ void __launch_bounds__( XF_THREADS, 1 ) exact_front_kernel( const flo
    for ( int i = tid; i < VB_BINS * 16; i += XF_THREADS )
    {
       const int f = i / VB_BINS, c = i - f * VB_BINS;
-      Wf[c * 32 + f] = wl[O.pw_w + i];
-      Wf[c * 32 + 16 + f] = wl[O.proj_w + i];
+      // [c][feature f]{pointwise, projection}: a thread's LDS.128 delivers (pw, proj) of two features -- the partners of (d, x) in an FMUL2
+      Wf[c * 32 + 2 * f] = wl[O.pw_w + i];
+      Wf[c * 32 + 2 * f + 1] = wl[O.proj_w + i];
    }
    for ( int i = tid; i < VB_BINS * 5; i += XF_THREADS ) dww[i] = wl[O.dw_w + i];
    for ( int i = tid; i < VB_BINS; i += XF_THREADS ) dwb[i] = wl[O.dw_b + i];
@@ -401,7 +402,7 @@ __global__ void __launch_bounds__( XF_THREADS, 1 ) exact_front_kernel( const flo
       if ( tok && g < ng )
       {
          const float *xc = Xs + g * ( VB_BINS * VB_FRAMES ) + t, *dc = Ds + g * ( VB_BINS * VB_FRAMES ) + t;
-         const float *wq = Wf + 4 * fq;
+         const float *wq = Wf + 8 * fq;
          const float mu = NORM ? MU[g] : 0.0f;
          float st[8][5]; // [output: 0..3 pointwise, 4..7 projection][tree stack: four folded entries + the leaf just pushed]
          constexpr int leaf[16] = { 0, 1, 2, 3, 8, 9, 10, 11, 4, 5, 6, 7, 12, 13, 14, 15 };
@@ -415,9 +416,12 @@ __global__ void __launch_bounds__( XF_THREADS, 1 ) exact_front_kernel( const flo
             {
                const int c = 16 * b + mm;
                const float dv = dc[c * VB_FRAMES], xv = NORM ? xe::sub( xc[c * VB_FRAMES], mu ) : xc[c * VB_FRAMES];
-               const float4 wp = ld4( wq + c * 32 ), wj = ld4( wq + c * 32 + 16 );
-               const float p[8] = { xe::mul( dv, wp.x ), xe::mul( dv, wp.y ), xe::mul( dv, wp.z ), xe::mul( dv, wp.w ),
-                                    xe::mul( xv, wj.x ), xe::mul( xv, wj.y ), xe::mul( xv, wj.z ), xe::mul( xv, wj.w ) };
+               const float4 w01 = ld4( wq + c * 32 ), w23 = ld4( wq + c * 32 + 4 );
+               float p[8];
+               xe::mul2f( dv, xv, w01.x, w01.y, p[0], p[4] );
+               xe::mul2f( dv, xv, w01.z, w01.w, p[1], p[5] );
+               xe::mul2f( dv, xv, w23.x, w23.y, p[2], p[6] );
+               xe::mul2f( dv, xv, w23.z, w23.w, p[3], p[7] );
 #pragma unroll
                for ( int o = 0; o < 8; ++o ) acc[o] = b == 0 ? p[o] : xe::add( acc[o], p[o] );
             }
@@ -435,9 +439,12 @@ __global__ void __launch_bounds__( XF_THREADS, 1 ) exact_front_kernel( const flo
             }
          }
          const float dv = dc[128 * VB_FRAMES], xv = NORM ? xe::sub( xc[128 * VB_FRAMES], mu ) : xc[128 * VB_FRAMES];
-         const float4 wp = ld4( wq + 128 * 32 ), wj = ld4( wq + 128 * 32 + 16 );
-         const float tp[8] = { xe::mul( dv, wp.x ), xe::mul( dv, wp.y ), xe::mul( dv, wp.z ), xe::mul( dv, wp.w ),
-                               xe::mul( xv, wj.x ), xe::mul( xv, wj.y ), xe::mul( xv, wj.z ), xe::mul( xv, wj.w ) };
+         const float4 w01 = ld4( wq + 128 * 32 ), w23 = ld4( wq + 128 * 32 + 4 );
+         float tp[8];
+         xe::mul2f( dv, xv, w01.x, w01.y, tp[0], tp[4] );
+         xe::mul2f( dv, xv, w01.z, w01.w, tp[1], tp[5] );
+         xe::mul2f( dv, xv, w23.x, w23.y, tp[2], tp[6] );
+         xe::mul2f( dv, xv, w23.z, w23.w, tp[3], tp[7] );
          float *dst = y1 + (size_t)( c0 + g ) * ( 16 * VB_FRAMES ) + t;
 #pragma unroll
          for ( int i = 0; i < 4; ++i )
