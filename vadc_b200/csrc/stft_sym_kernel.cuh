@@ -38,22 +38,15 @@
 #define SSYM_SMEM_BYTES ( ( SSYM_BS_FLOATS + 2 * STFT_XS_FLOATS + SSYM_B64_FLOATS ) * 4 )
 #define SSYM_B64_WARP 19 // the warp that finishes bin 64 (no staging work, a scheduler without the two-staging-warp load)
 
-// A frame pair's two values travel together. SSYM_PACKED 1: in a 64-bit register pair, every addition one FADD2 (common.cuh);
-// 0: two scalar FADDs. Measured (scripts/microbench/f32x2_throughput.cu): a stream of 2 FMUL + 1 FADD2 reaches 81 % of the FP32 pipe,
-// FMUL + FADD 98 % -- the packed add saves issue slots, but this loop is paced by the pipe, not by issue.
-#ifndef SSYM_PACKED
-#define SSYM_PACKED 0
-#endif
+// Packed arithmetic (sm_100 f32x2: two independently rounded IEEE operations in one issue slot, two cycles of the FP32 pipe).
+// Measured on this kernel, 131 072 chunks: all scalar 10.28 ms; additions packed over frame pairs (FADD2 fed by scalar FMULs) 10.04 ms;
+// PRODUCTS packed over adjacent taps -- FMUL2 on the register pairs an LDS.128 delivers, no moves -- with scalar additions 9.71 ms.
+// (scripts/microbench/f32x2_throughput.cu: a stream of 2 FMUL + FADD2 reaches 81 % of the FP32 pipe, FMUL2 + 2 FADD 90 %, FMUL + FADD
+// 98 % but at one issue slot per operation.) Never both: ptxas contracts a packed product feeding a packed add into FFMA2 (common.cuh).
 #ifndef SSYM_PACKED_MUL
-#define SSYM_PACKED_MUL 1 // products of adjacent taps as one FMUL2 (operands are the register pairs an LDS.128 delivers), additions scalar
+#define SSYM_PACKED_MUL 1
 #endif
-#if SSYM_PACKED
-typedef f32x2 ssym2;
-__device__ __forceinline__ ssym2 ssym_pack( float lo, float hi ) { return pk2( lo, hi ); }
-__device__ __forceinline__ void ssym_unpack( ssym2 v, float &lo, float &hi ) { unpk2( v, lo, hi ); }
-__device__ __forceinline__ ssym2 ssym_add2( ssym2 a, ssym2 b ) { return add2( a, b ); }
-__device__ __forceinline__ ssym2 ssym_sub2( ssym2 a, ssym2 b ) { return sub2( a, b ); }
-#else
+// a frame pair's two values travel together
 struct ssym2
 {
    float lo, hi;
@@ -62,7 +55,6 @@ __device__ __forceinline__ ssym2 ssym_pack( float lo, float hi ) { return ssym2{
 __device__ __forceinline__ void ssym_unpack( ssym2 v, float &lo, float &hi ) { lo = v.lo; hi = v.hi; }
 __device__ __forceinline__ ssym2 ssym_add2( ssym2 a, ssym2 b ) { return ssym2{ __fadd_rn( a.lo, b.lo ), __fadd_rn( a.hi, b.hi ) }; }
 __device__ __forceinline__ ssym2 ssym_sub2( ssym2 a, ssym2 b ) { return ssym2{ __fsub_rn( a.lo, b.lo ), __fsub_rn( a.hi, b.hi ) }; }
-#endif
 // stft_tree8 with packed multiplies: (p0,p1) (p2,p3) (p4,p5) (p6,p7) are four FMUL2, the tree's seven additions scalar
 __device__ __forceinline__ float ssym_tree8( const float4 xa, const float4 xb, const float4 b0, const float4 b1 )
 {
@@ -80,24 +72,12 @@ __device__ __forceinline__ float ssym_tree8( const float4 xa, const float4 xb, c
 // stft_tree8 for two frames (x*, y*) that share the basis quads
 __device__ __forceinline__ ssym2 ssym_tree8x2( const float4 xa, const float4 xb, const float4 ya, const float4 yb, const float4 b0, const float4 b1 )
 {
-#if SSYM_PACKED
-   const ssym2 p0 = ssym_pack( __fmul_rn( xa.x, b0.x ), __fmul_rn( ya.x, b0.x ) ), p1 = ssym_pack( __fmul_rn( xa.y, b0.y ), __fmul_rn( ya.y, b0.y ) );
-   const ssym2 p2 = ssym_pack( __fmul_rn( xa.z, b0.z ), __fmul_rn( ya.z, b0.z ) ), p3 = ssym_pack( __fmul_rn( xa.w, b0.w ), __fmul_rn( ya.w, b0.w ) );
-   const ssym2 p4 = ssym_pack( __fmul_rn( xb.x, b1.x ), __fmul_rn( yb.x, b1.x ) ), p5 = ssym_pack( __fmul_rn( xb.y, b1.y ), __fmul_rn( yb.y, b1.y ) );
-   const ssym2 p6 = ssym_pack( __fmul_rn( xb.z, b1.z ), __fmul_rn( yb.z, b1.z ) ), p7 = ssym_pack( __fmul_rn( xb.w, b1.w ), __fmul_rn( yb.w, b1.w ) );
-   return ssym_add2( ssym_add2( ssym_add2( p0, p1 ), ssym_add2( p2, p3 ) ), ssym_add2( ssym_add2( p4, p5 ), ssym_add2( p6, p7 ) ) );
-#else
    return ssym_pack( ssym_tree8( xa, xb, b0, b1 ), ssym_tree8( ya, yb, b0, b1 ) );
-#endif
 }
 
 // out_mode 0: log1p(mag * 2^20) (production); 1: raw magnitude (parity tap for stft.c alone)
 //
-// One __syncthreads per chunk (at its end) hands the double-buffered input tile over. Tried and measured slower (r02): a ring of four tiles with
-// mbarrier hand-over (full / empty) so that warps may run a chunk ahead of each other -- 15.8 ms instead of 13.0 ms per 131 072 chunks:
-// (every thread arriving) and 14.2 ms (one arrival per warp). The unrolled main loop is ~60 KB of code: warps that the barrier keeps in
-// step share their instruction fetches, warps that drift apart do not. A dedicated 21st producer warp does not fit (six warps on one
-// scheduler x 96 registers > its 16 384).
+// One __syncthreads per chunk (at its end) hands the double-buffered input tile over.
 template <bool F32>
 __global__ void __launch_bounds__( SSYM_THREADS, 1 )
 stft_sym_kernel( const void *__restrict__ in, long long stream_stride, int nw, int nchunks, const float *__restrict__ basis_sym /*[64][128][4]*/,
@@ -118,9 +98,13 @@ stft_sym_kernel( const void *__restrict__ in, long long stream_stride, int nw, i
       for ( int i = tid; i < SSYM_BS_FLOATS / 4; i += SSYM_THREADS ) dst[i] = __ldg( src + i );
    }
    // Staging: a chunk is NV 16-byte vectors; lanes 0..23 of the first NV / 24 warps take one each (8 or 16 warps: the same number on
-   // every scheduler). The tile of chunk n + 1 is written at the START of iteration n, from registers filled an iteration earlier, while
-   // the other warps are already in the main loop; the vectors of chunk n + 2 are requested right after. One barrier per chunk (at its
-   // end) hands the tile over and frees the other one. (r02c staged at the end of the iteration: every other warp waited for it.)
+   // every scheduler). The tile of chunk n + 1 is written at the START of iteration n (from registers filled an iteration earlier; the
+   // vectors of chunk n + 2 are requested right after) while the other warps are already in the main loop. One barrier per chunk, at
+   // its end, hands the tile over and frees the other one.
+   // Tried and measured slower (r02): letting warps run apart so that one group's epilogue (sqrt, log1p: mostly the other pipes) overlaps
+   // the other group's main loop (all FP32 pipe) -- a ring of four tiles with mbarrier hand-over: 15.8 / 14.2 ms against 13.0 ms; two
+   // groups skewed by the epilogue around the same barrier: 10.4 ms against 9.7 ms, with the epilogue rolled or unrolled. The main loop
+   // only reaches its 86 % of the FP32 pipe with all five warps of a scheduler inside it.
    constexpr int NV = F32 ? 384 : 192; // 16-byte vectors per chunk
    const int sv = w * 24 + lane;       // this lane's vector
    const bool stager = lane < 24 && w < NV / 24;
@@ -141,8 +125,13 @@ stft_sym_kernel( const void *__restrict__ in, long long stream_stride, int nw, i
          for ( int e = 0; e < 8; ++e ) stft_put( xs, 8 * sv + e, (float)hh[e] * ( 1.0f / 32768.0f ) );
       }
    };
+   // (a predicated load straight into `raw`: a conditional assignment made the compiler wait for the load at a register move)
    auto request = [&]( int c ) {
-      if ( c < nchunks && stager ) raw = __ldg( (const int4 *)stft_chunk_ptr<F32>( in, stream_stride, nw, c ) + sv );
+      const bool on = c < nchunks && stager;
+      const int4 *ptr = on ? (const int4 *)stft_chunk_ptr<F32>( in, stream_stride, nw, c ) + sv : (const int4 *)in;
+      asm volatile( "{\n .reg .pred p;\n setp.ne.s32 p, %4, 0;\n @p ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%5];\n}"
+                    : "+r"( raw.x ), "+r"( raw.y ), "+r"( raw.z ), "+r"( raw.w )
+                    : "r"( (int)on ), "l"( ptr ) );
    };
    int ci = blockIdx.x;
    request( ci );
@@ -150,18 +139,18 @@ stft_sym_kernel( const void *__restrict__ in, long long stream_stride, int nw, i
    request( ci + gridDim.x );
    __syncthreads();
 
-   // bin 64 of chunk `cprev` from the pairs the unit-0 lanes left in B64[pbuf] (the caller has passed a barrier since)
-   auto finish_bin64 = [&]( int cprev, int pbuf ) {
+   // bin 64 of chunk `c` from the pairs the unit-0 lanes left in B64[pbuf] (a barrier after the last of them has been passed)
+   auto finish_bin64 = [&]( int c, int pbuf ) {
       if ( w == SSYM_B64_WARP && lane < VB_FRAMES )
       {
          const float2 v = *reinterpret_cast<const float2 *>( B64 + ( pbuf * VB_FRAMES + lane ) * 2 );
          const float m2 = sqrtf( __fadd_rn( __fmul_rn( v.x, v.x ), __fmul_rn( v.y, v.y ) ) );
-         spec[(size_t)cprev * ( VB_BINS * VB_FRAMES ) + 64 * VB_FRAMES + lane] = out_mode ? m2 : lme::log1pf_ref( __fmul_rn( m2, 1048576.0f ) );
+         spec[(size_t)c * ( VB_BINS * VB_FRAMES ) + 64 * VB_FRAMES + lane] = out_mode ? m2 : lme::log1pf_ref( __fmul_rn( m2, 1048576.0f ) );
       }
    };
 
-   int buf = 0, cprev = -1;
-   for ( ; ci < nchunks; cprev = ci, ci += gridDim.x, buf ^= 1 )
+   int buf = 0, it = 0, cprev = -1;
+   for ( ; ci < nchunks; cprev = ci, ci += gridDim.x, buf ^= 1, ++it )
    {
       const float *xs = Xs_all + buf * STFT_XS_FLOATS;
       if ( ci + gridDim.x < nchunks )
@@ -169,14 +158,10 @@ stft_sym_kernel( const void *__restrict__ in, long long stream_stride, int nw, i
          stage( Xs_all + ( buf ^ 1 ) * STFT_XS_FLOATS );
          request( ci + 2 * gridDim.x );
       }
-      if ( cprev >= 0 ) finish_bin64( cprev, buf ^ 1 );
+      if ( cprev >= 0 ) finish_bin64( cprev, ( it - 1 ) & 1 );
 
-      // Frames go through in pairs (0,1), (2,3) + frame 4: the two frames of a pair share every basis value, their products are
-      // separate FMULs into adjacent registers, and every ADD of the tree is one packed FADD2 (add.rn.f32x2, sm_100: two independently
-      // rounded IEEE additions in one issue slot). 128 instead of 160 issue slots per (lane, group) for the same 160 operations; a
-      // FADD2 holds the FP32 pipe for two cycles, so the loop is paced by that pipe (155 cycles per 139 issue slots), which is the
-      // roofline this kernel is measured against. Multiplies stay scalar on purpose: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (even
-      // with --fmad=false), which would change the rounding; tests/test_host_logic.py checks the kernel's SASS for FFMA2.
+      // Frames go through in pairs (0,1), (2,3) + frame 4: the two frames of a pair share every basis value. Per 8-tap group and
+      // row: four FMUL2 + seven FADD; the FP32 pipe paces the loop (155 pipe cycles per 123 issue slots), it is 86 % busy inside it.
       ssym2 Sp[2][2], Sm[2][2]; // [row][pair]
       float Sp4[2], Sm4[2];     // frame 4
 #pragma unroll 1
@@ -265,25 +250,36 @@ stft_sym_kernel( const void *__restrict__ in, long long stream_stride, int nw, i
       }
 
       // lanes 0..3 (half 0) + lanes 4..7 (half 1): the half-0 thread takes the plain sums (bin u), the half-1 thread the alternating ones (bin 128-u)
-      float *o = spec + (size_t)ci * ( VB_BINS * VB_FRAMES ) + 5 * tg;
-      const int bin = half ? 128 - u : u;
+      float *o = spec + (size_t)ci * ( VB_BINS * VB_FRAMES ) + 5 * tg + ( half ? 128 - u : u ) * VB_FRAMES;
+      float yr[5], yi[5];
 #pragma unroll
       for ( int i = 0; i < 5; ++i )
       {
-         float y[2];
+         const float g0 = __shfl_xor_sync( 0xffffffffu, half ? Sps[0][i] : Sms[0][i], 16 );
+         const float g1 = __shfl_xor_sync( 0xffffffffu, half ? Sps[1][i] : Sms[1][i], 16 );
+         yr[i] = half ? __fadd_rn( g0, Sms[0][i] ) : __fadd_rn( Sps[0][i], g0 );
+         yi[i] = half ? __fadd_rn( g1, Sms[1][i] ) : __fadd_rn( Sps[1][i], g1 );
+      }
+      // magnitude + log1p per frame in a ROLLED loop (the values rotate through yr[0], yi[0]): a fifth of the code -- the kernel's hot
+      // code stays inside the 32 KB instruction cache of the SM
+      float *b64 = B64 + ( ( it & 1 ) * VB_FRAMES + 5 * tg ) * 2 + half;
+#pragma unroll 1
+      for ( int i = 0; i < 5; ++i )
+      {
+         const float re = yr[0], y1 = yi[0];
 #pragma unroll
-         for ( int a = 0; a < 2; ++a )
+         for ( int k = 0; k < 4; ++k )
          {
-            const float got = __shfl_xor_sync( 0xffffffffu, half ? Sps[a][i] : Sms[a][i], 16 );
-            y[a] = half ? __fadd_rn( got, Sms[a][i] ) : __fadd_rn( Sps[a][i], got );
+            yr[k] = yr[k + 1];
+            yi[k] = yi[k + 1];
          }
          // unit 0: half 0 holds re(bin 0), re(bin 64); half 1 holds re(bin 128), im(bin 64)
-         if ( special ) B64[( buf * VB_FRAMES + 5 * tg + i ) * 2 + half] = y[1];
-         const float re = y[0], im = special ? 0.0f : y[1];
+         if ( special ) b64[2 * i] = y1;
+         const float im = special ? 0.0f : y1;
          const float m = sqrtf( __fadd_rn( __fmul_rn( re, re ), __fmul_rn( im, im ) ) );
-         o[bin * VB_FRAMES + i] = out_mode ? m : lme::log1pf_ref( __fmul_rn( m, 1048576.0f ) );
+         o[i] = out_mode ? m : lme::log1pf_ref( __fmul_rn( m, 1048576.0f ) );
       }
       __syncthreads(); // the next tile is complete, this one and the other B64 buffer are free
    }
-   if ( cprev >= 0 ) finish_bin64( cprev, buf ^ 1 );
+   if ( cprev >= 0 ) finish_bin64( cprev, ( it - 1 ) & 1 );
 }
