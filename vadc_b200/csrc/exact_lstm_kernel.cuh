@@ -198,6 +198,12 @@ exact_lstm_kernel( const float *x0, float *h0seq, float *out1, float *__restrict
       __syncthreads();
       const int nsub = ( K + XL_SUB - 1 ) / XL_SUB;
       int buf = 0;
+#ifdef XL_TIMING // -DXL_TIMING: where the cycles of a step go, seen from the first row owner of the tanh gate (debug builds only)
+      long long tq[6] = { 0, 0, 0, 0, 0, 0 }, tl = clock64();
+#define XL_T( i ) { const long long now = clock64(); tq[i] += now - tl; tl = now; }
+#else
+#define XL_T( i )
+#endif
       for ( int step = 0; step < steps; ++step )
       {
          for ( int sb = 0; sb < nsub; ++sb, buf ^= 1 )
@@ -213,6 +219,7 @@ exact_lstm_kernel( const float *x0, float *h0seq, float *out1, float *__restrict
                wait_row( us, step + 1 );
                copy_row( xh + ( k0 + uk ) * XL_ROW + xn + uj, us, step + 1 );
             }
+            XL_T( 0 ) // copy issue (+ the consumer's wait)
             float *a = act + buf * ( XL_SUB * 256 );
             const bool spread = kn <= 4; // (measured: up to four streams the row owners' 1-2 evaluations + the cell's tanh beat five evaluations in the cell-update phase)
 #pragma unroll 1
@@ -240,6 +247,7 @@ exact_lstm_kernel( const float *x0, float *h0seq, float *out1, float *__restrict
                   lo[i] = half ? got : a0[i];   // lanes r0 r1 r4 r5 of my stream
                   hi[i] = half ? a1[i] : got;   // lanes r2 r3 r6 r7
                }
+               XL_T( 1 ) // contraction + exchange
                float z = 0.0f;
                z = __fadd_rn( z, lo[0] );
                z = __fadd_rn( z, lo[1] );
@@ -256,7 +264,9 @@ exact_lstm_kernel( const float *x0, float *h0seq, float *out1, float *__restrict
                // all five evaluations: there every thread does the same work and no warp is the slow one at the barrier.
                if ( !half || two ) a[( p + half ) * 256 + row] = !spread ? z : ( ( row >> 6 ) == 2 ? lme::tanhf_ref( z ) : lme::sigmoid_ref( z, exp_tab ) );
             }
+            XL_T( 2 ) // lane sum + the row's nonlinearity
             __syncthreads();
+            XL_T( 3 ) // barrier
             // gate nonlinearities and cell update (lstm.c:64-88) of (unit uj, stream k0 + uk)
             if ( upd )
             {
@@ -280,10 +290,17 @@ exact_lstm_kernel( const float *x0, float *h0seq, float *out1, float *__restrict
             // with a single sub-batch the next contraction reads what this update wrote; a wavefront producer publishes the step
             // after every thread's h of it has been stored (the barrier orders the stores before thread 0's release)
             const bool publish = WAVE && layer == 0 && sb == nsub - 1;
+            XL_T( 4 ) // cell update (threads of the first two warps only)
             if ( nsub == 1 || publish ) __syncthreads();
+            XL_T( 5 ) // barrier
             if ( publish && tid == 0 && !debug_stall_producer ) xl_st_release( progress, step + 1 );
          }
       }
+#ifdef XL_TIMING
+      if ( ( tid == 256 || tid == 0 ) && blockIdx.x < 2 )
+         printf( "XL_TIMING cta %d layer %d tid %d steps %d: copy/wait %lld contraction %lld nonlinearity %lld barrier %lld update %lld barrier %lld cycles per step\n", blockIdx.x, layer, tid,
+                 steps, tq[0] / steps, tq[1] / steps, tq[2] / steps, tq[3] / steps, tq[4] / steps, tq[5] / steps );
+#endif
       const int any_lost = __syncthreads_or( lost ? 1 : 0 );
       if ( !any_lost )
          for ( int e = tid; e < K * 64; e += XL_THREADS )

@@ -127,57 +127,45 @@ LME_FN float expm1f_ref( float x )
    r1 = fadd( one, fmul( hxs, fadd( Q1, fmul( hxs, fadd( Q2, fmul( hxs, fadd( Q3, fmul( hxs, fadd( Q4, fmul( hxs, Q5 ) ) ) ) ) ) ) ) ) );
    t = fsub( 3.0f, fmul( r1, hfx ) );
    e = fmul( hxs, fdiv( fsub( r1, t ), fsub( 6.0f, fmul( x, t ) ) ) );
-   if ( k == 0 ) return fsub( x, fsub( fmul( x, e ), hxs ) );
+   // fdlibm finishes by cases of k (0, -1, 1, k <= -2 or k > 56, k < 23, else). The lanes of a warp fall into most of them at once, and
+   // a warp executes every path some lane takes: all cases are evaluated here (each one's own arithmetic, a handful of operations,
+   // independent of each other) and one is selected. Results of the cases not selected may be anything; shift counts are masked.
+   const float r0 = fsub( x, fsub( fmul( x, e ), hxs ) ); // k == 0
    e = fsub( fmul( x, fsub( e, c ) ), c );
    e = fsub( e, hxs );
-   if ( k == -1 ) return fsub( fmul( 0.5f, fsub( x, e ) ), 0.5f );
-   if ( k == 1 )
-   {
-      if ( x < -0.25f ) return fmul( -2.0f, fsub( e, fadd( x, 0.5f ) ) );
-      return fadd( one, fmul( 2.0f, fsub( x, e ) ) );
-   }
-   if ( k <= -2 || k > 56 )
-   {
-      y = fsub( one, fsub( e, x ) );
-      y = word( __float_as_uint( y ) + ( (uint32_t)k << 23 ) );
-      return fsub( y, one );
-   }
-   if ( k < 23 )
-   {
-      t = word( 0x3f800000u - ( 0x1000000u >> k ) ); // 1 - 2^-k
-      y = fsub( t, fsub( e, x ) );
-      y = word( __float_as_uint( y ) + ( (uint32_t)k << 23 ) );
-   }
-   else
-   {
-      t = word( (uint32_t)( 0x7f - k ) << 23 ); // 2^-k
-      y = fsub( x, fadd( e, t ) );
-      y = fadd( y, one );
-      y = word( __float_as_uint( y ) + ( (uint32_t)k << 23 ) );
-   }
-   return y;
+   const float rm1 = fsub( fmul( 0.5f, fsub( x, e ) ), 0.5f ); // k == -1
+   const float rp1 = x < -0.25f ? fmul( -2.0f, fsub( e, fadd( x, 0.5f ) ) ) : fadd( one, fmul( 2.0f, fsub( x, e ) ) ); // k == 1
+   const uint32_t kbits = (uint32_t)k << 23;
+   const float emx = fsub( e, x );
+   const float ya = fsub( one, emx ); // k <= -2 || k > 56
+   const float ra = fsub( word( __float_as_uint( ya ) + kbits ), one );
+   const float yb = fsub( word( 0x3f800000u - ( 0x1000000u >> ( k & 31 ) ) ), emx ); // 2 <= k < 23: t = 1 - 2^-k
+   const float rb = word( __float_as_uint( yb ) + kbits );
+   const float yc = fadd( fsub( x, fadd( e, word( (uint32_t)( 0x7f - k ) << 23 ) ) ), one ); // 23 <= k <= 56: t = 2^-k
+   const float rc = word( __float_as_uint( yc ) + kbits );
+   y = k < 23 ? rb : rc;
+   y = ( k <= -2 || k > 56 ) ? ra : y;
+   y = k == 1 ? rp1 : y;
+   y = k == -1 ? rm1 : y;
+   return k == 0 ? r0 : y;
 }
 
 LME_FN float tanhf_ref( float x )
 {
    const float one = 1.0f, two = 2.0f, tiny = 1.0e-30f;
-   float t, z;
    const uint32_t jx = __float_as_uint( x ), ix = jx & 0x7fffffffu;
    if ( ix >= 0x7f800000u ) return ( (int)jx >= 0 ) ? fadd( fdiv( one, x ), one ) : fsub( fdiv( one, x ), one );
-   if ( ix < 0x41b00000u ) // |x| < 22
-   {
-      if ( ix == 0 ) return x;
-      if ( ix < 0x24000000u ) return fmul( x, fadd( one, x ) );
-      // one expm1f for both ranges (inlined twice, a warp with arguments on both sides of 1 ran both copies in turn):
-      // |x| >= 1: t = expm1f(2|x|), z = 1 - 2/(t+2);  |x| < 1: t = expm1f(-2|x|), z = -t/(t+2)
-      const bool big = ix >= 0x3f800000u;
-      t = expm1f_ref( fmul( big ? two : -two, fabsf( x ) ) );
-      const float q = fdiv( big ? two : -t, fadd( t, two ) );
-      z = big ? fsub( one, q ) : q;
-   }
-   else
-      z = fsub( one, tiny );
-   return ( (int)jx >= 0 ) ? z : -z;
+   // One expm1f for both ranges, and selects instead of fdlibm's early returns (the cell state of a silent stream sits beyond 22
+   // while its neighbours' are small: no warp may take two paths):
+   // |x| >= 1: t = expm1f(2|x|), z = 1 - 2/(t+2);  |x| < 1: t = expm1f(-2|x|), z = -t/(t+2);  |x| >= 22: 1 - tiny;  |x| < 2^-55: x (1 + x)
+   const bool big = ix >= 0x3f800000u;
+   const float t = expm1f_ref( fmul( big ? two : -two, fminf( fabsf( x ), 22.0f ) ) );
+   const float q = fdiv( big ? two : -t, fadd( t, two ) );
+   float z = big ? fsub( one, q ) : q;
+   z = ix < 0x41b00000u ? z : fsub( one, tiny );
+   z = ( (int)jx >= 0 ) ? z : -z;
+   z = ix < 0x24000000u ? fmul( x, fadd( one, x ) ) : z;
+   return ix == 0 ? x : z;
 }
 
 // fdlibm log1pf (s_log1pf.c) for x >= 0 (misc.c:40-46 applies it to magnitude * 2^20); checked on the host against the C library over
