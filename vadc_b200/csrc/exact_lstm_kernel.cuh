@@ -291,6 +291,9 @@ exact_lstm_kernel( const float *x0, float *h0seq, float *out1, float *__restrict
             // after every thread's h of it has been stored (the barrier orders the stores before thread 0's release)
             const bool publish = WAVE && layer == 0 && sb == nsub - 1;
             XL_T( 4 ) // cell update (threads of the first two warps only)
+            // (Tried, r02: with one stream per CTA, the x half of every row contracted a step ahead -- by the update warps after their
+            // sigmoid, by everybody else during the cell update, the same additions in the same order: 18.9 ms per 10 752 steps against
+            // 16.6 ms; the early work competes with the update, which IS the critical chain.)
             // (Tried, r02: the release and the consumer's acquire moved to warps that idle through the cell update, or into the slack
             // before the first barrier -- one stream 17.0 / 18.7 ms per 10 752 steps against 16.6 ms here: the release is a ~1000-cycle
             // fence wherever it sits, and a later publication only makes the consumer wait for it.)
