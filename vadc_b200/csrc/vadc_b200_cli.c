@@ -24,6 +24,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/types.h>
+#include <pthread.h>
+#include <sys/stat.h>
 #include <sys/wait.h>
 #include <time.h>
 #include <unistd.h>
@@ -34,6 +36,7 @@ typedef struct cli_opts
 {
    vadc_seg_params seg;
    int batch;
+   int batch_given; /* --batch on the command line */
    float start_seconds;
    int raw_probabilities, stats, device, audio_source;
    int devices[SILERO_B200_GROUP_MAX_DEVICES], ndevices;
@@ -89,7 +92,11 @@ static int parse_args( int argc, char **argv, cli_opts *o )
          if ( i + 1 < argc )
          {
             float v = (float)atof( argv[++i] );
-            if ( !strcmp( a, "--batch" ) && v > 0.0f ) o->batch = (int)v;
+            if ( !strcmp( a, "--batch" ) && v > 0.0f )
+            {
+               o->batch = (int)v;
+               o->batch_given = 1;
+            }
             if ( !strcmp( a, "--device" ) && v >= 0.0f ) o->device = (int)v;
             if ( !strcmp( a, "--audio_source" ) && v > 0.0f ) o->audio_source = (int)v; /* vadc.c:1122, 1215 */
          }
@@ -224,12 +231,52 @@ static int16_t *slurp_fd( int fd, long long *samples_out )
    return (int16_t *)buf;
 }
 
+/* The next batch is read while the GPU works on this one: a reader thread fills the other of two buffers (a 10-hour recording is
+   1.15 GB of reads, a sixth of its wall time when they alternate with the inference calls). Order, batch boundaries and therefore
+   the output are those of the sequential loop; on a live pipe a batch is still processed as soon as it is complete. */
+typedef struct prefetch
+{
+   int fd;
+   size_t cap_bytes;
+   int16_t *buf[2];
+   long long bytes[2]; /* what read_full returned for the buffer */
+   int filled[2];
+   int err;            /* errno of a failed read (errno itself is per thread) */
+   pthread_mutex_t m;
+   pthread_cond_t cv;
+} prefetch;
+
+static void *prefetch_main( void *arg )
+{
+   prefetch *p = (prefetch *)arg;
+   for ( int i = 0;; i ^= 1 )
+   {
+      pthread_mutex_lock( &p->m );
+      while ( p->filled[i] ) pthread_cond_wait( &p->cv, &p->m );
+      pthread_mutex_unlock( &p->m );
+      const long long r = read_full( p->fd, p->buf[i], p->cap_bytes );
+      if ( r < 0 ) p->err = errno;
+      pthread_mutex_lock( &p->m );
+      p->bytes[i] = r;
+      p->filled[i] = 1;
+      pthread_cond_broadcast( &p->cv );
+      pthread_mutex_unlock( &p->m );
+      if ( r < (long long)p->cap_bytes ) return 0; /* error or end of stream: the consumer stops after this buffer */
+   }
+}
+
 /* ---- one stream from a descriptor (stdin, or the ffmpeg pipe): the reference's own loop (vadc.c:852-1027) ---- */
 static int run_fd( silero_b200 *h, const cli_opts *o, int in_fd, int skip_on_read )
 {
-   const size_t cap_samples = (size_t)o->batch * SILERO_B200_CHUNK_SAMPLES;
-   int16_t *pcm = (int16_t *)malloc( cap_samples * sizeof( int16_t ) );
-   float *probs = (float *)malloc( (size_t)o->batch * sizeof( float ) );
+   /* Chunks per inference call: --batch (default 96, vadc.c:1116). The batch does not change a single output bit, only how often the
+      host and the GPU take turns; when the input is a regular FILE (nothing to wait for, no listener to keep up with) and the user
+      has not chosen, calls of 1536 chunks are used -- 10 % off a 10-hour recording's wall time. Pipes keep the reference's batch. */
+   int batch = o->batch;
+   struct stat st;
+   if ( !o->batch_given && fstat( in_fd, &st ) == 0 && S_ISREG( st.st_mode ) && batch < SILERO_B200_EXACT_TOKEN_MIN_CHUNKS ) batch = SILERO_B200_EXACT_TOKEN_MIN_CHUNKS;
+   const size_t cap_samples = (size_t)batch * SILERO_B200_CHUNK_SAMPLES;
+   int16_t *pcm = (int16_t *)malloc( 2 * cap_samples * sizeof( int16_t ) );
+   float *probs = (float *)malloc( (size_t)batch * sizeof( float ) );
    vadc_segment segs[64];
    if ( !pcm || !probs ) return 1;
    vadc_segmenter seg;
@@ -246,22 +293,44 @@ static int run_fd( silero_b200 *h, const cli_opts *o, int in_fd, int skip_on_rea
       if ( r <= 0 ) break;
       skip -= r;
    }
-   for ( ;; )
+   prefetch pf;
+   memset( &pf, 0, sizeof pf );
+   pf.fd = in_fd;
+   pf.cap_bytes = cap_samples * sizeof( int16_t );
+   pf.buf[0] = pcm;
+   pf.buf[1] = pcm + cap_samples;
+   pthread_mutex_init( &pf.m, 0 );
+   pthread_cond_init( &pf.cv, 0 );
+   pthread_t reader;
+   if ( pthread_create( &reader, 0, prefetch_main, &pf ) )
    {
-      long long bytes = read_full( in_fd, pcm, cap_samples * sizeof( int16_t ) );
+      fprintf( stderr, "Error: cannot start the reader thread\n" );
+      free( pcm );
+      free( probs );
+      return 1;
+   }
+   int rc = 0;
+   for ( int cur = 0;; cur ^= 1 )
+   {
+      pthread_mutex_lock( &pf.m );
+      while ( !pf.filled[cur] ) pthread_cond_wait( &pf.cv, &pf.m );
+      pthread_mutex_unlock( &pf.m );
+      const int16_t *batch = pf.buf[cur];
+      long long bytes = pf.bytes[cur];
       if ( bytes < 0 )
       {
-         fprintf( stderr, "Error: read failed: %s\n", strerror( errno ) );
+         fprintf( stderr, "Error: read failed: %s\n", strerror( pf.err ) );
          break;
       }
       const long long values_read = bytes / 2;
       const int nchunks = (int)( values_read / SILERO_B200_CHUNK_SAMPLES ); /* vadc.c:964: the trailing partial chunk is dropped */
       if ( nchunks > 0 )
       {
-         if ( silero_b200_run_streams( h, pcm, (long long)cap_samples, 0, 1, nchunks, probs, 0 ) )
+         if ( silero_b200_run_streams( h, batch, (long long)cap_samples, 0, 1, nchunks, probs, 0 ) )
          {
             fprintf( stderr, "Error: %s\n", silero_b200_last_error() );
-            return 1;
+            rc = 1;
+            break; /* (the reader is joined below; it ends at the end of its input) */
          }
          total_samples += (long long)nchunks * SILERO_B200_CHUNK_SAMPLES;
          if ( o->raw_probabilities )
@@ -276,7 +345,20 @@ static int run_fd( silero_b200 *h, const cli_opts *o, int in_fd, int skip_on_rea
          if ( o->stats ) print_stats( total_speech, total_samples, t0 );
       }
       if ( (size_t)bytes < cap_samples * sizeof( int16_t ) ) break; /* end of stream */
+      pthread_mutex_lock( &pf.m );
+      pf.filled[cur] = 0; /* the reader may overwrite it */
+      pthread_cond_broadcast( &pf.cv );
+      pthread_mutex_unlock( &pf.m );
    }
+   if ( rc )
+   {
+      pthread_cancel( reader ); /* blocked in read() or on the condition: both are cancellation points */
+      pthread_join( reader, 0 );
+      free( pcm );
+      free( probs );
+      return rc;
+   }
+   pthread_join( reader, 0 ); /* it has returned: the loop above ends with the reader's last buffer */
    if ( !o->raw_probabilities )
    {
       long long k = vadc_segmenter_finish( &seg, segs, 64 );
