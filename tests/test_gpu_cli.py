@@ -153,3 +153,31 @@ def test_multi_file_stats_count_speech(tmp_path):
     assert r.returncode == 0
     m = re.findall(r"([\d.]+) speech \(", r.stderr.decode(errors="replace"))
     assert m and float(m[-1]) > 1.0
+
+
+def test_pipe_in_pieces_and_file_input_give_the_same_output(tmp_path):
+    """The reader thread (next batch read while the GPU works) and the larger calls on regular-file input change when bytes are
+    read, not what is computed: a pipe fed in small, slow pieces, a regular file as stdin (calls of 1536 chunks), the same file with
+    an explicit --batch, and the one-shot pipe of the other tests all print the same segments."""
+    import time
+    pcm = vadc_b200.synth_pcm(321, 1536 * 3300 + 555)     # more than two 1536-chunk calls + a partial trailing chunk
+    data = pcm.tobytes()
+    want = cli(pcm)
+    assert want.count("\n") >= 20
+    path = tmp_path / "in.s16le"
+    path.write_bytes(data)
+    for args in ((), ("--batch", "96"), ("--batch", "1000")):
+        with open(path, "rb") as f:
+            r = subprocess.run([CLI, *args], stdin=f, capture_output=True, timeout=300)
+        assert r.returncode == 0, r.stderr.decode()
+        assert r.stdout.decode() == want, args
+    p = subprocess.Popen([CLI, "--batch", "7"], stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    step = 1536 * 2 * 5 + 123                             # pieces that straddle batch boundaries
+    for i in range(0, min(len(data), step * 40), step):
+        p.stdin.write(data[i:i + step])
+        p.stdin.flush()
+        time.sleep(0.002)
+    p.stdin.write(data[step * 40:])
+    out, err = p.communicate(timeout=300)
+    assert p.returncode == 0, err.decode()
+    assert out.decode() == want
