@@ -274,10 +274,8 @@ exact_lstm_kernel( const float *x0, float *h0seq, float *out1, float *__restrict
                float ig = av[uj], fg = av[64 + uj], gg = av[128 + uj], og = av[192 + uj];
                if ( !spread )
                {
-                  ig = lme::sigmoid_ref( ig, exp_tab );
-                  fg = lme::sigmoid_ref( fg, exp_tab );
+                  lme::sigmoid3_ref( ig, fg, og, exp_tab );
                   gg = lme::tanhf_ref( gg );
-                  og = lme::sigmoid_ref( og, exp_tab );
                }
                const int k = k0 + uk;
                const float cn = __fadd_rn( __fmul_rn( fg, cst[k * 64 + uj] ), __fmul_rn( ig, gg ) );

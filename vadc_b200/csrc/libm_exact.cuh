@@ -61,9 +61,8 @@ LME_FN float expf_ref( float x, const unsigned long long *tab = EXP2F_TAB )
    const double C0 = 0x1.c6af84b912394p-5 / 32.0 / 32.0 / 32.0, C1 = 0x1.ebfce50fac4f3p-3 / 32.0 / 32.0, C2 = 0x1.62e42ff0c52d6p-1 / 32.0;
    // e_expf.c: x > log(2^128) overflows; x < log(2^-150) = -0x1.9fe368p6 underflows to 0; x < log(2^-149) = -0x1.9d1d9ep6 takes
    // __math_may_uflowf, whose 0x1.4p-75f squared rounds to the smallest denormal; in between the double result rounds to a denormal
-   if ( x > 88.72283f ) return __int_as_float( 0x7f800000 );
-   if ( x < -0x1.9fe368p6f ) return 0.0f;
-   if ( x < -0x1.9d1d9ep6f ) return __int_as_float( 1 );
+   // (the three special ranges are SELECTED at the end, not branched to: the polynomial below is straight-line code that the compiler
+   // can interleave with a neighbour's -- sigmoid3_ref -- and whatever it computes for an out-of-range argument is discarded)
    double z = __dmul_rn( InvLn2N, (double)x );
    double kd = __dadd_rn( z, SHIFT );
    const unsigned long long ki = (unsigned long long)__double_as_longlong( kd );
@@ -75,7 +74,10 @@ LME_FN float expf_ref( float x, const unsigned long long *tab = EXP2F_TAB )
    double y = __dadd_rn( __dmul_rn( C2, r ), 1.0 );
    y = __dadd_rn( __dmul_rn( z, r2 ), y );
    y = __dmul_rn( y, s );
-   return __double2float_rn( y );
+   float res = __double2float_rn( y );
+   res = x < -0x1.9d1d9ep6f ? __int_as_float( 1 ) : res;
+   res = x < -0x1.9fe368p6f ? 0.0f : res;
+   return x > 88.72283f ? __int_as_float( 0x7f800000 ) : res;
 }
 
 LME_FN float fmul( float a, float b ) { return __fmul_rn( a, b ); }
@@ -246,6 +248,15 @@ LME_FN float log1pf_ref( float x )
 
 // maths.h:327-334: 1 / (1 + expf(-x))
 LME_FN float sigmoid_ref( float v, const unsigned long long *tab = EXP2F_TAB ) { return fdiv( 1.0f, fadd( 1.0f, expf_ref( -v, tab ) ) ); }
+// three at once (the input, forget and output gate of a cell): the three exponentials are independent straight-line chains
+LME_FN void sigmoid3_ref( float &a, float &b, float &c, const unsigned long long *tab = EXP2F_TAB )
+{
+   const float ea = expf_ref( -a, tab ), eb = expf_ref( -b, tab ), ec = expf_ref( -c, tab );
+   const float da = fadd( 1.0f, ea ), db = fadd( 1.0f, eb ), dc = fadd( 1.0f, ec );
+   a = fdiv( 1.0f, da );
+   b = fdiv( 1.0f, db );
+   c = fdiv( 1.0f, dc );
+}
 #if defined( __CUDACC__ )
 // copy of the table for expf_ref( x, tab ); call with all threads of the CTA, then synchronize
 LME_FN void stage_exp2f_tab( unsigned long long *dst, int tid )
