@@ -96,18 +96,10 @@ LME_FN float expm1f_ref( float x )
    uint32_t hx = __float_as_uint( x );
    const uint32_t xsb = hx & 0x80000000u;
    hx &= 0x7fffffffu;
-   if ( hx >= 0x4195b844u ) // |x| >= 27 ln 2
-   {
-      if ( xsb != 0 )
-      {
-         if ( fadd( x, tiny ) < 0.0f ) return fsub( tiny, one );
-      }
-   }
-   if ( hx < 0x33000000u ) // |x| < 2^-25
-   {
-      t = fadd( huge, x );
-      return fsub( x, fsub( t, fadd( huge, x ) ) );
-   }
+   // fdlibm's two early returns, selected at the end like everything else
+   const float x0 = x;
+   const bool sat = hx >= 0x4195b844u && xsb != 0 && fadd( x, tiny ) < 0.0f; // x <= -27 ln 2: tiny - one
+   const bool small = hx < 0x33000000u;                                       // |x| < 2^-25: x - ((huge + x) - (huge + x))
    // Argument reduction without divergence (the lanes of a warp hold pre-activations of all sizes, and every divergent path is
    // executed by the whole warp). fdlibm's three cases collapse into one formula: for 0.5 ln2 < |x| < 1.5 ln2 it sets k = +-1,
    // hi = x -+ ln2_hi, lo = +-ln2_lo -- exactly what the general case computes from t = (float)k = +-1 (1 * ln2_hi and 1 * ln2_lo are
@@ -149,14 +141,16 @@ LME_FN float expm1f_ref( float x )
    y = ( k <= -2 || k > 56 ) ? ra : y;
    y = k == 1 ? rp1 : y;
    y = k == -1 ? rm1 : y;
-   return k == 0 ? r0 : y;
+   y = k == 0 ? r0 : y;
+   t = fadd( huge, x0 );
+   y = small ? fsub( x0, fsub( t, fadd( huge, x0 ) ) ) : y;
+   return sat ? fsub( tiny, one ) : y;
 }
 
 LME_FN float tanhf_ref( float x )
 {
    const float one = 1.0f, two = 2.0f, tiny = 1.0e-30f;
    const uint32_t jx = __float_as_uint( x ), ix = jx & 0x7fffffffu;
-   if ( ix >= 0x7f800000u ) return ( (int)jx >= 0 ) ? fadd( fdiv( one, x ), one ) : fsub( fdiv( one, x ), one );
    // One expm1f for both ranges, and selects instead of fdlibm's early returns (the cell state of a silent stream sits beyond 22
    // while its neighbours' are small: no warp may take two paths):
    // |x| >= 1: t = expm1f(2|x|), z = 1 - 2/(t+2);  |x| < 1: t = expm1f(-2|x|), z = -t/(t+2);  |x| >= 22: 1 - tiny;  |x| < 2^-55: x (1 + x)
@@ -167,7 +161,10 @@ LME_FN float tanhf_ref( float x )
    z = ix < 0x41b00000u ? z : fsub( one, tiny );
    z = ( (int)jx >= 0 ) ? z : -z;
    z = ix < 0x24000000u ? fmul( x, fadd( one, x ) ) : z;
-   return ix == 0 ? x : z;
+   z = ix == 0 ? x : z;
+   // infinity -> +-1 (fdlibm: one / x +- one), NaN -> NaN
+   z = ix == 0x7f800000u ? ( (int)jx >= 0 ? one : -one ) : z;
+   return ix > 0x7f800000u ? fadd( x, x ) : z;
 }
 
 // fdlibm log1pf (s_log1pf.c) for x >= 0 (misc.c:40-46 applies it to magnitude * 2^20); checked on the host against the C library over
