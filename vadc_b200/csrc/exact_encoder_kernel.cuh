@@ -481,6 +481,7 @@ exact_layer_kernel( const float *__restrict__ in, float *__restrict__ out, const
    using Cfg = XeCfg<L>;
    constexpr xe::LayerOff O = Cfg::O;
    constexpr int CIN = O.cin, C = O.C, T = O.T, D = C / 2, GB = Cfg::GB, TOUT = O.Tout;
+   constexpr int UNR = C <= 16 ? 4 : 2; // output features in flight per thread: the narrow layer has the registers for four
    extern __shared__ __align__( 16 ) float wsm[];
    const int tid = threadIdx.x;
    {
@@ -536,7 +537,7 @@ exact_layer_kernel( const float *__restrict__ in, float *__restrict__ out, const
                }
                d[c] = xe::relu( xe::add( wsm[O.dw_b + c], r ) );
             }
-#pragma unroll 2
+#pragma unroll( UNR )
             for ( int f = 0; f < C; ++f )
             {
                float y = xe::conv1_e_r<CIN>( d, wsm + O.pw_w + f * CIN, wsm[O.pw_b + f] );
@@ -550,7 +551,7 @@ exact_layer_kernel( const float *__restrict__ in, float *__restrict__ out, const
             for ( int f = 0; f < C; ++f ) u[f] = R0[f * XE_THREADS];
          }
          // QKV = u qkv_w^T + b (tensor.h:675-723)
-#pragma unroll 2
+#pragma unroll( UNR )
          for ( int o = 0; o < 3 * C; ++o ) QKV[o * XE_THREADS] = xe::add( xe::dot_simd_r<C>( u, wsm + O.qkv_w + o * C ), wsm[O.qkv_b + o] );
       }
       __syncthreads(); // the chunk's q and v rows are complete
@@ -609,7 +610,7 @@ exact_layer_kernel( const float *__restrict__ in, float *__restrict__ out, const
 #pragma unroll
             for ( int i = 0; i < T; ++i ) A[i] = xe::mul( A[i], inv );
             // O_h[j] = dotproduct_simd( A row, V column j, T ): T = 25 one block + 9 tail taps, T = 13 / 7 all tail
-#pragma unroll 2
+#pragma unroll( UNR )
             for ( int j = 0; j < D; ++j )
             {
                const float *vcol = QKVg + (size_t)( 2 * C + h * D + j ) * XE_THREADS;
@@ -637,7 +638,7 @@ exact_layer_kernel( const float *__restrict__ in, float *__restrict__ out, const
          // out-projection + residual (transformer.c:178-190)
 #pragma unroll
          for ( int i = 0; i < C; ++i ) v[i] = R1[i * XE_THREADS];
-#pragma unroll 2
+#pragma unroll( UNR )
          for ( int o = 0; o < C; ++o )
          {
             const float att = xe::add( xe::dot_simd_r<C>( v, wsm + O.ao_w + o * C ), wsm[O.ao_b + o] );
@@ -649,11 +650,11 @@ exact_layer_kernel( const float *__restrict__ in, float *__restrict__ out, const
 #pragma unroll
          for ( int i = 0; i < C; ++i ) R1[i * XE_THREADS] = v[i];
          // feed-forward + residual
-#pragma unroll 2
+#pragma unroll( UNR )
          for ( int o = 0; o < C; ++o ) R0[o * XE_THREADS] = xe::relu( xe::add( xe::dot_simd_r<C>( v, wsm + O.l1_w + o * C ), wsm[O.l1_b + o] ) );
 #pragma unroll
          for ( int i = 0; i < C; ++i ) v[i] = R0[i * XE_THREADS];
-#pragma unroll 2
+#pragma unroll( UNR )
          for ( int o = 0; o < C; ++o )
          {
             const float f2 = xe::add( xe::dot_simd_r<C>( v, wsm + O.l2_w + o * C ), wsm[O.l2_b + o] );
@@ -666,7 +667,7 @@ exact_layer_kernel( const float *__restrict__ in, float *__restrict__ out, const
          if ( t % O.stride == 0 )
          {
             const int to = t / O.stride;
-#pragma unroll 2
+#pragma unroll( UNR )
             for ( int f = 0; f < C; ++f )
             {
                const float z = O.stride == 1 ? xe::conv1_e_r<C>( v, wsm + O.cv_w + f * C, wsm[O.cv_b + f] )
