@@ -85,8 +85,10 @@ typedef struct silero_b200 silero_b200; /* opaque engine handle */
 #define SILERO_B200_LAYERS_FP32 1
 #define SILERO_B200_LAYERS_TENSOR 2
 #define SILERO_B200_LAYERS_FAITHFUL 3
-#define SILERO_B200_EXACT_TOKEN_MIN_CHUNKS 1536   /* exact path: windows of at least this many chunks run the thread-per-token encoder
-                                                     (below: a CTA per chunk -- more parallelism for small windows; identical bits) */
+#define SILERO_B200_EXACT_TOKEN_MIN_CHUNKS 384    /* exact path: windows of at least this many chunks run the thread-per-token encoder
+                                                     (below: a CTA per chunk -- more parallelism for small windows; identical bits).
+                                                     Measured crossover (scripts/gpu_encoder_crossover.sh): 192 chunks 0.15 vs 0.18 ms,
+                                                     384 chunks 0.18 vs 0.18 ms, 768 chunks 0.31 vs 0.21 ms */
 
 typedef struct silero_b200_opts
 {

@@ -186,10 +186,11 @@ def test_lstm_kernels_agree_bit_for_bit():
 
 
 # ---- the whole path ----------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("S,N,window", [(75, 20, 7), (149, 12, 0), (149, 10, 0), (300, 30, 11), (1185, 9, 4)])
+@pytest.mark.parametrize("S,N,window", [(75, 20, 7), (75, 20, 5), (12, 31, 0), (12, 32, 0), (149, 12, 0), (149, 10, 0), (300, 30, 11), (1185, 9, 4)])
 def test_batch_shapes_around_the_kernel_switches(S, N, window):
     """Stream counts around the points where the engine changes mapping (LSTM wavefront launch <-> one launch per layer at 10 x SMs / 2 streams,
-    CTA-per-chunk <-> thread-per-token encoder at 1536 chunks per window; one and two streams per LSTM CTA): identical bits."""
+    CTA-per-chunk <-> thread-per-token encoder at 384 chunks per window -- 375 / 372 chunks below it, 384 / 525 above; layer batches of
+    fewer chunks than a CTA holds on small windows; one and two streams per LSTM CTA): identical bits."""
     base = [vadc_b200.synth_pcm(900 + 17 * i, CHUNK * N) for i in range(16)]
     pcm = np.stack([np.roll(base[s % 16], CHUNK * ((s // 16) % N)) for s in range(S)])
     e = vadc_b200.Engine(max_streams=S, window_chunks=window)
@@ -227,11 +228,11 @@ def test_long_streams_at_scale_gate():
 def test_throughput_does_not_fall_when_streams_are_added():
     """No regime cliff: with the kernel family fixed per engine, the device-resident rate (chunks per second) of a call must not drop when
     the caller adds streams -- across the points where the engine changes kernel mapping (740/741 streams: LSTM wavefront launch -> one launch per layer;
-    1536 chunks per window: encoder CTA-per-chunk -> thread-per-token). 10 % tolerance for timer noise on these short runs."""
+    384 chunks per window: encoder CTA-per-chunk -> thread-per-token). 10 % tolerance for timer noise on these short runs."""
     N = 32
     base = [vadc_b200.synth_pcm(100 + i, CHUNK * N) for i in range(8)]
     rates = []
-    sizes = (16, 64, 74, 75, 128, 129, 296, 297, 512, 740, 741, 1023, 1024, 4096)
+    sizes = (8, 11, 12, 16, 64, 74, 75, 128, 129, 296, 297, 512, 740, 741, 1023, 1024, 4096)
     e = vadc_b200.Engine(max_streams=max(sizes))
     for S in sizes:
         pcm = np.stack([base[s % 8] for s in range(S)])

@@ -226,7 +226,9 @@ def test_device_resident_path_equals_host_path():
     e.d2h(dev, d_probs)
     assert np.array_equal(dev, host)
     ms, launches = e.last_timing()
-    assert launches == 4 * 3 and ms["total"] > 0     # 33 streams: the faithful path, 4 kernels per window; windows of 16+16+8
+    # windows of 16 + 16 + 8 chunks x 33 streams: 528 chunks take the thread-per-token encoder (STFT, front, 4 layers, LSTM wavefront,
+    # decoder head = 8 launches), 264 chunks the CTA-per-chunk encoder (4 launches)
+    assert launches == 8 + 8 + 4 and ms["total"] > 0
     e.device_free(d_pcm); e.device_free(d_probs); e.close()
 
 

@@ -89,6 +89,7 @@ struct silero_b200
    int *err_word;            // mapped pinned host word a kernel raises when it gives up (wavefront consumer whose producer is lost)
    int *d_err_word;          // its device address
    int wave_spin_limit;      // polls before a wavefront consumer gives up (debug taps lower it)
+   int token_min_chunks;     // windows of at least this many chunks take the thread-per-token encoder (SILERO_B200_EXACT_TOKEN_MIN_CHUNKS; $SILERO_B200_TOKEN_MIN_CHUNKS for measurements)
    int debug_stall_producer; // test hook: layer-0 tasks never publish progress
    float *state_h, *state_c; // [max_streams][2][64]
    // window scratch (grow-only)
@@ -749,6 +750,9 @@ static int create_impl( const void *bytes, size_t nbytes, const silero_b200_opts
    *h->err_word = 0;
    CU_H( cudaHostGetDevicePointer( (void **)&h->d_err_word, h->err_word, 0 ) );
    h->wave_spin_limit = 1 << 24;
+   h->token_min_chunks = SILERO_B200_EXACT_TOKEN_MIN_CHUNKS;
+   if ( const char *e = getenv( "SILERO_B200_TOKEN_MIN_CHUNKS" ) )
+      if ( atoi( e ) > 0 ) h->token_min_chunks = atoi( e ); // (both mappings give the same bits: only speed depends on it)
    {
       size_t free_b = 0, total_b = 0;
       h->scratch_budget = (size_t)1536 << 20;
@@ -881,6 +885,7 @@ static int pick_window( const silero_b200 *h, int nstreams, int nchunks, bool ho
 // launches
 // ---------------------------------------------------------------------------------------------
 static inline int imin( int a, int b ) { return a < b ? a : b; }
+static inline int imax( int a, int b ) { return a > b ? a : b; }
 
 // mu (optional): receives the adaptive-normalization scalar per chunk when the selected kernel produces it (the FFT
 // kernel); the tensor-core and exact kernels leave it to the first layer (the caller checks stft_produces_mu)
@@ -1065,8 +1070,11 @@ template <int L>
 static int launch_exact_layer( silero_b200 *h, const float *in, float *out, int nchunks )
 {
    using Cfg = XeCfg<L>;
-   const int grid = imin( ( nchunks + Cfg::GB - 1 ) / Cfg::GB, h->sm_count );
-   exact_layer_kernel<L><<<grid, XE_THREADS, Cfg::SMEM_BYTES, h->stream>>>( in, out, h->fw.t[L == 0 ? 1 : ( L == 1 ? 25 : ( L == 2 ? 49 : 71 ) )], h->xe_scratch, nchunks );
+   // chunks per batch: a full CTA's worth (GB) when there is work for every SM, fewer when the window is small -- a window of 4 736
+   // chunks is 65 full batches of layer 4 (65 of 148 SMs busy) or 148 batches of 32 chunks
+   const int gb = imax( 1, imin( Cfg::GB, ( nchunks + h->sm_count - 1 ) / h->sm_count ) );
+   const int grid = imin( ( nchunks + gb - 1 ) / gb, h->sm_count );
+   exact_layer_kernel<L><<<grid, XE_THREADS, Cfg::SMEM_BYTES, h->stream>>>( in, out, h->fw.t[L == 0 ? 1 : ( L == 1 ? 25 : ( L == 2 ? 49 : 71 ) )], h->xe_scratch, nchunks, gb );
    h->launches++;
    CU( cudaGetLastError() );
    return 0;
@@ -1196,7 +1204,7 @@ static int run_window( silero_b200 *h, const void *d_in, int in_f32, long long s
       // of (stream, layer) CTAs while there are SM pairs for every stream, else CTAs that walk sets of streams together.
       // Stage times (profiling): [2] front + rest of layer 1, [3..5] layers 2..4, [6] LSTM layer 0, [7] LSTM layer 1 + decoder head
       // (small windows: [2] the whole encoder, [6] both LSTM layers).
-      if ( nchunks < SILERO_B200_EXACT_TOKEN_MIN_CHUNKS )
+      if ( nchunks < h->token_min_chunks )
       {
          if ( launch_faithful_encoder( h, h->spec, h->a4, nchunks ) ) return SILERO_B200_ERR_CUDA;
          CU( cudaEventRecord( h->ev_spec_free, h->stream ) );

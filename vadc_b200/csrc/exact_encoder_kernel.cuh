@@ -476,7 +476,7 @@ struct XeCfg
 // out: [chunk][C][Tout]; L == 3: [chunk][7][64]
 template <int L>
 __global__ void __launch_bounds__( XE_THREADS, 1 )
-exact_layer_kernel( const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ wl, float *scratch, int nchunks )
+exact_layer_kernel( const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ wl, float *scratch, int nchunks, int gb /* chunks per batch, <= GB */ )
 {
    using Cfg = XeCfg<L>;
    constexpr xe::LayerOff O = Cfg::O;
@@ -493,11 +493,11 @@ exact_layer_kernel( const float *__restrict__ in, float *__restrict__ out, const
    float *R1 = R0 + (size_t)C * XE_THREADS;
    float *QKV = R1 + (size_t)C * XE_THREADS;
    const int g = tid / T, t = tid - g * T;
-   const bool tok = g < GB;
+   const bool tok = g < gb;
    const float *QKVg = QKV - tid + g * T; // column of token 0 of my chunk
    __syncthreads();
 
-   for ( int c0 = blockIdx.x * GB; c0 < nchunks; c0 += gridDim.x * GB )
+   for ( int c0 = blockIdx.x * gb; c0 < nchunks; c0 += gridDim.x * gb )
    {
       const bool live = tok && c0 + g < nchunks;
       const int ci = c0 + g;

@@ -231,6 +231,8 @@ static int16_t *slurp_fd( int fd, long long *samples_out )
    return (int16_t *)buf;
 }
 
+#define CLI_FILE_BATCH 1536 /* chunks per call for regular-file input without --batch (147 s of audio, 4.7 MB) */
+
 /* The next batch is read while the GPU works on this one: a reader thread fills the other of two buffers (a 10-hour recording is
    1.15 GB of reads, a sixth of its wall time when they alternate with the inference calls). Order, batch boundaries and therefore
    the output are those of the sequential loop; on a live pipe a batch is still processed as soon as it is complete. */
@@ -270,10 +272,10 @@ static int run_fd( silero_b200 *h, const cli_opts *o, int in_fd, int skip_on_rea
 {
    /* Chunks per inference call: --batch (default 96, vadc.c:1116). The batch does not change a single output bit, only how often the
       host and the GPU take turns; when the input is a regular FILE (nothing to wait for, no listener to keep up with) and the user
-      has not chosen, calls of 1536 chunks are used -- 10 % off a 10-hour recording's wall time. Pipes keep the reference's batch. */
+      has not chosen, calls of CLI_FILE_BATCH chunks are used -- 10 % off a 10-hour recording's wall time. Pipes keep the reference's batch. */
    int batch = o->batch;
    struct stat st;
-   if ( !o->batch_given && fstat( in_fd, &st ) == 0 && S_ISREG( st.st_mode ) && batch < SILERO_B200_EXACT_TOKEN_MIN_CHUNKS ) batch = SILERO_B200_EXACT_TOKEN_MIN_CHUNKS;
+   if ( !o->batch_given && fstat( in_fd, &st ) == 0 && S_ISREG( st.st_mode ) && batch < CLI_FILE_BATCH ) batch = CLI_FILE_BATCH;
    const size_t cap_samples = (size_t)batch * SILERO_B200_CHUNK_SAMPLES;
    int16_t *pcm = (int16_t *)malloc( 2 * cap_samples * sizeof( int16_t ) );
    float *probs = (float *)malloc( (size_t)batch * sizeof( float ) );
