@@ -480,7 +480,7 @@ exact_layer_kernel( const float *__restrict__ in, float *__restrict__ out, const
 {
    using Cfg = XeCfg<L>;
    constexpr xe::LayerOff O = Cfg::O;
-   constexpr int CIN = O.cin, C = O.C, T = O.T, D = C / 2, GB = Cfg::GB, TOUT = O.Tout;
+   constexpr int CIN = O.cin, C = O.C, T = O.T, D = C / 2, TOUT = O.Tout;
    constexpr int UNR = C <= 16 ? 4 : 2; // output features in flight per thread: the narrow layer has the registers for four
    extern __shared__ __align__( 16 ) float wsm[];
    const int tid = threadIdx.x;
