@@ -80,9 +80,12 @@ struct DeviceWeights
 __device__ __forceinline__ float4 ld4( const float *p ) { return *reinterpret_cast<const float4 *>( p ); }
 __device__ __forceinline__ void st4( float *p, float4 v ) { *reinterpret_cast<float4 *>( p ) = v; }
 
-// Two fp32 values in a 64-bit register pair for the packed add of sm_100 (add.rn.f32x2 -> FADD2): each half is an independently
-// rounded IEEE addition, one issue slot for both. Multiplies stay scalar on purpose: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2
-// into FFMA2 (even with --fmad=false), which would change the rounding; tests/test_host_logic.py checks the SASS for FFMA2 / FMUL2.
+// Two fp32 values in a 64-bit register pair for the packed arithmetic of sm_100 (mul.rn.f32x2 -> FMUL2, add.rn.f32x2 -> FADD2): each
+// half is an independently rounded IEEE operation, one issue slot for both. ONE rule: a packed product never feeds a packed add --
+// ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (even with --fmad=false), which changes the rounding. The exact path
+// packs the PRODUCTS (operands are the register pairs an LDS.128 delivers) and adds scalar; the alternative -- scalar products,
+// packed adds -- measured slower and survives behind XL_PACKED_MUL 0. tests/test_host_logic.py reads the SASS: no FFMA2 in an
+// exact-path kernel, no kernel with both FMUL2 and FADD2.
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pk2( float lo, float hi )
 {
@@ -97,7 +100,7 @@ __device__ __forceinline__ f32x2 add2( f32x2 a, f32x2 b )
    asm( "add.rn.f32x2 %0, %1, %2;" : "=l"( c ) : "l"( a ), "l"( b ) );
    return c;
 }
-// (only where the products feed SCALAR additions: see above)
+// (only where the products feed SCALAR additions)
 __device__ __forceinline__ f32x2 mul2( f32x2 a, f32x2 b )
 {
    f32x2 c;
